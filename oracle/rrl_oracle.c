@@ -1,0 +1,488 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- plain-C CPU restatement of the reference hot path.
+ *
+ * Restates, in IEEE binary32 arithmetic with the reference's operation order and NO
+ * fused multiply-add (build with -ffp-contract=off, see oracle/build.py), the functions of
+ * SURVEY.md section 8(a).  Citations are file:line under /root/reference/code/.
+ *
+ *   a1  point<->line distance, local threshold, labels        loss.py:68-112
+ *   a2  per-(k,j) intersection points and squared distances   loss.py:115-167
+ *   a3  lower-median-scaled Welsch loss                       loss.py:170-232
+ *   a4  analytic gradient of a1-a3 (autograd in the reference; closed form SURVEY 9.1)
+ *   a5  se(3) exponential + row-vector rigid transform        loss.py:437-463,
+ *                                                             LieAlgebra/se3.py:83-106,
+ *                                                             LieAlgebra/so3.py:17-27,
+ *                                                             LieAlgebra/sinc.py:5-17,91-103,120-132
+ *   a6/a7 line sampler from supplied uniforms + AABB rejection loss.py:265-432
+ *   f1  chamfer_dist                                          loss.py:236-252
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product path (the CUDA library behind include/rrl_b200.h)
+ * never does and fails loudly when its own .so is missing.
+ *
+ * Numerics: sqrtf here is correctly rounded (IEEE); the reference's torch.sqrt CPU kernel is
+ * not (1 ulp off for ~0.7% of inputs).  Tests whose distance lies within 1 ulp of
+ * the threshold are therefore counted (`band`) and excluded from index-exact comparisons with
+ * the torch reference; against the CUDA kernels (also IEEE sqrt) the comparison is exact.
+ *
+ * Parity status: PINNED against the unmodified reference executed in the build container
+ * (oracle/make_golden.py -> the .npz files under tests/golden; tests/test_oracle_golden.py).  The reference
+ * ships no tests or golden vectors of its own.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define RRL_CAP 5            /* hit slots kept per line and cloud; lines with >4 hits are dropped */
+#define ADD_EPS 2e-4f        /* loss.py:88  */
+#define THR_SCALE 1.731f     /* loss.py:109 */
+
+int rrl_oracle_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void rrl_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* ---- a1 ------------------------------------------------------------------------------- */
+
+static inline float norm3_sq(float dx, float dy, float dz) {
+    return ((dx * dx) + (dy * dy)) + (dz * dz);          /* torch.sum over a size-3 dim: ((a+b)+c) */
+}
+
+/* thr_f = (delta_f * 1.731f) / 2, delta_f = ((|p1-p0| + |p2-p0|) + |p1-p2|) / 3   loss.py:94-109 */
+float rrl_oracle_triplet_thr(const float *t) {
+    float e01 = sqrtf(norm3_sq(t[3] - t[0], t[4] - t[1], t[5] - t[2]));
+    float e02 = sqrtf(norm3_sq(t[6] - t[0], t[7] - t[1], t[8] - t[2]));
+    float e12 = sqrtf(norm3_sq(t[3] - t[6], t[4] - t[7], t[5] - t[8]));
+    float delta = ((e01 + e02) + e12) / 3.0f;
+    return (delta * THR_SCALE) / 2.0f;
+}
+
+/* d = sqrt((|AC|^2 - (AC.u)^2) + 2e-4)   loss.py:84-88 */
+float rrl_oracle_point_line_d(const float *p, const float *line) {
+    float ax = p[0] - line[3], ay = p[1] - line[4], az = p[2] - line[5];
+    float dot = ((ax * line[0]) + (ay * line[1])) + (az * line[2]);
+    float proj = dot * dot;
+    float dac = ((ax * ax) + (ay * ay)) + (az * az);
+    return sqrtf((dac - proj) + ADD_EPS);
+}
+
+static inline float ulp_of(float x) { return nextafterf(x, INFINITY) - x; }
+
+/*
+ * Dense phase for one cloud.  counts[nl]: number of hit triplets per line (uncapped);
+ * hits[nl*RRL_CAP]: the first RRL_CAP hit triplet indices in ascending order (-1 padded);
+ * hit_d[nl*RRL_CAP*3]: their three distances.  stats[0] += #NaN distances (the reference
+ * exits on any, loss.py:89-91), stats[1] += #tests with |d-thr| <= 1 ulp(thr).
+ */
+void rrl_oracle_dense(const float *tri, int nf, const float *lines, int64_t nl,
+                      int32_t *counts, int32_t *hits, float *hit_d, int64_t *stats) {
+    float *thr = (float *)malloc(sizeof(float) * (size_t)(nf > 0 ? nf : 1));
+    for (int f = 0; f < nf; ++f) thr[f] = rrl_oracle_triplet_thr(tri + 9 * (size_t)f);
+    int64_t nan_total = 0, band_total = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : nan_total, band_total)
+    for (int64_t l = 0; l < nl; ++l) {
+        const float *ln = lines + 6 * l;
+        int c = 0;
+        for (int s = 0; s < RRL_CAP; ++s) {
+            hits[l * RRL_CAP + s] = -1;
+            if (hit_d) hit_d[(l * RRL_CAP + s) * 3] = hit_d[(l * RRL_CAP + s) * 3 + 1] = hit_d[(l * RRL_CAP + s) * 3 + 2] = 0.f;
+        }
+        for (int f = 0; f < nf; ++f) {
+            const float *t = tri + 9 * (size_t)f;
+            float d0 = rrl_oracle_point_line_d(t, ln);
+            float d1 = rrl_oracle_point_line_d(t + 3, ln);
+            float d2 = rrl_oracle_point_line_d(t + 6, ln);
+            float th = thr[f];
+            nan_total += (d0 != d0) + (d1 != d1) + (d2 != d2);
+            float u = ulp_of(th);
+            band_total += (fabsf(d0 - th) <= u) + (fabsf(d1 - th) <= u) + (fabsf(d2 - th) <= u);
+            if ((d0 < th) & (d1 < th) & (d2 < th)) {
+                if (c < RRL_CAP) {
+                    hits[l * RRL_CAP + c] = f;
+                    if (hit_d) {
+                        float *hd = hit_d + (l * RRL_CAP + c) * 3;
+                        hd[0] = d0; hd[1] = d1; hd[2] = d2;
+                    }
+                }
+                ++c;
+            }
+        }
+        counts[l] = c;
+    }
+    if (stats) { stats[0] += nan_total; stats[1] += band_total; }
+    free(thr);
+}
+
+/* ---- a2/a3/a4 --------------------------------------------------------------------------- */
+
+typedef struct {
+    int64_t line;
+    int k, j;
+    int idx1[4], idx2[4];
+    float w1[4][3], w2[4][3];
+    float q1[4][3], q2[4][3];
+    float D[4][4];
+} rrl_rec;
+
+static void make_q(const float *tri, const int32_t *hit, const float *hd, int n,
+                   int *idx, float w[4][3], float q[4][3]) {
+    for (int a = 0; a < n; ++a) {
+        idx[a] = hit[a];
+        const float *t = tri + 9 * (size_t)hit[a];
+        const float *d = hd + 3 * a;
+        float s = (d[0] + d[1]) + d[2];                          /* loss.py:92 */
+        w[a][0] = d[0] / s; w[a][1] = d[1] / s; w[a][2] = d[2] / s;
+        for (int c = 0; c < 3; ++c)                               /* loss.py:155-163: mean of 3 => sum / 3 */
+            q[a][c] = (((w[a][0] * t[c]) + (w[a][1] * t[3 + c])) + (w[a][2] * t[6 + c])) / 3.0f;
+    }
+}
+
+static int cmp_float(const void *a, const void *b) {
+    float x = *(const float *)a, y = *(const float *)b;
+    return (x > y) - (x < y);
+}
+
+/*
+ * Full loss for ONE pair, lines supplied.
+ *   out_scalars[0]=loss, [1]=median;  out_counts[0]=C (#non-empty combos), [1]=#selected lines,
+ *   [2]=#D entries, [3]=#NaN distances, [4]=#band tests;  n_kj[16] indexed (k-1)*4+(j-1) for
+ *   k,j in 1..4 (only combos inside [k_lo,k_hi)x[j_lo,j_hi) are populated).
+ *   grad1 (nf1*9) / grad2 (nf2*9): d loss / d points, may be NULL.
+ *   counts1/hits1/counts2/hits2: optional dense outputs (nl, nl*RRL_CAP), may be NULL.
+ *   D_out: optional, nl*16 floats, row-major (a*4+b) per line, zero where unused.
+ * Returns 0, or 1 when no combo is populated (the reference returns (None,None,None), loss.py:232).
+ */
+int rrl_oracle_loss(const float *tri1, int nf1, const float *tri2, int nf2,
+                    const float *lines, int64_t nl, int k_lo, int j_lo, int k_hi, int j_hi,
+                    float *out_scalars, int64_t *out_counts, int64_t *n_kj,
+                    float *grad1, float *grad2,
+                    int32_t *counts1, int32_t *hits1, int32_t *counts2, int32_t *hits2,
+                    float *D_out) {
+    size_t snl = (size_t)(nl > 0 ? nl : 1);
+    int32_t *c1 = (int32_t *)malloc(sizeof(int32_t) * snl), *c2 = (int32_t *)malloc(sizeof(int32_t) * snl);
+    int32_t *h1 = (int32_t *)malloc(sizeof(int32_t) * snl * RRL_CAP), *h2 = (int32_t *)malloc(sizeof(int32_t) * snl * RRL_CAP);
+    float *hd1 = (float *)malloc(sizeof(float) * snl * RRL_CAP * 3), *hd2 = (float *)malloc(sizeof(float) * snl * RRL_CAP * 3);
+    int64_t stats[2] = {0, 0};
+    rrl_oracle_dense(tri1, nf1, lines, nl, c1, h1, hd1, stats);
+    rrl_oracle_dense(tri2, nf2, lines, nl, c2, h2, hd2, stats);
+    if (counts1) memcpy(counts1, c1, sizeof(int32_t) * (size_t)nl);
+    if (counts2) memcpy(counts2, c2, sizeof(int32_t) * (size_t)nl);
+    if (hits1) memcpy(hits1, h1, sizeof(int32_t) * (size_t)nl * RRL_CAP);
+    if (hits2) memcpy(hits2, h2, sizeof(int32_t) * (size_t)nl * RRL_CAP);
+    if (D_out) memset(D_out, 0, sizeof(float) * (size_t)nl * 16);
+    if (grad1) memset(grad1, 0, sizeof(float) * (size_t)nf1 * 9);
+    if (grad2) memset(grad2, 0, sizeof(float) * (size_t)nf2 * 9);
+    for (int i = 0; i < 16; ++i) n_kj[i] = 0;
+
+    /* records of the selected lines, in line order */
+    int64_t nrec = 0, nD = 0;
+    for (int64_t l = 0; l < nl; ++l)
+        if (c1[l] >= k_lo && c1[l] < k_hi && c2[l] >= j_lo && c2[l] < j_hi && c1[l] <= 4 && c2[l] <= 4 && c1[l] >= 1 && c2[l] >= 1) {
+            ++nrec; nD += (int64_t)c1[l] * c2[l];
+        }
+    rrl_rec *rec = (rrl_rec *)malloc(sizeof(rrl_rec) * (size_t)(nrec > 0 ? nrec : 1));
+    float *allD = (float *)malloc(sizeof(float) * (size_t)(nD > 0 ? nD : 1));
+    int64_t r = 0, e = 0;
+    for (int64_t l = 0; l < nl; ++l) {
+        int k = c1[l], j = c2[l];
+        if (!(k >= k_lo && k < k_hi && j >= j_lo && j < j_hi && k <= 4 && j <= 4 && k >= 1 && j >= 1)) continue;
+        rrl_rec *R = rec + r++;
+        R->line = l; R->k = k; R->j = j;
+        make_q(tri1, h1 + l * RRL_CAP, hd1 + l * RRL_CAP * 3, k, R->idx1, R->w1, R->q1);
+        make_q(tri2, h2 + l * RRL_CAP, hd2 + l * RRL_CAP * 3, j, R->idx2, R->w2, R->q2);
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < j; ++b) {                          /* loss.py:38-52 */
+                float dx = R->q1[a][0] - R->q2[b][0], dy = R->q1[a][1] - R->q2[b][1], dz = R->q1[a][2] - R->q2[b][2];
+                float D = ((dx * dx) + (dy * dy)) + (dz * dz);
+                R->D[a][b] = D;
+                allD[e++] = D;
+                if (D_out) D_out[l * 16 + a * 4 + b] = D;
+            }
+        n_kj[(k - 1) * 4 + (j - 1)]++;
+    }
+    int C = 0;
+    for (int i = 0; i < 16; ++i) C += n_kj[i] > 0;
+    out_counts[0] = C; out_counts[1] = nrec; out_counts[2] = nD; out_counts[3] = stats[0]; out_counts[4] = stats[1];
+    int rc = 1;
+    out_scalars[0] = 0.f; out_scalars[1] = 0.f;
+    if (C > 0) {
+        rc = 0;
+        qsort(allD, (size_t)nD, sizeof(float), cmp_float);
+        float med = allD[(nD - 1) / 2];                            /* torch.median = lower median, loss.py:223 */
+        double S1[16], S2[16];
+        for (int i = 0; i < 16; ++i) S1[i] = S2[i] = 0.0;
+        for (int64_t i = 0; i < nrec; ++i) {
+            rrl_rec *R = rec + i;
+            int k = R->k, j = R->j, cb = (k - 1) * 4 + (j - 1);
+            float W[4][4];
+            for (int a = 0; a < k; ++a)
+                for (int b = 0; b < j; ++b) W[a][b] = 1.0f - expf(-((R->D[a][b] / med)) / 2.0f);   /* loss.py:20-21 */
+            int arg_b[4], arg_a[4];
+            for (int a = 0; a < k; ++a) {                          /* torch.min(.,2): first index on ties */
+                int m = 0;
+                for (int b = 1; b < j; ++b) if (W[a][b] < W[a][m]) m = b;
+                arg_b[a] = m; S1[cb] += (double)W[a][m];
+            }
+            for (int b = 0; b < j; ++b) {
+                int m = 0;
+                for (int a = 1; a < k; ++a) if (W[a][b] < W[m][b]) m = a;
+                arg_a[b] = m; S2[cb] += (double)W[m][b];
+            }
+            if (grad1 || grad2) {
+                double n = (double)n_kj[cb];
+                double c = exp(-0.5 * abs(k - j)) / (double)C;
+                double gq1[4][3] = {{0}}, gq2[4][3] = {{0}};
+                for (int a = 0; a < k; ++a)
+                    for (int b = 0; b < j; ++b) {
+                        double coef = (arg_b[a] == b ? c / (n * k) : 0.0) + (arg_a[b] == a ? c / (n * j) : 0.0);
+                        if (coef == 0.0) continue;
+                        double dWdD = exp(-(double)R->D[a][b] / (2.0 * (double)med)) / (2.0 * (double)med);
+                        for (int x = 0; x < 3; ++x) {
+                            double g = coef * dWdD * 2.0 * ((double)R->q1[a][x] - (double)R->q2[b][x]);
+                            gq1[a][x] += g; gq2[b][x] -= g;
+                        }
+                    }
+                if (grad1)
+                    for (int a = 0; a < k; ++a)
+                        for (int i3 = 0; i3 < 3; ++i3)
+                            for (int x = 0; x < 3; ++x)
+                                grad1[9 * (size_t)R->idx1[a] + 3 * i3 + x] += (float)((double)R->w1[a][i3] / 3.0 * gq1[a][x]);
+                if (grad2)
+                    for (int b = 0; b < j; ++b)
+                        for (int i3 = 0; i3 < 3; ++i3)
+                            for (int x = 0; x < 3; ++x)
+                                grad2[9 * (size_t)R->idx2[b] + 3 * i3 + x] += (float)((double)R->w2[b][i3] / 3.0 * gq2[b][x]);
+            }
+        }
+        double loss = 0.0;
+        for (int k = 1; k <= 4; ++k)
+            for (int j = 1; j <= 4; ++j) {
+                int cb = (k - 1) * 4 + (j - 1);
+                if (!n_kj[cb]) continue;
+                double n = (double)n_kj[cb];
+                loss += exp(-0.5 * abs(k - j)) * (S1[cb] / (n * k) + S2[cb] / (n * j));   /* loss.py:215,227-229 */
+            }
+        out_scalars[0] = (float)(loss / (double)C);                 /* loss.py:230 */
+        out_scalars[1] = med;
+    }
+    free(rec); free(allD); free(c1); free(c2); free(h1); free(h2); free(hd1); free(hd2);
+    return rc;
+}
+
+/* ---- a5 --------------------------------------------------------------------------------- */
+
+static void sinc123(double t, double *a, double *b, double *c, double *da, double *db, double *dc) {
+    double t2 = t * t;
+    if (fabs(t) < 0.01) {                                          /* Taylor branches, sinc.py:7-11,95-99,124-128 */
+        *a = 1 - t2 / 6 * (1 - t2 / 20 * (1 - t2 / 42));
+        *b = 0.5 * (1 - t2 / 12 * (1 - t2 / 30 * (1 - t2 / 56)));
+        *c = 1.0 / 6 * (1 - t2 / 20 * (1 - t2 / 42 * (1 - t2 / 72)));
+        *da = -t / 3 * (1 - t2 / 10 * (1 - t2 / 28 * (1 - t2 / 54)));
+        *db = -t / 12 * (1 - t2 / 5 * (1.0 / 3 - t2 / 56 * (1.0 / 2 - t2 / 135)));
+        *dc = -t / 60 * (1 - t2 / 21 * (1 - t2 / 24 * (1.0 / 2 - t2 / 165)));
+    } else {
+        double s = sin(t), co = cos(t);
+        *a = s / t;
+        *b = (1 - co) / t2;
+        *c = (t - s) / (t2 * t);
+        *da = co / t - s / t2;
+        *db = s / t2 - 2 * (1 - co) / (t2 * t);
+        *dc = (3 * s - t * (co + 2)) / (t2 * t2);
+    }
+}
+
+static void hat3(const double *w, double W[9]) {
+    W[0] = 0; W[1] = -w[2]; W[2] = w[1];
+    W[3] = w[2]; W[4] = 0; W[5] = -w[0];
+    W[6] = -w[1]; W[7] = w[0]; W[8] = 0;
+}
+
+static void mat3mul(const double *A, const double *B, double *C) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+
+/* twist[6]=[w,v] -> R[9] (row-major), T[3].  Computed in double, rounded once (the float32
+ * reference agrees to ~1e-7; the transform is outside the index-exact boundary). */
+void rrl_oracle_se3_exp(const float *twist, float *R, float *T) {
+    double w[3] = {twist[0], twist[1], twist[2]}, v[3] = {twist[3], twist[4], twist[5]};
+    double t = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double a, b, c, da, db, dc, W[9], S[9];
+    sinc123(t, &a, &b, &c, &da, &db, &dc);
+    hat3(w, W); mat3mul(W, W, S);
+    for (int i = 0; i < 9; ++i) {
+        double I = (i % 4 == 0) ? 1.0 : 0.0;
+        R[i] = (float)(I + a * W[i] + b * S[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0;
+        for (int j = 0; j < 3; ++j) {
+            double I = (i == j) ? 1.0 : 0.0;
+            acc += (I + b * W[3 * i + j] + c * S[3 * i + j]) * v[j];
+        }
+        T[i] = (float)acc;
+    }
+}
+
+/* p' = p @ R + T (row vectors, loss.py:460-461); n points */
+void rrl_oracle_rigid_apply(const float *R, const float *T, const float *p, int64_t n, float *out) {
+    for (int64_t i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c)
+            out[3 * i + c] = ((p[3 * i] * R[c] + p[3 * i + 1] * R[3 + c]) + p[3 * i + 2] * R[6 + c]) + T[c];
+}
+
+/* Chain rule of a5: G_R[m][n] = sum_p p[m] g[n], G_T = sum_p g  ->  d loss / d twist. */
+void rrl_oracle_se3_backward(const float *twist, const double *G_R, const double *G_T, double *g_twist) {
+    double w[3] = {twist[0], twist[1], twist[2]}, v[3] = {twist[3], twist[4], twist[5]};
+    double t = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double a, b, c, da, db, dc, W[9], S[9];
+    sinc123(t, &a, &b, &c, &da, &db, &dc);
+    hat3(w, W); mat3mul(W, W, S);
+    /* (x'/t) with the t->0 limits of the Taylor series: a'/t -> -1/3, b'/t -> -1/12, c'/t -> -1/60 */
+    double dat = t > 0 ? da / t : -1.0 / 3, dbt = t > 0 ? db / t : -1.0 / 12, dct = t > 0 ? dc / t : -1.0 / 60;
+    for (int k = 0; k < 3; ++k) {
+        double e[3] = {0, 0, 0}, E[9], EW[9], WE[9];
+        e[k] = 1; hat3(e, E); mat3mul(E, W, EW); mat3mul(W, E, WE);
+        double acc = 0;
+        for (int i = 0; i < 9; ++i) {
+            double dR = a * E[i] + b * (EW[i] + WE[i]) + dat * w[k] * W[i] + dbt * w[k] * S[i];
+            acc += dR * G_R[i];
+        }
+        for (int i = 0; i < 3; ++i) {
+            double row = 0;
+            for (int j = 0; j < 3; ++j) {
+                double dV = b * E[3 * i + j] + c * (EW[3 * i + j] + WE[3 * i + j]) + dbt * w[k] * W[3 * i + j] + dct * w[k] * S[3 * i + j];
+                row += dV * v[j];
+            }
+            acc += row * G_T[i];
+        }
+        g_twist[k] = acc;
+    }
+    for (int j = 0; j < 3; ++j) {
+        double acc = 0;
+        for (int i = 0; i < 3; ++i) {
+            double I = (i == j) ? 1.0 : 0.0;
+            acc += (I + b * W[3 * i + j] + c * S[3 * i + j]) * G_T[i];
+        }
+        g_twist[3 + j] = acc;
+    }
+}
+
+/* ---- a6/a7 ------------------------------------------------------------------------------ */
+
+static const int BOX_FACES[12][3] = {{2, 0, 6}, {0, 4, 6}, {5, 4, 0}, {5, 0, 1}, {6, 4, 5}, {5, 7, 6},
+                                     {3, 0, 2}, {1, 0, 3}, {3, 2, 6}, {6, 7, 3}, {5, 1, 3}, {3, 7, 5}};   /* loss.py:357-358 */
+
+/* lo/hi -> 12 triangles x 9 floats   loss.py:325-362 */
+void rrl_oracle_box_triangles(const float *lo, const float *hi, float *tris) {
+    static const int sel[8][3] = {{1, 1, 1}, {1, 1, 0}, {1, 0, 1}, {1, 0, 0}, {0, 1, 1}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+    float corner[8][3];
+    for (int i = 0; i < 8; ++i)
+        for (int a = 0; a < 3; ++a) corner[i][a] = sel[i][a] ? hi[a] : lo[a];
+    for (int f = 0; f < 12; ++f)
+        for (int v = 0; v < 3; ++v)
+            for (int a = 0; a < 3; ++a) tris[9 * f + 3 * v + a] = corner[BOX_FACES[f][v]][a];
+}
+
+static inline void cross3(const float *a, const float *b, float *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static inline float norm3(const float *a) { return sqrtf(norm3_sq(a[0], a[1], a[2])); }
+
+/* area test of loss.py:265-316: number of box triangles the line "hits" */
+int rrl_oracle_triangle_hits(const float *tris, const float *line) {
+    int hits = 0;
+    for (int f = 0; f < 12; ++f) {
+        const float *A = tris + 9 * f, *B = A + 3, *Cc = A + 6;
+        float e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, e2[3] = {Cc[0] - A[0], Cc[1] - A[1], Cc[2] - A[2]};
+        float n[3]; cross3(e1, e2, n);
+        float S = norm3(n);
+        float den = fmaxf(S, 1e-12f);                               /* F.normalize eps */
+        float nn[3] = {n[0] / den, n[1] / den, n[2] / den};
+        float num = ((nn[0] * (A[0] - line[3])) + (nn[1] * (A[1] - line[4]))) + (nn[2] * (A[2] - line[5]));
+        float dd = (((nn[0] * line[0]) + (nn[1] * line[1])) + (nn[2] * line[2])) + 1e-12f;
+        float t = num / dd;
+        float X[3] = {t * line[0] + line[3], t * line[1] + line[4], t * line[2] + line[5]};
+        float ca[3] = {X[0] - A[0], X[1] - A[1], X[2] - A[2]}, cb[3] = {X[0] - B[0], X[1] - B[1], X[2] - B[2]}, cc[3] = {X[0] - Cc[0], X[1] - Cc[1], X[2] - Cc[2]};
+        float x1[3], x2[3], x3[3];
+        cross3(cb, cc, x1); cross3(cc, ca, x2); cross3(ca, cb, x3);
+        float a = norm3(x1), b = norm3(x2), c = norm3(x3);
+        hits += (a > 0) && (b > 0) && (c > 0) && ((a + b) + c <= S);
+    }
+    return hits;
+}
+
+/* candidate line from 4 uniforms in [0,1)   loss.py:394-411 */
+void rrl_oracle_line_from_uniforms(float r, const float *center, float a1, float u1, float a2, float u2, float *line) {
+    const float PI32 = 3.14159274101257324f;                       /* torch.pi as float32, loss.py:9 */
+    float al1 = (a1 * 2) * PI32, z1 = u1 * 2 - 1.0f, al2 = (a2 * 2) * PI32, z2 = u2 * 2 - 1.0f;
+    float s1 = sqrtf(1 - z1 * z1), s2 = sqrtf(1 - z2 * z2);
+    float q1[3] = {r * s1 * cosf(al1), r * sinf(al1) * s1, r * z1};
+    float q2[3] = {r * s2 * cosf(al2), r * sinf(al2) * s2, r * z2};
+    float d[3] = {q2[0] - q1[0], q2[1] - q1[1], q2[2] - q1[2]};
+    float n = fmaxf(norm3(d), 1e-12f);
+    line[0] = d[0] / n; line[1] = d[1] / n; line[2] = d[2] / n;
+    line[3] = q1[0] + center[0]; line[4] = q1[1] + center[1]; line[5] = q1[2] + center[2];
+}
+
+/* ..._resample for one pair, uniforms[rounds][4][n] supplied   loss.py:415-432.  Returns #filled rows;
+ * rows >= filled stay all-zero like the reference. */
+int64_t rrl_oracle_sample_lines(float r, const float *center, int64_t n, const float *lo1, const float *hi1,
+                                const float *lo2, const float *hi2, const float *uniforms, int rounds, float *out) {
+    float t1[108], t2[108];
+    rrl_oracle_box_triangles(lo1, hi1, t1);
+    rrl_oracle_box_triangles(lo2, hi2, t2);
+    memset(out, 0, sizeof(float) * 6 * (size_t)n);
+    int64_t filled = 0;
+    for (int rd = 0; rd < rounds && filled < n; ++rd) {
+        const float *U = uniforms + (size_t)rd * 4 * (size_t)n;
+        for (int64_t i = 0; i < n && filled < n; ++i) {
+            float ln[6];
+            rrl_oracle_line_from_uniforms(r, center, U[i], U[n + i], U[2 * n + i], U[3 * n + i], ln);
+            if (rrl_oracle_triangle_hits(t1, ln) * rrl_oracle_triangle_hits(t2, ln) > 0) {
+                memcpy(out + 6 * filled, ln, sizeof(ln));
+                ++filled;
+            }
+        }
+    }
+    return filled;
+}
+
+/* ---- f1 --------------------------------------------------------------------------------- */
+
+/* chamfer_dist for one pair: mean over the concatenation of both directed min-sq-distances */
+float rrl_oracle_chamfer(const float *x, int64_t m, const float *y, int64_t n) {
+    double acc = 0;
+    float *best_y = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+    for (int64_t j = 0; j < n; ++j) best_y[j] = INFINITY;
+    for (int64_t i = 0; i < m; ++i) {
+        float bi = INFINITY;
+        for (int64_t j = 0; j < n; ++j) {
+            float dx = x[3 * i] - y[3 * j], dy = x[3 * i + 1] - y[3 * j + 1], dz = x[3 * i + 2] - y[3 * j + 2];
+            float d = ((dx * dx) + (dy * dy)) + (dz * dz);
+            if (d < bi) bi = d;
+            if (d < best_y[j]) best_y[j] = d;
+        }
+        acc += bi;
+    }
+    for (int64_t j = 0; j < n; ++j) acc += best_y[j];
+    free(best_y);
+    return (float)(acc / (double)(m + n));
+}
