@@ -1,0 +1,19 @@
+"""B200-native intersected-line robust registration loss (hot path of Dengzhi-USTC/A-robust-registration-loss).
+
+The directory name carries a hyphen, so import it through the repo-root shim:  `import rrl_b200`.
+
+    rrl_b200.intersected_line_loss(tri1, tri2, lines)      batched native API, per-pair losses (B,)
+    rrl_b200.se3_apply / se3_exp / rigid_apply             fused se(3) exponential + transform
+    rrl_b200.sample_lines                                  on-device line sampler (Philox4x32-10)
+    rrl_b200.chamfer                                       monitoring metric
+    rrl_b200.loss                                          drop-in module with the reference's names (code/loss.py)
+    rrl_b200.dist                                          batch-/line-sharded multi-GPU evaluation
+"""
+from . import _native
+from ._native import NativeError, launch_count
+from .ops import (LossInfo, chamfer, intersected_line_loss, rigid_apply, sample_lines, se3_apply, se3_exp)
+from . import loss  # noqa: E402  (reference-compatible names)
+from . import dist  # noqa: E402
+
+__all__ = ["NativeError", "launch_count", "LossInfo", "chamfer", "intersected_line_loss", "rigid_apply",
+           "sample_lines", "se3_apply", "se3_exp", "loss", "dist"]

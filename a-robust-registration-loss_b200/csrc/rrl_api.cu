@@ -1,0 +1,320 @@
+// extern "C" surface of librrl_b200.so (include/rrl_b200.h): argument checking, workspace carving, stage
+// sequencing on the caller's stream, the line-shard stage API and the host-buffer convenience context.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "rrl_common.cuh"
+
+namespace rrl {
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch() { return cudaGetLastError() == cudaSuccess ? RRL_OK : RRL_ERR_CUDA; }
+void set_dense_variant(int v);
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
+    Workspace w;
+    char *p = reinterpret_cast<char *>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *r = p + off;
+        off = align_up(off + bytes);
+        return r;
+    };
+    const size_t sB = (size_t)B, lines = (size_t)B * nl;
+    const int nf1p = pad_points(nf1), nf2p = pad_points(nf2);
+    w.hdr = reinterpret_cast<int *>(take(8 * sizeof(int)));
+    // ---- per-pair block, contiguous and zeroed by one memset in launch_prep (order matters) ----
+    char *pair = take(sB * (2 * 4 + 4 + 16 * 4 + 4 + 2 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
+    w.pmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
+    w.nrec = reinterpret_cast<int *>(pair);                           pair += sB * 4;
+    w.n_kj = reinterpret_cast<int *>(pair);                           pair += sB * 16 * 4;
+    w.med = reinterpret_cast<float *>(pair);                          pair += sB * 4;
+    w.flags = reinterpret_cast<int *>(pair);                          pair += sB * 2 * 4;
+    w.sums = reinterpret_cast<unsigned long long *>(pair);            pair += sB * 32 * 8;
+    w.stats = reinterpret_cast<long long *>(pair);                    pair += sB * RRL_NSTAT * 8;
+    w.gcounts = reinterpret_cast<long long *>(pair);
+    // ---- per triplet ----
+    w.tri4[0] = reinterpret_cast<float4 *>(take(sB * nf1p * sizeof(float4)));
+    w.tri4[1] = reinterpret_cast<float4 *>(take(sB * nf2p * sizeof(float4)));
+    w.thr[0] = reinterpret_cast<float *>(take(sB * nf1 * sizeof(float)));
+    w.thr[1] = reinterpret_cast<float *>(take(sB * nf2 * sizeof(float)));
+    // ---- per line ----
+    w.cnt[0] = reinterpret_cast<int *>(take(2 * lines * sizeof(int)));
+    w.cnt[1] = w.cnt[0] + lines;
+    w.hits[0] = reinterpret_cast<int *>(take(lines * kCap * sizeof(int)));
+    w.hits[1] = reinterpret_cast<int *>(take(lines * kCap * sizeof(int)));
+    // ---- per record ----
+    w.recD = reinterpret_cast<float *>(take(lines * 16 * sizeof(float)));
+    w.recMeta = reinterpret_cast<int *>(take(lines * 2 * sizeof(int)));
+    w.recIdx = reinterpret_cast<int *>(take(lines * 8 * sizeof(int)));
+    w.recW = reinterpret_cast<float *>(take(lines * 24 * sizeof(float)));
+    w.recQ = reinterpret_cast<float *>(take(lines * 24 * sizeof(float)));
+    w.bytes = off;
+    return w;
+}
+
+static bool geometry_ok(int B, int nf1, int nf2, int nl) {
+    return B > 0 && nf1 > 0 && nf2 > 0 && nl > 0 && B <= 32767 && (long long)B * nl <= (1LL << 30);
+}
+static bool window_ok(int k_lo, int j_lo, int k_hi, int j_hi) {
+    return k_lo >= 1 && j_lo >= 1 && k_hi <= 5 && j_hi <= 5 && k_lo < k_hi && j_lo < j_hi;
+}
+static Geometry make_geometry(int B, int nf1, int nf2, int nl) {
+    Geometry g;
+    g.B = B; g.nf1 = nf1; g.nf2 = nf2; g.nl = nl;
+    g.nf1p = pad_points(nf1); g.nf2p = pad_points(nf2);
+    return g;
+}
+
+static int stage_dense_and_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws,
+                                 const Geometry &g, int k_lo, int j_lo, int k_hi, int j_hi, cudaStream_t s) {
+    const int window = k_lo | (j_lo << 8) | (k_hi << 16) | (j_hi << 24);
+    int rc = launch_prep(tri1, tri2, ws, g, window, s);
+    if (rc) return rc;
+    rc = launch_dense(tri1, tri2, lines, ws, g, s);
+    if (rc) return rc;
+    return launch_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, s);
+}
+
+}  // namespace rrl
+
+using namespace rrl;
+
+extern "C" int rrl_version(void) { return RRL_VERSION; }
+
+extern "C" const char *rrl_error_string(int code) {
+    switch (code) {
+        case RRL_OK: return "ok";
+        case RRL_ERR_ARG: return "invalid argument (null pointer, non-positive size, or hit-count window outside 1..4)";
+        case RRL_ERR_WORKSPACE: return "workspace smaller than rrl_workspace_bytes()";
+        case RRL_ERR_CUDA: return "CUDA runtime call or kernel launch failed";
+        case RRL_ERR_STATE: return "workspace does not hold a forward pass for this geometry";
+        default: return "unknown error";
+    }
+}
+
+extern "C" long long rrl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" size_t rrl_workspace_bytes(int B, int nf1, int nf2, int nl) {
+    if (!geometry_ok(B, nf1, nf2, nl)) return 0;
+    return carve(nullptr, B, nf1, nf2, nl).bytes;
+}
+
+extern "C" int rrl_loss_forward(const float *tri1, const float *tri2, const float *lines, int B, int nf1, int nf2, int nl,
+                                int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes,
+                                float *out_loss, int *out_status, float *out_median, long long *out_stats, void *stream) {
+    if (!tri1 || !tri2 || !lines || !workspace || !out_loss) return RRL_ERR_ARG;
+    if (!geometry_ok(B, nf1, nf2, nl) || !window_ok(k_lo, j_lo, k_hi, j_hi)) return RRL_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return RRL_ERR_ARG;
+    const Workspace ws = carve(workspace, B, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    const Geometry g = make_geometry(B, nf1, nf2, nl);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = stage_dense_and_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, s);
+    if (rc) return rc;
+    if ((rc = launch_median(ws, g, s))) return rc;
+    if ((rc = launch_welsch(ws, g, s))) return rc;
+    return launch_finalize(ws, g, out_loss, out_status, out_median, out_stats, s);
+}
+
+extern "C" int rrl_loss_backward(const void *workspace, size_t workspace_bytes, const float *grad_out, int B, int nf1,
+                                 int nf2, int nl, float *grad_tri1, float *grad_tri2, void *stream) {
+    if (!workspace || !grad_out || !geometry_ok(B, nf1, nf2, nl)) return RRL_ERR_ARG;
+    const Workspace ws = carve(const_cast<void *>(workspace), B, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    if (!grad_tri1 && !grad_tri2) return RRL_OK;
+    return launch_backward(ws, make_geometry(B, nf1, nf2, nl), grad_out, grad_tri1, grad_tri2, (cudaStream_t)stream);
+}
+
+extern "C" int rrl_loss_export_hits(const void *workspace, size_t workspace_bytes, int B, int nf1, int nf2, int nl,
+                                    int cloud, int *out_counts, int *out_hits, void *stream) {
+    if (!workspace || !out_counts || !out_hits || !geometry_ok(B, nf1, nf2, nl) || (cloud != 1 && cloud != 2)) return RRL_ERR_ARG;
+    const Workspace ws = carve(const_cast<void *>(workspace), B, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    return launch_export_hits(ws, make_geometry(B, nf1, nf2, nl), cloud - 1, out_counts, out_hits, (cudaStream_t)stream);
+}
+
+// ---- line-shard stages (B = 1) -------------------------------------------------------------------------
+extern "C" int rrl_shard_stage1(const float *tri1, const float *tri2, const float *lines, int nf1, int nf2, int nl,
+                                int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!tri1 || !tri2 || !lines || !workspace) return RRL_ERR_ARG;
+    if (!geometry_ok(1, nf1, nf2, nl) || !window_ok(k_lo, j_lo, k_hi, j_hi)) return RRL_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return RRL_ERR_ARG;
+    const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    return stage_dense_and_build(tri1, tri2, lines, ws, make_geometry(1, nf1, nf2, nl), k_lo, j_lo, k_hi, j_hi, (cudaStream_t)stream);
+}
+
+extern "C" int rrl_shard_counts(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl, long long *counts18, void *stream) {
+    if (!workspace || !counts18 || !geometry_ok(1, nf1, nf2, nl)) return RRL_ERR_ARG;
+    const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int rc = launch_local_counts(ws, make_geometry(1, nf1, nf2, nl), s);
+    if (rc) return rc;
+    return cudaMemcpyAsync(counts18, ws.gcounts, 18 * sizeof(long long), cudaMemcpyDeviceToDevice, s) == cudaSuccess ? RRL_OK : RRL_ERR_CUDA;
+}
+
+extern "C" int rrl_shard_pack_entries(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl, float *out_entries,
+                                      long long capacity, void *stream) {
+    if (!workspace || !out_entries || capacity < 0 || !geometry_ok(1, nf1, nf2, nl)) return RRL_ERR_ARG;
+    const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    return launch_pack_entries(ws, make_geometry(1, nf1, nf2, nl), out_entries, capacity, (cudaStream_t)stream);
+}
+
+extern "C" int rrl_select_lower_median(const float *values, long long n, float *out_median, void *stream) {
+    if (!out_median || n < 0 || (n > 0 && !values)) return RRL_ERR_ARG;
+    return launch_select_median(values, n, out_median, (cudaStream_t)stream);
+}
+
+extern "C" int rrl_shard_stage2(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,
+                                const long long *global_counts18, const float *global_median, long long *sums32, void *stream) {
+    if (!workspace || !global_counts18 || !global_median || !sums32 || !geometry_ok(1, nf1, nf2, nl)) return RRL_ERR_ARG;
+    const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemcpyAsync(ws.gcounts, global_counts18, 18 * sizeof(long long), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return RRL_ERR_CUDA;
+    if (cudaMemcpyAsync(ws.med, global_median, sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return RRL_ERR_CUDA;
+    if (cudaMemsetAsync(ws.sums, 0, 32 * sizeof(unsigned long long), s) != cudaSuccess) return RRL_ERR_CUDA;
+    const int rc = launch_welsch(ws, make_geometry(1, nf1, nf2, nl), s);
+    if (rc) return rc;
+    return cudaMemcpyAsync(sums32, ws.sums, 32 * sizeof(long long), cudaMemcpyDeviceToDevice, s) == cudaSuccess ? RRL_OK : RRL_ERR_CUDA;
+}
+
+extern "C" int rrl_shard_stage3(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,
+                                const long long *global_sums32, float *out_loss, int *out_status, void *stream) {
+    if (!workspace || !global_sums32 || !out_loss || !geometry_ok(1, nf1, nf2, nl)) return RRL_ERR_ARG;
+    const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemcpyAsync(ws.sums, global_sums32, 32 * sizeof(long long), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return RRL_ERR_CUDA;
+    return launch_finalize(ws, make_geometry(1, nf1, nf2, nl), out_loss, out_status, nullptr, nullptr, s);
+}
+
+// ---- host-buffer context ---------------------------------------------------------------------------------
+struct rrl_host_ctx {
+    int B, nf1, nf2, nl, device;
+    size_t n_tri1, n_tri2, n_lines, ws_bytes;
+    float *d_tri1, *d_tri2, *d_lines, *d_loss, *d_gout, *d_grad1;
+    int *d_status;
+    void *d_ws;
+    float *p_tri1, *p_tri2, *p_lines, *p_loss, *p_grad1;
+    int *p_status;
+    cudaStream_t stream;
+};
+
+extern "C" void rrl_host_destroy(rrl_host_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_tri1); cudaFree(c->d_tri2); cudaFree(c->d_lines); cudaFree(c->d_loss); cudaFree(c->d_gout);
+    cudaFree(c->d_grad1); cudaFree(c->d_status); cudaFree(c->d_ws);
+    cudaFreeHost(c->p_tri1); cudaFreeHost(c->p_tri2); cudaFreeHost(c->p_lines); cudaFreeHost(c->p_loss);
+    cudaFreeHost(c->p_grad1); cudaFreeHost(c->p_status);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int rrl_host_create(int B, int nf1, int nf2, int nl, int device, rrl_host_ctx **out_ctx) {
+    if (!out_ctx || !geometry_ok(B, nf1, nf2, nl)) return RRL_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return RRL_ERR_CUDA;
+    rrl_host_ctx *c = new (std::nothrow) rrl_host_ctx();
+    if (!c) return RRL_ERR_CUDA;
+    std::memset(c, 0, sizeof(*c));
+    c->B = B; c->nf1 = nf1; c->nf2 = nf2; c->nl = nl; c->device = device;
+    c->n_tri1 = (size_t)B * nf1 * 9; c->n_tri2 = (size_t)B * nf2 * 9; c->n_lines = (size_t)B * nl * 6;
+    c->ws_bytes = rrl_workspace_bytes(B, nf1, nf2, nl);
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_tri1, c->n_tri1 * 4) == cudaSuccess && cudaMalloc(&c->d_tri2, c->n_tri2 * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_lines, c->n_lines * 4) == cudaSuccess && cudaMalloc(&c->d_loss, (size_t)B * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_gout, (size_t)B * 4) == cudaSuccess && cudaMalloc(&c->d_grad1, c->n_tri1 * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_status, (size_t)B * 4) == cudaSuccess && cudaMalloc(&c->d_ws, c->ws_bytes) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->p_tri1, c->n_tri1 * 4) == cudaSuccess && cudaMallocHost(&c->p_tri2, c->n_tri2 * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->p_lines, c->n_lines * 4) == cudaSuccess && cudaMallocHost(&c->p_loss, (size_t)B * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->p_grad1, c->n_tri1 * 4) == cudaSuccess && cudaMallocHost(&c->p_status, (size_t)B * 4) == cudaSuccess;
+    if (ok) {
+        for (int b = 0; b < B; ++b) c->p_loss[b] = 1.0f;
+        ok = cudaMemcpy(c->d_gout, c->p_loss, (size_t)B * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) {
+        rrl_host_destroy(c);
+        return RRL_ERR_CUDA;
+    }
+    *out_ctx = c;
+    return RRL_OK;
+}
+
+extern "C" float *rrl_host_pinned_tri1(rrl_host_ctx *c) { return c ? c->p_tri1 : nullptr; }
+extern "C" float *rrl_host_pinned_tri2(rrl_host_ctx *c) { return c ? c->p_tri2 : nullptr; }
+extern "C" float *rrl_host_pinned_lines(rrl_host_ctx *c) { return c ? c->p_lines : nullptr; }
+
+extern "C" int rrl_host_loss_fwd_bwd(rrl_host_ctx *c, const float *h_tri1, const float *h_tri2, const float *h_lines,
+                                     int k_lo, int j_lo, int k_hi, int j_hi, float *h_loss, int *h_status, float *h_grad_tri1) {
+    if (!c || !h_tri1 || !h_tri2 || !h_lines || !h_loss) return RRL_ERR_ARG;
+    if (cudaSetDevice(c->device) != cudaSuccess) return RRL_ERR_CUDA;
+    if (h_tri1 != c->p_tri1) std::memcpy(c->p_tri1, h_tri1, c->n_tri1 * 4);
+    if (h_tri2 != c->p_tri2) std::memcpy(c->p_tri2, h_tri2, c->n_tri2 * 4);
+    if (h_lines != c->p_lines) std::memcpy(c->p_lines, h_lines, c->n_lines * 4);
+    cudaStream_t s = c->stream;
+    bool ok = cudaMemcpyAsync(c->d_tri1, c->p_tri1, c->n_tri1 * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->d_tri2, c->p_tri2, c->n_tri2 * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->d_lines, c->p_lines, c->n_lines * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    if (!ok) return RRL_ERR_CUDA;
+    int rc = rrl_loss_forward(c->d_tri1, c->d_tri2, c->d_lines, c->B, c->nf1, c->nf2, c->nl, k_lo, j_lo, k_hi, j_hi, c->d_ws,
+                              c->ws_bytes, c->d_loss, c->d_status, nullptr, nullptr, s);
+    if (rc) return rc;
+    rc = rrl_loss_backward(c->d_ws, c->ws_bytes, c->d_gout, c->B, c->nf1, c->nf2, c->nl, c->d_grad1, nullptr, s);
+    if (rc) return rc;
+    ok = cudaMemcpyAsync(c->p_loss, c->d_loss, (size_t)c->B * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->p_status, c->d_status, (size_t)c->B * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+    if (h_grad_tri1) ok = ok && cudaMemcpyAsync(c->p_grad1, c->d_grad1, c->n_tri1 * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+    if (!ok) return RRL_ERR_CUDA;
+    std::memcpy(h_loss, c->p_loss, (size_t)c->B * 4);
+    if (h_status) std::memcpy(h_status, c->p_status, (size_t)c->B * 4);
+    if (h_grad_tri1) std::memcpy(h_grad_tri1, c->p_grad1, c->n_tri1 * 4);
+    return RRL_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------------------
+extern "C" int rrl_measure_dense(const float *tri1, const float *tri2, const float *lines, int B, int nf1, int nf2, int nl,
+                                 void *workspace, size_t workspace_bytes, int iters, float *out_ms_dense, float *out_ms_prep,
+                                 void *stream) {
+    if (!tri1 || !tri2 || !lines || !workspace || !out_ms_dense || iters <= 0 || !geometry_ok(B, nf1, nf2, nl)) return RRL_ERR_ARG;
+    const Workspace ws = carve(workspace, B, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    const Geometry g = make_geometry(B, nf1, nf2, nl);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    float td = 0.f, tp = 0.f;
+    int rc = RRL_OK;
+    for (int it = 0; it < iters + 1 && rc == RRL_OK; ++it) {
+        cudaEventRecord(e0, s);
+        rc = launch_prep(tri1, tri2, ws, g, 1 | (1 << 8) | (5 << 16) | (5 << 24), s);
+        cudaEventRecord(e1, s);
+        if (rc == RRL_OK) rc = launch_dense(tri1, tri2, lines, ws, g, s);
+        cudaEventRecord(e2, s);
+        cudaEventSynchronize(e2);
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        if (it > 0) { tp += a; td += b; }          // first iteration is warm-up
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    *out_ms_dense = td / iters;
+    if (out_ms_prep) *out_ms_prep = tp / iters;
+    return rc;
+}
+
+// selects the dense-kernel variant (1 = packed FFMA2 [default], 0 = scalar FFMA); measurement only
+extern "C" int rrl_debug_set_dense_variant(int v) {
+    set_dense_variant(v);
+    return RRL_OK;
+}

@@ -1,0 +1,119 @@
+// Shared definitions of the sm_100a kernels behind include/rrl_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/rrl_b200.h"
+
+namespace rrl {
+
+// ---- reference literals (file:line under /root/reference/code/) ----------------------------------
+constexpr float kAddEps = 2e-4f;      // loss.py:88   d = sqrt(... + 2e-4)
+constexpr float kThrScale = 1.731f;   // loss.py:109  thr = delta * 1.731 / 2
+constexpr int kCap = RRL_HIT_CAP;
+
+// ---- conservative filter (DESIGN.md "filtered predicate") ----------------------------------------
+// candidate  <=>  Q = (p.u)^2 + p.(2m) + (cut - |p|^2)  >  c - g,   g = kGuard * 2^-24 * (P + |x0|)^2
+// The derivation in DESIGN.md bounds the combined rounding error of the reference-order test and of the
+// FMA-contracted filter by 58 * 2^-24 * (P+|x0|)^2; kGuard doubles that.
+constexpr float kGuard = 128.0f;
+
+// ---- dense kernel geometry ---------------------------------------------------------------------------
+constexpr int kDenseThreads = 256;
+constexpr int kLinesPerThread = 4;
+constexpr int kLinesPerCta = kDenseThreads * kLinesPerThread;   // 1024
+constexpr int kTilePoints = 1024;                               // float4 per point: 16 KB per stage
+constexpr int kPointPad = 64;                                   // tri4 arrays are padded to this multiple with sentinels
+constexpr int kQueueCap = 2048;                                 // candidate queue entries per CTA
+
+// ---- fixed-point accumulation of Welsch sums (order-independent, hence run-to-run deterministic) ---
+constexpr double kFixScale = 1099511627776.0;                   // 2^40
+
+struct Geometry {
+    int B, nf1, nf2, nl;
+    int nf1p, nf2p;          // padded triplet counts
+};
+
+// One forward's scratch, carved out of the caller's workspace.  All pointers are device pointers.
+struct Workspace {
+    // header written by forward, read by backward (device side)
+    int *hdr;                // [8]: {magic, B, nf1, nf2, nl, k_lo|j_lo<<8|k_hi<<16|j_hi<<24, 0, 0}
+    // per triplet
+    float4 *tri4[2];         // (B, nfp): p0.xyz, (cut - |p0|^2); sentinel padded
+    float *thr[2];           // (B, nf): exact reference threshold
+    // per pair
+    unsigned int *pmax;      // (B, 2): bit pattern of max |p|^2 over all 9-float rows of the cloud
+    int *nrec;               // (B)
+    int *n_kj;               // (B,16)
+    float *med;              // (B)
+    int *flags;              // (B,2): {NaN seen in the Welsch stage, reserved}
+    unsigned long long *sums;// (B,32): S1[16], S2[16] fixed point
+    long long *stats;        // (B, RRL_NSTAT)
+    long long *gcounts;      // (B,18) global counts used by welsch/finalize/backward (== local unless line-sharded)
+    // per line
+    int *cnt[2];             // (B, nl) hit counters
+    int *hits[2];            // (B, nl, kCap)
+    // per record (capacity B*nl)
+    float *recD;             // (cap,16)
+    int *recMeta;            // (cap,2): {line, k | j<<8 | argmins<<16}
+    int *recIdx;             // (cap,8)
+    float *recW;             // (cap,24): w1[4][3], w2[4][3]
+    float *recQ;             // (cap,24): q1[4][3], q2[4][3]
+    size_t bytes;
+};
+
+constexpr int kMagic = 0x52524c31;   // "RRL1"
+
+inline int pad_points(int nf) { return ((nf + kPointPad - 1) / kPointPad) * kPointPad; }
+
+Workspace carve(void *base, int B, int nf1, int nf2, int nl);
+
+// ---- launch bookkeeping -------------------------------------------------------------------------------
+void count_launch(int n = 1);
+int check_launch();          // cudaGetLastError -> RRL_OK / RRL_ERR_CUDA
+
+// ---- stage launchers (rrl_dense.cu, rrl_sparse.cu) ------------------------------------------------------
+int launch_prep(const float *tri1, const float *tri2, const Workspace &ws, const Geometry &g, int window, cudaStream_t s);
+int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s);
+int launch_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
+                 int k_lo, int j_lo, int k_hi, int j_hi, cudaStream_t s);
+int launch_local_counts(const Workspace &ws, const Geometry &g, cudaStream_t s);
+int launch_median(const Workspace &ws, const Geometry &g, cudaStream_t s);
+int launch_welsch(const Workspace &ws, const Geometry &g, cudaStream_t s);
+int launch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
+                    long long *out_stats, cudaStream_t s);
+int launch_backward(const Workspace &ws, const Geometry &g, const float *grad_out, float *g1, float *g2, cudaStream_t s);
+int launch_export_hits(const Workspace &ws, const Geometry &g, int cloud, int *out_counts, int *out_hits, cudaStream_t s);
+int launch_pack_entries(const Workspace &ws, const Geometry &g, float *out, long long cap, cudaStream_t s);
+int launch_select_median(const float *vals, long long n, float *out, cudaStream_t s);
+
+#ifdef __CUDACC__
+// ---- exact reference-order arithmetic (never contracted into FMA) -----------------------------------
+__device__ __forceinline__ float sq3_rn(float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// thr_f of loss.py:94-109 for one 9-float triplet
+__device__ __forceinline__ float triplet_thr_exact(const float *t) {
+    float e01 = __fsqrt_rn(sq3_rn(__fsub_rn(t[3], t[0]), __fsub_rn(t[4], t[1]), __fsub_rn(t[5], t[2])));
+    float e02 = __fsqrt_rn(sq3_rn(__fsub_rn(t[6], t[0]), __fsub_rn(t[7], t[1]), __fsub_rn(t[8], t[2])));
+    float e12 = __fsqrt_rn(sq3_rn(__fsub_rn(t[3], t[6]), __fsub_rn(t[4], t[7]), __fsub_rn(t[5], t[8])));
+    float delta = __fdiv_rn(__fadd_rn(__fadd_rn(e01, e02), e12), 3.0f);
+    return __fmul_rn(__fmul_rn(delta, kThrScale), 0.5f);
+}
+
+// x = (|AC|^2 - (AC.u)^2) + 2e-4 of loss.py:84-88 (the argument of the sqrt)
+__device__ __forceinline__ float point_line_x_exact(float px, float py, float pz, const float *ln) {
+    float ax = __fsub_rn(px, ln[3]), ay = __fsub_rn(py, ln[4]), az = __fsub_rn(pz, ln[5]);
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(ax, ln[0]), __fmul_rn(ay, ln[1])), __fmul_rn(az, ln[2]));
+    float proj = __fmul_rn(dot, dot);
+    float dac = sq3_rn(ax, ay, az);
+    return __fadd_rn(__fsub_rn(dac, proj), kAddEps);
+}
+
+__device__ __forceinline__ float ulp_up(float x) { return __uint_as_float(__float_as_uint(x) + 1u) - x; }
+#endif
+
+}  // namespace rrl

@@ -1,0 +1,239 @@
+// On-device random line sampler with bounding-box rejection (sm_100a).  Compiled with -fmad=false: the
+// reference's area test is a floating-point knife edge whose acceptance statistics depend on
+// every product and sum being rounded separately, like ATen's eager kernels.
+//
+// Replaces Random_uniform_distribution_lines_batch_efficient_resample (/root/reference/code/loss.py:415-432):
+//   bbox_kernel    generate_bbox (loss.py:325-351): per-pair min/max of both clouds;
+//   flags_kernel   `rounds` x N candidate chords per pair (loss.py:384-412) from a counter-based Philox4x32-10
+//                  stream (or from supplied uniforms), each tested against the 12 triangles of both boxes with
+//                  the reference's area test (generate_mesh_by_bbox loss.py:354-362, step1/step2 loss.py:265-316);
+//   compact_kernel generate_lines (loss.py:365-381): the first N accepted candidates in (round, index) order;
+//                  rows that stay unfilled are all-zero, exactly like the reference.
+#include "rrl_common.cuh"
+
+namespace rrl {
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter = (index, round, pair, offset), key = seed -------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * 5.9604645e-8f; }   // [0,1), 24 bits like torch.rand
+
+struct BoxTris {
+    float A[12][3], Bv[12][3], C[12][3], n[12][3], S[12];
+};
+
+__device__ const int kBoxFaces[12][3] = {{2, 0, 6}, {0, 4, 6}, {5, 4, 0}, {5, 0, 1}, {6, 4, 5}, {5, 7, 6},
+                                         {3, 0, 2}, {1, 0, 3}, {3, 2, 6}, {6, 7, 3}, {5, 1, 3}, {3, 7, 5}};   // loss.py:357-358
+
+__device__ __forceinline__ void cross3(const float *a, const float *b, float *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ float norm3(const float *a) { return __fsqrt_rn((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]); }
+
+__device__ void make_box(const float *lo, const float *hi, BoxTris *bt, int f) {
+    // corner order of generate_bbox (loss.py:329-350)
+    const int sel[8][3] = {{1, 1, 1}, {1, 1, 0}, {1, 0, 1}, {1, 0, 0}, {0, 1, 1}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
+    float v[3][3];
+    for (int q = 0; q < 3; ++q)
+        for (int a = 0; a < 3; ++a) v[q][a] = sel[kBoxFaces[f][q]][a] ? hi[a] : lo[a];
+    float e1[3] = {v[1][0] - v[0][0], v[1][1] - v[0][1], v[1][2] - v[0][2]};
+    float e2[3] = {v[2][0] - v[0][0], v[2][1] - v[0][1], v[2][2] - v[0][2]};
+    float n[3];
+    cross3(e1, e2, n);
+    const float S = norm3(n);
+    const float den = fmaxf(S, 1e-12f);
+    for (int a = 0; a < 3; ++a) {
+        bt->A[f][a] = v[0][a]; bt->Bv[f][a] = v[1][a]; bt->C[f][a] = v[2][a];
+        bt->n[f][a] = n[a] / den;
+    }
+    bt->S[f] = S;
+}
+
+// number of box triangles the line "hits" by the reference's area test (loss.py:289-316)
+__device__ int triangle_hits(const BoxTris *bt, const float *ln) {
+    int hits = 0;
+#pragma unroll 1
+    for (int f = 0; f < 12; ++f) {
+        const float *A = bt->A[f], *Bp = bt->Bv[f], *C = bt->C[f], *n = bt->n[f];
+        const float num = (n[0] * (A[0] - ln[3]) + n[1] * (A[1] - ln[4])) + n[2] * (A[2] - ln[5]);
+        const float den = ((n[0] * ln[0] + n[1] * ln[1]) + n[2] * ln[2]) + 1e-12f;
+        const float t = num / den;
+        const float X[3] = {t * ln[0] + ln[3], t * ln[1] + ln[4], t * ln[2] + ln[5]};
+        const float ca[3] = {X[0] - A[0], X[1] - A[1], X[2] - A[2]};
+        const float cb[3] = {X[0] - Bp[0], X[1] - Bp[1], X[2] - Bp[2]};
+        const float cc[3] = {X[0] - C[0], X[1] - C[1], X[2] - C[2]};
+        float x1[3], x2[3], x3[3];
+        cross3(cb, cc, x1);
+        cross3(cc, ca, x2);
+        cross3(ca, cb, x3);
+        const float a = norm3(x1), b = norm3(x2), c = norm3(x3);
+        hits += (a > 0.f) && (b > 0.f) && (c > 0.f) && ((a + b) + c <= bt->S[f]);
+    }
+    return hits;
+}
+
+// candidate chord from four uniforms (loss.py:394-411)
+__device__ __forceinline__ void make_line(float r, const float *center, float a1, float u1, float a2, float u2, float *ln) {
+    const float PI32 = 3.14159274101257324f;                 // torch.pi rounded to float32 (loss.py:9)
+    const float al1 = (a1 * 2.0f) * PI32, z1 = u1 * 2.0f - 1.0f;
+    const float al2 = (a2 * 2.0f) * PI32, z2 = u2 * 2.0f - 1.0f;
+    const float s1 = __fsqrt_rn(1.0f - z1 * z1), s2 = __fsqrt_rn(1.0f - z2 * z2);
+    float sn1, cs1, sn2, cs2;
+    sincosf(al1, &sn1, &cs1);
+    sincosf(al2, &sn2, &cs2);
+    const float q1[3] = {(r * s1) * cs1, (r * sn1) * s1, r * z1};
+    const float q2[3] = {(r * s2) * cs2, (r * sn2) * s2, r * z2};
+    const float d[3] = {q2[0] - q1[0], q2[1] - q1[1], q2[2] - q1[2]};
+    const float nn = fmaxf(norm3(d), 1e-12f);
+    ln[0] = d[0] / nn; ln[1] = d[1] / nn; ln[2] = d[2] / nn;
+    ln[3] = q1[0] + center[0]; ln[4] = q1[1] + center[1]; ln[5] = q1[2] + center[2];
+}
+
+struct SamplerArgs {
+    const float *radius, *centers, *uniforms;
+    float *bbox;              // (B, 2, 6): lo, hi
+    unsigned char *flags;     // (B, rounds*N)
+    int B, N, rounds;
+    unsigned long long seed, offset;
+};
+
+__device__ __forceinline__ void candidate(const SamplerArgs &a, int b, int rd, int i, float *ln) {
+    float a1, u1, a2, u2;
+    if (a.uniforms) {
+        const float *U = a.uniforms + (((long long)b * a.rounds + rd) * 4) * a.N;
+        a1 = U[i]; u1 = U[a.N + i]; a2 = U[2LL * a.N + i]; u2 = U[3LL * a.N + i];
+    } else {
+        const uint4 x = philox4x32_10(make_uint4((unsigned)i, (unsigned)rd, (unsigned)b, (unsigned)a.offset),
+                                      make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32) ^ (unsigned)(a.offset >> 32)));
+        a1 = u01(x.x); u1 = u01(x.y); a2 = u01(x.z); u2 = u01(x.w);
+    }
+    make_line(a.radius[b], a.centers + b * 3, a1, u1, a2, u2, ln);
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float *__restrict__ v1, const float *__restrict__ v2, int n1, int n2, float *bbox) {
+    const int b = blockIdx.x, cloud = blockIdx.y;
+    const float *v = (cloud ? v2 : v1) + (long long)b * (cloud ? n2 : n1) * 3;
+    const int n = cloud ? n2 : n1;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        for (int a = 0; a < 3; ++a) {
+            const float x = v[3 * i + a];
+            lo[a] = fminf(lo[a], x);
+            hi[a] = fmaxf(hi[a], x);
+        }
+    __shared__ float s[8][6];
+    for (int a = 0; a < 3; ++a) {
+        float l = lo[a], h = hi[a];
+        for (int o = 16; o > 0; o >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][a] = l; s[threadIdx.x >> 5][3 + a] = h; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float r = s[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) r = threadIdx.x < 3 ? fminf(r, s[w][threadIdx.x]) : fmaxf(r, s[w][threadIdx.x]);
+        bbox[(b * 2 + cloud) * 6 + threadIdx.x] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) flags_kernel(SamplerArgs a) {
+    __shared__ BoxTris bt[2];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 24) make_box(a.bbox + (b * 2 + threadIdx.x / 12) * 6, a.bbox + (b * 2 + threadIdx.x / 12) * 6 + 3, &bt[threadIdx.x / 12], threadIdx.x % 12);
+    __syncthreads();
+    const long long total = (long long)a.rounds * a.N;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        float ln[6];
+        candidate(a, b, (int)(c / a.N), (int)(c % a.N), ln);
+        a.flags[(long long)b * total + c] = (triangle_hits(&bt[0], ln) * triangle_hits(&bt[1], ln)) > 0;   // loss.py:430
+    }
+}
+
+constexpr int kCompactThreads = 1024;
+
+__global__ void __launch_bounds__(kCompactThreads) compact_kernel(SamplerArgs a, float *out_lines, int *out_filled) {
+    __shared__ int warp_tot[32];
+    __shared__ int s_filled;
+    const int b = blockIdx.x;
+    const long long total = (long long)a.rounds * a.N;
+    const unsigned char *fl = a.flags + (long long)b * total;
+    float *out = out_lines + (long long)b * a.N * 6;
+    if (threadIdx.x == 0) s_filled = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (long long base = 0; base < total; base += kCompactThreads) {
+        const int filled = s_filled;
+        if (filled >= a.N) break;
+        const long long c = base + threadIdx.x;
+        const int f = c < total ? fl[c] : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, all = 0;
+        for (int w = 0; w < kCompactThreads / 32; ++w) {
+            const int t = warp_tot[w];
+            before += w < wid ? t : 0;
+            all += t;
+        }
+        const int pos = filled + before + __popc(bal & ((1u << lane) - 1u));
+        if (f && pos < a.N) {
+            float ln[6];
+            candidate(a, b, (int)(c / a.N), (int)(c % a.N), ln);
+            for (int q = 0; q < 6; ++q) out[(long long)pos * 6 + q] = ln[q];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_filled = min(a.N, filled + all);
+        __syncthreads();
+    }
+    const int filled = s_filled;
+    for (long long i = (long long)filled * 6 + threadIdx.x; i < (long long)a.N * 6; i += kCompactThreads) out[i] = 0.f;
+    if (threadIdx.x == 0) out_filled[b] = filled;
+}
+
+}  // namespace rrl
+
+using namespace rrl;
+
+extern "C" size_t rrl_sampler_workspace_bytes(int B, int N, int rounds) {
+    if (B <= 0 || N <= 0 || rounds <= 0) return 0;
+    return (size_t)B * 12 * sizeof(float) + 256 + (size_t)B * (size_t)rounds * (size_t)N;
+}
+
+extern "C" int rrl_sample_lines(const float *radius, const float *centers, const float *verts1, const float *verts2,
+                                int B, int n1, int n2, int N, int rounds, unsigned long long seed, unsigned long long offset,
+                                const float *uniforms, float *out_lines, int *out_filled,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    if (!radius || !centers || !verts1 || !verts2 || !out_lines || !out_filled || !workspace) return RRL_ERR_ARG;
+    if (B <= 0 || n1 <= 0 || n2 <= 0 || N <= 0 || rounds <= 0) return RRL_ERR_ARG;
+    if (workspace_bytes < rrl_sampler_workspace_bytes(B, N, rounds)) return RRL_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    SamplerArgs a;
+    a.radius = radius; a.centers = centers; a.uniforms = uniforms;
+    a.bbox = reinterpret_cast<float *>(workspace);
+    a.flags = reinterpret_cast<unsigned char *>(workspace) + (((size_t)B * 12 * sizeof(float) + 255) / 256) * 256;
+    a.B = B; a.N = N; a.rounds = rounds; a.seed = seed; a.offset = offset;
+    bbox_kernel<<<dim3(B, 2), 256, 0, s>>>(verts1, verts2, n1, n2, a.bbox);
+    const long long total = (long long)rounds * N;
+    int bx = (int)((total + 255) / 256);
+    const int cap = (148 * 8 + B - 1) / B;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    flags_kernel<<<dim3(bx, B), 256, 0, s>>>(a);
+    compact_kernel<<<B, kCompactThreads, 0, s>>>(a, out_lines, out_filled);
+    count_launch(3);
+    return check_launch();
+}

@@ -1,0 +1,123 @@
+"""Multi-GPU evaluation (one process per GPU, torch.distributed; NCCL on the B200 box, gloo in CPU tests of the
+host logic).  SURVEY 8(e):
+
+  batch shard  pairs are independent -> each rank evaluates its own pairs; the only exchange is an all-reduce of the
+               scalar loss (and whatever the caller logs).
+  line shard   one pair, lines split across ranks; the global lower median and the 1/(n_kj k) normalisers couple
+               all lines, so there is exactly one exchange step between the dense and the Welsch stage and one
+               all-reduce of the fixed-point partial sums; the point gradient (or the 12 pose-gradient floats)
+               is all-reduced in backward.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist_
+
+from . import _native as N
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous block partition of n items: the first n % world ranks get one extra item"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def batch_sharded_loss(tri1, tri2, lines, window=(1, 1, 5, 5), group=None, average: bool = False):
+    """Each rank passes ITS OWN pairs (any B, possibly different per rank).  Returns (local per-pair losses (B,),
+    global sum of all losses as a 0-dim tensor that carries gradient for the local pairs only)."""
+    from . import ops
+    local = ops.intersected_line_loss(tri1, tri2, lines, window)
+    total = local.sum()
+    if dist_.is_available() and dist_.is_initialized() and dist_.get_world_size(group) > 1:
+        red = total.detach().clone()
+        dist_.all_reduce(red, op=dist_.ReduceOp.SUM, group=group)
+        if average:
+            red = red / dist_.get_world_size(group)
+        total = total + (red - total.detach())       # value = global sum, gradient = local pairs
+    return local, total
+
+
+def combine_counts(local18: torch.Tensor, group=None) -> torch.Tensor:
+    out = local18.clone()
+    dist_.all_reduce(out, op=dist_.ReduceOp.SUM, group=group)
+    return out
+
+
+def gather_entries(local: torch.Tensor, n_local: int, counts: List[int], group=None) -> torch.Tensor:
+    """all-gather of variable-length float arrays: pad to the maximum, gather, strip"""
+    world = dist_.get_world_size(group)
+    cap = max(max(counts), 1)
+    buf = torch.zeros(cap, dtype=torch.float32, device=local.device)
+    buf[:n_local] = local[:n_local]
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist_.all_gather(outs, buf, group=group)
+    return torch.cat([o[:c] for o, c in zip(outs, counts)]) if sum(counts) else buf[:0]
+
+
+class _LineShardedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tri1, tri2, lines_local, window, group):
+        L = N.lib()
+        dev = tri1.device
+        nf1, nf2, nl = tri1.shape[0], tri2.shape[0], lines_local.shape[0]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        wsb = L.rrl_workspace_bytes(1, nf1, nf2, nl)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        N.check(L.rrl_shard_stage1(tri1.data_ptr(), tri2.data_ptr(), lines_local.data_ptr(), nf1, nf2, nl, window[0],
+                                   window[1], window[2], window[3], ws.data_ptr(), wsb, stream), "rrl_shard_stage1")
+        counts = torch.empty(18, dtype=torch.int64, device=dev)
+        N.check(L.rrl_shard_counts(ws.data_ptr(), wsb, nf1, nf2, nl, counts.data_ptr(), stream), "rrl_shard_counts")
+        world = dist_.get_world_size(group)
+        all_counts = [torch.empty_like(counts) for _ in range(world)]
+        dist_.all_gather(all_counts, counts, group=group)
+        per_rank_entries = [int(c[17].item()) for c in all_counts]         # one host read: sizes of the exchange
+        gcounts = torch.stack(all_counts).sum(0)
+        n_local = per_rank_entries[dist_.get_rank(group)]
+        local_entries = torch.empty(max(n_local, 1), dtype=torch.float32, device=dev)
+        N.check(L.rrl_shard_pack_entries(ws.data_ptr(), wsb, nf1, nf2, nl, local_entries.data_ptr(), n_local, stream),
+                "rrl_shard_pack_entries")
+        entries = gather_entries(local_entries, n_local, per_rank_entries, group)
+        med = torch.empty(1, dtype=torch.float32, device=dev)
+        N.check(L.rrl_select_lower_median(entries.data_ptr() if entries.numel() else None, entries.numel(),
+                                          med.data_ptr(), stream), "rrl_select_lower_median")
+        sums = torch.empty(32, dtype=torch.int64, device=dev)
+        N.check(L.rrl_shard_stage2(ws.data_ptr(), wsb, nf1, nf2, nl, gcounts.data_ptr(), med.data_ptr(), sums.data_ptr(),
+                                   stream), "rrl_shard_stage2")
+        dist_.all_reduce(sums, op=dist_.ReduceOp.SUM, group=group)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        status = torch.empty(1, dtype=torch.int32, device=dev)
+        N.check(L.rrl_shard_stage3(ws.data_ptr(), wsb, nf1, nf2, nl, sums.data_ptr(), loss.data_ptr(), status.data_ptr(),
+                                   stream), "rrl_shard_stage3")
+        ctx.ws, ctx.geom, ctx.group = ws, (nf1, nf2, nl), group
+        ctx.mark_non_differentiable(status, med)
+        return loss, status, med
+
+    @staticmethod
+    def backward(ctx, grad_loss, *_):
+        nf1, nf2, nl = ctx.geom
+        ws = ctx.ws
+        dev = ws.device
+        g = grad_loss.contiguous().float()
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g1 = torch.empty(nf1, 9, dtype=torch.float32, device=dev) if need1 else None
+        g2 = torch.empty(nf2, 9, dtype=torch.float32, device=dev) if need2 else None
+        N.check(N.lib().rrl_loss_backward(ws.data_ptr(), ws.numel(), g.data_ptr(), 1, nf1, nf2, nl,
+                                          g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None,
+                                          torch.cuda.current_stream(dev).cuda_stream), "rrl_loss_backward")
+        # every rank holds the replicated clouds, so the point gradient is summed over the line shards
+        for t in (g1, g2):
+            if t is not None:
+                dist_.all_reduce(t, op=dist_.ReduceOp.SUM, group=ctx.group)
+        return g1, g2, None, None, None
+
+
+def line_sharded_loss(tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None):
+    """ONE pair: tri1 (nf1,9) and tri2 (nf2,9) replicated on every rank, lines_local (nl_r,6) = this rank's shard.
+    Returns (loss (1,), status (1,), median (1,)) -- identical on all ranks; gradients are all-reduced."""
+    from .ops import _cuda_f32
+    if not (dist_.is_available() and dist_.is_initialized()):
+        raise RuntimeError("line_sharded_loss needs an initialised torch.distributed process group")
+    w = tuple(int(v) for v in window)
+    return _LineShardedLoss.apply(_cuda_f32(tri1, "points1"), _cuda_f32(tri2, "points2"),
+                                  _cuda_f32(lines_local.detach(), "line"), w, group)

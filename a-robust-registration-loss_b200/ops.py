@@ -1,0 +1,232 @@
+"""torch-facing operators: thin autograd.Function wrappers that hand raw device pointers and the current CUDA
+stream to the C ABI (include/rrl_b200.h).  torch is plumbing here (memory, streams, autograd graph); every
+number is produced by the sm_100a kernels."""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise N.NativeError("%s must live on a CUDA device: the B200 kernels are the only implementation "
+                            "(no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class LossInfo:
+    """Side channel of one forward call (everything stays on the device; reading it synchronises)."""
+
+    def __init__(self, status, median, stats, workspace, geom):
+        self.status = status            # (B,) int32 RRL_STATUS_* bits
+        self.median = median            # (B,) float32
+        self.stats = stats              # (B, 8) int64, see include/rrl_b200.h
+        self._ws = workspace
+        self._geom = geom
+
+    @property
+    def n_selected_lines(self):
+        return self.stats[:, 0]
+
+    @property
+    def n_entries(self):
+        return self.stats[:, 1]
+
+    @property
+    def band_tests(self):
+        """tests whose distance lies within 1 ulp of the threshold (reported separately, see north star)"""
+        return self.stats[:, 5]
+
+    def hits(self, cloud: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(counts (B,nl) int32, hits (B,nl,5) int32 ascending, -1 padded) of cloud 1 or 2."""
+        B, nf1, nf2, nl = self._geom
+        counts = torch.empty(B, nl, dtype=torch.int32, device=self._ws.device)
+        hits = torch.empty(B, nl, N.HIT_CAP, dtype=torch.int32, device=self._ws.device)
+        N.check(N.lib().rrl_loss_export_hits(self._ws.data_ptr(), self._ws.numel(), B, nf1, nf2, nl, cloud,
+                                             counts.data_ptr(), hits.data_ptr(), _stream(self._ws)), "rrl_loss_export_hits")
+        return counts, hits
+
+
+class _IntersectedLineLoss(torch.autograd.Function):
+    """loss[b] = reference loss of pair b (loss.py:170-232 on the B=1 slice); lines carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, tri1, tri2, lines, window, holder):
+        B, nf1, _ = tri1.shape
+        nf2, nl = tri2.shape[1], lines.shape[1]
+        dev = tri1.device
+        L = N.lib()
+        ws_bytes = L.rrl_workspace_bytes(B, nf1, nf2, nl)
+        if ws_bytes == 0:
+            raise ValueError("unsupported geometry B=%d nf1=%d nf2=%d nl=%d" % (B, nf1, nf2, nl))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        median = torch.empty(B, dtype=torch.float32, device=dev)
+        stats = torch.empty(B, N.NSTAT, dtype=torch.int64, device=dev)
+        N.check(L.rrl_loss_forward(tri1.data_ptr(), tri2.data_ptr(), lines.data_ptr(), B, nf1, nf2, nl,
+                                   window[0], window[1], window[2], window[3], ws.data_ptr(), ws_bytes,
+                                   loss.data_ptr(), status.data_ptr(), median.data_ptr(), stats.data_ptr(),
+                                   _stream(tri1)), "rrl_loss_forward")
+        ctx.ws = ws
+        ctx.geom = (B, nf1, nf2, nl)
+        ctx.mark_non_differentiable(status, median, stats)
+        if holder is not None:
+            holder.append(LossInfo(status, median, stats, ws, ctx.geom))
+        return loss, status, median, stats
+
+    @staticmethod
+    def backward(ctx, grad_loss, *_unused):
+        B, nf1, nf2, nl = ctx.geom
+        ws = ctx.ws
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g = grad_loss.contiguous().float()
+        g1 = torch.empty(B, nf1, 9, dtype=torch.float32, device=ws.device) if need1 else None
+        g2 = torch.empty(B, nf2, 9, dtype=torch.float32, device=ws.device) if need2 else None
+        N.check(N.lib().rrl_loss_backward(ws.data_ptr(), ws.numel(), g.data_ptr(), B, nf1, nf2, nl,
+                                          g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None,
+                                          _stream(ws)), "rrl_loss_backward")
+        return g1, g2, None, None, None
+
+
+def intersected_line_loss(tri1: torch.Tensor, tri2: torch.Tensor, lines: torch.Tensor,
+                          window=(1, 1, 5, 5), return_info: bool = False):
+    """Batched native API: tri1 (B,nf1,9), tri2 (B,nf2,9), lines (B,nl,6) -> per-pair losses (B,).
+
+    `window` = the reference's (s_m, s_n, e_m, e_n).  Differentiable w.r.t. tri1 and tri2.
+    A pair with no populated (k,j) combo yields loss 0 with zero gradient and status bit RRL_STATUS_EMPTY.
+    """
+    for name, t, last in (("points1", tri1, 9), ("points2", tri2, 9), ("line", lines, 6)):
+        if t.dim() != 3 or t.shape[-1] != last:
+            raise ValueError("%s must have shape (B, n, %d), got %s" % (name, last, tuple(t.shape)))
+    if not (tri1.shape[0] == tri2.shape[0] == lines.shape[0]):
+        raise ValueError("batch sizes differ")
+    w = tuple(int(v) for v in window)
+    if not (1 <= w[0] < w[2] <= 5 and 1 <= w[1] < w[3] <= 5):
+        raise ValueError("hit-count window must satisfy 1 <= lo < hi <= 5, got %s" % (w,))
+    tri1, tri2 = _cuda_f32(tri1, "points1"), _cuda_f32(tri2, "points2")
+    lines = _cuda_f32(lines.detach(), "line")
+    holder = [] if return_info else None
+    loss, _, _, _ = _IntersectedLineLoss.apply(tri1, tri2, lines, w, holder)
+    return (loss, holder[0]) if return_info else loss
+
+
+# --------------------------------------------------------------------------------------------------------
+class _Se3Apply(torch.autograd.Function):
+    """out = points @ R(twist) + T(twist)   (Reconstruction_point.forward, loss.py:458-463)"""
+
+    @staticmethod
+    def forward(ctx, twist, points):
+        B, n, _ = points.shape
+        out = torch.empty_like(points)
+        N.check(N.lib().rrl_se3_apply(twist.data_ptr(), points.data_ptr(), B, n, out.data_ptr(), _stream(points)),
+                "rrl_se3_apply")
+        ctx.save_for_backward(twist, points)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        twist, points = ctx.saved_tensors
+        B, n, _ = points.shape
+        g = grad_out.contiguous().float()
+        gt = torch.empty(B, 6, dtype=torch.float32, device=points.device)
+        scratch = torch.empty(B * 12, dtype=torch.float64, device=points.device)
+        N.check(N.lib().rrl_se3_apply_backward(twist.data_ptr(), points.data_ptr(), g.data_ptr(), B, n, gt.data_ptr(),
+                                               scratch.data_ptr(), _stream(points)), "rrl_se3_apply_backward")
+        return gt, None
+
+
+def se3_apply(twist: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
+    """twist (B,6) [w|v], points (B,n,3) -> (B,n,3); differentiable w.r.t. the twist."""
+    if twist.dim() != 2 or twist.shape[1] != 6 or points.dim() != 3 or points.shape[2] != 3:
+        raise ValueError("expected twist (B,6) and points (B,n,3)")
+    return _Se3Apply.apply(_cuda_f32(twist, "twist"), _cuda_f32(points.detach(), "points"))
+
+
+def se3_exp(twist: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """twist (B,6) -> R (B,3,3), T (B,3)   (se3.exp3, LieAlgebra/se3.py:83-106); no autograd."""
+    twist = _cuda_f32(twist.detach().reshape(-1, 6), "twist")
+    B = twist.shape[0]
+    R = torch.empty(B, 3, 3, dtype=torch.float32, device=twist.device)
+    T = torch.empty(B, 3, dtype=torch.float32, device=twist.device)
+    N.check(N.lib().rrl_se3_exp(twist.data_ptr(), B, R.data_ptr(), T.data_ptr(), _stream(twist)), "rrl_se3_exp")
+    return R, T
+
+
+class _RigidApply(torch.autograd.Function):
+    """out = R p + t for the DL hooks (utils.py:32-37, rpm se3.transform, fmr se3.transform)."""
+
+    @staticmethod
+    def forward(ctx, R, t, points):
+        B, n, _ = points.shape
+        out = torch.empty_like(points)
+        N.check(N.lib().rrl_rigid_apply(R.data_ptr(), t.data_ptr(), points.data_ptr(), B, n, out.data_ptr(),
+                                        _stream(points)), "rrl_rigid_apply")
+        ctx.save_for_backward(R, points)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        R, points = ctx.saved_tensors
+        B, n, _ = points.shape
+        g = grad_out.contiguous().float()
+        gR = torch.empty(B, 3, 3, dtype=torch.float32, device=points.device)
+        gt = torch.empty(B, 3, dtype=torch.float32, device=points.device)
+        gp = torch.empty_like(points) if ctx.needs_input_grad[2] else None
+        scratch = torch.empty(B * 12, dtype=torch.float64, device=points.device)
+        N.check(N.lib().rrl_rigid_apply_backward(R.data_ptr(), points.data_ptr(), g.data_ptr(), B, n, gR.data_ptr(),
+                                                 gt.data_ptr(), gp.data_ptr() if gp is not None else None,
+                                                 scratch.data_ptr(), _stream(points)), "rrl_rigid_apply_backward")
+        return gR, gt, gp
+
+
+def rigid_apply(R: torch.Tensor, t: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
+    """R (B,3,3), t (B,3), points (B,n,3) -> R p + t, differentiable w.r.t. all three."""
+    return _RigidApply.apply(_cuda_f32(R, "R"), _cuda_f32(t.reshape(-1, 3), "t"), _cuda_f32(points, "points"))
+
+
+# --------------------------------------------------------------------------------------------------------
+def sample_lines(radius: torch.Tensor, centers: torch.Tensor, n_lines: int, verts1: torch.Tensor, verts2: torch.Tensor,
+                 seed: int = 0, offset: int = 0, rounds: int = 10, uniforms: Optional[torch.Tensor] = None):
+    """On-device sampler: radius (B,) or (B,1), centers (B,3), verts (B,n,3) -> (lines (B,N,6), filled (B,) int32)."""
+    verts1, verts2 = _cuda_f32(verts1.detach(), "vertices1"), _cuda_f32(verts2.detach(), "vertices2")
+    B = verts1.shape[0]
+    dev = verts1.device
+    radius = _cuda_f32(radius.detach().reshape(-1).to(dev), "r")
+    centers = _cuda_f32(centers.detach().reshape(-1, 3).to(dev), "centers")
+    if radius.numel() != B or centers.shape[0] != B or verts2.shape[0] != B:
+        raise ValueError("batch sizes differ")
+    if uniforms is not None:
+        uniforms = _cuda_f32(uniforms.to(dev), "uniforms")
+        if tuple(uniforms.shape) != (B, rounds, 4, n_lines):
+            raise ValueError("uniforms must have shape (B, rounds, 4, N)")
+    L = N.lib()
+    wsb = L.rrl_sampler_workspace_bytes(B, n_lines, rounds)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    lines = torch.empty(B, n_lines, 6, dtype=torch.float32, device=dev)
+    filled = torch.empty(B, dtype=torch.int32, device=dev)
+    N.check(L.rrl_sample_lines(radius.data_ptr(), centers.data_ptr(), verts1.data_ptr(), verts2.data_ptr(), B,
+                               verts1.shape[1], verts2.shape[1], n_lines, rounds, seed & (2 ** 64 - 1),
+                               offset & (2 ** 64 - 1), uniforms.data_ptr() if uniforms is not None else None,
+                               lines.data_ptr(), filled.data_ptr(), ws.data_ptr(), wsb, _stream(verts1)),
+            "rrl_sample_lines")
+    return lines, filled
+
+
+def chamfer(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """chamfer_dist (loss.py:236-252): x (B,M,3), y (B,N,3) -> 0-dim tensor.  Monitoring only (no autograd)."""
+    x, y = _cuda_f32(x.detach(), "points_x"), _cuda_f32(y.detach(), "points_y")
+    B, M, _ = x.shape
+    Nn = y.shape[1]
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(B * (M + Nn), dtype=torch.float32, device=x.device)
+    N.check(N.lib().rrl_chamfer(x.data_ptr(), y.data_ptr(), B, M, Nn, out.data_ptr(), scratch.data_ptr(), _stream(x)),
+            "rrl_chamfer")
+    return out[0]

@@ -1,0 +1,201 @@
+/*
+ * rrl_b200.h -- C ABI of the B200-native intersected-line robust registration loss.
+ *
+ * The reference (Dengzhi-USTC/A-robust-registration-loss) is pure Python/PyTorch and has no FFI
+ * of its own; each entry point below names the reference function it replaces (file:line under
+ * /root/reference/code/).  INTEGRATION.md shows the ctypes binding a maintainer of the reference
+ * would add to route code/loss.py through this library.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with `h_` (host);
+ *   - all tensors are dense, row-major, float32 unless stated; the caller owns every buffer;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is enqueued on it
+ *     and nothing synchronises with the host (except the rrl_host_* and rrl_measure_* helpers);
+ *   - every function returns an int status: RRL_OK or a negative RRL_ERR_*; nothing ever exits the process
+ *     (the reference print()s and exit(0)s on bad rank or NaN, loss.py:69-71,89-91);
+ *   - the library keeps no global state besides a kernel-launch counter.
+ *
+ * Geometry of one call: B independent pairs; cloud c of pair b is `tri_c[b]` = nf_c triplets of 9 floats
+ * [p0 | p1 | p2] (a point and its two nearest neighbours, loss.py:481-485); `lines[b]` = nl lines of 6 floats
+ * [unit direction u | point x0] (loss.py:411).
+ */
+#ifndef RRL_B200_H
+#define RRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRL_VERSION 100            /* 0.1.0 */
+#define RRL_HIT_CAP 5              /* hit slots kept per (line, cloud); a line with >4 hits is never selected */
+#define RRL_NSTAT 8                /* int64 diagnostics per pair, see rrl_loss_forward */
+
+enum {
+    RRL_OK = 0,
+    RRL_ERR_ARG = -1,              /* null pointer / non-positive size / window outside 1..4 */
+    RRL_ERR_WORKSPACE = -2,        /* workspace smaller than rrl_workspace_bytes() */
+    RRL_ERR_CUDA = -3,             /* a CUDA runtime call or kernel launch failed */
+    RRL_ERR_STATE = -4             /* backward called on a workspace that holds no forward */
+};
+
+/* per-pair status bits written by rrl_loss_forward into out_status[b] */
+enum {
+    RRL_STATUS_EMPTY = 1,          /* no (k,j) combo populated: loss = 0, gradients = 0
+                                      (the reference returns the tuple (None, None, None), loss.py:232) */
+    RRL_STATUS_NAN = 2,            /* a candidate distance was NaN (reference: "Exit the systerm", loss.py:89-91) */
+    RRL_STATUS_NAN_RISK = 4        /* coordinates so large that |AC|^2 cancellation may exceed 2e-4 */
+};
+
+int rrl_version(void);
+const char *rrl_error_string(int code);
+/* number of kernels this library has launched since it was loaded (bench.py's gpu_launches) */
+long long rrl_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Loss: replaces cal_loss_intersection_batch_whole_median_pts_lines (loss.py:170-232) together with
+ * cal_intersection_batch2_points_with_line (loss.py:68-112) and
+ * cal_loss_intersection_batch_m_n_median_pts_lines (loss.py:115-167), per pair.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* bytes of scratch rrl_loss_forward needs for this geometry (also holds what backward re-reads) */
+size_t rrl_workspace_bytes(int B, int nf1, int nf2, int nl);
+
+/*
+ * Forward.  (k_lo, j_lo, k_hi, j_hi) are the reference's (s_m, s_n, e_m, e_n): half-open windows of hit
+ * counts, 1 <= lo < hi <= 5; every caller in the reference passes (1, 1, 5, 5).
+ *   out_loss   [B]          loss of each pair, defined as the reference called on that B=1 slice
+ *   out_status [B]          RRL_STATUS_* bits
+ *   out_median [B]          lower median of the pair's D entries (loss.py:223-224); may be NULL
+ *   out_stats  [B*RRL_NSTAT] int64: {0: #selected lines, 1: #D entries, 2: #non-empty combos C,
+ *                            3: #filter candidates cloud 1, 4: #filter candidates cloud 2,
+ *                            5: #tests within 1 ulp of the threshold (the north star's separately reported band),
+ *                            6: #NaN distances among candidates, 7: reserved}; may be NULL
+ */
+int rrl_loss_forward(const float *tri1, const float *tri2, const float *lines,
+                     int B, int nf1, int nf2, int nl,
+                     int k_lo, int j_lo, int k_hi, int j_hi,
+                     void *workspace, size_t workspace_bytes,
+                     float *out_loss, int *out_status, float *out_median, long long *out_stats,
+                     void *stream);
+
+/*
+ * Backward of the forward held in `workspace` (autograd of loss.py:170-232; closed form SURVEY 9.1).
+ * grad_out [B] is d(total)/d(out_loss[b]).  grad_tri1 (B,nf1,9) / grad_tri2 (B,nf2,9) are overwritten
+ * (zero where no selected line touches a triplet); either may be NULL when not needed.
+ */
+int rrl_loss_backward(const void *workspace, size_t workspace_bytes, const float *grad_out,
+                      int B, int nf1, int nf2, int nl,
+                      float *grad_tri1, float *grad_tri2, void *stream);
+
+/*
+ * Per-line intersection sets of the forward held in `workspace` (the reference's label tensor,
+ * loss.py:107-112, in sparse form).  cloud = 1 or 2.  out_counts (B,nl) int32 = number of hit triplets
+ * (uncapped); out_hits (B,nl,RRL_HIT_CAP) int32 = ascending triplet indices, -1 padded; when a line has more
+ * than RRL_HIT_CAP hits the slots hold an arbitrary RRL_HIT_CAP-subset (such lines are never selected).
+ */
+int rrl_loss_export_hits(const void *workspace, size_t workspace_bytes, int B, int nf1, int nf2, int nl,
+                         int cloud, int *out_counts, int *out_hits, void *stream);
+
+/*
+ * Line-sharded evaluation of ONE pair across ranks: each rank calls the three stages on its own
+ * slice of the lines (B = 1) and combines the small per-pair arrays between them with its collective library.
+ *   stage 1  dense + intersection points; then
+ *              rrl_shard_counts() -> 18 int64 {n_kj[16], #records, #D entries}: all-reduce(sum);
+ *              rrl_shard_pack_entries() -> the rank's D entries, flat: all-gather;
+ *   stage 2  given the global median and the all-reduced counts: Welsch sums -> 32 int64 fixed-point partial
+ *            sums: all-reduce(sum);
+ *   stage 3  given the all-reduced sums: loss (identical on every rank); backward then uses the global counts,
+ *            so every rank's point gradient is its lines' share: all-reduce(sum) of the gradient.
+ */
+int rrl_shard_stage1(const float *tri1, const float *tri2, const float *lines, int nf1, int nf2, int nl,
+                     int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes, void *stream);
+int rrl_shard_counts(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl, long long *counts18,
+                     void *stream);
+int rrl_shard_pack_entries(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,
+                           float *out_entries, long long capacity, void *stream);
+/* lower median of a flat device array of n non-negative floats (n read from the host argument) */
+int rrl_select_lower_median(const float *values, long long n, float *out_median, void *stream);
+int rrl_shard_stage2(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,
+                     const long long *global_counts18, const float *global_median, long long *sums32, void *stream);
+int rrl_shard_stage3(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,
+                     const long long *global_sums32, float *out_loss, int *out_status, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * se(3): replaces Reconstruction_point.forward / Transform (loss.py:455-463) and se3.exp3
+ * (LieAlgebra/se3.py:83-106, so3.py:17-27, sinc.py:5-17,91-103,120-132).
+ * twist (B,6) = [w | v];  R (B,3,3) row-major, T (B,3);  points (B,n,3);  out = points @ R + T (row vectors).
+ * ------------------------------------------------------------------------------------------------- */
+int rrl_se3_exp(const float *twist, int B, float *R, float *T, void *stream);
+int rrl_se3_apply(const float *twist, const float *points, int B, int n, float *out, void *stream);
+/* grad_out (B,n,3) = d loss / d out  ->  grad_twist (B,6).  scratch: B*12 doubles. */
+int rrl_se3_apply_backward(const float *twist, const float *points, const float *grad_out, int B, int n,
+                           float *grad_twist, double *scratch, void *stream);
+/* rigid transform with explicit (R,t) for the DCP / RPM-Net / FMR hooks (utils.py:32-37,
+ * rpm/common/math_torch/se3.py:55-82, fmr/se_math/se3.py:110-124): out = points @ R^T + t (column convention
+ * R p + t).  Backward: grad_R (B,3,3), grad_t (B,3), and optionally grad_points. */
+int rrl_rigid_apply(const float *R, const float *t, const float *points, int B, int n, float *out, void *stream);
+int rrl_rigid_apply_backward(const float *R, const float *points, const float *grad_out, int B, int n,
+                             float *grad_R, float *grad_t, float *grad_points, double *scratch, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Line sampler: replaces Random_uniform_distribution_lines_batch_efficient_resample (loss.py:415-432) with
+ * generate_bbox / generate_mesh_by_bbox / cal_intersection_batch2_rand_lines / generate_lines
+ * (loss.py:265-381) and Random_uniform_distribution_lines_batch_efficient (loss.py:384-412).
+ *   radius (B), centers (B,3), verts1 (B,n1,3), verts2 (B,n2,3) -> out_lines (B,N,6), out_filled (B) int32.
+ * Draws come from a counter-based Philox4x32-10 stream keyed by (seed, offset) -- reproducible and independent
+ * of launch geometry -- unless `uniforms` (B,rounds,4,N) is supplied, in which case exactly those draws are used
+ * (order alpha1, u1, alpha2, u2 per round, like the reference's four torch.rand calls).  Rows >= filled stay
+ * all-zero, exactly like the reference.  rounds = 10 in the reference.
+ * ------------------------------------------------------------------------------------------------- */
+size_t rrl_sampler_workspace_bytes(int B, int N, int rounds);
+int rrl_sample_lines(const float *radius, const float *centers, const float *verts1, const float *verts2,
+                     int B, int n1, int n2, int N, int rounds, unsigned long long seed, unsigned long long offset,
+                     const float *uniforms, float *out_lines, int *out_filled,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Monitoring metric: replaces chamfer_dist (loss.py:236-252).  x (B,M,3), y (B,N,3) -> out (1) = mean over the
+ * concatenation of both directed min-squared-distances of all pairs.  scratch: B*(M+N) floats.
+ * ------------------------------------------------------------------------------------------------- */
+int rrl_chamfer(const float *x, const float *y, int B, int M, int N, float *out, float *scratch, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Host-buffer convenience path (what an FFI caller without device memory uses; bench.py's e2e leg).
+ * The context owns device buffers, pinned staging and a stream for one geometry.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct rrl_host_ctx rrl_host_ctx;
+int rrl_host_create(int B, int nf1, int nf2, int nl, int device, rrl_host_ctx **out_ctx);
+void rrl_host_destroy(rrl_host_ctx *ctx);
+/* pinned staging owned by the context (write inputs here to avoid an extra host copy); sizes as the device tensors */
+float *rrl_host_pinned_tri1(rrl_host_ctx *ctx);
+float *rrl_host_pinned_tri2(rrl_host_ctx *ctx);
+float *rrl_host_pinned_lines(rrl_host_ctx *ctx);
+/* H2D of the three inputs, forward, backward w.r.t. cloud 1 with d(total)/d(loss[b]) = 1, D2H of loss [B], status [B]
+ * and (if h_grad_tri1 != NULL) the (B,nf1,9) gradient; returns after the stream has drained.  h_* inputs may be
+ * the context's own pinned buffers or any host memory (then they are staged through the pinned buffers). */
+int rrl_host_loss_fwd_bwd(rrl_host_ctx *ctx, const float *h_tri1, const float *h_tri2, const float *h_lines,
+                          int k_lo, int j_lo, int k_hi, int j_hi,
+                          float *h_loss, int *h_status, float *h_grad_tri1);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Measurement helpers used by bench.py (not part of the reference's interface).
+ * ------------------------------------------------------------------------------------------------- */
+/* FP32 FMA peak of the current device in TFLOP/s, measured with a register-resident FFMA loop (mode 0) or the
+ * packed FFMA2 form (mode 1); synchronises. */
+int rrl_measure_fp32_peak(int mode, double *out_tflops, double *out_ms);
+/* time (ms, CUDA events on `stream`) of the dense intersection kernel alone over the forward last staged in
+ * `workspace` (re-runs prep + dense `iters` times; synchronises) */
+int rrl_measure_dense(const float *tri1, const float *tri2, const float *lines, int B, int nf1, int nf2, int nl,
+                      void *workspace, size_t workspace_bytes, int iters, float *out_ms_dense, float *out_ms_prep,
+                      void *stream);
+
+/* selects the dense-kernel variant: 1 = packed FFMA2 (default), 0 = scalar FFMA.  Measurement / A-B testing only. */
+int rrl_debug_set_dense_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRL_B200_H */

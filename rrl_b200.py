@@ -1,0 +1,12 @@
+"""Import shim: the package directory is named `a-robust-registration-loss_b200` (not a valid identifier), so this
+module loads it under the importable name `rrl_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "a-robust-registration-loss_b200")
+_spec = importlib.util.spec_from_file_location("rrl_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["rrl_b200"] = _mod
+_spec.loader.exec_module(_mod)

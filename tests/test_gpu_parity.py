@@ -1,0 +1,235 @@
+"""Parity of the sm_100a path against the oracles and the reference-minted golden vectors.  Needs a GPU.
+
+Bars (north star): per-line selected triplet indices bit-exact; tests within 1 ulp of the threshold are counted
+and reported (`band`); loss and gradients within 1e-5 relative (Frobenius for tensors)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, hits_to_lists
+from oracle import c_oracle as co
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def rrl():
+    import rrl_b200
+    assert torch.cuda.is_available()
+    return rrl_b200
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _run(rrl, tri1, tri2, lines, window=(1, 1, 5, 5)):
+    t1 = torch.from_numpy(tri1).cuda().reshape(1, -1, 9).requires_grad_(True)
+    t2 = torch.from_numpy(tri2).cuda().reshape(1, -1, 9).requires_grad_(True)
+    ln = torch.from_numpy(lines).cuda().reshape(1, -1, 6)
+    loss, info = rrl.intersected_line_loss(t1, t2, ln, window, return_info=True)
+    loss.sum().backward()
+    c1, h1 = info.hits(1)
+    c2, h2 = info.hits(2)
+    return dict(loss=loss.item(), status=int(info.status[0]), median=float(info.median[0]), stats=info.stats[0].cpu().numpy(),
+                counts1=c1[0].cpu().numpy(), hits1=h1[0].cpu().numpy(), counts2=c2[0].cpu().numpy(), hits2=h2[0].cpu().numpy(),
+                grad1=t1.grad[0].cpu().numpy(), grad2=t2.grad[0].cpu().numpy())
+
+
+def _check_against_oracle(out, orc, check_grad=True):
+    assert np.array_equal(out["counts1"], orc.counts1)
+    assert np.array_equal(out["counts2"], orc.counts2)
+    for cnt, mine, ref in ((orc.counts1, out["hits1"], orc.hits1), (orc.counts2, out["hits2"], orc.hits2)):
+        keep = cnt <= co.CAP                      # beyond the cap only the count is defined
+        assert np.array_equal(mine[keep], ref[keep])
+    assert int(out["stats"][0]) == orc.n_selected and int(out["stats"][1]) == orc.n_entries
+    assert int(out["stats"][2]) == orc.n_combos
+    assert int(out["stats"][5]) == orc.band        # candidates cover every test within 1 ulp of its threshold
+    if orc.status == 1:
+        assert out["status"] & 1 and out["loss"] == 0.0
+        return
+    assert out["median"] == orc.median             # exact selection
+    assert abs(out["loss"] - orc.loss) <= REL_TOL * abs(orc.loss)
+    if check_grad:
+        assert _rel(out["grad1"], orc.grad1) <= REL_TOL
+        assert _rel(out["grad2"], orc.grad2) <= REL_TOL
+
+
+@pytest.mark.parametrize("name", ["demo_step0", "synth_sphere", "synth_ragged", "synth_rpm_like", "synth_window"])
+def test_golden_cases(rrl, name):
+    g = golden(name)
+    w = tuple(int(v) for v in g["krange"])
+    out = _run(rrl, g["tri1"], g["tri2"], g["lines"], w)
+    orc = co.loss(g["tri1"], g["tri2"], g["lines"], *w)
+    _check_against_oracle(out, orc)
+    # ... and directly against what the unmodified reference produced
+    if out["stats"][5] == 0:
+        assert np.array_equal(out["counts1"], g["ref_counts1"]) and np.array_equal(out["counts2"], g["ref_counts2"])
+        for counts, nz, hits in ((g["ref_counts1"], g["ref_hits1"], out["hits1"]), (g["ref_counts2"], g["ref_hits2"], out["hits2"])):
+            for l, lst in enumerate(hits_to_lists(counts, nz)):
+                if len(lst) <= co.CAP:
+                    assert list(hits[l][:len(lst)]) == lst
+    assert abs(out["loss"] - float(g["ref_loss"][0])) <= REL_TOL * float(g["ref_loss"][0])
+    assert _rel(out["grad1"], g["ref_grad1"]) <= REL_TOL
+    assert _rel(out["grad2"], g["ref_grad2"]) <= REL_TOL
+
+
+def test_empty_selection(rrl):
+    g = golden("synth_empty")
+    out = _run(rrl, g["tri1"], g["tri2"], g["lines"])
+    assert out["status"] & 1 and out["loss"] == 0.0
+    assert not out["grad1"].any() and not out["grad2"].any()
+    rrl.loss.STRICT_EMPTY_RETURN = True
+    res = rrl.loss.cal_loss_intersection_batch_whole_median_pts_lines(
+        1, 1, 5, 5, torch.from_numpy(g["tri1"]).cuda()[None], torch.from_numpy(g["tri2"]).cuda()[None],
+        torch.from_numpy(g["lines"]).cuda()[None], "cuda")
+    assert res == (None, None, None)                # loss.py:232
+
+
+@pytest.mark.parametrize("seed,nf,nl,kw", [
+    (101, 64, 257, {}),                                        # smaller than one point tile / one line tile
+    (102, 1, 40, {}),                                          # a single triplet
+    (103, 1024, 3000, {"shape": "torus"}),
+    (104, 1500, 2049, {"nf2": 700, "zero_frac": 0.3}),         # ragged clouds, many all-zero (unfilled) lines
+    (105, 2048, 1500, {"noise": 0.01, "outlier_frac": 0.1, "keep_frac": 0.7, "radius_scale": 1.0}),
+    (106, 5000, 1024, {"shape": "box"}),                       # several point tiles per CTA
+])
+def test_seeded_synthetic_vs_oracle(rrl, seed, nf, nl, kw):
+    if nf == 1:
+        rng = np.random.default_rng(seed)
+        tri = rng.normal(size=(1, 9)).astype(np.float32) * 0.05
+        p = dict(tri1=tri, tri2=tri + 0.01, lines=synth.chord_lines(rng, nl, 0.5, np.zeros(3), -np.ones(3) * .1, np.ones(3) * .1, -np.ones(3) * .1, np.ones(3) * .1))
+    else:
+        p = synth.make_pair(seed, nf, nl, **kw)
+    out = _run(rrl, p["tri1"], p["tri2"], p["lines"])
+    orc = co.loss(p["tri1"], p["tri2"], p["lines"])
+    _check_against_oracle(out, orc)
+
+
+def test_large_coordinates_keep_exactness(rrl):
+    """the filter's guard band scales with (|p| + |x0|)^2: translate everything far from the origin"""
+    p = synth.make_pair(107, 600, 1500)
+    shift = np.array([7.0, -9.0, 5.0], np.float32)
+    tri1 = (p["tri1"].reshape(-1, 3) + shift).reshape(-1, 9)
+    tri2 = (p["tri2"].reshape(-1, 3) + shift).reshape(-1, 9)
+    lines = p["lines"].copy()
+    lines[:, 3:] += shift
+    out = _run(rrl, tri1, tri2, lines)
+    _check_against_oracle(out, co.loss(tri1, tri2, lines))
+
+
+def test_scalar_and_packed_variants_agree(rrl):
+    p = synth.make_pair(108, 1024, 4000)
+    L = rrl._native.lib()
+    try:
+        L.rrl_debug_set_dense_variant(0)
+        a = _run(rrl, p["tri1"], p["tri2"], p["lines"])
+    finally:
+        L.rrl_debug_set_dense_variant(1)
+    b = _run(rrl, p["tri1"], p["tri2"], p["lines"])
+    for k in ("counts1", "counts2", "hits1", "hits2"):
+        assert np.array_equal(a[k], b[k])
+    assert a["loss"] == b["loss"] and a["median"] == b["median"]
+
+
+def test_batched_equals_per_pair_and_is_permutation_invariant(rrl):
+    pairs = [synth.make_pair(200 + i, 512, 2000) for i in range(5)]
+    t1 = torch.from_numpy(np.stack([p["tri1"] for p in pairs])).cuda().requires_grad_(True)
+    t2 = torch.from_numpy(np.stack([p["tri2"] for p in pairs])).cuda()
+    ln = torch.from_numpy(np.stack([p["lines"] for p in pairs])).cuda()
+    loss = rrl.intersected_line_loss(t1, t2, ln)
+    (loss * torch.arange(1, 6, device="cuda")).sum().backward()
+    for i, p in enumerate(pairs):
+        orc = co.loss(p["tri1"], p["tri2"], p["lines"])
+        assert abs(loss[i].item() - orc.loss) <= REL_TOL * orc.loss
+        assert _rel(t1.grad[i].cpu().numpy(), (i + 1) * orc.grad1) <= REL_TOL
+    # shuffling the lines of a pair must not change its loss at all: sums are order-independent fixed point
+    perm = torch.randperm(ln.shape[1], generator=torch.Generator().manual_seed(0)).cuda()
+    loss2 = rrl.intersected_line_loss(t1.detach(), t2, ln[:, perm])
+    assert torch.equal(loss2, loss.detach())
+
+
+def test_raw_c_abi_calls(rrl):
+    """the same path through bare ctypes: raw device pointers, explicit workspace, explicit stream"""
+    L = rrl._native.lib()
+    p = synth.make_pair(300, 700, 1800)
+    t1 = torch.from_numpy(p["tri1"]).cuda(); t2 = torch.from_numpy(p["tri2"]).cuda(); ln = torch.from_numpy(p["lines"]).cuda()
+    nf1, nf2, nl = t1.shape[0], t2.shape[0], ln.shape[0]
+    wsb = L.rrl_workspace_bytes(1, nf1, nf2, nl)
+    assert wsb > 0
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    loss = torch.zeros(1, device="cuda"); status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    assert L.rrl_loss_forward(t1.data_ptr(), t2.data_ptr(), ln.data_ptr(), 1, nf1, nf2, nl, 1, 1, 5, 5, ws.data_ptr(), wsb,
+                              loss.data_ptr(), status.data_ptr(), None, None, s.cuda_stream) == 0
+    g1 = torch.empty(nf1, 9, device="cuda"); go = torch.ones(1, device="cuda")
+    assert L.rrl_loss_backward(ws.data_ptr(), wsb, go.data_ptr(), 1, nf1, nf2, nl, g1.data_ptr(), None, s.cuda_stream) == 0
+    s.synchronize()
+    orc = co.loss(p["tri1"], p["tri2"], p["lines"])
+    assert abs(loss.item() - orc.loss) <= REL_TOL * orc.loss
+    assert _rel(g1.cpu().numpy(), orc.grad1) <= REL_TOL
+    # error conventions: status codes, never exit
+    assert L.rrl_loss_forward(None, t2.data_ptr(), ln.data_ptr(), 1, nf1, nf2, nl, 1, 1, 5, 5, ws.data_ptr(), wsb,
+                              loss.data_ptr(), None, None, None, None) == -1
+    assert L.rrl_loss_forward(t1.data_ptr(), t2.data_ptr(), ln.data_ptr(), 1, nf1, nf2, nl, 0, 1, 5, 5, ws.data_ptr(), wsb,
+                              loss.data_ptr(), None, None, None, None) == -1
+    assert L.rrl_loss_forward(t1.data_ptr(), t2.data_ptr(), ln.data_ptr(), 1, nf1, nf2, nl, 1, 1, 5, 5, ws.data_ptr(), 1024,
+                              loss.data_ptr(), None, None, None, None) == -2
+    with pytest.raises(ValueError):
+        rrl.intersected_line_loss(t1, t2[None], ln[None])
+    with pytest.raises(rrl.NativeError):
+        rrl.intersected_line_loss(t1.cpu()[None], t2.cpu()[None], ln.cpu()[None])      # no CPU fallback
+
+
+def test_host_buffer_entry(rrl):
+    L = rrl._native.lib()
+    pairs = [synth.make_pair(400 + i, 300, 1000) for i in range(3)]
+    tri1 = np.ascontiguousarray(np.stack([p["tri1"] for p in pairs])); tri2 = np.ascontiguousarray(np.stack([p["tri2"] for p in pairs]))
+    lines = np.ascontiguousarray(np.stack([p["lines"] for p in pairs]))
+    ctx = C.c_void_p()
+    assert L.rrl_host_create(3, 300, 300, 1000, 0, C.byref(ctx)) == 0
+    try:
+        loss = np.zeros(3, np.float32); status = np.zeros(3, np.int32); g1 = np.zeros_like(tri1)
+        assert L.rrl_host_loss_fwd_bwd(ctx, tri1.ctypes.data, tri2.ctypes.data, lines.ctypes.data, 1, 1, 5, 5,
+                                       loss.ctypes.data, status.ctypes.data, g1.ctypes.data) == 0
+    finally:
+        L.rrl_host_destroy(ctx)
+    for i, p in enumerate(pairs):
+        orc = co.loss(p["tri1"], p["tri2"], p["lines"])
+        assert abs(loss[i] - orc.loss) <= REL_TOL * orc.loss
+        assert _rel(g1[i], orc.grad1) <= REL_TOL
+
+
+def test_full_size_dcp_batch_properties(rrl):
+    """BASELINE config 2 at full size (32 x 1024 triplets x 15000 lines): the oracle checks a few pairs completely,
+    every pair through size-independent properties."""
+    B, nf, nl = 32, 1024, 15000
+    pairs = [synth.make_pair(2000 + i, nf, nl) for i in range(B)]
+    t1 = torch.from_numpy(np.stack([p["tri1"] for p in pairs])).cuda()
+    t2 = torch.from_numpy(np.stack([p["tri2"] for p in pairs])).cuda()
+    ln = torch.from_numpy(np.stack([p["lines"] for p in pairs])).cuda()
+    loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True)
+    c1, h1 = info.hits(1)
+    for i in (0, 13, 31):
+        orc = co.loss(pairs[i]["tri1"], pairs[i]["tri2"], pairs[i]["lines"], want_grad=False)
+        assert np.array_equal(c1[i].cpu().numpy(), orc.counts1)
+        keep = orc.counts1 <= co.CAP
+        assert np.array_equal(h1[i].cpu().numpy()[keep], orc.hits1[keep])
+        assert float(info.median[i]) == orc.median
+        assert abs(loss[i].item() - orc.loss) <= REL_TOL * orc.loss
+    # swapping the clouds of every pair transposes every D matrix: same medians, same losses (symmetry of loss.py:227-229)
+    loss_sw, info_sw = rrl.intersected_line_loss(t2, t1, ln, return_info=True)
+    assert torch.equal(info_sw.median, info.median)
+    assert torch.allclose(loss_sw, loss, rtol=1e-6, atol=0)
+    # hit lists are sorted and inside range
+    h = h1.cpu().numpy(); c = c1.cpu().numpy()
+    for s in range(co.CAP - 1):
+        ok = (c > s + 1)
+        assert np.all(h[..., s][ok] < h[..., s + 1][ok])
+    assert h.max() < nf and int(info.stats[:, 6].sum()) == 0
