@@ -29,8 +29,10 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     const int nf1p = pad_points(nf1), nf2p = pad_points(nf2);
     w.hdr = reinterpret_cast<int *>(take(8 * sizeof(int)));
     // ---- per-pair block, contiguous and zeroed by one memset in launch_prep (order matters) ----
-    char *pair = take(sB * (2 * 4 + 4 + 16 * 4 + 4 + 2 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
+    char *pair = take(sB * (3 * 2 * 4 + 4 + 16 * 4 + 4 + 2 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
     w.pmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
+    w.xmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
+    w.rmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.nrec = reinterpret_cast<int *>(pair);                           pair += sB * 4;
     w.n_kj = reinterpret_cast<int *>(pair);                           pair += sB * 16 * 4;
     w.med = reinterpret_cast<float *>(pair);                          pair += sB * 4;
@@ -39,11 +41,18 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.stats = reinterpret_cast<long long *>(pair);                    pair += sB * RRL_NSTAT * 8;
     w.gcounts = reinterpret_cast<long long *>(pair);
     // ---- per triplet ----
-    w.tri4[0] = reinterpret_cast<float4 *>(take(sB * nf1p * sizeof(float4)));
-    w.tri4[1] = reinterpret_cast<float4 *>(take(sB * nf2p * sizeof(float4)));
     w.thr[0] = reinterpret_cast<float *>(take(sB * nf1 * sizeof(float)));
     w.thr[1] = reinterpret_cast<float *>(take(sB * nf2 * sizeof(float)));
+    w.perm[0] = reinterpret_cast<int *>(take(sB * nf1p * sizeof(int)));
+    w.perm[1] = reinterpret_cast<int *>(take(sB * nf2p * sizeof(int)));
+    w.pt4[0] = reinterpret_cast<float4 *>(take(sB * nf1p * sizeof(float4)));
+    w.pt4[1] = reinterpret_cast<float4 *>(take(sB * nf2p * sizeof(float4)));
+    w.node4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kNode) * sizeof(float4)));
+    w.node4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kNode) * sizeof(float4)));
+    w.sortbuf_bytes = sort_scratch_bytes(nf1p > nf2p ? nf1p : nf2p);
+    w.sortbuf = reinterpret_cast<unsigned long long *>(take(w.sortbuf_bytes));
     // ---- per line ----
+    w.lineC = reinterpret_cast<float4 *>(take(lines * 2 * sizeof(float4)));
     w.cnt[0] = reinterpret_cast<int *>(take(2 * lines * sizeof(int)));
     w.cnt[1] = w.cnt[0] + lines;
     w.hits[0] = reinterpret_cast<int *>(take(lines * kCap * sizeof(int)));
@@ -74,7 +83,7 @@ static Geometry make_geometry(int B, int nf1, int nf2, int nl) {
 static int stage_dense_and_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws,
                                  const Geometry &g, int k_lo, int j_lo, int k_hi, int j_hi, cudaStream_t s) {
     const int window = k_lo | (j_lo << 8) | (k_hi << 16) | (j_hi << 24);
-    int rc = launch_prep(tri1, tri2, ws, g, window, s);
+    int rc = launch_prep(tri1, tri2, lines, ws, g, window, s);
     if (rc) return rc;
     rc = launch_dense(tri1, tri2, lines, ws, g, s);
     if (rc) return rc;
@@ -297,7 +306,7 @@ extern "C" int rrl_measure_dense(const float *tri1, const float *tri2, const flo
     int rc = RRL_OK;
     for (int it = 0; it < iters + 1 && rc == RRL_OK; ++it) {
         cudaEventRecord(e0, s);
-        rc = launch_prep(tri1, tri2, ws, g, 1 | (1 << 8) | (5 << 16) | (5 << 24), s);
+        rc = launch_prep(tri1, tri2, lines, ws, g, 1 | (1 << 8) | (5 << 16) | (5 << 24), s);
         cudaEventRecord(e1, s);
         if (rc == RRL_OK) rc = launch_dense(tri1, tri2, lines, ws, g, s);
         cudaEventRecord(e2, s);

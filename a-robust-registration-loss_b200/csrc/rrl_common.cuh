@@ -14,37 +14,45 @@ constexpr float kAddEps = 2e-4f;      // loss.py:88   d = sqrt(... + 2e-4)
 constexpr float kThrScale = 1.731f;   // loss.py:109  thr = delta * 1.731 / 2
 constexpr int kCap = RRL_HIT_CAP;
 
-// ---- conservative filter (DESIGN.md "filtered predicate") ----------------------------------------
-// candidate  <=>  Q = (p.u)^2 + p.(2m) + (cut - |p|^2)  >  c - g,   g = kGuard * 2^-24 * (P + |x0|)^2
-// The derivation in DESIGN.md bounds the combined rounding error of the reference-order test and of the
-// FMA-contracted filter by 58 * 2^-24 * (P+|x0|)^2; kGuard doubles that.
-constexpr float kGuard = 128.0f;
+// ---- conservative filters (DESIGN.md "filtered predicate") ---------------------------------------
+// F(p) = |p-x0|^2 - ((p-x0).u)^2 is evaluated as  F = |p|^2 - (p.u)^2 - p.M + c  with per-line constants
+// M = 2 (x0 - (x0.u) u), c = |x0|^2 - (x0.u)^2 (double precision, rounded once).  A record (centre q, nw) is a
+// candidate for a line when   Q = (q.u)^2 + q.M + nw  >  tl,   i.e.  F(q) < nw + |q|^2 + (c - tl).
+//   point record : nw = cut_f - |p0|^2,   cut_f = thr_f^2 - 2e-4                  (tl = c - g)
+//   node record  : nw = R^2 - |q|^2,      R >= sqrt(cut_f + E) + |p0_f - q| for every triplet f of the node
+// g = kGuardFast * 2^-24 * (P + |x0|)^2 bounds the rounding of the reference-order test plus the FMA chain
+// (derivation in DESIGN.md: <= 58 * 2^-24 * (P+|x0|)^2); E = kGuardRef * 2^-24 * (P + Xmax)^2 bounds the
+// reference-order test alone (<= 30 * 2^-24 * (P+|x0|)^2).
+constexpr float kGuardFast = 128.0f;
+constexpr float kGuardRef = 64.0f;
+constexpr float kEps24 = 5.9604645e-8f;
 
 // ---- dense kernel geometry ---------------------------------------------------------------------------
+constexpr int kNode = 16;                                       // triplets per bounding-sphere node
 constexpr int kDenseThreads = 256;
 constexpr int kLinesPerThread = 4;
 constexpr int kLinesPerCta = kDenseThreads * kLinesPerThread;   // 1024
-constexpr int kTilePoints = 1024;                               // float4 per point: 16 KB per stage
-constexpr int kPointPad = 64;                                   // tri4 arrays are padded to this multiple with sentinels
-constexpr int kQueueCap = 2048;                                 // candidate queue entries per CTA
+constexpr int kTileNodes = 1024;                                // float4 per node: 16 KB per stage
+constexpr int kNodePad = 16;                                    // node arrays are padded to this multiple (sentinels)
+constexpr int kPointPad = kNode * kNodePad;                     // => triplet arrays padded to 256
+constexpr int kWarpQueue = 1024;                                // candidate (line, node) entries per warp
+constexpr int kSortSmall = 4096;                                // clouds up to this many (padded) triplets sort in one CTA
 
 // ---- fixed-point accumulation of Welsch sums (order-independent, hence run-to-run deterministic) ---
 constexpr double kFixScale = 1099511627776.0;                   // 2^40
 
 struct Geometry {
     int B, nf1, nf2, nl;
-    int nf1p, nf2p;          // padded triplet counts
+    int nf1p, nf2p;          // padded triplet counts (multiples of kPointPad)
 };
 
 // One forward's scratch, carved out of the caller's workspace.  All pointers are device pointers.
 struct Workspace {
-    // header written by forward, read by backward (device side)
-    int *hdr;                // [8]: {magic, B, nf1, nf2, nl, k_lo|j_lo<<8|k_hi<<16|j_hi<<24, 0, 0}
-    // per triplet
-    float4 *tri4[2];         // (B, nfp): p0.xyz, (cut - |p0|^2); sentinel padded
-    float *thr[2];           // (B, nf): exact reference threshold
-    // per pair
-    unsigned int *pmax;      // (B, 2): bit pattern of max |p|^2 over all 9-float rows of the cloud
+    int *hdr;                // [8]: {magic, B, nf1, nf2, nl, window, 0, 0}
+    // per pair (one contiguous block, zeroed by a single memset)
+    unsigned int *pmax;      // (B,2): bits of max |p|^2 over all 3 points of all triplets of the cloud
+    unsigned int *xmax;      // (B,2): [0] bits of max |x0|^2 over the pair's lines, [1] reserved
+    unsigned int *rmax;      // (B,2): bits of the largest node radius of the cloud
     int *nrec;               // (B)
     int *n_kj;               // (B,16)
     float *med;              // (B)
@@ -52,7 +60,15 @@ struct Workspace {
     unsigned long long *sums;// (B,32): S1[16], S2[16] fixed point
     long long *stats;        // (B, RRL_NSTAT)
     long long *gcounts;      // (B,18) global counts used by welsch/finalize/backward (== local unless line-sharded)
+    // per triplet
+    float *thr[2];           // (B, nf): exact reference threshold, original order
+    int *perm[2];            // (B, nfp): sorted position -> original triplet index (-1 = padding)
+    float4 *pt4[2];          // (B, nfp): sorted order, {p0.xyz, cut - |p0|^2}; sentinel padded
+    float4 *node4[2];        // (B, nfp/kNode): pair-interleaved {xA,xB,yA,yB}{zA,zB,wA,wB}; w = R^2 - |q|^2
+    unsigned long long *sortbuf; // scratch for the large-cloud sort (keys/values double buffers + cub temp)
+    size_t sortbuf_bytes;
     // per line
+    float4 *lineC;           // (B, nl, 2): {u.xyz, |x0|}, {M.xyz, c}
     int *cnt[2];             // (B, nl) hit counters
     int *hits[2];            // (B, nl, kCap)
     // per record (capacity B*nl)
@@ -67,6 +83,7 @@ struct Workspace {
 constexpr int kMagic = 0x52524c31;   // "RRL1"
 
 inline int pad_points(int nf) { return ((nf + kPointPad - 1) / kPointPad) * kPointPad; }
+size_t sort_scratch_bytes(int nfp_max);
 
 Workspace carve(void *base, int B, int nf1, int nf2, int nl);
 
@@ -75,7 +92,8 @@ void count_launch(int n = 1);
 int check_launch();          // cudaGetLastError -> RRL_OK / RRL_ERR_CUDA
 
 // ---- stage launchers (rrl_dense.cu, rrl_sparse.cu) ------------------------------------------------------
-int launch_prep(const float *tri1, const float *tri2, const Workspace &ws, const Geometry &g, int window, cudaStream_t s);
+int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
+                int window, cudaStream_t s);
 int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s);
 int launch_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                  int k_lo, int j_lo, int k_hi, int j_hi, cudaStream_t s);
@@ -114,6 +132,12 @@ __device__ __forceinline__ float point_line_x_exact(float px, float py, float pz
 }
 
 __device__ __forceinline__ float ulp_up(float x) { return __uint_as_float(__float_as_uint(x) + 1u) - x; }
+
+// warp-aggregated atomicMax of non-negative floats (which order like their bit patterns)
+__device__ __forceinline__ void warp_atomic_max_bits(unsigned int *addr, float v) {
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(addr, m);
+}
 #endif
 
 }  // namespace rrl

@@ -4,88 +4,277 @@
 // triplet) decide whether all three points of the triplet lie closer to the line than the triplet's local
 // threshold, WITHOUT materialising the (nl, nf, 3, 3) tensors the reference builds.
 //
-//   prep_kernel   per triplet: exact threshold thr_f (reference op order, IEEE sqrt), the filter record
-//                 float4(p0, cut_f - |p0|^2) in a point-pair interleaved layout, the cloud's max |p|^2;
-//                 also zeroes the per-line hit counters.
-//   dense_kernel  streams tiles of filter records through shared memory with 1-D TMA bulk copies
-//                 (cp.async.bulk + mbarrier, double buffered) against register-resident lines, evaluates a
-//                 conservative FMA-contracted predicate on point 0 of every triplet (7 FP32 ops per
-//                 (line, triplet), packed as FFMA2) and queues the rare candidate groups; the queue is drained
-//                 with the exact reference-order test of all three points, and confirmed hits are written to
-//                 fixed-capacity per-line slots.
+//   prep_kernel    per triplet: exact threshold thr_f (reference op order, IEEE sqrt) and the cloud's max |p|^2;
+//                  per line: the filter constants {u, |x0|, M, c} in double precision, the pair's max |x0|^2;
+//                  zeroes the per-line hit counters.
+//   sort kernels   Morton order of every cloud's points (one CTA bitonic sort up to 4096 triplets, CUB radix sort
+//                  above) so that kNode consecutive triplets are spatial neighbours.
+//   node_kernel    per node of kNode sorted triplets: bounding sphere (centre q, radius R covering every
+//                  triplet's hit cylinder) -> node record float4(q, R^2 - |q|^2); per triplet the point record
+//                  float4(p0, cut_f - |p0|^2) in sorted order.
+//   dense_kernel   streams tiles of NODE records through shared memory with 1-D TMA bulk copies
+//                  (cp.async.bulk + mbarrier, double buffered) against register-resident lines.  7 packed FP32
+//                  ops (FFMA2) decide per (line, node) whether the line can touch the node's sphere; results
+//                  are accumulated branch-free into per-line bit masks, pushed to warp-private queues once per
+//                  32 groups, and drained with (1) the same predicate per triplet of the node and (2) the EXACT
+//                  reference-order test of all three points.  Confirmed hits go to fixed-capacity per-line slots.
 //
-// The filter is a superset test ("filtered predicate"): the decision itself is always taken by the
-// exact arithmetic of loss.py:84-110, so selected indices are bit-exact against the oracle.
+// Both filters are superset tests ("filtered predicate"); the decision itself is always taken by the
+// literal arithmetic of loss.py:84-110, so the selected indices are bit-exact against the oracle.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "rrl_common.cuh"
 
 namespace rrl {
 
 // ------------------------------------------------------------------------------------------------------
-// prep
+// prep: thresholds, line constants, extents
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
-                                                   Workspace ws, Geometry g, int window) {
-    const long long n1 = (long long)g.B * g.nf1p, n2 = (long long)g.B * g.nf2p;
-    const long long nlines = 2LL * g.B * g.nl;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid0 == 0) {
+                                                   const float *__restrict__ lines, Workspace ws, Geometry g, int window) {
+    const int b = blockIdx.y;
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0 && t0 == 0) {
         ws.hdr[0] = kMagic; ws.hdr[1] = g.B; ws.hdr[2] = g.nf1; ws.hdr[3] = g.nf2; ws.hdr[4] = g.nl; ws.hdr[5] = window;
     }
-    // zero the hit counters of both clouds (cnt[0] and cnt[1] are contiguous)
-    for (long long i = tid0; i < nlines; i += stride) ws.cnt[0][i] = 0;
-
-    for (long long i = tid0; i < n1 + n2; i += stride) {
-        const int cloud = i >= n1;
-        const long long r = cloud ? i - n1 : i;
-        const int nfp = cloud ? g.nf2p : g.nf1p, nf = cloud ? g.nf2 : g.nf1;
-        const int b = (int)(r / nfp), f = (int)(r % nfp);
-        float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);     // sentinel: never a candidate
-        float pm = 0.f;
-        if (f < nf) {
-            const float *t = (cloud ? tri2 : tri1) + ((long long)b * nf + f) * 9;
-            float v[9];
+#pragma unroll 1
+    for (int cloud = 0; cloud < 2; ++cloud) {
+        const int nf = cloud ? g.nf2 : g.nf1;
+        const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
+        float *thr = ws.thr[cloud] + (long long)b * nf;
+        for (int base = blockIdx.x * blockDim.x; base < nf; base += stride) {      // warp-uniform trip count
+            const int f = base + threadIdx.x;
+            float pm = 0.f;
+            if (f < nf) {
+                float v[9];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) v[q] = __ldg(t + q);
-            const float thr = triplet_thr_exact(v);
-            ws.thr[cloud][(long long)b * nf + f] = thr;
-            const double cut = (double)thr * (double)thr - (double)kAddEps;
-            const double p2 = (double)v[0] * v[0] + (double)v[1] * v[1] + (double)v[2] * v[2];
-            rec = make_float4(v[0], v[1], v[2], (float)(cut - p2));
-            pm = fmaxf(fmaxf(sq3_rn(v[0], v[1], v[2]), sq3_rn(v[3], v[4], v[5])), sq3_rn(v[6], v[7], v[8]));
-            if (!(pm == pm)) pm = INFINITY;
+                for (int q = 0; q < 9; ++q) v[q] = __ldg(tri + (long long)f * 9 + q);
+                thr[f] = triplet_thr_exact(v);
+                pm = fmaxf(fmaxf(sq3_rn(v[0], v[1], v[2]), sq3_rn(v[3], v[4], v[5])), sq3_rn(v[6], v[7], v[8]));
+                if (!(pm == pm)) pm = INFINITY;
+            }
+            warp_atomic_max_bits(ws.pmax + b * 2 + cloud, pm);
         }
-        // pair-interleaved layout: points (2i, 2i+1) -> {xA,xB,yA,yB}, {zA,zB,wA,wB}
-        float *dst = reinterpret_cast<float *>(ws.tri4[cloud] + ((long long)b * nfp + (f & ~1)));
-        const int h = f & 1;
-        dst[0 + h] = rec.x; dst[2 + h] = rec.y; dst[4 + h] = rec.z; dst[6 + h] = rec.w;
-        // cloud max |p|^2 (non-negative floats order like their bit patterns)
-        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(pm));
-        // lanes of one warp may straddle a pair boundary: fall back to per-lane atomics in that (rare) case
-        const int b0 = __shfl_sync(0xffffffffu, b, 0), c0 = __shfl_sync(0xffffffffu, cloud, 0);
-        const bool uniform = __all_sync(0xffffffffu, b == b0 && cloud == c0);
-        if (uniform) {
-            if ((threadIdx.x & 31) == 0) atomicMax(ws.pmax + b * 2 + cloud, m);
-        } else {
-            atomicMax(ws.pmax + b * 2 + cloud, __float_as_uint(pm));
+    }
+    const float *lb = lines + (long long)b * g.nl * 6;
+    for (int base = blockIdx.x * blockDim.x; base < g.nl; base += stride) {
+        const int l = base + threadIdx.x;
+        float xm = 0.f;
+        if (l < g.nl) {
+            const float *ln = lb + (long long)l * 6;
+            const float u0 = __ldg(ln), u1 = __ldg(ln + 1), u2 = __ldg(ln + 2);
+            const double x = __ldg(ln + 3), y = __ldg(ln + 4), z = __ldg(ln + 5);
+            const double sd = x * u0 + y * u1 + z * u2;
+            const double xx = x * x + y * y + z * z;
+            const long long gl = (long long)b * g.nl + l;
+            ws.lineC[gl * 2] = make_float4(u0, u1, u2, (float)sqrt(xx) * 1.000001f);
+            ws.lineC[gl * 2 + 1] = make_float4((float)(2.0 * (x - sd * u0)), (float)(2.0 * (y - sd * u1)),
+                                               (float)(2.0 * (z - sd * u2)), (float)(xx - sd * sd));
+            ws.cnt[0][gl] = 0;
+            ws.cnt[1][gl] = 0;
+            xm = (float)xx * 1.000001f;
+            if (!(xm == xm)) xm = INFINITY;
         }
+        warp_atomic_max_bits(ws.xmax + b * 2, xm);
     }
 }
 
-int launch_prep(const float *tri1, const float *tri2, const Workspace &ws, const Geometry &g, int window, cudaStream_t s) {
-    // per-pair block {pmax, nrec, n_kj, med, sums, stats, gcounts} is contiguous, see carve()
+// ------------------------------------------------------------------------------------------------------
+// Morton order
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__device__ __forceinline__ unsigned morton_key(const float *p, float P) {
+    const float s = P > 0.f ? 512.0f / P : 0.f;              // [-P, P] -> [0, 1024)
+    const int qx = min(1023, max(0, (int)((p[0] + P) * s)));
+    const int qy = min(1023, max(0, (int)((p[1] + P) * s)));
+    const int qz = min(1023, max(0, (int)((p[2] + P) * s)));
+    return spread10((unsigned)qx) | (spread10((unsigned)qy) << 1) | (spread10((unsigned)qz) << 2);
+}
+
+// one CTA sorts one cloud (nfp <= kSortSmall) with a bitonic network on (key << 32 | index)
+__global__ void __launch_bounds__(1024) sort_small_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
+                                                          Workspace ws, Geometry g, int sorted) {
+    extern __shared__ unsigned long long skeys[];
+    const int b = blockIdx.x, cloud = blockIdx.y;
+    const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
+    const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
+    const float P = sqrtf(__uint_as_float(ws.pmax[b * 2 + cloud]));
+    int n2 = 1;
+    while (n2 < nfp) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned long long v = 0xFFFFFFFFFFFFFFFFull;
+        if (i < nf) {
+            const float p[3] = {__ldg(tri + (long long)i * 9), __ldg(tri + (long long)i * 9 + 1), __ldg(tri + (long long)i * 9 + 2)};
+            const unsigned key = sorted ? morton_key(p, P) : 0u;
+            v = ((unsigned long long)key << 32) | (unsigned)i;
+        }
+        skeys[i] = v;
+    }
+    __syncthreads();
+    if (sorted) {
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = skeys[i], c = skeys[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > c) == up) { skeys[i] = c; skeys[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+    }
+    int *perm = ws.perm[cloud] + (long long)b * nfp;
+    for (int i = threadIdx.x; i < nfp; i += blockDim.x) {
+        const unsigned idx = (unsigned)(skeys[i] & 0xFFFFFFFFull);
+        perm[i] = idx < (unsigned)nf ? (int)idx : -1;
+    }
+}
+
+// large clouds: keys for the CUB radix sort
+__global__ void __launch_bounds__(256) sort_keys_kernel(const float *__restrict__ tri, int nf, int nfp, float P, const unsigned int *pmax_bits,
+                                                        unsigned *keys, int *vals, int sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nfp) return;
+    const float Pm = sqrtf(__uint_as_float(*pmax_bits));
+    (void)P;
+    unsigned key = 0xFFFFFFFFu;
+    int val = -1;
+    if (i < nf) {
+        const float p[3] = {__ldg(tri + (long long)i * 9), __ldg(tri + (long long)i * 9 + 1), __ldg(tri + (long long)i * 9 + 2)};
+        key = sorted ? morton_key(p, Pm) : 0u;
+        val = i;
+    }
+    keys[i] = key;
+    vals[i] = val;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// nodes
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g) {
+    const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
+    const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
+    const int nnodes = nfp / kNode;
+    const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
+    const float *thr = ws.thr[cloud] + (long long)b * nf;
+    const int *perm = ws.perm[cloud] + (long long)b * nfp;
+    const double P = sqrt((double)__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001;
+    const double Xm = sqrt((double)__uint_as_float(ws.xmax[b * 2])) * 1.000001;
+    const double E = (double)kGuardRef * (double)kEps24 * (P + Xm) * (P + Xm) + 1e-12;
+    for (int base = blockIdx.x * blockDim.x; base < nnodes; base += gridDim.x * blockDim.x) {   // warp-uniform trip count
+        const int n = base + threadIdx.x;
+        float rad = 0.f;
+        if (n < nnodes) {
+            double cx = 0, cy = 0, cz = 0;
+            int cntv = 0;
+            for (int s = 0; s < kNode; ++s) {
+                const int f = perm[n * kNode + s];
+                if (f >= 0) {
+                    cx += __ldg(tri + (long long)f * 9); cy += __ldg(tri + (long long)f * 9 + 1); cz += __ldg(tri + (long long)f * 9 + 2);
+                    ++cntv;
+                }
+            }
+            float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);               // empty node: never a candidate
+            if (cntv > 0) {
+                cx /= cntv; cy /= cntv; cz /= cntv;
+                const float qx = (float)cx, qy = (float)cy, qz = (float)cz;   // the record's centre is the ROUNDED centroid
+                double R = 0;
+                for (int s = 0; s < kNode; ++s) {
+                    const int f = perm[n * kNode + s];
+                    float4 pr = make_float4(0.f, 0.f, 0.f, -INFINITY);
+                    if (f >= 0) {
+                        const double px = __ldg(tri + (long long)f * 9), py = __ldg(tri + (long long)f * 9 + 1), pz = __ldg(tri + (long long)f * 9 + 2);
+                        const double th = __ldg(thr + f);
+                        const double cut = th * th - (double)kAddEps;
+                        pr = make_float4((float)px, (float)py, (float)pz, (float)(cut - (px * px + py * py + pz * pz)));
+                        const double dx = px - qx, dy = py - qy, dz = pz - qz;
+                        const double reach = sqrt(fmax(cut + E, 0.0)) + sqrt(dx * dx + dy * dy + dz * dz);
+                        R = fmax(R, reach);
+                    }
+                    ws.pt4[cloud][(long long)b * nfp + n * kNode + s] = pr;
+                }
+                R *= 1.000002;
+                rad = (float)R * 1.000001f;
+                const double q2 = (double)qx * qx + (double)qy * qy + (double)qz * qz;
+                // round the record's slack UP: a larger w only admits more candidates
+                float w = (float)(R * R - q2);
+                w = w + fabsf(w) * 2.4e-7f + 1e-30f;
+                rec = make_float4(qx, qy, qz, w);
+            } else {
+                for (int s = 0; s < kNode; ++s) ws.pt4[cloud][(long long)b * nfp + n * kNode + s] = make_float4(0.f, 0.f, 0.f, -INFINITY);
+            }
+            float *dst = reinterpret_cast<float *>(ws.node4[cloud] + ((long long)b * nnodes + (n & ~1)));
+            const int h = n & 1;
+            dst[0 + h] = rec.x; dst[2 + h] = rec.y; dst[4 + h] = rec.z; dst[6 + h] = rec.w;
+        }
+        warp_atomic_max_bits(ws.rmax + b * 2 + cloud, rad);
+    }
+}
+
+size_t sort_scratch_bytes(int nfp_max) {
+    if (nfp_max <= kSortSmall) return 0;
+    // keys_in, keys_out, vals_in (vals_out is perm) + CUB temp: CUB's requirement is checked at launch time
+    return (size_t)nfp_max * 4 * 3 + 768 + (size_t)nfp_max * 8 + (4u << 20);
+}
+
+static int g_dense_variant = 1;        // 1 = Morton-sorted nodes (default), 0 = nodes in input order (A/B measurement)
+void set_dense_variant(int v) { g_dense_variant = v; }
+
+int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
+                int window, cudaStream_t s) {
+    // per-pair block {pmax ... gcounts} is contiguous, see carve()
     const size_t pair_bytes = (size_t)((char *)(ws.gcounts + (size_t)g.B * 18) - (char *)ws.pmax);
     if (cudaMemsetAsync(ws.pmax, 0, pair_bytes, s) != cudaSuccess) return RRL_ERR_CUDA;
-    const long long work = (long long)g.B * (g.nf1p + g.nf2p);
-    const long long lines = 2LL * g.B * g.nl;
-    long long want = (work > lines / 4 ? work : lines / 4);
-    int blocks = (int)((want + 255) / 256);
-    if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    // the warp-uniform __reduce/__shfl calls need whole warps in the loop: the loop bounds are uniform per warp
-    // only if every lane runs the same trip count, which grid-stride loops do not guarantee -> pad the triplet
-    // loop by running it over a multiple of 32 (nf*p are multiples of 64, so B*(nf1p+nf2p) is).
-    prep_kernel<<<blocks, 256, 0, s>>>(tri1, tri2, ws, g, window);
+    const int most = g.nl > g.nf1 ? (g.nl > g.nf2 ? g.nl : g.nf2) : (g.nf1 > g.nf2 ? g.nf1 : g.nf2);
+    int bx = (most + 255) / 256;
+    const int cap = (148 * 8 + g.B - 1) / g.B;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    prep_kernel<<<dim3(bx, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, window);
+    count_launch();
+    const int sorted = g_dense_variant ? 1 : 0;
+    const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
+    if (nfp_max <= kSortSmall) {
+        int n2 = 1;
+        while (n2 < nfp_max) n2 <<= 1;
+        sort_small_kernel<<<dim3(g.B, 2), 1024, (size_t)n2 * 8, s>>>(tri1, tri2, ws, g, sorted);
+        count_launch();
+    } else {
+        unsigned *keys_in = reinterpret_cast<unsigned *>(ws.sortbuf);
+        unsigned *keys_out = keys_in + nfp_max;
+        int *vals_in = reinterpret_cast<int *>(keys_out + nfp_max);
+        char *temp = reinterpret_cast<char *>(vals_in + nfp_max);
+        temp = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(temp) + 255) / 256 * 256);
+        const size_t temp_avail = ws.sortbuf_bytes - (size_t)(temp - reinterpret_cast<char *>(ws.sortbuf));
+        for (int b = 0; b < g.B; ++b)
+            for (int cloud = 0; cloud < 2; ++cloud) {
+                const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
+                const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
+                sort_keys_kernel<<<(nfp + 255) / 256, 256, 0, s>>>(tri, nf, nfp, 0.f, ws.pmax + b * 2 + cloud, keys_in, vals_in, sorted);
+                count_launch();
+                size_t need = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, need, keys_in, keys_out, vals_in, ws.perm[cloud] + (long long)b * nfp, nfp, 0, 32, s);
+                if (need > temp_avail) return RRL_ERR_WORKSPACE;
+                if (cub::DeviceRadixSort::SortPairs(temp, need, keys_in, keys_out, vals_in, ws.perm[cloud] + (long long)b * nfp, nfp, 0, 32, s) != cudaSuccess)
+                    return RRL_ERR_CUDA;
+                count_launch(4);
+            }
+    }
+    const int nn_max = nfp_max / kNode;
+    int nbx = (nn_max + 127) / 128;
+    if (nbx > 1024) nbx = 1024;
+    node_kernel<<<dim3(nbx, g.B * 2), 128, 0, s>>>(tri1, tri2, ws, g);
     count_launch();
     return check_launch();
 }
@@ -122,7 +311,7 @@ __device__ __forceinline__ void tma_bulk_load(void *dst_smem, const void *src_gm
 struct DenseArgs {
     const float *tri[2];      // (B, nf, 9) original triplets
     const float *lines;       // (B, nl, 6)
-    int chunk_points;         // points per blockIdx.y chunk (multiple of kPointPad)
+    int chunk_nodes;          // nodes per blockIdx.y chunk (multiple of kNodePad)
 };
 
 // Exact test of one (line, triplet) -- literal restatement of loss.py:84-110 -- and hit recording.
@@ -132,8 +321,7 @@ __device__ __forceinline__ void exact_test_and_record(const float *__restrict__ 
     const float *t = tri + (long long)f * 9;
     const float thr = __ldg(thr_arr + f);
     const float ulp = ulp_up(thr);
-    const float x0 = point_line_x_exact(__ldg(t + 0), __ldg(t + 1), __ldg(t + 2), ln);
-    const float d0 = __fsqrt_rn(x0);
+    const float d0 = __fsqrt_rn(point_line_x_exact(__ldg(t + 0), __ldg(t + 1), __ldg(t + 2), ln));
     nan += (d0 != d0);
     band += (fabsf(d0 - thr) <= ulp);
     if (!(d0 < thr)) return;
@@ -147,167 +335,185 @@ __device__ __forceinline__ void exact_test_and_record(const float *__restrict__ 
     }
 }
 
-template <bool kPacked>
+constexpr int kDenseSmem = 2 * kTileNodes * 16 + (kDenseThreads / 32) * kWarpQueue * 4;
+
 __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
-    __shared__ __align__(128) float4 stage[2][kTilePoints];
+    extern __shared__ __align__(128) unsigned char dsm[];
+    float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kTileNodes]
+    unsigned *wq_all = reinterpret_cast<unsigned *>(dsm + 2 * kTileNodes * 16);             // [8][kWarpQueue]
     __shared__ __align__(8) unsigned long long mbar[2];
-    __shared__ unsigned queue[kQueueCap];
-    __shared__ int q_count;
+    __shared__ int wq_n[kDenseThreads / 32];
     __shared__ int s_band, s_nan, s_cand;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.z >> 1, cloud = blockIdx.z & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
-    const int p_begin = blockIdx.y * a.chunk_points;
-    if (p_begin >= nfp) return;
-    const int p_end = min(nfp, p_begin + a.chunk_points);
+    const int nnodes = nfp / kNode;
+    const int n_begin = blockIdx.y * a.chunk_nodes;
+    if (n_begin >= nnodes) return;
+    const int n_end = min(nnodes, n_begin + a.chunk_nodes);
     const int line_base = blockIdx.x * kLinesPerCta;
+    unsigned *wq = wq_all + wid * kWarpQueue;
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        q_count = 0; s_band = 0; s_nan = 0; s_cand = 0;
+        s_band = 0; s_nan = 0; s_cand = 0;
     }
+    if (lane == 0) wq_n[wid] = 0;
 
-    // ---- per-thread lines -> filter constants (double precision, rounded once) --------------------------
-    const float *lines_b = a.lines + (long long)b * g.nl * 6;
+    // ---- per-thread lines -> filter thresholds ------------------------------------------------------------
     const float P = sqrtf(__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001f;
+    const float Rmax = __uint_as_float(ws.rmax[b * 2 + cloud]);
+    const float4 *lineC = ws.lineC + (long long)b * g.nl * 2;
     float ux[kLinesPerThread], uy[kLinesPerThread], uz[kLinesPerThread];
     float mx[kLinesPerThread], my[kLinesPerThread], mz[kLinesPerThread], tl[kLinesPerThread];
+    // threshold of the point-level predicate and of the node-level predicate for a line
+    auto thresholds = [&](const float4 &c0, const float4 &c1, float &tl_point, float &tl_node) {
+        const float PX = P + c0.w;
+        const float guard = kGuardFast * kEps24 * PX * PX + 1e-12f;
+        tl_point = c1.w - guard - fabsf(c1.w) * 1.2e-7f;                    // rounded down: admits more
+        // |u| > 1 makes F slightly indefinite; e bounds the deficit, 0 for |u| <= 1 (incl. all-zero lines)
+        const float s2 = (c0.x * c0.x + c0.y * c0.y + c0.z * c0.z) * 1.0000004f;
+        const float e = fmaxf(s2 - 1.0f, 0.f) * PX * PX;
+        const float slack = (2.0f * Rmax * sqrtf(e) + 2.0f * e) * 1.00001f;
+        tl_node = tl_point - slack - fabsf(tl_point) * 1.2e-7f;
+    };
 #pragma unroll
     for (int i = 0; i < kLinesPerThread; ++i) {
         const int l = line_base + tid + i * kDenseThreads;
         ux[i] = uy[i] = uz[i] = mx[i] = my[i] = mz[i] = 0.f;
         tl[i] = INFINITY;                                         // Q > +inf never holds: padding lines are inert
         if (l < g.nl) {
-            const float *ln = lines_b + (long long)l * 6;
-            const float u0 = __ldg(ln), u1 = __ldg(ln + 1), u2 = __ldg(ln + 2);
-            const double x = __ldg(ln + 3), y = __ldg(ln + 4), z = __ldg(ln + 5);
-            const double sd = x * u0 + y * u1 + z * u2;
-            const double xx = x * x + y * y + z * z;
-            ux[i] = u0; uy[i] = u1; uz[i] = u2;
-            mx[i] = (float)(2.0 * (x - sd * u0));
-            my[i] = (float)(2.0 * (y - sd * u1));
-            mz[i] = (float)(2.0 * (z - sd * u2));
-            const float X = (float)sqrt(xx) * 1.000001f;
-            const float guard = kGuard * 5.9604645e-8f * (P + X) * (P + X) + 1e-12f;
-            tl[i] = (float)((xx - sd * sd) - (double)guard);
+            const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
+            ux[i] = c0.x; uy[i] = c0.y; uz[i] = c0.z;
+            mx[i] = c1.x; my[i] = c1.y; mz[i] = c1.z;
+            float tp;
+            thresholds(c0, c1, tp, tl[i]);
         }
     }
     __syncthreads();
 
-    const float4 *src = ws.tri4[cloud] + (long long)b * nfp;
-    const int ntiles = (p_end - p_begin + kTilePoints - 1) / kTilePoints;
+    const float4 *src = ws.node4[cloud] + (long long)b * nnodes;
+    const int ntiles = (n_end - n_begin + kTileNodes - 1) / kTileNodes;
     auto issue = [&](int t) {
-        const int s0 = p_begin + t * kTilePoints;
-        const int n = min(kTilePoints, p_end - s0);
+        const int s0 = n_begin + t * kTileNodes;
+        const int n = min(kTileNodes, n_end - s0);
         const unsigned bytes = (unsigned)n * 16u;
         mbar_expect_tx(&mbar[t & 1], bytes);
-        tma_bulk_load(&stage[t & 1][0], src + s0, bytes, &mbar[t & 1]);
+        tma_bulk_load(stage + (t & 1) * kTileNodes, src + s0, bytes, &mbar[t & 1]);
     };
     if (tid == 0) issue(0);
 
     int band = 0, nan = 0, ncand = 0;
+    const float *lines_b = a.lines + (long long)b * g.nl * 6;
+    const float *tri_b = a.tri[cloud] + (long long)b * nf * 9;
+    const float *thr_b = ws.thr[cloud] + (long long)b * nf;
+    const int *perm_b = ws.perm[cloud] + (long long)b * nfp;
+    const float4 *pt4_b = ws.pt4[cloud] + (long long)b * nfp;
+    const float *node_f = reinterpret_cast<const float *>(src);
 
-    // exact re-test of every queued candidate group; entry = tid<<22 | (group index inside the chunk)
-    auto drain = [&]() {
-        const int n = min(q_count, kQueueCap);
-        for (int e = tid; e < n; e += kDenseThreads) {
-            const unsigned ent = queue[e];
-            const int owner = ent >> 22;
-            const int f0 = p_begin + (int)(ent & 0x3fffffu) * 4;
+    // resolve one queued entry: (line, group of 4 nodes) -> node predicate -> triplet predicate -> exact test
+    auto resolve = [&](unsigned ent) {
+        const int l = line_base + (int)(ent >> 20);
+        const int n0 = n_begin + (int)(ent & 0xFFFFFu) * 4;
+        const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
+        float tl_point, tl_node;
+        thresholds(c0, c1, tl_point, tl_node);
+        float ln[6];
+        bool have_line = false;
+        const long long gl = (long long)b * g.nl + l;
 #pragma unroll 1
-            for (int i = 0; i < kLinesPerThread; ++i) {
-                const int l = line_base + owner + i * kDenseThreads;
-                if (l >= g.nl) break;
-                float ln[6];
+        for (int q = 0; q < 4; ++q) {
+            const int n = n0 + q;
+            const float *nr = node_f + (long long)(n >> 1) * 8 + (n & 1);
+            const float nx = nr[0], ny = nr[2], nz = nr[4], nw = nr[6];
+            const float tt = fmaf(nz, c0.z, fmaf(ny, c0.y, nx * c0.x));
+            const float ss = fmaf(nz, c1.z, fmaf(ny, c1.y, fmaf(nx, c1.x, nw)));
+            if (!(fmaf(tt, tt, ss) > tl_node)) continue;
+#pragma unroll 1
+            for (int s = 0; s < kNode; ++s) {
+                const float4 pr = __ldg(pt4_b + n * kNode + s);
+                const float t2 = fmaf(pr.z, c0.z, fmaf(pr.y, c0.y, pr.x * c0.x));
+                const float s2 = fmaf(pr.z, c1.z, fmaf(pr.y, c1.y, fmaf(pr.x, c1.x, pr.w)));
+                if (!(fmaf(t2, t2, s2) > tl_point)) continue;
+                if (!have_line) {
 #pragma unroll
-                for (int q = 0; q < 6; ++q) ln[q] = __ldg(lines_b + (long long)l * 6 + q);
-                const long long gl = (long long)b * g.nl + l;
-#pragma unroll 1
-                for (int p = 0; p < 4; ++p) {
-                    const int f = f0 + p;
-                    if (f < nf)
-                        exact_test_and_record(a.tri[cloud] + (long long)b * nf * 9, ws.thr[cloud] + (long long)b * nf, ln, f,
-                                              ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
+                    for (int c = 0; c < 6; ++c) ln[c] = __ldg(lines_b + (long long)l * 6 + c);
+                    have_line = true;
                 }
+                const int f = __ldg(perm_b + n * kNode + s);
+                exact_test_and_record(tri_b, thr_b, ln, f, ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
             }
         }
+    };
+    auto drain_warp = [&]() {
+        __syncwarp();
+        const int n = min(*(volatile int *)&wq_n[wid], kWarpQueue);
+        for (int e = lane; e < n; e += 32) resolve(wq[e]);
+        __syncwarp();
+        if (lane == 0) wq_n[wid] = 0;
+        __syncwarp();
     };
 
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + 1 < ntiles) issue(t + 1);
         mbar_wait(&mbar[t & 1], (t >> 1) & 1);
-        const int npts = min(kTilePoints, p_end - (p_begin + t * kTilePoints));     // multiple of kPointPad
-        const float4 *sp = &stage[t & 1][0];
-        const int group0 = t * (kTilePoints / 4);
+        const int nn = min(kTileNodes, n_end - (n_begin + t * kTileNodes));      // multiple of kNodePad
+        const float4 *sp = stage + (t & 1) * kTileNodes;
+        const int ngroups = nn / 4;
+        const int group0 = t * (kTileNodes / 4);
+        for (int w0 = 0; w0 < ngroups; w0 += 32) {
+            const int ng = min(32, ngroups - w0);
+            unsigned m[kLinesPerThread];
+#pragma unroll
+            for (int i = 0; i < kLinesPerThread; ++i) m[i] = 0u;
 #pragma unroll 2
-        for (int gi = 0; gi < npts / 4; ++gi) {
-            // 4 points = two interleaved pairs: {xA,xB,yA,yB} {zA,zB,wA,wB}
-            const float4 a0 = sp[gi * 4 + 0], a1 = sp[gi * 4 + 1], b0 = sp[gi * 4 + 2], b1 = sp[gi * 4 + 3];
-            bool any = false;
-            if constexpr (kPacked) {
+            for (int gi = 0; gi < ng; ++gi) {
+                // 4 nodes = two interleaved pairs: {xA,xB,yA,yB} {zA,zB,wA,wB}
+                const float4 a0 = sp[(w0 + gi) * 4 + 0], a1 = sp[(w0 + gi) * 4 + 1], b0 = sp[(w0 + gi) * 4 + 2], b1 = sp[(w0 + gi) * 4 + 3];
                 const float2 xa = make_float2(a0.x, a0.y), ya = make_float2(a0.z, a0.w), za = make_float2(a1.x, a1.y), wa = make_float2(a1.z, a1.w);
                 const float2 xb = make_float2(b0.x, b0.y), yb = make_float2(b0.z, b0.w), zb = make_float2(b1.x, b1.y), wb = make_float2(b1.z, b1.w);
+                const unsigned bit = 1u << gi;
 #pragma unroll
                 for (int i = 0; i < kLinesPerThread; ++i) {
                     const float2 u0 = make_float2(ux[i], ux[i]), u1 = make_float2(uy[i], uy[i]), u2 = make_float2(uz[i], uz[i]);
                     const float2 m0 = make_float2(mx[i], mx[i]), m1 = make_float2(my[i], my[i]), m2 = make_float2(mz[i], mz[i]);
-                    float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
-                    float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
-                    float2 qa = __ffma2_rn(ta, ta, sa);
-                    float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
-                    float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
-                    float2 qb = __ffma2_rn(tb, tb, sb);
-                    any |= (qa.x > tl[i]) | (qa.y > tl[i]) | (qb.x > tl[i]) | (qb.y > tl[i]);
+                    const float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
+                    const float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
+                    const float2 qa = __ffma2_rn(ta, ta, sa);
+                    const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
+                    const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
+                    const float2 qb = __ffma2_rn(tb, tb, sb);
+                    const float qmax = fmaxf(fmaxf(qa.x, qa.y), fmaxf(qb.x, qb.y));
+                    m[i] |= (qmax > tl[i]) ? bit : 0u;
                 }
-            } else {
-                const float px[4] = {a0.x, a0.y, b0.x, b0.y}, py[4] = {a0.z, a0.w, b0.z, b0.w};
-                const float pz[4] = {a1.x, a1.y, b1.x, b1.y}, pw[4] = {a1.z, a1.w, b1.z, b1.w};
+            }
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < kLinesPerThread; ++i) any |= (m[i] != 0u);
+            if (any) {
 #pragma unroll
                 for (int i = 0; i < kLinesPerThread; ++i) {
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const float tt = fmaf(pz[p], uz[i], fmaf(py[p], uy[i], px[p] * ux[i]));
-                        const float ss = fmaf(pz[p], mz[i], fmaf(py[p], my[i], fmaf(px[p], mx[i], pw[p])));
-                        any |= fmaf(tt, tt, ss) > tl[i];
+                    unsigned mm = m[i];
+                    while (mm) {
+                        const int gi = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const unsigned ent = ((unsigned)(tid + i * kDenseThreads) << 20) | (unsigned)(group0 + w0 + gi);
+                        const int pos = atomicAdd(&wq_n[wid], 1);
+                        ++ncand;
+                        if (pos < kWarpQueue) wq[pos] = ent;
+                        else resolve(ent);                          // queue full (rare): resolve in place, still exact
                     }
                 }
             }
-            if (any) {
-                const int pos = atomicAdd(&q_count, 1);
-                ++ncand;
-                if (pos < kQueueCap) {
-                    queue[pos] = ((unsigned)tid << 22) | (unsigned)(group0 + gi);
-                } else {
-                    // queue full: resolve this group right here (rare; keeps the result exact)
-                    const int f0 = p_begin + (group0 + gi) * 4;
-#pragma unroll 1
-                    for (int i = 0; i < kLinesPerThread; ++i) {
-                        const int l = line_base + tid + i * kDenseThreads;
-                        if (l >= g.nl) break;
-                        float ln[6];
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) ln[q] = __ldg(lines_b + (long long)l * 6 + q);
-                        const long long gl = (long long)b * g.nl + l;
-#pragma unroll 1
-                        for (int p = 0; p < 4; ++p)
-                            if (f0 + p < nf)
-                                exact_test_and_record(a.tri[cloud] + (long long)b * nf * 9, ws.thr[cloud] + (long long)b * nf, ln,
-                                                      f0 + p, ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
-                    }
-                }
-            }
+            __syncwarp();
+            if (*(volatile int *)&wq_n[wid] > kWarpQueue / 2) drain_warp();
         }
-        __syncthreads();                       // everyone is done with stage[t&1] (and with pushing to the queue)
-        if (q_count > kQueueCap / 2 || t + 1 == ntiles) {
-            drain();
-            __syncthreads();
-            if (tid == 0) q_count = 0;
-            __syncthreads();
-        }
+        __syncthreads();                       // everyone is done with this stage before it is refilled
     }
+    drain_warp();
 
     // ---- diagnostics ---------------------------------------------------------------------------------
     if (band) atomicAdd(&s_band, band);
@@ -322,29 +528,30 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     }
 }
 
-static int g_dense_variant = 1;        // 1 = packed FFMA2, 0 = scalar FFMA (selectable for measurement)
-void set_dense_variant(int v) { g_dense_variant = v; }
-
 int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
+        attr_set = true;
+    }
     DenseArgs a;
     a.tri[0] = tri1; a.tri[1] = tri2; a.lines = lines;
     const int line_tiles = (g.nl + kLinesPerCta - 1) / kLinesPerCta;
-    const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
-    // split the points so that the grid covers the 148 SMs a few times over when the line tiles alone do not
+    const int nn_max = (g.nf1p > g.nf2p ? g.nf1p : g.nf2p) / kNode;
+    // split the nodes so that the grid covers the 148 SMs (2 CTAs each) about eight times over when the line
+    // tiles alone do not; never below 64 nodes (1024 triplets) per CTA
     const long long base_ctas = (long long)line_tiles * g.B * 2;
-    const long long target = 148LL * 2 * 3;
+    const long long target = 148LL * 2 * 8;
     int chunks = 1;
     if (base_ctas < target) chunks = (int)((target + base_ctas - 1) / base_ctas);
-    int chunk_points = (nfp_max + chunks - 1) / chunks;
-    chunk_points = ((chunk_points + 255) / 256) * 256;                 // >= 256 points per CTA, multiple of kPointPad
-    if (chunk_points > (1 << 22) * 4) return RRL_ERR_ARG;
-    chunks = (nfp_max + chunk_points - 1) / chunk_points;
-    a.chunk_points = chunk_points;
+    int chunk_nodes = (nn_max + chunks - 1) / chunks;
+    if (chunk_nodes < 64) chunk_nodes = 64;
+    chunk_nodes = ((chunk_nodes + kNodePad - 1) / kNodePad) * kNodePad;
+    if (chunk_nodes / 4 >= (1 << 20)) return RRL_ERR_ARG;
+    chunks = (nn_max + chunk_nodes - 1) / chunk_nodes;
+    a.chunk_nodes = chunk_nodes;
     dim3 grid(line_tiles, chunks, g.B * 2);
-    if (g_dense_variant)
-        dense_kernel<true><<<grid, kDenseThreads, 0, s>>>(a, ws, g);
-    else
-        dense_kernel<false><<<grid, kDenseThreads, 0, s>>>(a, ws, g);
+    dense_kernel<<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
     count_launch();
     return check_launch();
 }

@@ -243,7 +243,9 @@ int launch_pack_entries(const Workspace &ws, const Geometry &g, float *out, long
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float welsch(float D, float med) {
     // 1 - exp(-((x / c)) / 2.0)   loss.py:21
-    return __fsub_rn(1.0f, expf(-__fdiv_rn(__fdiv_rn(D, med), 2.0f)));
+    // exp evaluated in double and rounded once: a well-defined (correctly rounded) float exp, so that the row/column
+    // argmin of near-tied entries does not depend on a vendor expf's last bit (the oracle does the same)
+    return __fsub_rn(1.0f, (float)exp((double)(-__fdiv_rn(__fdiv_rn(D, med), 2.0f))));
 }
 
 __global__ void __launch_bounds__(256) welsch_kernel(Workspace ws, Geometry g) {

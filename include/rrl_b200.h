@@ -70,7 +70,7 @@ size_t rrl_workspace_bytes(int B, int nf1, int nf2, int nl);
  *   out_status [B]          RRL_STATUS_* bits
  *   out_median [B]          lower median of the pair's D entries (loss.py:223-224); may be NULL
  *   out_stats  [B*RRL_NSTAT] int64: {0: #selected lines, 1: #D entries, 2: #non-empty combos C,
- *                            3: #filter candidates cloud 1, 4: #filter candidates cloud 2,
+ *                            3: #queued (line, node-group) candidates cloud 1, 4: same for cloud 2,
  *                            5: #tests within 1 ulp of the threshold (the north star's separately reported band),
  *                            6: #NaN distances among candidates, 7: reserved}; may be NULL
  */
@@ -192,7 +192,8 @@ int rrl_measure_dense(const float *tri1, const float *tri2, const float *lines, 
                       void *workspace, size_t workspace_bytes, int iters, float *out_ms_dense, float *out_ms_prep,
                       void *stream);
 
-/* selects the dense-kernel variant: 1 = packed FFMA2 (default), 0 = scalar FFMA.  Measurement / A-B testing only. */
+/* selects the dense-stage variant: 1 = Morton-sorted bounding-sphere nodes (default), 0 = nodes in input order.
+ * Results are identical; measurement / A-B testing only. */
 int rrl_debug_set_dense_variant(int variant);
 
 #ifdef __cplusplus

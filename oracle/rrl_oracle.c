@@ -231,7 +231,7 @@ int rrl_oracle_loss(const float *tri1, int nf1, const float *tri2, int nf2,
             int k = R->k, j = R->j, cb = (k - 1) * 4 + (j - 1);
             float W[4][4];
             for (int a = 0; a < k; ++a)
-                for (int b = 0; b < j; ++b) W[a][b] = 1.0f - expf(-((R->D[a][b] / med)) / 2.0f);   /* loss.py:20-21 */
+                for (int b = 0; b < j; ++b) W[a][b] = 1.0f - (float)exp((double)(-((R->D[a][b] / med)) / 2.0f));   /* loss.py:20-21; exp correctly rounded via double */
             int arg_b[4], arg_a[4];
             for (int a = 0; a < k; ++a) {                          /* torch.min(.,2): first index on ties */
                 int m = 0;

@@ -111,6 +111,34 @@ def test_seeded_synthetic_vs_oracle(rrl, seed, nf, nl, kw):
     _check_against_oracle(out, orc)
 
 
+def test_unnormalised_and_degenerate_lines(rrl):
+    """the culling bounds must hold for |u| != 1 (the reference never checks), for all-zero rows and for duplicates"""
+    p = synth.make_pair(109, 900, 1600, zero_frac=0.2)
+    lines = p["lines"].copy()
+    rng = np.random.default_rng(5)
+    lines[:300, :3] *= rng.uniform(1.0, 1.01, size=(300, 1)).astype(np.float32)      # slightly too long
+    lines[300:500, :3] *= rng.uniform(0.3, 1.0, size=(200, 1)).astype(np.float32)    # too short
+    lines[500:520, :3] *= 3.0                                                         # far too long
+    lines[520:560] = lines[0]                                                         # duplicates
+    out = _run(rrl, p["tri1"], p["tri2"], lines)
+    _check_against_oracle(out, co.loss(p["tri1"], p["tri2"], lines))
+
+
+def test_clustered_cloud_with_duplicate_points(rrl):
+    """many coincident triplets (zero-radius nodes, zero thresholds) and a tight cluster next to a sparse shell"""
+    rng = np.random.default_rng(11)
+    a = synth.surface_points(rng, 500, "sphere")
+    bpts = (rng.normal(size=(300, 3)) * 0.02 + np.array([1.0, 2.0, 0.5])).astype(np.float32)
+    dup = np.repeat(a[:20], 5, axis=0)
+    src = np.concatenate([a, bpts, dup]).astype(np.float32)
+    tri1 = synth.knn_triplets(src)
+    tri2 = synth.knn_triplets((src[::-1] * np.float32(1.01)).copy())
+    lo, hi = src.min(0), src.max(0)
+    lines = synth.chord_lines(rng, 2500, 0.7 * float(np.linalg.norm(hi - lo)), src.mean(0), lo, hi, lo, hi)
+    out = _run(rrl, tri1, tri2, lines)
+    _check_against_oracle(out, co.loss(tri1, tri2, lines))
+
+
 def test_large_coordinates_keep_exactness(rrl):
     """the filter's guard band scales with (|p| + |x0|)^2: translate everything far from the origin"""
     p = synth.make_pair(107, 600, 1500)
@@ -123,7 +151,8 @@ def test_large_coordinates_keep_exactness(rrl):
     _check_against_oracle(out, co.loss(tri1, tri2, lines))
 
 
-def test_scalar_and_packed_variants_agree(rrl):
+def test_sorted_and_unsorted_node_variants_agree(rrl):
+    """Morton-sorted bounding-sphere nodes vs nodes in input order: different candidate sets, identical results"""
     p = synth.make_pair(108, 1024, 4000)
     L = rrl._native.lib()
     try:

@@ -45,7 +45,7 @@ def measure(B, nf, nl, tag):
         res["prep_ms"] = mp.value
         res["tests_per_s_v%d" % variant] = tests / (md.value * 1e-3)
         res["alg_tflops_v%d" % variant] = 48 * tests / (md.value * 1e-3) / 1e12
-        res["exec_tflops_v%d" % variant] = 14 * tests / (md.value * 1e-3) / 1e12
+        res["exec_tflops_v%d" % variant] = 14 * tests / 16 / (md.value * 1e-3) / 1e12
     L.rrl_debug_set_dense_variant(1)
     # whole forward+backward through the autograd op
     t1g = t1.clone().requires_grad_(True)
@@ -66,7 +66,7 @@ def measure(B, nf, nl, tag):
     st = info.stats.cpu().numpy()
     res["selected_per_pair"] = float(st[:, 0].mean())
     res["cand_groups_per_pair"] = float((st[:, 3] + st[:, 4]).mean())
-    res["cand_group_rate"] = float((st[:, 3] + st[:, 4]).sum() / (B * nl * 2.0 * nf / 16))
+    res["cand_group_rate"] = float((st[:, 3] + st[:, 4]).sum() / (B * nl * 2.0 * nf / 64))
     res["band"] = int(st[:, 5].sum())
     out[tag] = res
     print(tag, json.dumps(res), flush=True)
