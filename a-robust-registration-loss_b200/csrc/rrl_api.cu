@@ -47,8 +47,8 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.perm[1] = reinterpret_cast<int *>(take(sB * nf2p * sizeof(int)));
     w.pt4[0] = reinterpret_cast<float4 *>(take(sB * nf1p * sizeof(float4)));
     w.pt4[1] = reinterpret_cast<float4 *>(take(sB * nf2p * sizeof(float4)));
-    w.node4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kNode) * sizeof(float4)));
-    w.node4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kNode) * sizeof(float4)));
+    w.node4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kMinNode) * sizeof(float4)));
+    w.node4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kMinNode) * sizeof(float4)));
     w.sortbuf_bytes = sort_scratch_bytes(nf1p > nf2p ? nf1p : nf2p);
     w.sortbuf = reinterpret_cast<unsigned long long *>(take(w.sortbuf_bytes));
     // ---- per line ----

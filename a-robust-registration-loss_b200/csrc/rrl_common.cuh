@@ -28,13 +28,13 @@ constexpr float kGuardRef = 64.0f;
 constexpr float kEps24 = 5.9604645e-8f;
 
 // ---- dense kernel geometry ---------------------------------------------------------------------------
-constexpr int kNode = 16;                                       // triplets per bounding-sphere node
 constexpr int kDenseThreads = 256;
 constexpr int kLinesPerThread = 4;
 constexpr int kLinesPerCta = kDenseThreads * kLinesPerThread;   // 1024
 constexpr int kTileNodes = 1024;                                // float4 per node: 16 KB per stage
 constexpr int kNodePad = 16;                                    // node arrays are padded to this multiple (sentinels)
-constexpr int kPointPad = kNode * kNodePad;                     // => triplet arrays padded to 256
+constexpr int kPointPad = 256;                                  // triplet arrays padded to 16 nodes of 16 (= 32 nodes of 8)
+constexpr int kMinNode = 8;                                     // smallest node size (sizes the node arrays)
 constexpr int kWarpQueue = 1024;                                // candidate (line, node) entries per warp
 constexpr int kSortSmall = 4096;                                // clouds up to this many (padded) triplets sort in one CTA
 
@@ -64,7 +64,7 @@ struct Workspace {
     float *thr[2];           // (B, nf): exact reference threshold, original order
     int *perm[2];            // (B, nfp): sorted position -> original triplet index (-1 = padding)
     float4 *pt4[2];          // (B, nfp): sorted order, {p0.xyz, cut - |p0|^2}; sentinel padded
-    float4 *node4[2];        // (B, nfp/kNode): pair-interleaved {xA,xB,yA,yB}{zA,zB,wA,wB}; w = R^2 - |q|^2
+    float4 *node4[2];        // (B, nfp/node_size): pair-interleaved {xA,xB,yA,yB}{zA,zB,wA,wB}; w = R^2 - |q|^2
     unsigned long long *sortbuf; // scratch for the large-cloud sort (keys/values double buffers + cub temp)
     size_t sortbuf_bytes;
     // per line
@@ -84,6 +84,7 @@ constexpr int kMagic = 0x52524c31;   // "RRL1"
 
 inline int pad_points(int nf) { return ((nf + kPointPad - 1) / kPointPad) * kPointPad; }
 size_t sort_scratch_bytes(int nfp_max);
+int node_size(const Geometry &g);       // triplets per bounding-sphere node for this geometry (8 or 16)
 
 Workspace carve(void *base, int B, int nf1, int nf2, int nl);
 

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) sort_keys_kernel(const float *__restrict_
 // ------------------------------------------------------------------------------------------------------
 // nodes
 // ------------------------------------------------------------------------------------------------------
+template <int kNode>
 __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g) {
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
@@ -228,6 +229,9 @@ size_t sort_scratch_bytes(int nfp_max) {
     return (size_t)nfp_max * 4 * 3 + 768 + (size_t)nfp_max * 8 + (4u << 20);
 }
 
+// triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
+int node_size(const Geometry &g) { return (g.nf1 > g.nf2 ? g.nf1 : g.nf2) >= 16384 ? 16 : 8; }
+
 static int g_dense_variant = 1;        // 1 = Morton-sorted nodes (default), 0 = nodes in input order (A/B measurement)
 void set_dense_variant(int v) { g_dense_variant = v; }
 
@@ -271,10 +275,12 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
                 count_launch(4);
             }
     }
-    const int nn_max = nfp_max / kNode;
+    const int G = node_size(g);
+    const int nn_max = nfp_max / G;
     int nbx = (nn_max + 127) / 128;
     if (nbx > 1024) nbx = 1024;
-    node_kernel<<<dim3(nbx, g.B * 2), 128, 0, s>>>(tri1, tri2, ws, g);
+    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 128, 0, s>>>(tri1, tri2, ws, g);
+    else node_kernel<16><<<dim3(nbx, g.B * 2), 128, 0, s>>>(tri1, tri2, ws, g);
     count_launch();
     return check_launch();
 }
@@ -335,14 +341,21 @@ __device__ __forceinline__ void exact_test_and_record(const float *__restrict__ 
     }
 }
 
-constexpr int kDenseSmem = 2 * kTileNodes * 16 + (kDenseThreads / 32) * kWarpQueue * 4;
+constexpr int kSmemPoints = 2048;      // point records are staged in shared memory when a chunk has <= this many
+constexpr int kExactQueue = 256;       // (line, triplet) entries awaiting the exact test, per warp
+constexpr int kNumWarps = kDenseThreads / 32;
+constexpr int kOffQueue = 2 * kTileNodes * 16;
+constexpr int kOffExact = kOffQueue + kNumWarps * kWarpQueue * 4;
+constexpr int kOffPoints = kOffExact + kNumWarps * kExactQueue * 4;
+constexpr int kDenseSmem = kOffPoints + kSmemPoints * 16;
 
+template <int kNode>
 __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
     extern __shared__ __align__(128) unsigned char dsm[];
     float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kTileNodes]
-    unsigned *wq_all = reinterpret_cast<unsigned *>(dsm + 2 * kTileNodes * 16);             // [8][kWarpQueue]
-    __shared__ __align__(8) unsigned long long mbar[2];
-    __shared__ int wq_n[kDenseThreads / 32];
+    float4 *spts = reinterpret_cast<float4 *>(dsm + kOffPoints);                           // [kSmemPoints]
+    __shared__ __align__(8) unsigned long long mbar[3];
+    __shared__ int xq_n[kNumWarps];
     __shared__ int s_band, s_nan, s_cand;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -353,15 +366,17 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     if (n_begin >= nnodes) return;
     const int n_end = min(nnodes, n_begin + a.chunk_nodes);
     const int line_base = blockIdx.x * kLinesPerCta;
-    unsigned *wq = wq_all + wid * kWarpQueue;
+    unsigned *wq = reinterpret_cast<unsigned *>(dsm + kOffQueue) + wid * kWarpQueue;       // (line, node group) entries
+    unsigned *xq = reinterpret_cast<unsigned *>(dsm + kOffExact) + wid * kExactQueue;      // (line, triplet) entries
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
+        mbar_init(&mbar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_band = 0; s_nan = 0; s_cand = 0;
     }
-    if (lane == 0) wq_n[wid] = 0;
+    if (lane == 0) xq_n[wid] = 0;
 
     // ---- per-thread lines -> filter thresholds ------------------------------------------------------------
     const float P = sqrtf(__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001f;
@@ -404,59 +419,109 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         mbar_expect_tx(&mbar[t & 1], bytes);
         tma_bulk_load(stage + (t & 1) * kTileNodes, src + s0, bytes, &mbar[t & 1]);
     };
-    if (tid == 0) issue(0);
+    // the chunk's point records (drain stage) go to shared memory when they fit, else they are read through L2
+    const float4 *pt4_b = ws.pt4[cloud] + (long long)b * nfp;
+    const bool pts_in_smem = (n_end - n_begin) * kNode <= kSmemPoints;
+    const float4 *pts = pts_in_smem ? spts : pt4_b + (long long)n_begin * kNode;          // indexed from the chunk start
+    if (tid == 0) {
+        issue(0);
+        if (pts_in_smem) {
+            const unsigned bytes = (unsigned)(n_end - n_begin) * kNode * 16u;
+            mbar_expect_tx(&mbar[2], bytes);
+            tma_bulk_load(spts, pt4_b + (long long)n_begin * kNode, bytes, &mbar[2]);
+        }
+    }
+    if (pts_in_smem) mbar_wait(&mbar[2], 0);
 
     int band = 0, nan = 0, ncand = 0;
     const float *lines_b = a.lines + (long long)b * g.nl * 6;
     const float *tri_b = a.tri[cloud] + (long long)b * nf * 9;
     const float *thr_b = ws.thr[cloud] + (long long)b * nf;
-    const int *perm_b = ws.perm[cloud] + (long long)b * nfp;
-    const float4 *pt4_b = ws.pt4[cloud] + (long long)b * nfp;
-    const float *node_f = reinterpret_cast<const float *>(src);
+    const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)n_begin * kNode;   // from the chunk start
+    const float4 *node_c = src + n_begin;                                                  // from the chunk start
 
-    // resolve one queued entry: (line, group of 4 nodes) -> node predicate -> triplet predicate -> exact test
+    // level 3: the exact reference-order test of one (line, triplet)
+    auto exact = [&](unsigned xent) {
+        const int l = line_base + (int)(xent >> 22);
+        const int f = __ldg(perm_c + (int)(xent & 0x3FFFFFu));
+        float ln[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ln[c] = __ldg(lines_b + (long long)l * 6 + c);
+        const long long gl = (long long)b * g.nl + l;
+        exact_test_and_record(tri_b, thr_b, ln, f, ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
+    };
+    auto drain_exact = [&]() {
+        __syncwarp();
+        const int n = min(*(volatile int *)&xq_n[wid], kExactQueue);
+        for (int base = 0; base < n; base += 32)
+            if (base + lane < n) exact(xq[base + lane]);
+        __syncwarp();
+        if (lane == 0) xq_n[wid] = 0;
+        __syncwarp();
+    };
+    // levels 1+2, one queued entry per lane: (line, group of 4 nodes) -> node predicate -> triplet predicate.
+    // Each level first collects a bit mask branch-free and then iterates over the set bits, so the lanes of a warp
+    // stay aligned on "their k-th fired node" instead of serialising on the node index; fired triplets are handed
+    // to the exact queue so that the (expensive, rare) exact test runs with full warps.
     auto resolve = [&](unsigned ent) {
-        const int l = line_base + (int)(ent >> 20);
-        const int n0 = n_begin + (int)(ent & 0xFFFFFu) * 4;
+        const int lrel = (int)(ent >> 20);
+        const int l = line_base + lrel;
+        const int q0 = (int)(ent & 0xFFFFFu) * 4;                  // first node of the group, relative to the chunk
         const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
         float tl_point, tl_node;
         thresholds(c0, c1, tl_point, tl_node);
-        float ln[6];
-        bool have_line = false;
-        const long long gl = (long long)b * g.nl + l;
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            const int n = n0 + q;
-            const float *nr = node_f + (long long)(n >> 1) * 8 + (n & 1);
-            const float nx = nr[0], ny = nr[2], nz = nr[4], nw = nr[6];
-            const float tt = fmaf(nz, c0.z, fmaf(ny, c0.y, nx * c0.x));
-            const float ss = fmaf(nz, c1.z, fmaf(ny, c1.y, fmaf(nx, c1.x, nw)));
-            if (!(fmaf(tt, tt, ss) > tl_node)) continue;
-#pragma unroll 1
-            for (int s = 0; s < kNode; ++s) {
-                const float4 pr = __ldg(pt4_b + n * kNode + s);
-                const float t2 = fmaf(pr.z, c0.z, fmaf(pr.y, c0.y, pr.x * c0.x));
-                const float s2 = fmaf(pr.z, c1.z, fmaf(pr.y, c1.y, fmaf(pr.x, c1.x, pr.w)));
-                if (!(fmaf(t2, t2, s2) > tl_point)) continue;
-                if (!have_line) {
+        const float4 *nr4 = node_c + q0;                           // 4 nodes = 2 interleaved pairs = 4 float4
+        const float4 A0 = __ldg(nr4), A1 = __ldg(nr4 + 1), B0 = __ldg(nr4 + 2), B1 = __ldg(nr4 + 3);
+        const float nx[4] = {A0.x, A0.y, B0.x, B0.y}, ny[4] = {A0.z, A0.w, B0.z, B0.w};
+        const float nz[4] = {A1.x, A1.y, B1.x, B1.y}, nw[4] = {A1.z, A1.w, B1.z, B1.w};
+        unsigned nm = 0;
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) ln[c] = __ldg(lines_b + (long long)l * 6 + c);
-                    have_line = true;
+        for (int q = 0; q < 4; ++q) {
+            const float tt = fmaf(nz[q], c0.z, fmaf(ny[q], c0.y, nx[q] * c0.x));
+            const float ss = fmaf(nz[q], c1.z, fmaf(ny[q], c1.y, fmaf(nx[q], c1.x, nw[q])));
+            nm |= (fmaf(tt, tt, ss) > tl_node) ? (1u << q) : 0u;
+        }
+        while (nm) {
+            const int nrel = q0 + __ffs(nm) - 1;
+            nm &= nm - 1;
+            const float4 *pp = pts + nrel * kNode;
+            unsigned pm = 0;
+#pragma unroll
+            for (int h = 0; h < kNode; h += 8) {
+                float4 pr[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) pr[s] = pp[h + s];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const float t2 = fmaf(pr[s].z, c0.z, fmaf(pr[s].y, c0.y, pr[s].x * c0.x));
+                    const float s2 = fmaf(pr[s].z, c1.z, fmaf(pr[s].y, c1.y, fmaf(pr[s].x, c1.x, pr[s].w)));
+                    pm |= (fmaf(t2, t2, s2) > tl_point) ? (1u << (h + s)) : 0u;
                 }
-                const int f = __ldg(perm_b + n * kNode + s);
-                exact_test_and_record(tri_b, thr_b, ln, f, ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
+            }
+            if (pm) {
+                int pos = atomicAdd(&xq_n[wid], __popc(pm));
+                while (pm) {
+                    const int s = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    const unsigned xent = ((unsigned)lrel << 22) | (unsigned)(nrel * kNode + s);
+                    if (pos < kExactQueue) xq[pos] = xent;
+                    else exact(xent);                             // exact queue full (rare): test in place
+                    ++pos;
+                }
             }
         }
     };
-    auto drain_warp = [&]() {
+    auto drain_warp = [&](int n) {
         __syncwarp();
-        const int n = min(*(volatile int *)&wq_n[wid], kWarpQueue);
-        for (int e = lane; e < n; e += 32) resolve(wq[e]);
-        __syncwarp();
-        if (lane == 0) wq_n[wid] = 0;
+        for (int base = 0; base < n; base += 32) {
+            if (base + lane < n) resolve(wq[base + lane]);
+            __syncwarp();
+            if (*(volatile int *)&xq_n[wid] > kExactQueue / 2) drain_exact();
+        }
         __syncwarp();
     };
 
+    int wq_cnt = 0;                                              // warp-uniform fill level of this warp's queue
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + 1 < ntiles) issue(t + 1);
         mbar_wait(&mbar[t & 1], (t >> 1) & 1);
@@ -490,30 +555,38 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
                     m[i] |= (qmax > tl[i]) ? bit : 0u;
                 }
             }
-            bool any = false;
+            // warp-synchronous, ordered push of the fired (line, group) pairs: no atomics, never overflows
 #pragma unroll
-            for (int i = 0; i < kLinesPerThread; ++i) any |= (m[i] != 0u);
-            if (any) {
+            for (int i = 0; i < kLinesPerThread; ++i) {
+                unsigned mi = m[i];
+                if (__any_sync(0xffffffffu, mi != 0u)) {
+                    const int c = __popc(mi);
+                    int inc = c;
 #pragma unroll
-                for (int i = 0; i < kLinesPerThread; ++i) {
-                    unsigned mm = m[i];
-                    while (mm) {
-                        const int gi = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        const unsigned ent = ((unsigned)(tid + i * kDenseThreads) << 20) | (unsigned)(group0 + w0 + gi);
-                        const int pos = atomicAdd(&wq_n[wid], 1);
-                        ++ncand;
-                        if (pos < kWarpQueue) wq[pos] = ent;
-                        else resolve(ent);                          // queue full (rare): resolve in place, still exact
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffffu, inc, d);
+                        if (lane >= d) inc += up;
                     }
+                    const int total = __shfl_sync(0xffffffffu, inc, 31);        // <= 32 lanes x 32 groups = kWarpQueue
+                    if (wq_cnt + total > kWarpQueue) {
+                        drain_warp(wq_cnt);
+                        wq_cnt = 0;
+                    }
+                    int pos = wq_cnt + inc - c;
+                    while (mi) {
+                        const int gi = __ffs(mi) - 1;
+                        mi &= mi - 1;
+                        wq[pos++] = ((unsigned)(tid + i * kDenseThreads) << 20) | (unsigned)(group0 + w0 + gi);
+                    }
+                    wq_cnt += total;
+                    ncand += c;
                 }
             }
-            __syncwarp();
-            if (*(volatile int *)&wq_n[wid] > kWarpQueue / 2) drain_warp();
         }
         __syncthreads();                       // everyone is done with this stage before it is refilled
     }
-    drain_warp();
+    drain_warp(wq_cnt);
+    drain_exact();
 
     // ---- diagnostics ---------------------------------------------------------------------------------
     if (band) atomicAdd(&s_band, band);
@@ -531,15 +604,17 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
 int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
+        if (cudaFuncSetAttribute(dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
+        if (cudaFuncSetAttribute(dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
         attr_set = true;
     }
     DenseArgs a;
     a.tri[0] = tri1; a.tri[1] = tri2; a.lines = lines;
+    const int G = node_size(g);
     const int line_tiles = (g.nl + kLinesPerCta - 1) / kLinesPerCta;
-    const int nn_max = (g.nf1p > g.nf2p ? g.nf1p : g.nf2p) / kNode;
+    const int nn_max = (g.nf1p > g.nf2p ? g.nf1p : g.nf2p) / G;
     // split the nodes so that the grid covers the 148 SMs (2 CTAs each) about eight times over when the line
-    // tiles alone do not; never below 64 nodes (1024 triplets) per CTA
+    // tiles alone do not; never below 64 nodes per CTA
     const long long base_ctas = (long long)line_tiles * g.B * 2;
     const long long target = 148LL * 2 * 8;
     int chunks = 1;
@@ -547,11 +622,12 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     int chunk_nodes = (nn_max + chunks - 1) / chunks;
     if (chunk_nodes < 64) chunk_nodes = 64;
     chunk_nodes = ((chunk_nodes + kNodePad - 1) / kNodePad) * kNodePad;
-    if (chunk_nodes / 4 >= (1 << 20)) return RRL_ERR_ARG;
+    if (chunk_nodes / 4 >= (1 << 20) || (long long)chunk_nodes * G >= (1 << 22)) return RRL_ERR_ARG;
     chunks = (nn_max + chunk_nodes - 1) / chunk_nodes;
     a.chunk_nodes = chunk_nodes;
     dim3 grid(line_tiles, chunks, g.B * 2);
-    dense_kernel<<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
+    if (G == 8) dense_kernel<8><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
+    else dense_kernel<16><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
     count_launch();
     return check_launch();
 }

@@ -161,8 +161,10 @@ def test_sorted_and_unsorted_node_variants_agree(rrl):
     finally:
         L.rrl_debug_set_dense_variant(1)
     b = _run(rrl, p["tri1"], p["tri2"], p["lines"])
-    for k in ("counts1", "counts2", "hits1", "hits2"):
-        assert np.array_equal(a[k], b[k])
+    for c, h in (("counts1", "hits1"), ("counts2", "hits2")):
+        assert np.array_equal(a[c], b[c])
+        keep = a[c] <= co.CAP                      # beyond the cap the kept subset is arbitrary
+        assert np.array_equal(a[h][keep], b[h][keep])
     assert a["loss"] == b["loss"] and a["median"] == b["median"]
 
 
