@@ -267,13 +267,12 @@ extern "C" int rrl_host_loss_fwd_bwd(rrl_host_ctx *c, const float *h_tri1, const
                                      int k_lo, int j_lo, int k_hi, int j_hi, float *h_loss, int *h_status, float *h_grad_tri1) {
     if (!c || !h_tri1 || !h_tri2 || !h_lines || !h_loss) return RRL_ERR_ARG;
     if (cudaSetDevice(c->device) != cudaSuccess) return RRL_ERR_CUDA;
-    if (h_tri1 != c->p_tri1) std::memcpy(c->p_tri1, h_tri1, c->n_tri1 * 4);
-    if (h_tri2 != c->p_tri2) std::memcpy(c->p_tri2, h_tri2, c->n_tri2 * 4);
-    if (h_lines != c->p_lines) std::memcpy(c->p_lines, h_lines, c->n_lines * 4);
+    // straight from the caller's memory: asynchronous when it is pinned (the context's own buffers or any
+    // cudaHostAlloc/cudaHostRegister'ed range), staged by the driver when it is pageable
     cudaStream_t s = c->stream;
-    bool ok = cudaMemcpyAsync(c->d_tri1, c->p_tri1, c->n_tri1 * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(c->d_tri2, c->p_tri2, c->n_tri2 * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(c->d_lines, c->p_lines, c->n_lines * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    bool ok = cudaMemcpyAsync(c->d_tri1, h_tri1, c->n_tri1 * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->d_tri2, h_tri2, c->n_tri2 * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(c->d_lines, h_lines, c->n_lines * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
     if (!ok) return RRL_ERR_CUDA;
     int rc = rrl_loss_forward(c->d_tri1, c->d_tri2, c->d_lines, c->B, c->nf1, c->nf2, c->nl, k_lo, j_lo, k_hi, j_hi, c->d_ws,
                               c->ws_bytes, c->d_loss, c->d_status, nullptr, nullptr, s);

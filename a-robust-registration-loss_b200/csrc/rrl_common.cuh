@@ -31,7 +31,7 @@ constexpr float kEps24 = 5.9604645e-8f;
 constexpr int kDenseThreads = 256;
 constexpr int kLinesPerThread = 4;
 constexpr int kLinesPerCta = kDenseThreads * kLinesPerThread;   // 1024
-constexpr int kTileNodes = 1024;                                // float4 per node: 16 KB per stage
+constexpr int kTileNodes = 512;                                 // float4 per node: 8 KB per stage
 constexpr int kNodePad = 16;                                    // node arrays are padded to this multiple (sentinels)
 constexpr int kPointPad = 256;                                  // triplet arrays padded to 16 nodes of 16 (= 32 nodes of 8)
 constexpr int kMinNode = 8;                                     // smallest node size (sizes the node arrays)

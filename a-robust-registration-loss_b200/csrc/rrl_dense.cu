@@ -7,7 +7,7 @@
 //   prep_kernel    per triplet: exact threshold thr_f (reference op order, IEEE sqrt) and the cloud's max |p|^2;
 //                  per line: the filter constants {u, |x0|, M, c} in double precision, the pair's max |x0|^2;
 //                  zeroes the per-line hit counters.
-//   sort kernels   Morton order of every cloud's points (one CTA bitonic sort up to 4096 triplets, CUB radix sort
+//   sort kernels   Hilbert-curve order of every cloud's points (one CTA bitonic sort up to 4096 triplets, CUB radix sort
 //                  above) so that kNode consecutive triplets are spatial neighbours.
 //   node_kernel    per node of kNode sorted triplets: bounding sphere (centre q, radius R covering every
 //                  triplet's hit cylinder) -> node record float4(q, R^2 - |q|^2); per triplet the point record
@@ -15,9 +15,10 @@
 //   dense_kernel   streams tiles of NODE records through shared memory with 1-D TMA bulk copies
 //                  (cp.async.bulk + mbarrier, double buffered) against register-resident lines.  7 packed FP32
 //                  ops (FFMA2) decide per (line, node) whether the line can touch the node's sphere; results
-//                  are accumulated branch-free into per-line bit masks, pushed to warp-private queues once per
-//                  32 groups, and drained with (1) the same predicate per triplet of the node and (2) the EXACT
-//                  reference-order test of all three points.  Confirmed hits go to fixed-capacity per-line slots.
+//                  are accumulated branch-free into per-line bit masks and pushed (ordered, by warp scans) to
+//                  warp-private queues; three further levels -- node predicate, triplet predicate, EXACT
+//                  reference-order test of all three points -- each run one queue entry per lane with converged
+//                  warps.  Confirmed hits go to fixed-capacity per-line slots.
 //
 // Both filters are superset tests ("filtered predicate"); the decision itself is always taken by the
 // literal arithmetic of loss.py:84-110, so the selected indices are bit-exact against the oracle.
@@ -92,12 +93,29 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {
     return v;
 }
 
+// Hilbert-curve index (Skilling's transpose algorithm, 10 bits per axis): unlike Morton order, consecutive keys
+// are always neighbouring cells, so kNode consecutive triplets form compact nodes
 __device__ __forceinline__ unsigned morton_key(const float *p, float P) {
     const float s = P > 0.f ? 512.0f / P : 0.f;              // [-P, P] -> [0, 1024)
-    const int qx = min(1023, max(0, (int)((p[0] + P) * s)));
-    const int qy = min(1023, max(0, (int)((p[1] + P) * s)));
-    const int qz = min(1023, max(0, (int)((p[2] + P) * s)));
-    return spread10((unsigned)qx) | (spread10((unsigned)qy) << 1) | (spread10((unsigned)qz) << 2);
+    unsigned X[3];
+    X[0] = (unsigned)min(1023, max(0, (int)((p[0] + P) * s)));
+    X[1] = (unsigned)min(1023, max(0, (int)((p[1] + P) * s)));
+    X[2] = (unsigned)min(1023, max(0, (int)((p[2] + P) * s)));
+    for (unsigned Q = 512u; Q > 1u; Q >>= 1) {
+        const unsigned Pm = Q - 1u;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) X[0] ^= Pm;
+            else { const unsigned t = (X[0] ^ X[i]) & Pm; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    unsigned t = 0;
+    for (unsigned Q = 512u; Q > 1u; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1u;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);
 }
 
 // one CTA sorts one cloud (nfp <= kSortSmall) with a bitonic network on (key << 32 | index)
@@ -203,7 +221,11 @@ __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri
                         const double reach = sqrt(fmax(cut + E, 0.0)) + sqrt(dx * dx + dy * dy + dz * dz);
                         R = fmax(R, reach);
                     }
-                    ws.pt4[cloud][(long long)b * nfp + n * kNode + s] = pr;
+                    {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB}
+                        const long long si = (long long)b * nfp + n * kNode + s;
+                        float *dp = reinterpret_cast<float *>(ws.pt4[cloud] + (si & ~1LL)) + (si & 1);
+                        dp[0] = pr.x; dp[2] = pr.y; dp[4] = pr.z; dp[6] = pr.w;
+                    }
                 }
                 R *= 1.000002;
                 rad = (float)R * 1.000001f;
@@ -213,7 +235,10 @@ __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri
                 w = w + fabsf(w) * 2.4e-7f + 1e-30f;
                 rec = make_float4(qx, qy, qz, w);
             } else {
-                for (int s = 0; s < kNode; ++s) ws.pt4[cloud][(long long)b * nfp + n * kNode + s] = make_float4(0.f, 0.f, 0.f, -INFINITY);
+                for (int s = 0; s < kNode; s += 2) {
+                    ws.pt4[cloud][(long long)b * nfp + n * kNode + s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ws.pt4[cloud][(long long)b * nfp + n * kNode + s + 1] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
+                }
             }
             float *dst = reinterpret_cast<float *>(ws.node4[cloud] + ((long long)b * nnodes + (n & ~1)));
             const int h = n & 1;
@@ -341,21 +366,40 @@ __device__ __forceinline__ void exact_test_and_record(const float *__restrict__ 
     }
 }
 
-constexpr int kSmemPoints = 2048;      // point records are staged in shared memory when a chunk has <= this many
-constexpr int kExactQueue = 256;       // (line, triplet) entries awaiting the exact test, per warp
+constexpr int kSmemPoints = 1024;      // point records are staged in shared memory when a chunk has <= this many
 constexpr int kNumWarps = kDenseThreads / 32;
+constexpr int kNodeQueue = 512;        // (line, node) entries per warp; one level-1 pass appends <= 128
+constexpr int kExactQueue = 768;       // (line, triplet) entries per warp; one level-2 pass appends <= 32 * node size
 constexpr int kOffQueue = 2 * kTileNodes * 16;
-constexpr int kOffExact = kOffQueue + kNumWarps * kWarpQueue * 4;
+constexpr int kOffNodeQ = kOffQueue + kNumWarps * kWarpQueue * 4;
+constexpr int kOffExact = kOffNodeQ + kNumWarps * kNodeQueue * 4;
 constexpr int kOffPoints = kOffExact + kNumWarps * kExactQueue * 4;
 constexpr int kDenseSmem = kOffPoints + kSmemPoints * 16;
 
+// exclusive prefix sum of c over the lanes of a (converged) warp
+__device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += up;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - c;
+}
+
+// Three-level candidate pipeline of one warp (all queues in shared memory, all pushes ordered by warp scans, so
+// there are no atomics, no overflow paths, and every level runs with converged, fully populated warps):
+//   main loop : (line, node) sphere predicate, packed FFMA2, branch-free bit masks  -> wq: (line, group of 4 nodes)
+//   level 1   : one wq entry per lane, the 4 node predicates again                  -> nq: (line, node)
+//   level 2   : one nq entry per lane, the triplet predicate on the node's triplets -> xq: (line, triplet)
+//   level 3   : one xq entry per lane, the EXACT reference-order test, hit recording
 template <int kNode>
 __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
     extern __shared__ __align__(128) unsigned char dsm[];
     float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kTileNodes]
     float4 *spts = reinterpret_cast<float4 *>(dsm + kOffPoints);                           // [kSmemPoints]
     __shared__ __align__(8) unsigned long long mbar[3];
-    __shared__ int xq_n[kNumWarps];
     __shared__ int s_band, s_nan, s_cand;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -366,8 +410,9 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     if (n_begin >= nnodes) return;
     const int n_end = min(nnodes, n_begin + a.chunk_nodes);
     const int line_base = blockIdx.x * kLinesPerCta;
-    unsigned *wq = reinterpret_cast<unsigned *>(dsm + kOffQueue) + wid * kWarpQueue;       // (line, node group) entries
-    unsigned *xq = reinterpret_cast<unsigned *>(dsm + kOffExact) + wid * kExactQueue;      // (line, triplet) entries
+    unsigned *wq = reinterpret_cast<unsigned *>(dsm + kOffQueue) + wid * kWarpQueue;
+    unsigned *nq = reinterpret_cast<unsigned *>(dsm + kOffNodeQ) + wid * kNodeQueue;
+    unsigned *xq = reinterpret_cast<unsigned *>(dsm + kOffExact) + wid * kExactQueue;
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -376,7 +421,6 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_band = 0; s_nan = 0; s_cand = 0;
     }
-    if (lane == 0) xq_n[wid] = 0;
 
     // ---- per-thread lines -> filter thresholds ------------------------------------------------------------
     const float P = sqrtf(__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001f;
@@ -384,7 +428,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     const float4 *lineC = ws.lineC + (long long)b * g.nl * 2;
     float ux[kLinesPerThread], uy[kLinesPerThread], uz[kLinesPerThread];
     float mx[kLinesPerThread], my[kLinesPerThread], mz[kLinesPerThread], tl[kLinesPerThread];
-    // threshold of the point-level predicate and of the node-level predicate for a line
+    // threshold of the triplet-level predicate and of the node-level predicate for a line
     auto thresholds = [&](const float4 &c0, const float4 &c1, float &tl_point, float &tl_node) {
         const float PX = P + c0.w;
         const float guard = kGuardFast * kEps24 * PX * PX + 1e-12f;
@@ -419,7 +463,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         mbar_expect_tx(&mbar[t & 1], bytes);
         tma_bulk_load(stage + (t & 1) * kTileNodes, src + s0, bytes, &mbar[t & 1]);
     };
-    // the chunk's point records (drain stage) go to shared memory when they fit, else they are read through L2
+    // the chunk's triplet records (level 2) go to shared memory when they fit, else they are read through L2
     const float4 *pt4_b = ws.pt4[cloud] + (long long)b * nfp;
     const bool pts_in_smem = (n_end - n_begin) * kNode <= kSmemPoints;
     const float4 *pts = pts_in_smem ? spts : pt4_b + (long long)n_begin * kNode;          // indexed from the chunk start
@@ -439,89 +483,105 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     const float *thr_b = ws.thr[cloud] + (long long)b * nf;
     const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)n_begin * kNode;   // from the chunk start
     const float4 *node_c = src + n_begin;                                                  // from the chunk start
+    int wq_cnt = 0, nq_cnt = 0, xq_cnt = 0;                      // warp-uniform fill levels
 
-    // level 3: the exact reference-order test of one (line, triplet)
-    auto exact = [&](unsigned xent) {
-        const int l = line_base + (int)(xent >> 22);
-        const int f = __ldg(perm_c + (int)(xent & 0x3FFFFFu));
-        float ln[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) ln[c] = __ldg(lines_b + (long long)l * 6 + c);
-        const long long gl = (long long)b * g.nl + l;
-        exact_test_and_record(tri_b, thr_b, ln, f, ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
-    };
-    auto drain_exact = [&]() {
+    // level 3: the exact reference-order test of (line, triplet) entries
+    auto run_exact = [&]() {
         __syncwarp();
-        const int n = min(*(volatile int *)&xq_n[wid], kExactQueue);
-        for (int base = 0; base < n; base += 32)
-            if (base + lane < n) exact(xq[base + lane]);
-        __syncwarp();
-        if (lane == 0) xq_n[wid] = 0;
-        __syncwarp();
-    };
-    // levels 1+2, one queued entry per lane: (line, group of 4 nodes) -> node predicate -> triplet predicate.
-    // Each level first collects a bit mask branch-free and then iterates over the set bits, so the lanes of a warp
-    // stay aligned on "their k-th fired node" instead of serialising on the node index; fired triplets are handed
-    // to the exact queue so that the (expensive, rare) exact test runs with full warps.
-    auto resolve = [&](unsigned ent) {
-        const int lrel = (int)(ent >> 20);
-        const int l = line_base + lrel;
-        const int q0 = (int)(ent & 0xFFFFFu) * 4;                  // first node of the group, relative to the chunk
-        const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
-        float tl_point, tl_node;
-        thresholds(c0, c1, tl_point, tl_node);
-        const float4 *nr4 = node_c + q0;                           // 4 nodes = 2 interleaved pairs = 4 float4
-        const float4 A0 = __ldg(nr4), A1 = __ldg(nr4 + 1), B0 = __ldg(nr4 + 2), B1 = __ldg(nr4 + 3);
-        const float nx[4] = {A0.x, A0.y, B0.x, B0.y}, ny[4] = {A0.z, A0.w, B0.z, B0.w};
-        const float nz[4] = {A1.x, A1.y, B1.x, B1.y}, nw[4] = {A1.z, A1.w, B1.z, B1.w};
-        unsigned nm = 0;
+        for (int base = 0; base < xq_cnt; base += 32) {
+            if (base + lane < xq_cnt) {
+                const unsigned xent = xq[base + lane];
+                const int l = line_base + (int)(xent >> 22);
+                const int f = __ldg(perm_c + (int)(xent & 0x3FFFFFu));
+                float ln[6];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float tt = fmaf(nz[q], c0.z, fmaf(ny[q], c0.y, nx[q] * c0.x));
-            const float ss = fmaf(nz[q], c1.z, fmaf(ny[q], c1.y, fmaf(nx[q], c1.x, nw[q])));
-            nm |= (fmaf(tt, tt, ss) > tl_node) ? (1u << q) : 0u;
-        }
-        while (nm) {
-            const int nrel = q0 + __ffs(nm) - 1;
-            nm &= nm - 1;
-            const float4 *pp = pts + nrel * kNode;
-            unsigned pm = 0;
-#pragma unroll
-            for (int h = 0; h < kNode; h += 8) {
-                float4 pr[8];
-#pragma unroll
-                for (int s = 0; s < 8; ++s) pr[s] = pp[h + s];
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const float t2 = fmaf(pr[s].z, c0.z, fmaf(pr[s].y, c0.y, pr[s].x * c0.x));
-                    const float s2 = fmaf(pr[s].z, c1.z, fmaf(pr[s].y, c1.y, fmaf(pr[s].x, c1.x, pr[s].w)));
-                    pm |= (fmaf(t2, t2, s2) > tl_point) ? (1u << (h + s)) : 0u;
-                }
-            }
-            if (pm) {
-                int pos = atomicAdd(&xq_n[wid], __popc(pm));
-                while (pm) {
-                    const int s = __ffs(pm) - 1;
-                    pm &= pm - 1;
-                    const unsigned xent = ((unsigned)lrel << 22) | (unsigned)(nrel * kNode + s);
-                    if (pos < kExactQueue) xq[pos] = xent;
-                    else exact(xent);                             // exact queue full (rare): test in place
-                    ++pos;
-                }
+                for (int c = 0; c < 6; ++c) ln[c] = __ldg(lines_b + (long long)l * 6 + c);
+                const long long gl = (long long)b * g.nl + l;
+                exact_test_and_record(tri_b, thr_b, ln, f, ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
             }
         }
-    };
-    auto drain_warp = [&](int n) {
         __syncwarp();
-        for (int base = 0; base < n; base += 32) {
-            if (base + lane < n) resolve(wq[base + lane]);
+        xq_cnt = 0;
+    };
+    // level 2: triplet predicate on the triplets of (line, node) entries, packed two triplets per FFMA2
+    auto run_nodes = [&]() {
+        __syncwarp();
+        for (int base = 0; base < nq_cnt; base += 32) {
+            if (xq_cnt + 32 * kNode > kExactQueue) run_exact();
+            unsigned pm = 0, key = 0;
+            if (base + lane < nq_cnt) {
+                const unsigned ent = nq[base + lane];
+                const int lrel = (int)(ent >> 22), nrel = (int)(ent & 0x3FFFFFu);
+                const int l = line_base + lrel;
+                const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
+                const float PX = P + c0.w;
+                const float tl_point = c1.w - (kGuardFast * kEps24 * PX * PX + 1e-12f) - fabsf(c1.w) * 1.2e-7f;
+                const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
+                const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
+                const float4 *pp = pts + nrel * kNode;
+#pragma unroll
+                for (int j = 0; j < kNode / 2; ++j) {
+                    const float4 A = pp[2 * j], Bq = pp[2 * j + 1];
+                    const float2 x2 = make_float2(A.x, A.y), y2 = make_float2(A.z, A.w), z2 = make_float2(Bq.x, Bq.y), w2 = make_float2(Bq.z, Bq.w);
+                    const float2 t2 = __ffma2_rn(z2, u2, __ffma2_rn(y2, u1, __fmul2_rn(x2, u0)));
+                    const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
+                    const float2 q2 = __ffma2_rn(t2, t2, s2);
+                    pm |= (q2.x > tl_point) ? (1u << (2 * j)) : 0u;
+                    pm |= (q2.y > tl_point) ? (2u << (2 * j)) : 0u;
+                }
+                key = ((unsigned)lrel << 22) | (unsigned)(nrel * kNode);
+            }
+            int total;
+            int pos = xq_cnt + warp_excl_scan(__popc(pm), lane, total);
+            while (pm) {
+                const int s = __ffs(pm) - 1;
+                pm &= pm - 1;
+                xq[pos++] = key + (unsigned)s;
+            }
+            xq_cnt += total;
             __syncwarp();
-            if (*(volatile int *)&xq_n[wid] > kExactQueue / 2) drain_exact();
         }
+        nq_cnt = 0;
+    };
+    // level 1: node predicate on the 4 nodes of (line, group) entries
+    auto run_groups = [&]() {
         __syncwarp();
+        for (int base = 0; base < wq_cnt; base += 32) {
+            if (nq_cnt + 128 > kNodeQueue) run_nodes();
+            unsigned nm = 0, key = 0;
+            if (base + lane < wq_cnt) {
+                const unsigned ent = wq[base + lane];
+                const int lrel = (int)(ent >> 20);
+                const int l = line_base + lrel;
+                const int q0 = (int)(ent & 0xFFFFFu) * 4;              // first node of the group, relative to the chunk
+                const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
+                float tl_point, tl_node;
+                thresholds(c0, c1, tl_point, tl_node);
+                const float4 *nr4 = node_c + q0;                       // 4 nodes = 2 interleaved pairs = 4 float4
+                const float4 A0 = __ldg(nr4), A1 = __ldg(nr4 + 1), B0 = __ldg(nr4 + 2), B1 = __ldg(nr4 + 3);
+                const float nx[4] = {A0.x, A0.y, B0.x, B0.y}, ny[4] = {A0.z, A0.w, B0.z, B0.w};
+                const float nz[4] = {A1.x, A1.y, B1.x, B1.y}, nw[4] = {A1.z, A1.w, B1.z, B1.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float tt = fmaf(nz[q], c0.z, fmaf(ny[q], c0.y, nx[q] * c0.x));
+                    const float ss = fmaf(nz[q], c1.z, fmaf(ny[q], c1.y, fmaf(nx[q], c1.x, nw[q])));
+                    nm |= (fmaf(tt, tt, ss) > tl_node) ? (1u << q) : 0u;
+                }
+                key = ((unsigned)lrel << 22) | (unsigned)q0;
+            }
+            int total;
+            int pos = nq_cnt + warp_excl_scan(__popc(nm), lane, total);
+            while (nm) {
+                const int q = __ffs(nm) - 1;
+                nm &= nm - 1;
+                nq[pos++] = key + (unsigned)q;
+            }
+            nq_cnt += total;
+            __syncwarp();
+        }
+        wq_cnt = 0;
     };
 
-    int wq_cnt = 0;                                              // warp-uniform fill level of this warp's queue
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + 1 < ntiles) issue(t + 1);
         mbar_wait(&mbar[t & 1], (t >> 1) & 1);
@@ -555,24 +615,16 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
                     m[i] |= (qmax > tl[i]) ? bit : 0u;
                 }
             }
-            // warp-synchronous, ordered push of the fired (line, group) pairs: no atomics, never overflows
+            // ordered push of the fired (line, group) pairs
 #pragma unroll
             for (int i = 0; i < kLinesPerThread; ++i) {
                 unsigned mi = m[i];
                 if (__any_sync(0xffffffffu, mi != 0u)) {
                     const int c = __popc(mi);
-                    int inc = c;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int up = __shfl_up_sync(0xffffffffu, inc, d);
-                        if (lane >= d) inc += up;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, inc, 31);        // <= 32 lanes x 32 groups = kWarpQueue
-                    if (wq_cnt + total > kWarpQueue) {
-                        drain_warp(wq_cnt);
-                        wq_cnt = 0;
-                    }
-                    int pos = wq_cnt + inc - c;
+                    int total;                                            // <= 32 lanes x 32 groups = kWarpQueue
+                    const int off = warp_excl_scan(c, lane, total);
+                    if (wq_cnt + total > kWarpQueue) run_groups();
+                    int pos = wq_cnt + off;
                     while (mi) {
                         const int gi = __ffs(mi) - 1;
                         mi &= mi - 1;
@@ -585,8 +637,9 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         }
         __syncthreads();                       // everyone is done with this stage before it is refilled
     }
-    drain_warp(wq_cnt);
-    drain_exact();
+    run_groups();
+    run_nodes();
+    run_exact();
 
     // ---- diagnostics ---------------------------------------------------------------------------------
     if (band) atomicAdd(&s_band, band);

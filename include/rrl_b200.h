@@ -175,7 +175,8 @@ float *rrl_host_pinned_tri2(rrl_host_ctx *ctx);
 float *rrl_host_pinned_lines(rrl_host_ctx *ctx);
 /* H2D of the three inputs, forward, backward w.r.t. cloud 1 with d(total)/d(loss[b]) = 1, D2H of loss [B], status [B]
  * and (if h_grad_tri1 != NULL) the (B,nf1,9) gradient; returns after the stream has drained.  h_* inputs may be
- * the context's own pinned buffers or any host memory (then they are staged through the pinned buffers). */
+ * the context's own pinned buffers, any other pinned memory (copied asynchronously) or pageable memory (staged by
+ * the CUDA driver). */
 int rrl_host_loss_fwd_bwd(rrl_host_ctx *ctx, const float *h_tri1, const float *h_tri2, const float *h_lines,
                           int k_lo, int j_lo, int k_hi, int j_hi,
                           float *h_loss, int *h_status, float *h_grad_tri1);
