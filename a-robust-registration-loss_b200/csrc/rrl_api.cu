@@ -45,10 +45,11 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.thr[1] = reinterpret_cast<float *>(take(sB * nf2 * sizeof(float)));
     w.perm[0] = reinterpret_cast<int *>(take(sB * nf1p * sizeof(int)));
     w.perm[1] = reinterpret_cast<int *>(take(sB * nf2p * sizeof(int)));
-    w.pt4[0] = reinterpret_cast<float4 *>(take(sB * nf1p * sizeof(float4)));
-    w.pt4[1] = reinterpret_cast<float4 *>(take(sB * nf2p * sizeof(float4)));
-    w.node4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kMinNode) * sizeof(float4)));
-    w.node4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kMinNode) * sizeof(float4)));
+    // triplet records: kNode + 1 float4 per node; node records: 5 float4 per group of 4 nodes (sized for kMinNode)
+    w.pt4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kMinNode) * (kMinNode + 1) * sizeof(float4)));
+    w.pt4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kMinNode) * (kMinNode + 1) * sizeof(float4)));
+    w.node4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kMinNode / 4) * 5 * sizeof(float4)));
+    w.node4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kMinNode / 4) * 5 * sizeof(float4)));
     w.sortbuf_bytes = sort_scratch_bytes(nf1p > nf2p ? nf1p : nf2p);
     w.sortbuf = reinterpret_cast<unsigned long long *>(take(w.sortbuf_bytes));
     // ---- per line ----

@@ -35,7 +35,7 @@ constexpr int kTileNodes = 512;                                 // float4 per no
 constexpr int kNodePad = 16;                                    // node arrays are padded to this multiple (sentinels)
 constexpr int kPointPad = 256;                                  // triplet arrays padded to 16 nodes of 16 (= 32 nodes of 8)
 constexpr int kMinNode = 8;                                     // smallest node size (sizes the node arrays)
-constexpr int kWarpQueue = 1024;                                // candidate (line, node) entries per warp
+constexpr int kWarpQueue = 512;                                 // candidate (line, node group) entries per warp
 constexpr int kSortSmall = 4096;                                // clouds up to this many (padded) triplets sort in one CTA
 
 // ---- fixed-point accumulation of Welsch sums (order-independent, hence run-to-run deterministic) ---
@@ -63,8 +63,8 @@ struct Workspace {
     // per triplet
     float *thr[2];           // (B, nf): exact reference threshold, original order
     int *perm[2];            // (B, nfp): sorted position -> original triplet index (-1 = padding)
-    float4 *pt4[2];          // (B, nfp): sorted order, {p0.xyz, cut - |p0|^2}; sentinel padded
-    float4 *node4[2];        // (B, nfp/node_size): pair-interleaved {xA,xB,yA,yB}{zA,zB,wA,wB}; w = R^2 - |q|^2
+    float4 *pt4[2];          // (B, nnodes, node_size + 1): sorted order, pair-interleaved {p0.xyz, cut - |p0|^2}, 1 pad per node
+    float4 *node4[2];        // (B, nnodes/4, 5): pair-interleaved {xA,xB,yA,yB}{zA,zB,wA,wB} x2 + 1 pad; w = R^2 - |q|^2
     unsigned long long *sortbuf; // scratch for the large-cloud sort (keys/values double buffers + cub temp)
     size_t sortbuf_bytes;
     // per line

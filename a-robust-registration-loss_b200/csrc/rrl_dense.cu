@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri
     const double P = sqrt((double)__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001;
     const double Xm = sqrt((double)__uint_as_float(ws.xmax[b * 2])) * 1.000001;
     const double E = (double)kGuardRef * (double)kEps24 * (P + Xm) * (P + Xm) + 1e-12;
+    float4 *pt_base = ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1);
     for (int base = blockIdx.x * blockDim.x; base < nnodes; base += gridDim.x * blockDim.x) {   // warp-uniform trip count
         const int n = base + threadIdx.x;
         float rad = 0.f;
@@ -221,9 +222,9 @@ __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri
                         const double reach = sqrt(fmax(cut + E, 0.0)) + sqrt(dx * dx + dy * dy + dz * dz);
                         R = fmax(R, reach);
                     }
-                    {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB}
-                        const long long si = (long long)b * nfp + n * kNode + s;
-                        float *dp = reinterpret_cast<float *>(ws.pt4[cloud] + (si & ~1LL)) + (si & 1);
+                    {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB};
+                        // a node occupies kNode + 1 float4 (odd stride: lanes reading different nodes hit different banks)
+                        float *dp = reinterpret_cast<float *>(pt_base + (long long)n * (kNode + 1) + (s & ~1)) + (s & 1);
                         dp[0] = pr.x; dp[2] = pr.y; dp[4] = pr.z; dp[6] = pr.w;
                     }
                 }
@@ -236,13 +237,16 @@ __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri
                 rec = make_float4(qx, qy, qz, w);
             } else {
                 for (int s = 0; s < kNode; s += 2) {
-                    ws.pt4[cloud][(long long)b * nfp + n * kNode + s] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    ws.pt4[cloud][(long long)b * nfp + n * kNode + s + 1] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
+                    pt_base[(long long)n * (kNode + 1) + s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    pt_base[(long long)n * (kNode + 1) + s + 1] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
                 }
             }
-            float *dst = reinterpret_cast<float *>(ws.node4[cloud] + ((long long)b * nnodes + (n & ~1)));
-            const int h = n & 1;
-            dst[0 + h] = rec.x; dst[2 + h] = rec.y; dst[4 + h] = rec.z; dst[6 + h] = rec.w;
+            pt_base[(long long)n * (kNode + 1) + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);            // pad slot
+            // node records: a group of 4 nodes = two interleaved pairs + one pad = 5 float4 (odd stride again)
+            float4 *grp = ws.node4[cloud] + (long long)b * (nnodes / 4) * 5 + (long long)(n >> 2) * 5;
+            float *dst = reinterpret_cast<float *>(grp + ((n >> 1) & 1) * 2) + (n & 1);
+            dst[0] = rec.x; dst[2] = rec.y; dst[4] = rec.z; dst[6] = rec.w;
+            if ((n & 3) == 0) grp[4] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         warp_atomic_max_bits(ws.rmax + b * 2 + cloud, rad);
     }
@@ -366,26 +370,33 @@ __device__ __forceinline__ void exact_test_and_record(const float *__restrict__ 
     }
 }
 
-constexpr int kSmemPoints = 1024;      // point records are staged in shared memory when a chunk has <= this many
+constexpr int kSmemPtsF4 = 992;        // triplet records (float4, incl. pads) staged in shared memory when a chunk fits
+constexpr int kStageF4 = (kTileNodes / 4) * 5;                          // float4 per stage: 5 per group of 4 nodes
 constexpr int kNumWarps = kDenseThreads / 32;
-constexpr int kNodeQueue = 512;        // (line, node) entries per warp; one level-1 pass appends <= 128
-constexpr int kExactQueue = 768;       // (line, triplet) entries per warp; one level-2 pass appends <= 32 * node size
-constexpr int kOffQueue = 2 * kTileNodes * 16;
+constexpr int kNodeQueue = 256;        // (line, node) entries per warp; one level-1 pass appends <= 128
+constexpr int kExactQueue = 640;       // (line, triplet) entries per warp; one level-2 pass appends <= 32 * node size
+constexpr int kOffLineC = 2 * kStageF4 * 16;                           // the CTA's line constants: L1 has no room left
+constexpr int kOffQueue = kOffLineC + kLinesPerCta * 32;
 constexpr int kOffNodeQ = kOffQueue + kNumWarps * kWarpQueue * 4;
 constexpr int kOffExact = kOffNodeQ + kNumWarps * kNodeQueue * 4;
 constexpr int kOffPoints = kOffExact + kNumWarps * kExactQueue * 4;
-constexpr int kDenseSmem = kOffPoints + kSmemPoints * 16;
+constexpr int kDenseSmem = kOffPoints + kSmemPtsF4 * 16;
+static_assert(2 * (kDenseSmem + 2048) <= 227 * 1024, "two CTAs per SM must fit (dynamic + static + 1 KB reserved each)");
 
-// exclusive prefix sum of c over the lanes of a (converged) warp
+// exclusive prefix sum over the lanes of a (converged) warp of a count c < 2^kBits, by bit planes: kBits independent
+// ballots instead of a dependent chain of five shuffles (the queue levels are latency bound, not issue bound)
+template <int kBits>
 __device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
-    int inc = c;
+    const unsigned lt = (1u << lane) - 1u;
+    int off = 0;
+    total = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += up;
+    for (int bit = 0; bit < kBits; ++bit) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (c >> bit) & 1);
+        off += __popc(bal & lt) << bit;
+        total += __popc(bal) << bit;
     }
-    total = __shfl_sync(0xffffffffu, inc, 31);
-    return inc - c;
+    return off;
 }
 
 // Three-level candidate pipeline of one warp (all queues in shared memory, all pushes ordered by warp scans, so
@@ -397,8 +408,10 @@ __device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
 template <int kNode>
 __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
     extern __shared__ __align__(128) unsigned char dsm[];
-    float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kTileNodes]
-    float4 *spts = reinterpret_cast<float4 *>(dsm + kOffPoints);                           // [kSmemPoints]
+    float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kStageF4]
+    float4 *spts = reinterpret_cast<float4 *>(dsm + kOffPoints);                           // [kSmemPtsF4]
+    float4 *slineU = reinterpret_cast<float4 *>(dsm + kOffLineC);                          // [kLinesPerCta] {u, tl_node}
+    float4 *slineM = slineU + kLinesPerCta;                                                // [kLinesPerCta] {M, tl_point}
     __shared__ __align__(8) unsigned long long mbar[3];
     __shared__ int s_band, s_nan, s_cand;
 
@@ -450,29 +463,31 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
             mx[i] = c1.x; my[i] = c1.y; mz[i] = c1.z;
             float tp;
             thresholds(c0, c1, tp, tl[i]);
+            // only ever re-read by this warp's queue levels, which need the thresholds rather than |x0| and c
+            slineU[tid + i * kDenseThreads] = make_float4(c0.x, c0.y, c0.z, tl[i]);
+            slineM[tid + i * kDenseThreads] = make_float4(c1.x, c1.y, c1.z, tp);
         }
     }
     __syncthreads();
 
-    const float4 *src = ws.node4[cloud] + (long long)b * nnodes;
+    const float4 *src = ws.node4[cloud] + (long long)b * (nnodes / 4) * 5 + (long long)(n_begin / 4) * 5;   // chunk start
     const int ntiles = (n_end - n_begin + kTileNodes - 1) / kTileNodes;
     auto issue = [&](int t) {
-        const int s0 = n_begin + t * kTileNodes;
-        const int n = min(kTileNodes, n_end - s0);
-        const unsigned bytes = (unsigned)n * 16u;
+        const int n = min(kTileNodes, n_end - (n_begin + t * kTileNodes));
+        const unsigned bytes = (unsigned)(n / 4) * 5u * 16u;
         mbar_expect_tx(&mbar[t & 1], bytes);
-        tma_bulk_load(stage + (t & 1) * kTileNodes, src + s0, bytes, &mbar[t & 1]);
+        tma_bulk_load(stage + (t & 1) * kStageF4, src + (long long)t * kStageF4, bytes, &mbar[t & 1]);
     };
     // the chunk's triplet records (level 2) go to shared memory when they fit, else they are read through L2
-    const float4 *pt4_b = ws.pt4[cloud] + (long long)b * nfp;
-    const bool pts_in_smem = (n_end - n_begin) * kNode <= kSmemPoints;
-    const float4 *pts = pts_in_smem ? spts : pt4_b + (long long)n_begin * kNode;          // indexed from the chunk start
+    const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + n_begin) * (kNode + 1);   // chunk start
+    const bool pts_in_smem = (n_end - n_begin) * (kNode + 1) <= kSmemPtsF4;
+    const float4 *pts = pts_in_smem ? spts : pt4_c;
     if (tid == 0) {
         issue(0);
         if (pts_in_smem) {
-            const unsigned bytes = (unsigned)(n_end - n_begin) * kNode * 16u;
+            const unsigned bytes = (unsigned)(n_end - n_begin) * (kNode + 1) * 16u;
             mbar_expect_tx(&mbar[2], bytes);
-            tma_bulk_load(spts, pt4_b + (long long)n_begin * kNode, bytes, &mbar[2]);
+            tma_bulk_load(spts, pt4_c, bytes, &mbar[2]);
         }
     }
     if (pts_in_smem) mbar_wait(&mbar[2], 0);
@@ -482,7 +497,8 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     const float *tri_b = a.tri[cloud] + (long long)b * nf * 9;
     const float *thr_b = ws.thr[cloud] + (long long)b * nf;
     const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)n_begin * kNode;   // from the chunk start
-    const float4 *node_c = src + n_begin;                                                  // from the chunk start
+    // node records for level 1: a single-tile chunk stays resident in stage 0, otherwise re-read through L2
+    const float4 *node_src = (ntiles == 1) ? stage : src;                                  // from the chunk start
     int wq_cnt = 0, nq_cnt = 0, xq_cnt = 0;                      // warp-uniform fill levels
 
     // level 3: the exact reference-order test of (line, triplet) entries
@@ -512,13 +528,11 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
             if (base + lane < nq_cnt) {
                 const unsigned ent = nq[base + lane];
                 const int lrel = (int)(ent >> 22), nrel = (int)(ent & 0x3FFFFFu);
-                const int l = line_base + lrel;
-                const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
-                const float PX = P + c0.w;
-                const float tl_point = c1.w - (kGuardFast * kEps24 * PX * PX + 1e-12f) - fabsf(c1.w) * 1.2e-7f;
+                const float4 c0 = slineU[lrel], c1 = slineM[lrel];
+                const float tl_point = c1.w;
                 const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
                 const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
-                const float4 *pp = pts + nrel * kNode;
+                const float4 *pp = pts + nrel * (kNode + 1);
 #pragma unroll
                 for (int j = 0; j < kNode / 2; ++j) {
                     const float4 A = pp[2 * j], Bq = pp[2 * j + 1];
@@ -532,7 +546,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
                 key = ((unsigned)lrel << 22) | (unsigned)(nrel * kNode);
             }
             int total;
-            int pos = xq_cnt + warp_excl_scan(__popc(pm), lane, total);
+            int pos = xq_cnt + warp_excl_scan<(kNode == 8 ? 4 : 5)>(__popc(pm), lane, total);
             while (pm) {
                 const int s = __ffs(pm) - 1;
                 pm &= pm - 1;
@@ -552,13 +566,12 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
             if (base + lane < wq_cnt) {
                 const unsigned ent = wq[base + lane];
                 const int lrel = (int)(ent >> 20);
-                const int l = line_base + lrel;
-                const int q0 = (int)(ent & 0xFFFFFu) * 4;              // first node of the group, relative to the chunk
-                const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
-                float tl_point, tl_node;
-                thresholds(c0, c1, tl_point, tl_node);
-                const float4 *nr4 = node_c + q0;                       // 4 nodes = 2 interleaved pairs = 4 float4
-                const float4 A0 = __ldg(nr4), A1 = __ldg(nr4 + 1), B0 = __ldg(nr4 + 2), B1 = __ldg(nr4 + 3);
+                const int grp = (int)(ent & 0xFFFFFu);                 // group of 4 nodes, relative to the chunk
+                const int q0 = grp * 4;
+                const float4 c0 = slineU[lrel], c1 = slineM[lrel];
+                const float tl_node = c0.w;
+                const float4 *nr4 = node_src + grp * 5;                // 4 nodes = 2 interleaved pairs (+ 1 pad float4)
+                const float4 A0 = nr4[0], A1 = nr4[1], B0 = nr4[2], B1 = nr4[3];
                 const float nx[4] = {A0.x, A0.y, B0.x, B0.y}, ny[4] = {A0.z, A0.w, B0.z, B0.w};
                 const float nz[4] = {A1.x, A1.y, B1.x, B1.y}, nw[4] = {A1.z, A1.w, B1.z, B1.w};
 #pragma unroll
@@ -570,7 +583,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
                 key = ((unsigned)lrel << 22) | (unsigned)q0;
             }
             int total;
-            int pos = nq_cnt + warp_excl_scan(__popc(nm), lane, total);
+            int pos = nq_cnt + warp_excl_scan<3>(__popc(nm), lane, total);
             while (nm) {
                 const int q = __ffs(nm) - 1;
                 nm &= nm - 1;
@@ -586,7 +599,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         if (tid == 0 && t + 1 < ntiles) issue(t + 1);
         mbar_wait(&mbar[t & 1], (t >> 1) & 1);
         const int nn = min(kTileNodes, n_end - (n_begin + t * kTileNodes));      // multiple of kNodePad
-        const float4 *sp = stage + (t & 1) * kTileNodes;
+        const float4 *sp = stage + (t & 1) * kStageF4;
         const int ngroups = nn / 4;
         const int group0 = t * (kTileNodes / 4);
         for (int w0 = 0; w0 < ngroups; w0 += 32) {
@@ -597,7 +610,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
 #pragma unroll 2
             for (int gi = 0; gi < ng; ++gi) {
                 // 4 nodes = two interleaved pairs: {xA,xB,yA,yB} {zA,zB,wA,wB}
-                const float4 a0 = sp[(w0 + gi) * 4 + 0], a1 = sp[(w0 + gi) * 4 + 1], b0 = sp[(w0 + gi) * 4 + 2], b1 = sp[(w0 + gi) * 4 + 3];
+                const float4 a0 = sp[(w0 + gi) * 5 + 0], a1 = sp[(w0 + gi) * 5 + 1], b0 = sp[(w0 + gi) * 5 + 2], b1 = sp[(w0 + gi) * 5 + 3];
                 const float2 xa = make_float2(a0.x, a0.y), ya = make_float2(a0.z, a0.w), za = make_float2(a1.x, a1.y), wa = make_float2(a1.z, a1.w);
                 const float2 xb = make_float2(b0.x, b0.y), yb = make_float2(b0.z, b0.w), zb = make_float2(b1.x, b1.y), wb = make_float2(b1.z, b1.w);
                 const unsigned bit = 1u << gi;
@@ -620,18 +633,23 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
             for (int i = 0; i < kLinesPerThread; ++i) {
                 unsigned mi = m[i];
                 if (__any_sync(0xffffffffu, mi != 0u)) {
-                    const int c = __popc(mi);
-                    int total;                                            // <= 32 lanes x 32 groups = kWarpQueue
-                    const int off = warp_excl_scan(c, lane, total);
-                    if (wq_cnt + total > kWarpQueue) run_groups();
-                    int pos = wq_cnt + off;
-                    while (mi) {
-                        const int gi = __ffs(mi) - 1;
-                        mi &= mi - 1;
-                        wq[pos++] = ((unsigned)(tid + i * kDenseThreads) << 20) | (unsigned)(group0 + w0 + gi);
+                    ncand += __popc(mi);
+                    // two halves of 16 groups: each appends <= 32 lanes x 16 groups = kWarpQueue entries
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        unsigned mh = half ? (mi >> 16) : (mi & 0xFFFFu);
+                        if (!__any_sync(0xffffffffu, mh != 0u)) continue;
+                        int total;
+                        const int off = warp_excl_scan<5>(__popc(mh), lane, total);
+                        if (wq_cnt + total > kWarpQueue) run_groups();
+                        int pos = wq_cnt + off;
+                        while (mh) {
+                            const int gi = __ffs(mh) - 1 + half * 16;
+                            mh &= mh - 1;
+                            wq[pos++] = ((unsigned)(tid + i * kDenseThreads) << 20) | (unsigned)(group0 + w0 + gi);
+                        }
+                        wq_cnt += total;
                     }
-                    wq_cnt += total;
-                    ncand += c;
                 }
             }
         }
