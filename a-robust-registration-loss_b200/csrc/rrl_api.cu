@@ -13,6 +13,7 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int check_launch() { return cudaGetLastError() == cudaSuccess ? RRL_OK : RRL_ERR_CUDA; }
 void set_dense_variant(int v);
+void set_param(int id, int v);
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -325,5 +326,11 @@ extern "C" int rrl_measure_dense(const float *tri1, const float *tri2, const flo
 // selects the dense-kernel variant (1 = packed FFMA2 [default], 0 = scalar FFMA); measurement only
 extern "C" int rrl_debug_set_dense_variant(int v) {
     set_dense_variant(v);
+    return RRL_OK;
+}
+
+// tuning knobs for A/B measurements: 1 = node size override (0 auto, 8, 16), 2 = target waves of CTAs, 3 = min nodes per chunk
+extern "C" int rrl_debug_set_param(int id, int value) {
+    set_param(id, value);
     return RRL_OK;
 }

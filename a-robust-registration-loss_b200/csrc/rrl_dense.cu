@@ -259,7 +259,12 @@ size_t sort_scratch_bytes(int nfp_max) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-int node_size(const Geometry &g) { return (g.nf1 > g.nf2 ? g.nf1 : g.nf2) >= 16384 ? 16 : 8; }
+static int g_param[8] = {0, 0, 8, 64, 0, 0, 0, 0};   // [1] node size override, [2] target waves, [3] min nodes per chunk
+void set_param(int id, int v) { if (id > 0 && id < 8) g_param[id] = v; }
+int node_size(const Geometry &g) {
+    if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
+    return (g.nf1 > g.nf2 ? g.nf1 : g.nf2) >= 16384 ? 16 : 8;
+}
 
 static int g_dense_variant = 1;        // 1 = Morton-sorted nodes (default), 0 = nodes in input order (A/B measurement)
 void set_dense_variant(int v) { g_dense_variant = v; }
@@ -687,11 +692,11 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     // split the nodes so that the grid covers the 148 SMs (2 CTAs each) about eight times over when the line
     // tiles alone do not; never below 64 nodes per CTA
     const long long base_ctas = (long long)line_tiles * g.B * 2;
-    const long long target = 148LL * 2 * 8;
+    const long long target = 148LL * 2 * g_param[2];
     int chunks = 1;
     if (base_ctas < target) chunks = (int)((target + base_ctas - 1) / base_ctas);
     int chunk_nodes = (nn_max + chunks - 1) / chunks;
-    if (chunk_nodes < 64) chunk_nodes = 64;
+    if (chunk_nodes < g_param[3]) chunk_nodes = g_param[3];
     chunk_nodes = ((chunk_nodes + kNodePad - 1) / kNodePad) * kNodePad;
     if (chunk_nodes / 4 >= (1 << 20) || (long long)chunk_nodes * G >= (1 << 22)) return RRL_ERR_ARG;
     chunks = (nn_max + chunk_nodes - 1) / chunk_nodes;

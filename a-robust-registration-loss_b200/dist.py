@@ -23,19 +23,23 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def batch_sharded_loss(tri1, tri2, lines, window=(1, 1, 5, 5), group=None, average: bool = False):
-    """Each rank passes ITS OWN pairs (any B, possibly different per rank).  Returns (local per-pair losses (B,),
-    global sum of all losses as a 0-dim tensor that carries gradient for the local pairs only)."""
-    from . import ops
-    local = ops.intersected_line_loss(tri1, tri2, lines, window)
-    total = local.sum()
+def global_sum_with_local_grad(total: torch.Tensor, group=None, average: bool = False) -> torch.Tensor:
+    """all-reduce(sum) of a scalar: the value is the sum over ranks, the gradient flows to the local term only"""
     if dist_.is_available() and dist_.is_initialized() and dist_.get_world_size(group) > 1:
         red = total.detach().clone()
         dist_.all_reduce(red, op=dist_.ReduceOp.SUM, group=group)
         if average:
             red = red / dist_.get_world_size(group)
-        total = total + (red - total.detach())       # value = global sum, gradient = local pairs
-    return local, total
+        total = total + (red - total.detach())
+    return total
+
+
+def batch_sharded_loss(tri1, tri2, lines, window=(1, 1, 5, 5), group=None, average: bool = False):
+    """Each rank passes ITS OWN pairs (any B, possibly different per rank).  Returns (local per-pair losses (B,),
+    global sum of all losses as a 0-dim tensor that carries gradient for the local pairs only)."""
+    from . import ops
+    local = ops.intersected_line_loss(tri1, tri2, lines, window)
+    return local, global_sum_with_local_grad(local.sum(), group, average)
 
 
 def combine_counts(local18: torch.Tensor, group=None) -> torch.Tensor:
@@ -55,41 +59,83 @@ def gather_entries(local: torch.Tensor, n_local: int, counts: List[int], group=N
     return torch.cat([o[:c] for o, c in zip(outs, counts)]) if sum(counts) else buf[:0]
 
 
+class NativeShardBackend:
+    """The per-rank stages of the line-sharded evaluation on the C ABI (include/rrl_b200.h, rrl_shard_*)."""
+
+    def __init__(self, tri1, tri2, lines_local, window):
+        self.L = N.lib()
+        self.dev = tri1.device
+        self.nf1, self.nf2, self.nl = tri1.shape[0], tri2.shape[0], lines_local.shape[0]
+        self.tri1, self.tri2, self.lines, self.window = tri1, tri2, lines_local, window
+        self.wsb = self.L.rrl_workspace_bytes(1, self.nf1, self.nf2, self.nl)
+        self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=self.dev)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _geom(self):
+        return self.ws.data_ptr(), self.wsb, self.nf1, self.nf2, self.nl
+
+    def stage1_counts(self):
+        w = self.window
+        N.check(self.L.rrl_shard_stage1(self.tri1.data_ptr(), self.tri2.data_ptr(), self.lines.data_ptr(), self.nf1,
+                                        self.nf2, self.nl, w[0], w[1], w[2], w[3], self.ws.data_ptr(), self.wsb,
+                                        self._stream()), "rrl_shard_stage1")
+        counts = torch.empty(18, dtype=torch.int64, device=self.dev)
+        N.check(self.L.rrl_shard_counts(*self._geom(), counts.data_ptr(), self._stream()), "rrl_shard_counts")
+        return counts
+
+    def pack_entries(self, n_local):
+        out = torch.empty(max(n_local, 1), dtype=torch.float32, device=self.dev)
+        N.check(self.L.rrl_shard_pack_entries(*self._geom(), out.data_ptr(), n_local, self._stream()),
+                "rrl_shard_pack_entries")
+        return out
+
+    def median(self, entries):
+        med = torch.empty(1, dtype=torch.float32, device=self.dev)
+        N.check(self.L.rrl_select_lower_median(entries.data_ptr() if entries.numel() else None, entries.numel(),
+                                               med.data_ptr(), self._stream()), "rrl_select_lower_median")
+        return med
+
+    def stage2_sums(self, gcounts, med):
+        sums = torch.empty(32, dtype=torch.int64, device=self.dev)
+        N.check(self.L.rrl_shard_stage2(*self._geom(), gcounts.data_ptr(), med.data_ptr(), sums.data_ptr(),
+                                        self._stream()), "rrl_shard_stage2")
+        return sums
+
+    def stage3_loss(self, gsums):
+        loss = torch.empty(1, dtype=torch.float32, device=self.dev)
+        status = torch.empty(1, dtype=torch.int32, device=self.dev)
+        N.check(self.L.rrl_shard_stage3(*self._geom(), gsums.data_ptr(), loss.data_ptr(), status.data_ptr(),
+                                        self._stream()), "rrl_shard_stage3")
+        return loss, status
+
+
+def line_shard_forward(backend, group=None):
+    """The exchange protocol of SURVEY 8(e), independent of where the stages run (the CPU tests drive it with an
+    oracle-backed backend over gloo).  Exactly three collectives: all-gather of the 18 per-rank counts, all-gather
+    of the D entries, all-reduce of the 32 fixed-point partial sums."""
+    counts = backend.stage1_counts()
+    world = dist_.get_world_size(group)
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist_.all_gather(all_counts, counts, group=group)
+    per_rank_entries = [int(c[17].item()) for c in all_counts]             # one host read: sizes of the exchange
+    gcounts = torch.stack(all_counts).sum(0)
+    n_local = per_rank_entries[dist_.get_rank(group)]
+    entries = gather_entries(backend.pack_entries(n_local), n_local, per_rank_entries, group)
+    med = backend.median(entries)
+    sums = backend.stage2_sums(gcounts, med)
+    dist_.all_reduce(sums, op=dist_.ReduceOp.SUM, group=group)
+    loss, status = backend.stage3_loss(sums)
+    return loss, status, med
+
+
 class _LineShardedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tri1, tri2, lines_local, window, group):
-        L = N.lib()
-        dev = tri1.device
-        nf1, nf2, nl = tri1.shape[0], tri2.shape[0], lines_local.shape[0]
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        wsb = L.rrl_workspace_bytes(1, nf1, nf2, nl)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        N.check(L.rrl_shard_stage1(tri1.data_ptr(), tri2.data_ptr(), lines_local.data_ptr(), nf1, nf2, nl, window[0],
-                                   window[1], window[2], window[3], ws.data_ptr(), wsb, stream), "rrl_shard_stage1")
-        counts = torch.empty(18, dtype=torch.int64, device=dev)
-        N.check(L.rrl_shard_counts(ws.data_ptr(), wsb, nf1, nf2, nl, counts.data_ptr(), stream), "rrl_shard_counts")
-        world = dist_.get_world_size(group)
-        all_counts = [torch.empty_like(counts) for _ in range(world)]
-        dist_.all_gather(all_counts, counts, group=group)
-        per_rank_entries = [int(c[17].item()) for c in all_counts]         # one host read: sizes of the exchange
-        gcounts = torch.stack(all_counts).sum(0)
-        n_local = per_rank_entries[dist_.get_rank(group)]
-        local_entries = torch.empty(max(n_local, 1), dtype=torch.float32, device=dev)
-        N.check(L.rrl_shard_pack_entries(ws.data_ptr(), wsb, nf1, nf2, nl, local_entries.data_ptr(), n_local, stream),
-                "rrl_shard_pack_entries")
-        entries = gather_entries(local_entries, n_local, per_rank_entries, group)
-        med = torch.empty(1, dtype=torch.float32, device=dev)
-        N.check(L.rrl_select_lower_median(entries.data_ptr() if entries.numel() else None, entries.numel(),
-                                          med.data_ptr(), stream), "rrl_select_lower_median")
-        sums = torch.empty(32, dtype=torch.int64, device=dev)
-        N.check(L.rrl_shard_stage2(ws.data_ptr(), wsb, nf1, nf2, nl, gcounts.data_ptr(), med.data_ptr(), sums.data_ptr(),
-                                   stream), "rrl_shard_stage2")
-        dist_.all_reduce(sums, op=dist_.ReduceOp.SUM, group=group)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
-        status = torch.empty(1, dtype=torch.int32, device=dev)
-        N.check(L.rrl_shard_stage3(ws.data_ptr(), wsb, nf1, nf2, nl, sums.data_ptr(), loss.data_ptr(), status.data_ptr(),
-                                   stream), "rrl_shard_stage3")
-        ctx.ws, ctx.geom, ctx.group = ws, (nf1, nf2, nl), group
+        backend = NativeShardBackend(tri1, tri2, lines_local, window)
+        loss, status, med = line_shard_forward(backend, group)
+        ctx.ws, ctx.geom, ctx.group = backend.ws, (backend.nf1, backend.nf2, backend.nl), group
         ctx.mark_non_differentiable(status, med)
         return loss, status, med
 

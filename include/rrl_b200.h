@@ -196,6 +196,9 @@ int rrl_measure_dense(const float *tri1, const float *tri2, const float *lines, 
 /* selects the dense-stage variant: 1 = Morton-sorted bounding-sphere nodes (default), 0 = nodes in input order.
  * Results are identical; measurement / A-B testing only. */
 int rrl_debug_set_dense_variant(int variant);
+/* launch-geometry knobs for A/B measurements: id 1 = triplets per node (0 auto, 8, 16), 2 = target waves of CTAs,
+ * 3 = minimum nodes per CTA chunk.  Results never depend on them. */
+int rrl_debug_set_param(int id, int value);
 
 #ifdef __cplusplus
 }
