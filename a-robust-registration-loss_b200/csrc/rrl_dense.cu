@@ -259,7 +259,7 @@ size_t sort_scratch_bytes(int nfp_max) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[8] = {0, 0, 8, 64, 0, 0, 0, 0};   // [1] node size override, [2] target waves, [3] min nodes per chunk
+static int g_param[8] = {0, 0, 16, 32, 0, 0, 0, 0};   // [1] node size override, [2] target waves, [3] min nodes per chunk
 void set_param(int id, int v) { if (id > 0 && id < 8) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -410,7 +410,10 @@ __device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
 //   level 1   : one wq entry per lane, the 4 node predicates again                  -> nq: (line, node)
 //   level 2   : one nq entry per lane, the triplet predicate on the node's triplets -> xq: (line, triplet)
 //   level 3   : one xq entry per lane, the EXACT reference-order test, hit recording
-template <int kNode>
+// kPerNode (small, hit-dense clouds): the main loop keeps one mask per node of a group and feeds (line, node) entries
+// straight to level 2 -- level 1 would otherwise re-evaluate nearly every group (half of all (line, group) pairs
+// fire on a 1024-triplet cloud).
+template <int kNode, bool kPerNode>
 __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
     extern __shared__ __align__(128) unsigned char dsm[];
     float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kStageF4]
@@ -418,6 +421,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     float4 *slineU = reinterpret_cast<float4 *>(dsm + kOffLineC);                          // [kLinesPerCta] {u, tl_node}
     float4 *slineM = slineU + kLinesPerCta;                                                // [kLinesPerCta] {M, tl_point}
     __shared__ __align__(8) unsigned long long mbar[3];
+    __shared__ int tile_done[2];
     __shared__ int s_band, s_nan, s_cand;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -429,7 +433,9 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     const int n_end = min(nnodes, n_begin + a.chunk_nodes);
     const int line_base = blockIdx.x * kLinesPerCta;
     unsigned *wq = reinterpret_cast<unsigned *>(dsm + kOffQueue) + wid * kWarpQueue;
-    unsigned *nq = reinterpret_cast<unsigned *>(dsm + kOffNodeQ) + wid * kNodeQueue;
+    // the (line, node) queue: in kPerNode mode the main loop fills it directly and it takes over the larger region
+    constexpr int kNodeCap = kPerNode ? kWarpQueue : kNodeQueue;
+    unsigned *nq = kPerNode ? wq : reinterpret_cast<unsigned *>(dsm + kOffNodeQ) + wid * kNodeQueue;
     unsigned *xq = reinterpret_cast<unsigned *>(dsm + kOffExact) + wid * kExactQueue;
 
     if (tid == 0) {
@@ -438,6 +444,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         mbar_init(&mbar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_band = 0; s_nan = 0; s_cand = 0;
+        tile_done[0] = 0; tile_done[1] = 0;
     }
 
     // ---- per-thread lines -> filter thresholds ------------------------------------------------------------
@@ -489,6 +496,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     const float4 *pts = pts_in_smem ? spts : pt4_c;
     if (tid == 0) {
         issue(0);
+        if (ntiles > 1) issue(1);
         if (pts_in_smem) {
             const unsigned bytes = (unsigned)(n_end - n_begin) * (kNode + 1) * 16u;
             mbar_expect_tx(&mbar[2], bytes);
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     auto run_groups = [&]() {
         __syncwarp();
         for (int base = 0; base < wq_cnt; base += 32) {
-            if (nq_cnt + 128 > kNodeQueue) run_nodes();
+            if (nq_cnt + 128 > kNodeCap) run_nodes();
             unsigned nm = 0, key = 0;
             if (base + lane < wq_cnt) {
                 const unsigned ent = wq[base + lane];
@@ -601,7 +609,6 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     };
 
     for (int t = 0; t < ntiles; ++t) {
-        if (tid == 0 && t + 1 < ntiles) issue(t + 1);
         mbar_wait(&mbar[t & 1], (t >> 1) & 1);
         const int nn = min(kTileNodes, n_end - (n_begin + t * kTileNodes));      // multiple of kNodePad
         const float4 *sp = stage + (t & 1) * kStageF4;
@@ -609,9 +616,12 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         const int group0 = t * (kTileNodes / 4);
         for (int w0 = 0; w0 < ngroups; w0 += 32) {
             const int ng = min(32, ngroups - w0);
-            unsigned m[kLinesPerThread];
+            constexpr int kMasks = kPerNode ? 4 : 1;
+            unsigned m[kLinesPerThread][kMasks];
 #pragma unroll
-            for (int i = 0; i < kLinesPerThread; ++i) m[i] = 0u;
+            for (int i = 0; i < kLinesPerThread; ++i)
+#pragma unroll
+                for (int q = 0; q < kMasks; ++q) m[i][q] = 0u;
 #pragma unroll 2
             for (int gi = 0; gi < ng; ++gi) {
                 // 4 nodes = two interleaved pairs: {xA,xB,yA,yB} {zA,zB,wA,wB}
@@ -629,15 +639,61 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
                     const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
                     const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
                     const float2 qb = __ffma2_rn(tb, tb, sb);
-                    const float qmax = fmaxf(fmaxf(qa.x, qa.y), fmaxf(qb.x, qb.y));
-                    m[i] |= (qmax > tl[i]) ? bit : 0u;
+                    if constexpr (kPerNode) {
+                        m[i][0] |= (qa.x > tl[i]) ? bit : 0u;
+                        m[i][1] |= (qa.y > tl[i]) ? bit : 0u;
+                        m[i][2] |= (qb.x > tl[i]) ? bit : 0u;
+                        m[i][3] |= (qb.y > tl[i]) ? bit : 0u;
+                    } else {
+                        const float qmax = fmaxf(fmaxf(qa.x, qa.y), fmaxf(qb.x, qb.y));
+                        m[i][0] |= (qmax > tl[i]) ? bit : 0u;
+                    }
                 }
             }
-            // ordered push of the fired (line, group) pairs
+            // ordered push of the fired pairs
 #pragma unroll
             for (int i = 0; i < kLinesPerThread; ++i) {
-                unsigned mi = m[i];
-                if (__any_sync(0xffffffffu, mi != 0u)) {
+                const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
+                if constexpr (kPerNode) {
+                    const int c = __popc(m[i][0]) + __popc(m[i][1]) + __popc(m[i][2]) + __popc(m[i][3]);   // <= 128
+                    if (!__any_sync(0xffffffffu, c != 0)) continue;
+                    ncand += c;
+                    int total;
+                    const int off = warp_excl_scan<8>(c, lane, total);
+                    if (total <= kNodeCap) {
+                        if (nq_cnt + total > kNodeCap) run_nodes();
+                        int pos = nq_cnt + off;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            unsigned mm = m[i][q];
+                            while (mm) {
+                                const int gi = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                nq[pos++] = (lrel << 22) | (unsigned)((group0 + w0 + gi) * 4 + q);
+                            }
+                        }
+                        nq_cnt += total;
+                    } else {                                       // rare: more than a queue-full from one window
+#pragma unroll 1
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll 1
+                            for (int half = 0; half < 2; ++half) {
+                                unsigned mh = half ? (m[i][q] >> 16) : (m[i][q] & 0xFFFFu);
+                                int tot2;
+                                const int off2 = warp_excl_scan<5>(__popc(mh), lane, tot2);      // <= 32 x 16 = kNodeCap
+                                if (nq_cnt + tot2 > kNodeCap) run_nodes();
+                                int pos = nq_cnt + off2;
+                                while (mh) {
+                                    const int gi = __ffs(mh) - 1 + half * 16;
+                                    mh &= mh - 1;
+                                    nq[pos++] = (lrel << 22) | (unsigned)((group0 + w0 + gi) * 4 + q);
+                                }
+                                nq_cnt += tot2;
+                            }
+                    }
+                } else {
+                    const unsigned mi = m[i][0];
+                    if (!__any_sync(0xffffffffu, mi != 0u)) continue;
                     ncand += __popc(mi);
                     // two halves of 16 groups: each appends <= 32 lanes x 16 groups = kWarpQueue entries
 #pragma unroll
@@ -651,16 +707,27 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
                         while (mh) {
                             const int gi = __ffs(mh) - 1 + half * 16;
                             mh &= mh - 1;
-                            wq[pos++] = ((unsigned)(tid + i * kDenseThreads) << 20) | (unsigned)(group0 + w0 + gi);
+                            wq[pos++] = (lrel << 20) | (unsigned)(group0 + w0 + gi);
                         }
                         wq_cnt += total;
                     }
                 }
             }
         }
-        __syncthreads();                       // everyone is done with this stage before it is refilled
+        // stage t&1 is free once every warp is past it: the last warp to arrive refills it with tile t+2 -- no CTA-wide
+        // barrier, so warps with long candidate queues do not hold up the others
+        if (t + 2 < ntiles) {
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&tile_done[t & 1], 1) == kNumWarps - 1) {
+                    tile_done[t & 1] = 0;
+                    issue(t + 2);
+                }
+            }
+        }
     }
-    run_groups();
+    if constexpr (!kPerNode) run_groups();
     run_nodes();
     run_exact();
 
@@ -680,8 +747,9 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
 int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
-        if (cudaFuncSetAttribute(dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
+        if (cudaFuncSetAttribute(dense_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
+        if (cudaFuncSetAttribute(dense_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
+        if (cudaFuncSetAttribute(dense_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
         attr_set = true;
     }
     DenseArgs a;
@@ -702,8 +770,9 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     chunks = (nn_max + chunk_nodes - 1) / chunk_nodes;
     a.chunk_nodes = chunk_nodes;
     dim3 grid(line_tiles, chunks, g.B * 2);
-    if (G == 8) dense_kernel<8><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
-    else dense_kernel<16><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
+    if (G == 8 && g_param[4] == 0) dense_kernel<8, true><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
+    else if (G == 8) dense_kernel<8, false><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
+    else dense_kernel<16, false><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
     count_launch();
     return check_launch();
 }

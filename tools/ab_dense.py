@@ -11,7 +11,9 @@ import rrl_b200
 from oracle import synth
 
 L = rrl_b200._native.lib()
-CONFIGS = {"demo": (1, 1024, 20000), "dcp": (32, 1024, 15000), "rpm": (64, 2048, 10000), "large": (1, 500000, 100000)}
+WAVES = (16, 32, 64, 128)
+CHUNKS = (16, 32)
+CONFIGS = {"fmr": (128, 1024, 15000), "demo": (1, 1024, 20000), "dcp": (32, 1024, 15000), "rpm": (64, 2048, 10000), "large": (1, 500000, 100000)}
 
 
 def batch(B, nf, nl):
@@ -35,8 +37,8 @@ for name in (sys.argv[1:] or ["dcp", "large", "rpm", "demo"]):
     t1, t2, ln = batch(B, nf, nl)
     res = {}
     for G in (8, 16):
-        for waves in (4, 8, 16):
-            for minch in (32, 64, 128):
+        for waves in WAVES:
+            for minch in CHUNKS:
                 L.rrl_debug_set_param(1, G); L.rrl_debug_set_param(2, waves); L.rrl_debug_set_param(3, minch)
                 d, p = dense_ms(t1, t2, ln, B, nf, nl, 5)
                 res["G%d_w%d_c%d" % (G, waves, minch)] = round(d, 4)
