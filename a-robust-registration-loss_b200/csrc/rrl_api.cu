@@ -13,6 +13,14 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int check_launch() { return cudaGetLastError() == cudaSuccess ? RRL_OK : RRL_ERR_CUDA; }
 void set_dense_variant(int v);
+
+// ---- per-stage timing hook (rrl_measure_stages) ----
+constexpr int kStages = 10;
+static bool g_timing = false;
+static cudaEvent_t g_ev[kStages + 1];
+void stage_mark(int stage, cudaStream_t s) {
+    if (g_timing && stage >= 0 && stage <= kStages) cudaEventRecord(g_ev[stage], s);
+}
 void set_param(int id, int v);
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -126,11 +134,13 @@ extern "C" int rrl_loss_forward(const float *tri1, const float *tri2, const floa
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
     const Geometry g = make_geometry(B, nf1, nf2, nl);
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = stage_dense_and_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, s);
+    const int window = k_lo | (j_lo << 8) | (k_hi << 16) | (j_hi << 24);
+    int rc = launch_prep(tri1, tri2, lines, ws, g, window, s);
     if (rc) return rc;
+    if ((rc = launch_dense(tri1, tri2, lines, ws, g, s))) return rc;
+    if ((rc = launch_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, s))) return rc;
     if ((rc = launch_median(ws, g, s))) return rc;
-    if ((rc = launch_welsch(ws, g, s))) return rc;
-    return launch_finalize(ws, g, out_loss, out_status, out_median, out_stats, s);
+    return launch_welsch_finalize(ws, g, out_loss, out_status, out_median, out_stats, s);
 }
 
 extern "C" int rrl_loss_backward(const void *workspace, size_t workspace_bytes, const float *grad_out, int B, int nf1,
@@ -333,4 +343,45 @@ extern "C" int rrl_debug_set_dense_variant(int v) {
 extern "C" int rrl_debug_set_param(int id, int value) {
     set_param(id, value);
     return RRL_OK;
+}
+
+// Per-stage device times (ms, CUDA events, averaged over `iters` hot repetitions) of forward + backward:
+// out_ms[0..9] = {memset+prep, sort, node, dense, select, build, median, welsch+finalize, backward, total}
+extern "C" int rrl_measure_stages(const float *tri1, const float *tri2, const float *lines, int B, int nf1, int nf2, int nl,
+                                  void *workspace, size_t workspace_bytes, int iters, float *out_ms, void *stream) {
+    if (!tri1 || !tri2 || !lines || !workspace || !out_ms || iters <= 0 || !geometry_ok(B, nf1, nf2, nl)) return RRL_ERR_ARG;
+    if (workspace_bytes < rrl_workspace_bytes(B, nf1, nf2, nl)) return RRL_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    float *loss = nullptr, *gout = nullptr, *grad = nullptr;
+    int *status = nullptr;
+    if (cudaMalloc(&loss, 4 * (size_t)B) != cudaSuccess || cudaMalloc(&gout, 4 * (size_t)B) != cudaSuccess ||
+        cudaMalloc(&status, 4 * (size_t)B) != cudaSuccess || cudaMalloc(&grad, 36 * (size_t)B * nf1) != cudaSuccess)
+        return RRL_ERR_CUDA;
+    cudaMemset(gout, 0, 4 * (size_t)B);
+    for (int i = 0; i <= kStages; ++i) cudaEventCreate(&g_ev[i]);
+    double acc[kStages] = {0};
+    int rc = RRL_OK;
+    for (int it = 0; it < iters + 2 && rc == RRL_OK; ++it) {
+        g_timing = true;
+        stage_mark(0, s);
+        rc = rrl_loss_forward(tri1, tri2, lines, B, nf1, nf2, nl, 1, 1, 5, 5, workspace, workspace_bytes, loss, status, nullptr, nullptr, s);
+        if (rc == RRL_OK) rc = rrl_loss_backward(workspace, workspace_bytes, gout, B, nf1, nf2, nl, grad, nullptr, s);
+        stage_mark(10, s);
+        g_timing = false;
+        cudaEventSynchronize(g_ev[10]);
+        if (it >= 2) {
+            for (int i = 0; i < 9; ++i) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, g_ev[i], g_ev[i + 1]);
+                acc[i] += ms;
+            }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, g_ev[0], g_ev[10]);
+            acc[9] += ms;
+        }
+    }
+    for (int i = 0; i < kStages; ++i) out_ms[i] = (float)(acc[i] / iters);
+    for (int i = 0; i <= kStages; ++i) cudaEventDestroy(g_ev[i]);
+    cudaFree(loss); cudaFree(gout); cudaFree(status); cudaFree(grad);
+    return rc;
 }

@@ -56,7 +56,7 @@ struct Workspace {
     int *nrec;               // (B)
     int *n_kj;               // (B,16)
     float *med;              // (B)
-    int *flags;              // (B,2): {NaN seen in the Welsch stage, reserved}
+    int *flags;              // (B,2): {NaN seen in the Welsch stage, block ticket of the Welsch stage}
     unsigned long long *sums;// (B,32): S1[16], S2[16] fixed point
     long long *stats;        // (B, RRL_NSTAT)
     long long *gcounts;      // (B,18) global counts used by welsch/finalize/backward (== local unless line-sharded)
@@ -76,7 +76,7 @@ struct Workspace {
     int *recMeta;            // (cap,2): {line, k | j<<8 | argmins<<16}
     int *recIdx;             // (cap,8)
     float *recW;             // (cap,24): w1[4][3], w2[4][3]
-    float *recQ;             // (cap,24): q1[4][3], q2[4][3]
+    float *recQ;             // (cap,24): q1[4][3], q2[4][3]; overwritten by the gradient vectors G1, G2 in the Welsch stage
     size_t bytes;
 };
 
@@ -91,6 +91,7 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl);
 // ---- launch bookkeeping -------------------------------------------------------------------------------
 void count_launch(int n = 1);
 int check_launch();          // cudaGetLastError -> RRL_OK / RRL_ERR_CUDA
+void stage_mark(int stage, cudaStream_t s);   // measurement hook: records an event after stage `stage` when enabled
 
 // ---- stage launchers (rrl_dense.cu, rrl_sparse.cu) ------------------------------------------------------
 int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
@@ -103,6 +104,8 @@ int launch_median(const Workspace &ws, const Geometry &g, cudaStream_t s);
 int launch_welsch(const Workspace &ws, const Geometry &g, cudaStream_t s);
 int launch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
                     long long *out_stats, cudaStream_t s);
+int launch_welsch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
+                           long long *out_stats, cudaStream_t s);
 int launch_backward(const Workspace &ws, const Geometry &g, const float *grad_out, float *g1, float *g2, cudaStream_t s);
 int launch_export_hits(const Workspace &ws, const Geometry &g, int cloud, int *out_counts, int *out_hits, cudaStream_t s);
 int launch_pack_entries(const Workspace &ws, const Geometry &g, float *out, long long cap, cudaStream_t s);

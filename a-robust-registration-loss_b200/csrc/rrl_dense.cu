@@ -281,6 +281,7 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     if (bx < 1) bx = 1;
     prep_kernel<<<dim3(bx, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, window);
     count_launch();
+    stage_mark(1, s);
     const int sorted = g_dense_variant ? 1 : 0;
     const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
     if (nfp_max <= kSortSmall) {
@@ -309,6 +310,7 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
                 count_launch(4);
             }
     }
+    stage_mark(2, s);
     const int G = node_size(g);
     const int nn_max = nfp_max / G;
     int nbx = (nn_max + 127) / 128;
@@ -316,6 +318,7 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 128, 0, s>>>(tri1, tri2, ws, g);
     else node_kernel<16><<<dim3(nbx, g.B * 2), 128, 0, s>>>(tri1, tri2, ws, g);
     count_launch();
+    stage_mark(3, s);
     return check_launch();
 }
 
@@ -774,6 +777,7 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     else if (G == 8) dense_kernel<8, false><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
     else dense_kernel<16, false><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
     count_launch();
+    stage_mark(4, s);
     return check_launch();
 }
 

@@ -193,6 +193,10 @@ int rrl_measure_dense(const float *tri1, const float *tri2, const float *lines, 
                       void *workspace, size_t workspace_bytes, int iters, float *out_ms_dense, float *out_ms_prep,
                       void *stream);
 
+/* per-stage device times (ms) of forward + backward to points1, averaged over `iters` hot repetitions:
+ * out_ms[10] = {memset+prep, sort, node, dense, select, build, median, welsch+finalize, backward, total}; synchronises */
+int rrl_measure_stages(const float *tri1, const float *tri2, const float *lines, int B, int nf1, int nf2, int nl,
+                       void *workspace, size_t workspace_bytes, int iters, float *out_ms, void *stream);
 /* selects the dense-stage variant: 1 = Morton-sorted bounding-sphere nodes (default), 0 = nodes in input order.
  * Results are identical; measurement / A-B testing only. */
 int rrl_debug_set_dense_variant(int variant);
