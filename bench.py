@@ -87,52 +87,96 @@ def make_inputs(workload, rank, n_sets, n_base=None):
 # clocks
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event reasons sampled DURING the timed region.
 
-    def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(prefix="rrl_clocks_", suffix=".csv")
-        self.proc = None
+    A step lasts well under a millisecond, so `nvidia-smi -lms 100` would return nothing for a short run: NVML is polled
+    in-process from a thread every 2 ms instead (the ctypes calls drop the GIL); nvidia-smi is the fallback."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu_index, period_s=0.002):
+        import threading
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._thread, self._smi, self._path = None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = [(pynvml.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                    (pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                    (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                    (pynvml.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for bit, nme in bits:
+                            if r & bit:
+                                self.reasons.add(nme)
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    except Exception:
+                        pass
+                    self._stop.wait(period_s)
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._thread = None
+            try:
+                self._path = tempfile.mktemp(prefix="rrl_clocks_", suffix=".csv")
+                fields = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                          "clocks_event_reasons.sw_power_cap")
+                self._smi = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + fields,
+                                              "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=open(self._path, "w"), stderr=subprocess.DEVNULL)
+            except Exception:
+                self._smi = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, reasons, mx = [], set(), None
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for row in open(self.path):
-                f = [x.strip() for x in row.split(",")]
-                if len(f) < 7:
-                    continue
-                try:
-                    sm.append(float(f[0]))
-                    mx = float(f[1])
-                except ValueError:
-                    continue
-                for nme, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-            out["sm_max_mhz"] = mx
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            out["source"] = "nvml polled every 2 ms inside the timed region"
+        elif self._smi is not None:
+            self._smi.terminate()
+            try:
+                self._smi.wait(timeout=5)
+            except Exception:
+                self._smi.kill()
+            try:
+                for row in open(self._path):
+                    f = [x.strip() for x in row.split(",")]
+                    if len(f) < 7:
+                        continue
+                    try:
+                        self.samples.append(float(f[0]))
+                        self.max_mhz = float(f[1])
+                    except ValueError:
+                        continue
+                    for nme, v in zip(self.NAMES, f[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(nme)
+                os.unlink(self._path)
+            except Exception:
+                pass
+            out["source"] = "nvidia-smi -lms 20"
+        if self.samples:
+            out["sm_mhz"] = float(np.median(self.samples))
+            out["sm_min_mhz"] = float(np.min(self.samples))
+            out["samples"] = len(self.samples)
+        if self.power:
+            out["power_w"] = float(np.median(self.power))
+        out["sm_max_mhz"] = self.max_mhz
+        out["reasons"] = sorted(self.reasons)
         return out
 
 
@@ -374,8 +418,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dcp", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
