@@ -2,6 +2,7 @@
 // sequencing on the caller's stream, the line-shard stage API and the host-buffer convenience context.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -38,14 +39,15 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     const int nf1p = pad_points(nf1), nf2p = pad_points(nf2);
     w.hdr = reinterpret_cast<int *>(take(8 * sizeof(int)));
     // ---- per-pair block, contiguous and zeroed by one memset in launch_prep (order matters) ----
-    char *pair = take(sB * (3 * 2 * 4 + 4 + 16 * 4 + 4 + 2 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
+    char *pair = take(16 + sB * (3 * 2 * 4 + 4 + 16 * 4 + 4 + 4 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
+    w.xcursor = reinterpret_cast<unsigned long long *>(pair);         pair += 16;
     w.pmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.xmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.rmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.nrec = reinterpret_cast<int *>(pair);                           pair += sB * 4;
     w.n_kj = reinterpret_cast<int *>(pair);                           pair += sB * 16 * 4;
     w.med = reinterpret_cast<float *>(pair);                          pair += sB * 4;
-    w.flags = reinterpret_cast<int *>(pair);                          pair += sB * 2 * 4;
+    w.flags = reinterpret_cast<int *>(pair);                          pair += sB * 4 * 4;
     w.sums = reinterpret_cast<unsigned long long *>(pair);            pair += sB * 32 * 8;
     w.stats = reinterpret_cast<long long *>(pair);                    pair += sB * RRL_NSTAT * 8;
     w.gcounts = reinterpret_cast<long long *>(pair);
@@ -57,6 +59,8 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     // triplet records: kNode + 1 float4 per node; node records: 5 float4 per group of 4 nodes (sized for kMinNode)
     w.pt4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kMinNode) * (kMinNode + 1) * sizeof(float4)));
     w.pt4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kMinNode) * (kMinNode + 1) * sizeof(float4)));
+    w.pt12[0] = reinterpret_cast<float4 *>(take(sB * nf1p * 2 * sizeof(float4)));
+    w.pt12[1] = reinterpret_cast<float4 *>(take(sB * nf2p * 2 * sizeof(float4)));
     w.node4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kMinNode / 4) * 5 * sizeof(float4)));
     w.node4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kMinNode / 4) * 5 * sizeof(float4)));
     w.sortbuf_bytes = sort_scratch_bytes(nf1p > nf2p ? nf1p : nf2p);
@@ -67,6 +71,8 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.cnt[1] = w.cnt[0] + lines;
     w.hits[0] = reinterpret_cast<int *>(take(lines * kCap * sizeof(int)));
     w.hits[1] = reinterpret_cast<int *>(take(lines * kCap * sizeof(int)));
+    w.xcap = (long long)lines * kExactPerLine;
+    w.xcand = reinterpret_cast<uint2 *>(take((size_t)w.xcap * sizeof(uint2)));
     // ---- per record ----
     w.recD = reinterpret_cast<float *>(take(lines * 16 * sizeof(float)));
     w.recMeta = reinterpret_cast<int *>(take(lines * 2 * sizeof(int)));
@@ -219,26 +225,44 @@ extern "C" int rrl_shard_stage3(void *workspace, size_t workspace_bytes, int nf1
 }
 
 // ---- host-buffer context ---------------------------------------------------------------------------------
+// The batch is cut into up to kMaxSub sub-batches of whole pairs (pairs are independent), each with its own stream
+// and workspace: the H2D copy of sub-batch s+1 runs under the kernels of sub-batch s, and the latency-bound sparse
+// stages of one sub-batch run under the dense stage of the next.
+constexpr int kMaxSub = 8;
 struct rrl_host_ctx {
-    int B, nf1, nf2, nl, device;
-    size_t n_tri1, n_tri2, n_lines, ws_bytes;
+    int B, nf1, nf2, nl, device, S;
+    int first[kMaxSub + 1];                      // pairs [first[s], first[s+1]) form sub-batch s
+    size_t n_tri1, n_tri2, n_lines;
+    size_t ws_bytes[kMaxSub];
     float *d_tri1, *d_tri2, *d_lines, *d_loss, *d_gout, *d_grad1;
     int *d_status;
-    void *d_ws;
+    void *d_ws[kMaxSub];
     float *p_tri1, *p_tri2, *p_lines, *p_loss, *p_grad1;
     int *p_status;
-    cudaStream_t stream;
+    cudaStream_t stream[kMaxSub];
 };
+
+static int host_subbatches(int B) {
+    int S = B / 8;                               // >= 8 pairs per sub-batch keep the dense grids full
+    if (const char *e = getenv("RRL_HOST_SUBBATCHES")) S = atoi(e);
+    if (S > kMaxSub) S = kMaxSub;
+    if (S > B) S = B;
+    if (S < 1) S = 1;
+    return S;
+}
 
 extern "C" void rrl_host_destroy(rrl_host_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int s = 0; s < c->S; ++s)
+        if (c->stream[s]) cudaStreamSynchronize(c->stream[s]);
     cudaFree(c->d_tri1); cudaFree(c->d_tri2); cudaFree(c->d_lines); cudaFree(c->d_loss); cudaFree(c->d_gout);
-    cudaFree(c->d_grad1); cudaFree(c->d_status); cudaFree(c->d_ws);
+    cudaFree(c->d_grad1); cudaFree(c->d_status);
+    for (int s = 0; s < c->S; ++s) cudaFree(c->d_ws[s]);
     cudaFreeHost(c->p_tri1); cudaFreeHost(c->p_tri2); cudaFreeHost(c->p_lines); cudaFreeHost(c->p_loss);
     cudaFreeHost(c->p_grad1); cudaFreeHost(c->p_status);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    for (int s = 0; s < c->S; ++s)
+        if (c->stream[s]) cudaStreamDestroy(c->stream[s]);
     delete c;
 }
 
@@ -249,13 +273,19 @@ extern "C" int rrl_host_create(int B, int nf1, int nf2, int nl, int device, rrl_
     if (!c) return RRL_ERR_CUDA;
     std::memset(c, 0, sizeof(*c));
     c->B = B; c->nf1 = nf1; c->nf2 = nf2; c->nl = nl; c->device = device;
+    c->S = host_subbatches(B);
+    for (int s = 0; s <= c->S; ++s) c->first[s] = (int)((long long)B * s / c->S);
     c->n_tri1 = (size_t)B * nf1 * 9; c->n_tri2 = (size_t)B * nf2 * 9; c->n_lines = (size_t)B * nl * 6;
-    c->ws_bytes = rrl_workspace_bytes(B, nf1, nf2, nl);
-    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    bool ok = true;
+    for (int s = 0; s < c->S && ok; ++s) {
+        c->ws_bytes[s] = rrl_workspace_bytes(c->first[s + 1] - c->first[s], nf1, nf2, nl);
+        ok = cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaMalloc(&c->d_ws[s], c->ws_bytes[s]) == cudaSuccess;
+    }
     ok = ok && cudaMalloc(&c->d_tri1, c->n_tri1 * 4) == cudaSuccess && cudaMalloc(&c->d_tri2, c->n_tri2 * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_lines, c->n_lines * 4) == cudaSuccess && cudaMalloc(&c->d_loss, (size_t)B * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_gout, (size_t)B * 4) == cudaSuccess && cudaMalloc(&c->d_grad1, c->n_tri1 * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_status, (size_t)B * 4) == cudaSuccess && cudaMalloc(&c->d_ws, c->ws_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_status, (size_t)B * 4) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->p_tri1, c->n_tri1 * 4) == cudaSuccess && cudaMallocHost(&c->p_tri2, c->n_tri2 * 4) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->p_lines, c->n_lines * 4) == cudaSuccess && cudaMallocHost(&c->p_loss, (size_t)B * 4) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->p_grad1, c->n_tri1 * 4) == cudaSuccess && cudaMallocHost(&c->p_status, (size_t)B * 4) == cudaSuccess;
@@ -274,27 +304,43 @@ extern "C" int rrl_host_create(int B, int nf1, int nf2, int nl, int device, rrl_
 extern "C" float *rrl_host_pinned_tri1(rrl_host_ctx *c) { return c ? c->p_tri1 : nullptr; }
 extern "C" float *rrl_host_pinned_tri2(rrl_host_ctx *c) { return c ? c->p_tri2 : nullptr; }
 extern "C" float *rrl_host_pinned_lines(rrl_host_ctx *c) { return c ? c->p_lines : nullptr; }
+extern "C" int rrl_host_subbatches(rrl_host_ctx *c) { return c ? c->S : 0; }
 
 extern "C" int rrl_host_loss_fwd_bwd(rrl_host_ctx *c, const float *h_tri1, const float *h_tri2, const float *h_lines,
                                      int k_lo, int j_lo, int k_hi, int j_hi, float *h_loss, int *h_status, float *h_grad_tri1) {
     if (!c || !h_tri1 || !h_tri2 || !h_lines || !h_loss) return RRL_ERR_ARG;
     if (cudaSetDevice(c->device) != cudaSuccess) return RRL_ERR_CUDA;
+    const size_t t1 = (size_t)c->nf1 * 9, t2 = (size_t)c->nf2 * 9, tl = (size_t)c->nl * 6;
     // straight from the caller's memory: asynchronous when it is pinned (the context's own buffers or any
-    // cudaHostAlloc/cudaHostRegister'ed range), staged by the driver when it is pageable
-    cudaStream_t s = c->stream;
-    bool ok = cudaMemcpyAsync(c->d_tri1, h_tri1, c->n_tri1 * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(c->d_tri2, h_tri2, c->n_tri2 * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(c->d_lines, h_lines, c->n_lines * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    // cudaHostAlloc/cudaHostRegister'ed range), staged by the driver when it is pageable.  All copies are queued
+    // first, in sub-batch order, so that the copy engine never waits for the host to get through the launches.
+    bool ok = true;
+    for (int s = 0; s < c->S && ok; ++s) {
+        const size_t b0 = (size_t)c->first[s], nb = (size_t)(c->first[s + 1] - c->first[s]);
+        cudaStream_t st = c->stream[s];
+        ok = cudaMemcpyAsync(c->d_tri1 + b0 * t1, h_tri1 + b0 * t1, nb * t1 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(c->d_tri2 + b0 * t2, h_tri2 + b0 * t2, nb * t2 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(c->d_lines + b0 * tl, h_lines + b0 * tl, nb * tl * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    }
     if (!ok) return RRL_ERR_CUDA;
-    int rc = rrl_loss_forward(c->d_tri1, c->d_tri2, c->d_lines, c->B, c->nf1, c->nf2, c->nl, k_lo, j_lo, k_hi, j_hi, c->d_ws,
-                              c->ws_bytes, c->d_loss, c->d_status, nullptr, nullptr, s);
-    if (rc) return rc;
-    rc = rrl_loss_backward(c->d_ws, c->ws_bytes, c->d_gout, c->B, c->nf1, c->nf2, c->nl, c->d_grad1, nullptr, s);
-    if (rc) return rc;
-    ok = cudaMemcpyAsync(c->p_loss, c->d_loss, (size_t)c->B * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(c->p_status, c->d_status, (size_t)c->B * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
-    if (h_grad_tri1) ok = ok && cudaMemcpyAsync(c->p_grad1, c->d_grad1, c->n_tri1 * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
-    ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+    for (int s = 0; s < c->S; ++s) {
+        const size_t b0 = (size_t)c->first[s];
+        const int nb = c->first[s + 1] - c->first[s];
+        cudaStream_t st = c->stream[s];
+        int rc = rrl_loss_forward(c->d_tri1 + b0 * t1, c->d_tri2 + b0 * t2, c->d_lines + b0 * tl, nb, c->nf1, c->nf2, c->nl,
+                                  k_lo, j_lo, k_hi, j_hi, c->d_ws[s], c->ws_bytes[s], c->d_loss + b0, c->d_status + b0, nullptr,
+                                  nullptr, st);
+        if (rc) return rc;
+        rc = rrl_loss_backward(c->d_ws[s], c->ws_bytes[s], c->d_gout + b0, nb, c->nf1, c->nf2, c->nl, c->d_grad1 + b0 * t1,
+                               nullptr, st);
+        if (rc) return rc;
+        ok = cudaMemcpyAsync(c->p_loss + b0, c->d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(c->p_status + b0, c->d_status + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        if (h_grad_tri1)
+            ok = ok && cudaMemcpyAsync(c->p_grad1 + b0 * t1, c->d_grad1 + b0 * t1, (size_t)nb * t1 * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        if (!ok) return RRL_ERR_CUDA;
+    }
+    for (int s = 0; s < c->S; ++s) ok = (cudaStreamSynchronize(c->stream[s]) == cudaSuccess) && ok;
     if (!ok) return RRL_ERR_CUDA;
     std::memcpy(h_loss, c->p_loss, (size_t)c->B * 4);
     if (h_status) std::memcpy(h_status, c->p_status, (size_t)c->B * 4);

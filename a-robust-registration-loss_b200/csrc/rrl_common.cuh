@@ -31,11 +31,12 @@ constexpr float kEps24 = 5.9604645e-8f;
 constexpr int kDenseThreads = 256;
 constexpr int kLinesPerThread = 4;
 constexpr int kLinesPerCta = kDenseThreads * kLinesPerThread;   // 1024
-constexpr int kTileNodes = 512;                                 // float4 per node: 8 KB per stage
+constexpr int kTileNodes = 256;                                 // 5 float4 per 4 nodes: 5 KB per stage
 constexpr int kNodePad = 16;                                    // node arrays are padded to this multiple (sentinels)
 constexpr int kPointPad = 256;                                  // triplet arrays padded to 16 nodes of 16 (= 32 nodes of 8)
 constexpr int kMinNode = 8;                                     // smallest node size (sizes the node arrays)
 constexpr int kWarpQueue = 512;                                 // candidate (line, node group) entries per warp
+constexpr int kExactPerLine = 12;                               // capacity of the exact-candidate queue, entries per line
 constexpr int kSortSmall = 4096;                                // clouds up to this many (padded) triplets sort in one CTA
 
 // ---- fixed-point accumulation of Welsch sums (order-independent, hence run-to-run deterministic) ---
@@ -49,14 +50,16 @@ struct Geometry {
 // One forward's scratch, carved out of the caller's workspace.  All pointers are device pointers.
 struct Workspace {
     int *hdr;                // [8]: {magic, B, nf1, nf2, nl, window, 0, 0}
-    // per pair (one contiguous block, zeroed by a single memset)
+    // launch-wide + per pair (one contiguous block, zeroed by a single memset)
+    unsigned long long *xcursor; // [2]: {entries reserved in xcand, reserved}
     unsigned int *pmax;      // (B,2): bits of max |p|^2 over all 3 points of all triplets of the cloud
     unsigned int *xmax;      // (B,2): [0] bits of max |x0|^2 over the pair's lines, [1] reserved
     unsigned int *rmax;      // (B,2): bits of the largest node radius of the cloud
     int *nrec;               // (B)
     int *n_kj;               // (B,16)
     float *med;              // (B)
-    int *flags;              // (B,2): {NaN seen in the Welsch stage, block ticket of the Welsch stage}
+    int *flags;              // (B,4): {NaN seen in the Welsch stage, block ticket of the Welsch stage,
+                             //         reserved, reserved}
     unsigned long long *sums;// (B,32): S1[16], S2[16] fixed point
     long long *stats;        // (B, RRL_NSTAT)
     long long *gcounts;      // (B,18) global counts used by welsch/finalize/backward (== local unless line-sharded)
@@ -64,6 +67,7 @@ struct Workspace {
     float *thr[2];           // (B, nf): exact reference threshold, original order
     int *perm[2];            // (B, nfp): sorted position -> original triplet index (-1 = padding)
     float4 *pt4[2];          // (B, nnodes, node_size + 1): sorted order, pair-interleaved {p0.xyz, cut - |p0|^2}, 1 pad per node
+    float4 *pt12[2];         // (B, nfp, 2): sorted order, {p1.xyz, cut - |p1|^2}, {p2.xyz, cut - |p2|^2}
     float4 *node4[2];        // (B, nnodes/4, 5): pair-interleaved {xA,xB,yA,yB}{zA,zB,wA,wB} x2 + 1 pad; w = R^2 - |q|^2
     unsigned long long *sortbuf; // scratch for the large-cloud sort (keys/values double buffers + cub temp)
     size_t sortbuf_bytes;
@@ -71,6 +75,8 @@ struct Workspace {
     float4 *lineC;           // (B, nl, 2): {u.xyz, |x0|}, {M.xyz, c}
     int *cnt[2];             // (B, nl) hit counters
     int *hits[2];            // (B, nl, kCap)
+    uint2 *xcand;            // (xcap): (line, triplet) pairs that passed the filters: {b*nl + l, f | cloud << 31}
+    long long xcap;
     // per record (capacity B*nl)
     float *recD;             // (cap,16)
     int *recMeta;            // (cap,2): {line, k | j<<8 | argmins<<16}
@@ -96,6 +102,8 @@ void stage_mark(int stage, cudaStream_t s);   // measurement hook: records an ev
 // ---- stage launchers (rrl_dense.cu, rrl_sparse.cu) ------------------------------------------------------
 int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                 int window, cudaStream_t s);
+int launch_bruteforce(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
+                      int force, cudaStream_t s);
 int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s);
 int launch_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                  int k_lo, int j_lo, int k_hi, int j_hi, cudaStream_t s);

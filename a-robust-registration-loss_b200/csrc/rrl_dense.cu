@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri
     const double Xm = sqrt((double)__uint_as_float(ws.xmax[b * 2])) * 1.000001;
     const double E = (double)kGuardRef * (double)kEps24 * (P + Xm) * (P + Xm) + 1e-12;
     float4 *pt_base = ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1);
+    float4 *pt12 = ws.pt12[cloud] + (long long)b * nfp * 2;
     for (int base = blockIdx.x * blockDim.x; base < nnodes; base += gridDim.x * blockDim.x) {   // warp-uniform trip count
         const int n = base + threadIdx.x;
         float rad = 0.f;
@@ -213,15 +214,22 @@ __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri
                 for (int s = 0; s < kNode; ++s) {
                     const int f = perm[n * kNode + s];
                     float4 pr = make_float4(0.f, 0.f, 0.f, -INFINITY);
+                    float4 pr1 = pr, pr2 = pr;
                     if (f >= 0) {
                         const double px = __ldg(tri + (long long)f * 9), py = __ldg(tri + (long long)f * 9 + 1), pz = __ldg(tri + (long long)f * 9 + 2);
                         const double th = __ldg(thr + f);
                         const double cut = th * th - (double)kAddEps;
                         pr = make_float4((float)px, (float)py, (float)pz, (float)(cut - (px * px + py * py + pz * pz)));
+                        const double ax = __ldg(tri + (long long)f * 9 + 3), ay = __ldg(tri + (long long)f * 9 + 4), az = __ldg(tri + (long long)f * 9 + 5);
+                        const double bx = __ldg(tri + (long long)f * 9 + 6), by = __ldg(tri + (long long)f * 9 + 7), bz = __ldg(tri + (long long)f * 9 + 8);
+                        pr1 = make_float4((float)ax, (float)ay, (float)az, (float)(cut - (ax * ax + ay * ay + az * az)));
+                        pr2 = make_float4((float)bx, (float)by, (float)bz, (float)(cut - (bx * bx + by * by + bz * bz)));
                         const double dx = px - qx, dy = py - qy, dz = pz - qz;
                         const double reach = sqrt(fmax(cut + E, 0.0)) + sqrt(dx * dx + dy * dy + dz * dz);
                         R = fmax(R, reach);
                     }
+                    pt12[((long long)n * kNode + s) * 2] = pr1;
+                    pt12[((long long)n * kNode + s) * 2 + 1] = pr2;
                     {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB};
                         // a node occupies kNode + 1 float4 (odd stride: lanes reading different nodes hit different banks)
                         float *dp = reinterpret_cast<float *>(pt_base + (long long)n * (kNode + 1) + (s & ~1)) + (s & 1);
@@ -240,6 +248,7 @@ __global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri
                     pt_base[(long long)n * (kNode + 1) + s] = make_float4(0.f, 0.f, 0.f, 0.f);
                     pt_base[(long long)n * (kNode + 1) + s + 1] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
                 }
+                for (int s = 0; s < 2 * kNode; ++s) pt12[(long long)n * kNode * 2 + s] = make_float4(0.f, 0.f, 0.f, -INFINITY);
             }
             pt_base[(long long)n * (kNode + 1) + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);            // pad slot
             // node records: a group of 4 nodes = two interleaved pairs + one pad = 5 float4 (odd stride again)
@@ -259,7 +268,7 @@ size_t sort_scratch_bytes(int nfp_max) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[8] = {0, 0, 16, 32, 0, 0, 0, 0};   // [1] node size override, [2] target waves, [3] min nodes per chunk
+static int g_param[8] = {0, 0, 16, 32, 0, 0, 0, 0};   // [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force
 void set_param(int id, int v) { if (id > 0 && id < 8) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -272,8 +281,8 @@ void set_dense_variant(int v) { g_dense_variant = v; }
 int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                 int window, cudaStream_t s) {
     // per-pair block {pmax ... gcounts} is contiguous, see carve()
-    const size_t pair_bytes = (size_t)((char *)(ws.gcounts + (size_t)g.B * 18) - (char *)ws.pmax);
-    if (cudaMemsetAsync(ws.pmax, 0, pair_bytes, s) != cudaSuccess) return RRL_ERR_CUDA;
+    const size_t pair_bytes = (size_t)((char *)(ws.gcounts + (size_t)g.B * 18) - (char *)ws.xcursor);
+    if (cudaMemsetAsync(ws.xcursor, 0, pair_bytes, s) != cudaSuccess) return RRL_ERR_CUDA;
     const int most = g.nl > g.nf1 ? (g.nl > g.nf2 ? g.nl : g.nf2) : (g.nf1 > g.nf2 ? g.nf1 : g.nf2);
     int bx = (most + 255) / 256;
     const int cap = (148 * 8 + g.B - 1) / g.B;
@@ -378,7 +387,8 @@ __device__ __forceinline__ void exact_test_and_record(const float *__restrict__ 
     }
 }
 
-constexpr int kSmemPtsF4 = 992;        // triplet records (float4, incl. pads) staged in shared memory when a chunk fits
+constexpr int kSmemPtsF4 = 576;        // point-0 records (float4, incl. pads) staged in shared memory when a chunk fits (64 nodes of 8)
+constexpr int kSmemPts12F4 = 1024;     // point-1/2 records of the chunk, staged when the chunk has <= 512 triplets
 constexpr int kStageF4 = (kTileNodes / 4) * 5;                          // float4 per stage: 5 per group of 4 nodes
 constexpr int kNumWarps = kDenseThreads / 32;
 constexpr int kNodeQueue = 256;        // (line, node) entries per warp; one level-1 pass appends <= 128
@@ -388,7 +398,8 @@ constexpr int kOffQueue = kOffLineC + kLinesPerCta * 32;
 constexpr int kOffNodeQ = kOffQueue + kNumWarps * kWarpQueue * 4;
 constexpr int kOffExact = kOffNodeQ + kNumWarps * kNodeQueue * 4;
 constexpr int kOffPoints = kOffExact + kNumWarps * kExactQueue * 4;
-constexpr int kDenseSmem = kOffPoints + kSmemPtsF4 * 16;
+constexpr int kOffPoints12 = kOffPoints + kSmemPtsF4 * 16;
+constexpr int kDenseSmem = kOffPoints12 + kSmemPts12F4 * 16;
 static_assert(2 * (kDenseSmem + 2048) <= 227 * 1024, "two CTAs per SM must fit (dynamic + static + 1 KB reserved each)");
 
 // exclusive prefix sum over the lanes of a (converged) warp of a count c < 2^kBits, by bit planes: kBits independent
@@ -421,11 +432,11 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     extern __shared__ __align__(128) unsigned char dsm[];
     float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kStageF4]
     float4 *spts = reinterpret_cast<float4 *>(dsm + kOffPoints);                           // [kSmemPtsF4]
+    float4 *spts12 = reinterpret_cast<float4 *>(dsm + kOffPoints12);                       // [kSmemPts12F4]
     float4 *slineU = reinterpret_cast<float4 *>(dsm + kOffLineC);                          // [kLinesPerCta] {u, tl_node}
     float4 *slineM = slineU + kLinesPerCta;                                                // [kLinesPerCta] {M, tl_point}
-    __shared__ __align__(8) unsigned long long mbar[3];
+    __shared__ __align__(8) unsigned long long mbar[4];
     __shared__ int tile_done[2];
-    __shared__ int s_band, s_nan, s_cand;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.z >> 1, cloud = blockIdx.z & 1;
@@ -445,8 +456,8 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         mbar_init(&mbar[2], 1);
+        mbar_init(&mbar[3], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_band = 0; s_nan = 0; s_cand = 0;
         tile_done[0] = 0; tile_done[1] = 0;
     }
 
@@ -497,6 +508,10 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + n_begin) * (kNode + 1);   // chunk start
     const bool pts_in_smem = (n_end - n_begin) * (kNode + 1) <= kSmemPtsF4;
     const float4 *pts = pts_in_smem ? spts : pt4_c;
+    // point-1/2 records of the chunk (refine pass before the hand-off to the exact kernel)
+    const float4 *pt12_c = ws.pt12[cloud] + ((long long)b * nfp + (long long)n_begin * kNode) * 2;
+    const bool pts12_in_smem = (n_end - n_begin) * kNode * 2 <= kSmemPts12F4;
+    const float4 *pts12 = pts12_in_smem ? spts12 : pt12_c;
     if (tid == 0) {
         issue(0);
         if (ntiles > 1) issue(1);
@@ -505,31 +520,75 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
             mbar_expect_tx(&mbar[2], bytes);
             tma_bulk_load(spts, pt4_c, bytes, &mbar[2]);
         }
+        if (pts12_in_smem) {
+            const unsigned bytes = (unsigned)(n_end - n_begin) * kNode * 2u * 16u;
+            mbar_expect_tx(&mbar[3], bytes);
+            tma_bulk_load(spts12, pt12_c, bytes, &mbar[3]);
+        }
     }
     if (pts_in_smem) mbar_wait(&mbar[2], 0);
+    if (pts12_in_smem) mbar_wait(&mbar[3], 0);
 
-    int band = 0, nan = 0, ncand = 0;
-    const float *lines_b = a.lines + (long long)b * g.nl * 6;
-    const float *tri_b = a.tri[cloud] + (long long)b * nf * 9;
-    const float *thr_b = ws.thr[cloud] + (long long)b * nf;
+    int ncand = 0;
     const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)n_begin * kNode;   // from the chunk start
     // node records for level 1: a single-tile chunk stays resident in stage 0, otherwise re-read through L2
     const float4 *node_src = (ntiles == 1) ? stage : src;                                  // from the chunk start
     int wq_cnt = 0, nq_cnt = 0, xq_cnt = 0;                      // warp-uniform fill levels
 
-    // level 3: the exact reference-order test of (line, triplet) entries
+    // level 3 hand-off: (line, triplet) entries that passed both filters go to the launch-wide queue of the exact
+    // kernel (one reservation per flush).  When the queue is full the warp runs the exact test itself.
     auto run_exact = [&]() {
         __syncwarp();
-        for (int base = 0; base < xq_cnt; base += 32) {
-            if (base + lane < xq_cnt) {
-                const unsigned xent = xq[base + lane];
+        // refine: the same conservative FMA predicate on points 1 and 2 (one entry per lane, compacted in place):
+        // about one in eight entries that passed on point 0 survives
+        {
+            int kept = 0;
+            for (int base = 0; base < xq_cnt; base += 32) {
+                bool keep = false;
+                unsigned xent = 0;
+                if (base + lane < xq_cnt) {
+                    xent = xq[base + lane];
+                    const int lrel = (int)(xent >> 22), pos = (int)(xent & 0x3FFFFFu);
+                    const float4 c0 = slineU[lrel], c1 = slineM[lrel];
+                    const float4 A = pts12[pos * 2], Bq = pts12[pos * 2 + 1];
+                    const float t1 = fmaf(A.z, c0.z, fmaf(A.y, c0.y, A.x * c0.x));
+                    const float s1 = fmaf(A.z, c1.z, fmaf(A.y, c1.y, fmaf(A.x, c1.x, A.w)));
+                    const float t2 = fmaf(Bq.z, c0.z, fmaf(Bq.y, c0.y, Bq.x * c0.x));
+                    const float s2 = fmaf(Bq.z, c1.z, fmaf(Bq.y, c1.y, fmaf(Bq.x, c1.x, Bq.w)));
+                    keep = (fmaf(t1, t1, s1) > c1.w) & (fmaf(t2, t2, s2) > c1.w);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) xq[kept + __popc(bal & ((1u << lane) - 1u))] = xent;
+                kept += __popc(bal);
+                __syncwarp();
+            }
+            xq_cnt = kept;
+        }
+        if (xq_cnt > 0) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(ws.xcursor, (unsigned long long)xq_cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const bool fits = (long long)(base + (unsigned long long)xq_cnt) <= ws.xcap;
+            for (int i = lane; i < xq_cnt; i += 32) {
+                const unsigned xent = xq[i];
                 const int l = line_base + (int)(xent >> 22);
                 const int f = __ldg(perm_c + (int)(xent & 0x3FFFFFu));
-                float ln[6];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) ln[c] = __ldg(lines_b + (long long)l * 6 + c);
                 const long long gl = (long long)b * g.nl + l;
-                exact_test_and_record(tri_b, thr_b, ln, f, ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
+                if (fits) {
+                    ws.xcand[base + i] = make_uint2((unsigned)gl, (unsigned)f | ((unsigned)cloud << 31));
+                } else {
+                    // the reserved slots that still lie inside the queue become sentinels
+                    if ((long long)(base + i) < ws.xcap) ws.xcand[base + i] = make_uint2(0xFFFFFFFFu, 0u);
+                    float ln[6];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) ln[c] = __ldg(a.lines + gl * 6 + c);
+                    int band = 0, nan = 0;
+                    exact_test_and_record(a.tri[cloud] + (long long)b * nf * 9, ws.thr[cloud] + (long long)b * nf, ln, f,
+                                          ws.cnt[cloud] + gl, ws.hits[cloud] + gl * kCap, band, nan);
+                    long long *st = ws.stats + (long long)b * RRL_NSTAT;
+                    if (band) atomicAdd((unsigned long long *)(st + 5), (unsigned long long)band);
+                    if (nan) atomicAdd((unsigned long long *)(st + 6), (unsigned long long)nan);
+                }
             }
         }
         __syncwarp();
@@ -735,16 +794,111 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     run_exact();
 
     // ---- diagnostics ---------------------------------------------------------------------------------
-    if (band) atomicAdd(&s_band, band);
-    if (nan) atomicAdd(&s_nan, nan);
-    if (ncand) atomicAdd(&s_cand, ncand);
-    __syncthreads();
-    if (tid == 0) {
-        long long *st = ws.stats + (long long)b * RRL_NSTAT;
-        if (s_cand) atomicAdd((unsigned long long *)(st + 3 + cloud), (unsigned long long)s_cand);
-        if (s_band) atomicAdd((unsigned long long *)(st + 5), (unsigned long long)s_band);
-        if (s_nan) atomicAdd((unsigned long long *)(st + 6), (unsigned long long)s_nan);
+    ncand = __reduce_add_sync(0xffffffffu, ncand);
+    if (lane == 0 && ncand) atomicAdd((unsigned long long *)(ws.stats + (long long)b * RRL_NSTAT + 3 + cloud), (unsigned long long)ncand);
+}
+
+// Level 3: the EXACT reference-order test of every queued (line, triplet) pair.  The chain entry -> line/triplet ->
+// counter -> slot is four dependent memory round trips, so every thread keeps kExactIlp entries in flight.
+constexpr int kExactIlp = 2;
+__global__ void __launch_bounds__(256) exact_kernel(DenseArgs a, Workspace ws, Geometry g) {
+    const unsigned long long reserved = *ws.xcursor;
+    const long long n = reserved < (unsigned long long)ws.xcap ? (long long)reserved : ws.xcap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * kExactIlp) {
+        uint2 e[kExactIlp];
+#pragma unroll
+        for (int u = 0; u < kExactIlp; ++u) {
+            const long long i = i0 + u * stride;
+            e[u] = i < n ? ws.xcand[i] : make_uint2(0xFFFFFFFFu, 0u);
+        }
+        float ln[kExactIlp][6], t[kExactIlp][9], thr[kExactIlp];
+#pragma unroll
+        for (int u = 0; u < kExactIlp; ++u) {
+            const bool ok = e[u].x != 0xFFFFFFFFu;
+            const long long gl = ok ? e[u].x : 0;
+            const int cloud = (int)(e[u].y >> 31), f = (int)(e[u].y & 0x7FFFFFFFu);
+            const int b = (int)(gl / g.nl);
+            const int nf = cloud ? g.nf2 : g.nf1;
+            const float *tp = a.tri[cloud] + ((long long)b * nf + f) * 9;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) ln[u][c] = __ldg(a.lines + gl * 6 + c);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) t[u][c] = __ldg(tp + c);
+            thr[u] = __ldg(ws.thr[cloud] + (long long)b * nf + f);
+        }
+#pragma unroll
+        for (int u = 0; u < kExactIlp; ++u) {
+            if (e[u].x == 0xFFFFFFFFu) continue;
+            const long long gl = e[u].x;
+            const int cloud = (int)(e[u].y >> 31), f = (int)(e[u].y & 0x7FFFFFFFu);
+            const float ulp = ulp_up(thr[u]);
+            const float d0 = __fsqrt_rn(point_line_x_exact(t[u][0], t[u][1], t[u][2], ln[u]));
+            const float d1 = __fsqrt_rn(point_line_x_exact(t[u][3], t[u][4], t[u][5], ln[u]));
+            const float d2 = __fsqrt_rn(point_line_x_exact(t[u][6], t[u][7], t[u][8], ln[u]));
+            // band / NaN accounting as in exact_test_and_record: points 1 and 2 only count when point 0 passes
+            const bool p0 = d0 < thr[u];
+            const int nan = (d0 != d0) + (p0 ? (d1 != d1) + (d2 != d2) : 0);
+            const int band = (fabsf(d0 - thr[u]) <= ulp) + (p0 ? (fabsf(d1 - thr[u]) <= ulp) + (fabsf(d2 - thr[u]) <= ulp) : 0);
+            if (p0 & (d1 < thr[u]) & (d2 < thr[u])) {
+                const int slot = atomicAdd(ws.cnt[cloud] + gl, 1);
+                if (slot < kCap) ws.hits[cloud][gl * kCap + slot] = f;
+            }
+            if (band | nan) {
+                long long *st = ws.stats + (gl / g.nl) * RRL_NSTAT;
+                if (band) atomicAdd((unsigned long long *)(st + 5), (unsigned long long)band);
+                if (nan) atomicAdd((unsigned long long *)(st + 6), (unsigned long long)nan);
+            }
+        }
     }
+}
+
+// The reference's own formulation, every (line, triplet) tested exactly: one thread per (line, cloud).  Not on the
+// product path: rrl_debug_set_param(5, 1) selects it as an on-device cross-check of the filtered pipeline.
+__global__ void __launch_bounds__(128) bruteforce_kernel(DenseArgs a, Workspace ws, Geometry g, int force) {
+    const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
+    (void)force;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= g.nl) return;
+    const int nf = cloud ? g.nf2 : g.nf1;
+    const long long gl = (long long)b * g.nl + l;
+    const float *tri = a.tri[cloud] + (long long)b * nf * 9;
+    const float *thr_arr = ws.thr[cloud] + (long long)b * nf;
+    float ln[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ln[c] = __ldg(a.lines + gl * 6 + c);
+    int count = 0, band = 0, nan = 0;
+    int *hits_line = ws.hits[cloud] + gl * kCap;
+    for (int f = 0; f < nf; ++f) {                  // same early exit (and band/NaN accounting) as exact_test_and_record
+        const float *t = tri + (long long)f * 9;
+        const float thr = __ldg(thr_arr + f);
+        const float ulp = ulp_up(thr);
+        const float d0 = __fsqrt_rn(point_line_x_exact(__ldg(t + 0), __ldg(t + 1), __ldg(t + 2), ln));
+        nan += (d0 != d0);
+        band += (fabsf(d0 - thr) <= ulp);
+        if (!(d0 < thr)) continue;
+        const float d1 = __fsqrt_rn(point_line_x_exact(__ldg(t + 3), __ldg(t + 4), __ldg(t + 5), ln));
+        const float d2 = __fsqrt_rn(point_line_x_exact(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8), ln));
+        nan += (d1 != d1) + (d2 != d2);
+        band += (fabsf(d1 - thr) <= ulp) + (fabsf(d2 - thr) <= ulp);
+        if ((d1 < thr) & (d2 < thr)) {
+            if (count < kCap) hits_line[count] = f;
+            ++count;
+        }
+    }
+    ws.cnt[cloud][gl] = count;
+    long long *st = ws.stats + (long long)b * RRL_NSTAT;
+    if (band) atomicAdd((unsigned long long *)(st + 5), (unsigned long long)band);
+    if (nan) atomicAdd((unsigned long long *)(st + 6), (unsigned long long)nan);
+}
+
+int launch_bruteforce(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
+                      int force, cudaStream_t s) {
+    DenseArgs a;
+    a.tri[0] = tri1; a.tri[1] = tri2; a.lines = lines; a.chunk_nodes = 0;
+    bruteforce_kernel<<<dim3((g.nl + 127) / 128, g.B * 2), 128, 0, s>>>(a, ws, g, force);
+    count_launch();
+    return check_launch();
 }
 
 int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s) {
@@ -757,6 +911,7 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     }
     DenseArgs a;
     a.tri[0] = tri1; a.tri[1] = tri2; a.lines = lines;
+    if (g_param[5]) return launch_bruteforce(tri1, tri2, lines, ws, g, 1, s);      // measurement / cross-check only
     const int G = node_size(g);
     const int line_tiles = (g.nl + kLinesPerCta - 1) / kLinesPerCta;
     const int nn_max = (g.nf1p > g.nf2p ? g.nf1p : g.nf2p) / G;
@@ -776,6 +931,8 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     if (G == 8 && g_param[4] == 0) dense_kernel<8, true><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
     else if (G == 8) dense_kernel<8, false><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
     else dense_kernel<16, false><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
+    count_launch();
+    exact_kernel<<<148 * 8, 256, 0, s>>>(a, ws, g);
     count_launch();
     stage_mark(4, s);
     return check_launch();

@@ -433,7 +433,7 @@ __device__ __forceinline__ void finalize_pair(const Workspace &ws, int b, float 
     long long *st = ws.stats + (long long)b * RRL_NSTAT;
     st[0] = gc[16]; st[1] = gc[17]; st[2] = C;
     if (st[6] > 0) status |= RRL_STATUS_NAN;
-    if (ws.flags[b * 2]) { status |= RRL_STATUS_NAN; loss = __longlong_as_double(0x7ff8000000000000LL); }
+    if (ws.flags[b * 4]) { status |= RRL_STATUS_NAN; loss = __longlong_as_double(0x7ff8000000000000LL); }
     // |AC|^2 <= (P + X)^2: flag clouds whose own extent already makes the 2e-4 offset smaller than a few ulps of
     // |p|^2 (|AC|^2 >~ 1e3)
     const float pm = fmaxf(__uint_as_float(ws.pmax[b * 2]), __uint_as_float(ws.pmax[b * 2 + 1]));
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(256) welsch_kernel(Workspace ws, Geometry g, f
         const int combo = (k - 1) * 4 + (j - 1);
         double s1, s2;
         welsch_record(ws, r, ws.med[b], exp(-0.5 * (double)abs(k - j)) / (double)C / (double)gc[combo], k, j, s1, s2);
-        if (!(s1 == s1) || !(s2 == s2)) { ws.flags[b * 2] = 1; s1 = s2 = 0.0; }    // e.g. median 0: the reference's loss is NaN too
+        if (!(s1 == s1) || !(s2 == s2)) { ws.flags[b * 4] = 1; s1 = s2 = 0.0; }    // e.g. median 0: the reference's loss is NaN too
         atomicAdd(&s_sum[combo], (unsigned long long)__double2ll_rn(s1 * kFixScale));
         atomicAdd(&s_sum[16 + combo], (unsigned long long)__double2ll_rn(s2 * kFixScale));
     }
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256) welsch_kernel(Workspace ws, Geometry g, f
     const int nblocks = nrec > 0 ? (int)((nrec + blockDim.x - 1) / blockDim.x) : 1;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ws.flags + b * 2 + 1, 1) == nblocks - 1);
+    if (threadIdx.x == 0) s_last = (atomicAdd(ws.flags + b * 4 + 1, 1) == nblocks - 1);
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence();

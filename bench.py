@@ -335,6 +335,7 @@ def run_gpu(args):
         rrl_b200._native.check(L.rrl_host_create(B, nf, nf, nl, local_rank, C.byref(ctx)), "rrl_host_create")
         pinned = [torch.from_numpy(np.ascontiguousarray(np.concatenate([x.reshape(-1) for x in s]))).pin_memory()
                   for s in host_sets]
+        n_sub = int(L.rrl_host_subbatches(ctx))
         n1, n2 = B * nf * 9, B * nf * 9
         h_loss = np.zeros(B, np.float32)
         h_status = np.zeros(B, np.int32)
@@ -358,8 +359,9 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * nl / (float(t.item()) / args.steps), "unit": "pairs*lines/s",
                "h2d_bytes_per_step": bytes_per_set, "d2h_bytes_per_step": 8 * B,
-               "api": "rrl_host_loss_fwd_bwd (C ABI, host pointers; per step: 3 H2D copies from pinned memory, forward, "
-                      "backward to points1, D2H of loss+status, stream sync)",
+               "api": "rrl_host_loss_fwd_bwd (C ABI, host pointers; per step: H2D of the three inputs from pinned memory, "
+                      "forward, backward to points1, D2H of loss+status, sync; pipelined over %d sub-batches of pairs so "
+                      "that copies run under the kernels of the previous sub-batch)" % n_sub,
                "ms_per_step": float(t.item()) / args.steps * 1e3}
 
     if rank != 0:

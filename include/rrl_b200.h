@@ -173,6 +173,8 @@ void rrl_host_destroy(rrl_host_ctx *ctx);
 float *rrl_host_pinned_tri1(rrl_host_ctx *ctx);
 float *rrl_host_pinned_tri2(rrl_host_ctx *ctx);
 float *rrl_host_pinned_lines(rrl_host_ctx *ctx);
+/* number of sub-batches (streams) the context pipelines a call over: H2D of one runs under the kernels of the previous */
+int rrl_host_subbatches(rrl_host_ctx *ctx);
 /* H2D of the three inputs, forward, backward w.r.t. cloud 1 with d(total)/d(loss[b]) = 1, D2H of loss [B], status [B]
  * and (if h_grad_tri1 != NULL) the (B,nf1,9) gradient; returns after the stream has drained.  h_* inputs may be
  * the context's own pinned buffers, any other pinned memory (copied asynchronously) or pageable memory (staged by

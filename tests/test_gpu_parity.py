@@ -168,6 +168,55 @@ def test_sorted_and_unsorted_node_variants_agree(rrl):
     assert a["loss"] == b["loss"] and a["median"] == b["median"]
 
 
+def test_bruteforce_kernel_agrees_with_filtered_path(rrl):
+    """every (line, triplet) tested exactly on the device (the reference's own formulation) vs the filtered pipeline"""
+    p = synth.make_pair(131, 1500, 5000, zero_frac=0.1)
+    L = rrl._native.lib()
+    try:
+        L.rrl_debug_set_param(5, 1)
+        a = _run(rrl, p["tri1"], p["tri2"], p["lines"])
+    finally:
+        L.rrl_debug_set_param(5, 0)
+    b = _run(rrl, p["tri1"], p["tri2"], p["lines"])
+    for c, h in (("counts1", "hits1"), ("counts2", "hits2")):
+        assert np.array_equal(a[c], b[c])
+        keep = a[c] <= co.CAP
+        assert np.array_equal(a[h][keep], b[h][keep])
+    assert a["loss"] == b["loss"] and a["median"] == b["median"]
+    _check_against_oracle(a, co.loss(p["tri1"], p["tri2"], p["lines"]))
+
+
+def test_candidate_queue_overflow_runs_the_exact_test_in_place(rrl):
+    """hundreds of triplets on every line: far more exact candidates than the queue holds
+    (12 per line), so the warps that find it full run the exact test themselves; results stay exact"""
+    rng = np.random.default_rng(17)
+    shell = synth.surface_points(rng, 400, "sphere")
+    # 600 points 0.02 apart on a straight segment (thr ~ 0.023 > sqrt(2e-4)) and lines running along it
+    seg = np.stack([np.arange(600) * 0.02 - 6.0, np.zeros(600), np.zeros(600)], 1) + rng.normal(size=(600, 3)) * 1e-4
+    src = np.concatenate([shell, seg]).astype(np.float32)
+    tri1 = synth.knn_triplets(src)
+    tri2 = synth.knn_triplets((src * np.float32(0.999)).copy())
+    d = np.array([1.0, 0, 0]) + rng.normal(size=(1200, 3)) * 2e-4
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    x0 = rng.normal(size=(1200, 3)) * 1e-3 + d * rng.uniform(-1, 1, size=(1200, 1))
+    lines = np.concatenate([d, x0], 1).astype(np.float32)
+    lines[::7] = synth.make_pair(5, 300, 1200)["lines"][::7]                          # and some ordinary lines
+    out = _run(rrl, tri1, tri2, lines)
+    orc = co.loss(tri1, tri2, lines)
+    assert orc.counts1.mean() > 24                                                    # the premise: the queue must overflow
+    _check_against_oracle(out, orc)
+    # together with an ordinary pair in one batch
+    q = synth.make_pair(132, 1000, 1200)
+    t1 = torch.from_numpy(np.stack([tri1, q["tri1"]])).cuda()
+    t2 = torch.from_numpy(np.stack([tri2, q["tri2"]])).cuda()
+    ln = torch.from_numpy(np.stack([lines, q["lines"]])).cuda()
+    loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True)
+    oq = co.loss(q["tri1"], q["tri2"], q["lines"])
+    c1, _ = info.hits(1)
+    assert np.array_equal(c1[0].cpu().numpy(), orc.counts1) and np.array_equal(c1[1].cpu().numpy(), oq.counts1)
+    assert abs(float(loss[1]) - oq.loss) <= REL_TOL * oq.loss
+
+
 def test_batched_equals_per_pair_and_is_permutation_invariant(rrl):
     pairs = [synth.make_pair(200 + i, 512, 2000) for i in range(5)]
     t1 = torch.from_numpy(np.stack([p["tri1"] for p in pairs])).cuda().requires_grad_(True)
@@ -218,15 +267,19 @@ def test_raw_c_abi_calls(rrl):
         rrl.intersected_line_loss(t1.cpu()[None], t2.cpu()[None], ln.cpu()[None])      # no CPU fallback
 
 
-def test_host_buffer_entry(rrl):
+@pytest.mark.parametrize("subbatches", [1, 2, 5])
+def test_host_buffer_entry(rrl, subbatches, monkeypatch):
+    """host pointers in, host pointers out; the call is pipelined over `subbatches` streams (uneven split for 2)"""
+    monkeypatch.setenv("RRL_HOST_SUBBATCHES", str(subbatches))
     L = rrl._native.lib()
-    pairs = [synth.make_pair(400 + i, 300, 1000) for i in range(3)]
+    pairs = [synth.make_pair(400 + i, 300, 1000) for i in range(5)]
     tri1 = np.ascontiguousarray(np.stack([p["tri1"] for p in pairs])); tri2 = np.ascontiguousarray(np.stack([p["tri2"] for p in pairs]))
     lines = np.ascontiguousarray(np.stack([p["lines"] for p in pairs]))
     ctx = C.c_void_p()
-    assert L.rrl_host_create(3, 300, 300, 1000, 0, C.byref(ctx)) == 0
+    assert L.rrl_host_create(5, 300, 300, 1000, 0, C.byref(ctx)) == 0
     try:
-        loss = np.zeros(3, np.float32); status = np.zeros(3, np.int32); g1 = np.zeros_like(tri1)
+        assert L.rrl_host_subbatches(ctx) == subbatches
+        loss = np.zeros(5, np.float32); status = np.zeros(5, np.int32); g1 = np.zeros_like(tri1)
         assert L.rrl_host_loss_fwd_bwd(ctx, tri1.ctypes.data, tri2.ctypes.data, lines.ctypes.data, 1, 1, 5, 5,
                                        loss.ctypes.data, status.ctypes.data, g1.ctypes.data) == 0
     finally:
