@@ -29,13 +29,9 @@ constexpr float kEps24 = 5.9604645e-8f;
 
 // ---- dense kernel geometry ---------------------------------------------------------------------------
 constexpr int kDenseThreads = 256;
-constexpr int kLinesPerThread = 4;
-constexpr int kLinesPerCta = kDenseThreads * kLinesPerThread;   // 1024
-constexpr int kTileNodes = 256;                                 // 5 float4 per 4 nodes: 5 KB per stage
 constexpr int kNodePad = 16;                                    // node arrays are padded to this multiple (sentinels)
 constexpr int kPointPad = 256;                                  // triplet arrays padded to 16 nodes of 16 (= 32 nodes of 8)
 constexpr int kMinNode = 8;                                     // smallest node size (sizes the node arrays)
-constexpr int kWarpQueue = 512;                                 // candidate (line, node group) entries per warp
 constexpr int kExactPerLine = 12;                               // capacity of the exact-candidate queue, entries per line
 constexpr int kSortSmall = 4096;                                // clouds up to this many (padded) triplets sort in one CTA
 

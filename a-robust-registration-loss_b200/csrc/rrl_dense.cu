@@ -268,7 +268,7 @@ size_t sort_scratch_bytes(int nfp_max) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[8] = {0, 0, 16, 32, 0, 0, 0, 0};   // [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force
+static int g_param[8] = {0, 0, 16, 32, 0, 0, 0, 0};   // [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = chunks may exceed the shared-memory point cache
 void set_param(int id, int v) { if (id > 0 && id < 8) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -387,20 +387,31 @@ __device__ __forceinline__ void exact_test_and_record(const float *__restrict__ 
     }
 }
 
-constexpr int kSmemPtsF4 = 576;        // point-0 records (float4, incl. pads) staged in shared memory when a chunk fits (64 nodes of 8)
-constexpr int kSmemPts12F4 = 1024;     // point-1/2 records of the chunk, staged when the chunk has <= 512 triplets
-constexpr int kStageF4 = (kTileNodes / 4) * 5;                          // float4 per stage: 5 per group of 4 nodes
 constexpr int kNumWarps = kDenseThreads / 32;
-constexpr int kNodeQueue = 256;        // (line, node) entries per warp; one level-1 pass appends <= 128
-constexpr int kExactQueue = 640;       // (line, triplet) entries per warp; one level-2 pass appends <= 32 * node size
-constexpr int kOffLineC = 2 * kStageF4 * 16;                           // the CTA's line constants: L1 has no room left
-constexpr int kOffQueue = kOffLineC + kLinesPerCta * 32;
-constexpr int kOffNodeQ = kOffQueue + kNumWarps * kWarpQueue * 4;
-constexpr int kOffExact = kOffNodeQ + kNumWarps * kNodeQueue * 4;
-constexpr int kOffPoints = kOffExact + kNumWarps * kExactQueue * 4;
-constexpr int kOffPoints12 = kOffPoints + kSmemPtsF4 * 16;
-constexpr int kDenseSmem = kOffPoints12 + kSmemPts12F4 * 16;
-static_assert(2 * (kDenseSmem + 2048) <= 227 * 1024, "two CTAs per SM must fit (dynamic + static + 1 KB reserved each)");
+
+// Shared-memory plan of one dense CTA.  LPT = lines per thread: 4 lines amortise every broadcast node read over more
+// arithmetic (2 CTAs per SM, 128 registers), 2 lines halve the register and shared-memory footprint so that 4 CTAs
+// (32 warps) fit an SM and cover the latency of the queue levels.
+template <int kNode, bool kPerNode, int LPT>
+struct DenseCfg {
+    static constexpr int kLines = kDenseThreads * LPT;                 // lines per CTA
+    static constexpr int kTile = LPT >= 4 ? 256 : 128;                 // nodes per TMA stage
+    static constexpr int kStage = (kTile / 4) * 5;                     // float4 per stage: 5 per group of 4 nodes
+    static constexpr int kWq = LPT >= 4 ? 512 : 256;                   // per warp: (line, group) entries, or (line, node) when kPerNode
+    static constexpr int kNq = 256;                                    // per warp: (line, node) entries of the 3-level pipeline
+    static constexpr int kXq = 32 * kNode + 64;                        // per warp: (line, triplet); one level-2 pass appends <= 32 * kNode
+    static constexpr int kPts = LPT >= 4 ? 576 : 288;                  // point-0 records (float4, incl. pads) staged when the chunk fits
+    static constexpr int kPts12 = LPT >= 4 ? 1024 : 512;               // point-1/2 records of the chunk
+    static constexpr int kOffLine = 2 * kStage * 16;
+    static constexpr int kOffWq = kOffLine + kLines * 32;
+    static constexpr int kOffNq = kOffWq + kNumWarps * kWq * 4;
+    static constexpr int kOffXq = kOffNq + (kPerNode ? 0 : kNumWarps * kNq * 4);
+    static constexpr int kOffPts = kOffXq + kNumWarps * kXq * 4;
+    static constexpr int kOffPts12 = kOffPts + kPts * 16;
+    static constexpr int kSmem = kOffPts12 + kPts12 * 16;
+    static constexpr int kMinBlocks = (227 * 1024) / (kSmem + 2048) >= 4 && LPT < 4 ? 4 : ((227 * 1024) / (kSmem + 2048) >= 3 && LPT < 4 ? 3 : 2);
+    static_assert(kMinBlocks * (kSmem + 2048) <= 227 * 1024, "CTAs per SM must fit (dynamic + static + 1 KB reserved each)");
+};
 
 // exclusive prefix sum over the lanes of a (converged) warp of a count c < 2^kBits, by bit planes: kBits independent
 // ballots instead of a dependent chain of five shuffles (the queue levels are latency bound, not issue bound)
@@ -427,13 +438,17 @@ __device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
 // kPerNode (small, hit-dense clouds): the main loop keeps one mask per node of a group and feeds (line, node) entries
 // straight to level 2 -- level 1 would otherwise re-evaluate nearly every group (half of all (line, group) pairs
 // fire on a 1024-triplet cloud).
-template <int kNode, bool kPerNode>
-__global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
+template <int kNode, bool kPerNode, int LPT>
+__global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>::kMinBlocks) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
+    using Cfg = DenseCfg<kNode, kPerNode, LPT>;
+    constexpr int kLinesPerThread = LPT, kLinesPerCta = Cfg::kLines, kTileNodes = Cfg::kTile, kStageF4 = Cfg::kStage;
+    constexpr int kWarpQueue = Cfg::kWq, kNodeQueue = Cfg::kNq, kExactQueue = Cfg::kXq;
+    constexpr int kSmemPtsF4 = Cfg::kPts, kSmemPts12F4 = Cfg::kPts12;
     extern __shared__ __align__(128) unsigned char dsm[];
     float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kStageF4]
-    float4 *spts = reinterpret_cast<float4 *>(dsm + kOffPoints);                           // [kSmemPtsF4]
-    float4 *spts12 = reinterpret_cast<float4 *>(dsm + kOffPoints12);                       // [kSmemPts12F4]
-    float4 *slineU = reinterpret_cast<float4 *>(dsm + kOffLineC);                          // [kLinesPerCta] {u, tl_node}
+    float4 *spts = reinterpret_cast<float4 *>(dsm + Cfg::kOffPts);                         // [kSmemPtsF4]
+    float4 *spts12 = reinterpret_cast<float4 *>(dsm + Cfg::kOffPts12);                     // [kSmemPts12F4]
+    float4 *slineU = reinterpret_cast<float4 *>(dsm + Cfg::kOffLine);                      // [kLinesPerCta] {u, tl_node}
     float4 *slineM = slineU + kLinesPerCta;                                                // [kLinesPerCta] {M, tl_point}
     __shared__ __align__(8) unsigned long long mbar[4];
     __shared__ int tile_done[2];
@@ -446,11 +461,11 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
     if (n_begin >= nnodes) return;
     const int n_end = min(nnodes, n_begin + a.chunk_nodes);
     const int line_base = blockIdx.x * kLinesPerCta;
-    unsigned *wq = reinterpret_cast<unsigned *>(dsm + kOffQueue) + wid * kWarpQueue;
+    unsigned *wq = reinterpret_cast<unsigned *>(dsm + Cfg::kOffWq) + wid * kWarpQueue;
     // the (line, node) queue: in kPerNode mode the main loop fills it directly and it takes over the larger region
     constexpr int kNodeCap = kPerNode ? kWarpQueue : kNodeQueue;
-    unsigned *nq = kPerNode ? wq : reinterpret_cast<unsigned *>(dsm + kOffNodeQ) + wid * kNodeQueue;
-    unsigned *xq = reinterpret_cast<unsigned *>(dsm + kOffExact) + wid * kExactQueue;
+    unsigned *nq = kPerNode ? wq : reinterpret_cast<unsigned *>(dsm + Cfg::kOffNq) + wid * kNodeQueue;
+    unsigned *xq = reinterpret_cast<unsigned *>(dsm + Cfg::kOffXq) + wid * kExactQueue;
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -676,98 +691,120 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_kernel(DenseArgs a, Wo
         const float4 *sp = stage + (t & 1) * kStageF4;
         const int ngroups = nn / 4;
         const int group0 = t * (kTileNodes / 4);
-        for (int w0 = 0; w0 < ngroups; w0 += 32) {
-            const int ng = min(32, ngroups - w0);
-            constexpr int kMasks = kPerNode ? 4 : 1;
-            unsigned m[kLinesPerThread][kMasks];
+        if constexpr (kPerNode) {
+            // window = 8 groups = 32 nodes: ONE mask word per line, bit = node index inside the window
+            for (int w0 = 0; w0 < ngroups; w0 += 8) {
+                const int ng = min(8, ngroups - w0);
+                unsigned m[kLinesPerThread];
 #pragma unroll
-            for (int i = 0; i < kLinesPerThread; ++i)
-#pragma unroll
-                for (int q = 0; q < kMasks; ++q) m[i][q] = 0u;
+                for (int i = 0; i < kLinesPerThread; ++i) m[i] = 0u;
 #pragma unroll 2
-            for (int gi = 0; gi < ng; ++gi) {
-                // 4 nodes = two interleaved pairs: {xA,xB,yA,yB} {zA,zB,wA,wB}
-                const float4 a0 = sp[(w0 + gi) * 5 + 0], a1 = sp[(w0 + gi) * 5 + 1], b0 = sp[(w0 + gi) * 5 + 2], b1 = sp[(w0 + gi) * 5 + 3];
-                const float2 xa = make_float2(a0.x, a0.y), ya = make_float2(a0.z, a0.w), za = make_float2(a1.x, a1.y), wa = make_float2(a1.z, a1.w);
-                const float2 xb = make_float2(b0.x, b0.y), yb = make_float2(b0.z, b0.w), zb = make_float2(b1.x, b1.y), wb = make_float2(b1.z, b1.w);
-                const unsigned bit = 1u << gi;
+                for (int gi = 0; gi < ng; ++gi) {
+                    // 4 nodes = two interleaved pairs: {xA,xB,yA,yB} {zA,zB,wA,wB}
+                    const float4 a0 = sp[(w0 + gi) * 5 + 0], a1 = sp[(w0 + gi) * 5 + 1], b0 = sp[(w0 + gi) * 5 + 2], b1 = sp[(w0 + gi) * 5 + 3];
+                    const float2 xa = make_float2(a0.x, a0.y), ya = make_float2(a0.z, a0.w), za = make_float2(a1.x, a1.y), wa = make_float2(a1.z, a1.w);
+                    const float2 xb = make_float2(b0.x, b0.y), yb = make_float2(b0.z, b0.w), zb = make_float2(b1.x, b1.y), wb = make_float2(b1.z, b1.w);
+                    const unsigned bit = 1u << (gi * 4);
 #pragma unroll
-                for (int i = 0; i < kLinesPerThread; ++i) {
-                    const float2 u0 = make_float2(ux[i], ux[i]), u1 = make_float2(uy[i], uy[i]), u2 = make_float2(uz[i], uz[i]);
-                    const float2 m0 = make_float2(mx[i], mx[i]), m1 = make_float2(my[i], my[i]), m2 = make_float2(mz[i], mz[i]);
-                    const float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
-                    const float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
-                    const float2 qa = __ffma2_rn(ta, ta, sa);
-                    const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
-                    const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
-                    const float2 qb = __ffma2_rn(tb, tb, sb);
-                    if constexpr (kPerNode) {
-                        m[i][0] |= (qa.x > tl[i]) ? bit : 0u;
-                        m[i][1] |= (qa.y > tl[i]) ? bit : 0u;
-                        m[i][2] |= (qb.x > tl[i]) ? bit : 0u;
-                        m[i][3] |= (qb.y > tl[i]) ? bit : 0u;
-                    } else {
-                        const float qmax = fmaxf(fmaxf(qa.x, qa.y), fmaxf(qb.x, qb.y));
-                        m[i][0] |= (qmax > tl[i]) ? bit : 0u;
+                    for (int i = 0; i < kLinesPerThread; ++i) {
+                        const float2 u0 = make_float2(ux[i], ux[i]), u1 = make_float2(uy[i], uy[i]), u2 = make_float2(uz[i], uz[i]);
+                        const float2 m0 = make_float2(mx[i], mx[i]), m1 = make_float2(my[i], my[i]), m2 = make_float2(mz[i], mz[i]);
+                        const float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
+                        const float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
+                        const float2 qa = __ffma2_rn(ta, ta, sa);
+                        const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
+                        const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
+                        const float2 qb = __ffma2_rn(tb, tb, sb);
+                        m[i] |= (qa.x > tl[i]) ? bit : 0u;
+                        m[i] |= (qa.y > tl[i]) ? (bit << 1) : 0u;
+                        m[i] |= (qb.x > tl[i]) ? (bit << 2) : 0u;
+                        m[i] |= (qb.y > tl[i]) ? (bit << 3) : 0u;
                     }
                 }
-            }
-            // ordered push of the fired pairs
+                // ordered push of the fired (line, node) pairs: one scan and one bit loop per line
+                const unsigned node0 = (unsigned)((group0 + w0) * 4);
 #pragma unroll
-            for (int i = 0; i < kLinesPerThread; ++i) {
-                const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
-                if constexpr (kPerNode) {
-                    const int c = __popc(m[i][0]) + __popc(m[i][1]) + __popc(m[i][2]) + __popc(m[i][3]);   // <= 128
+                for (int i = 0; i < kLinesPerThread; ++i) {
+                    const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
+                    const int c = __popc(m[i]);                                    // <= 32
                     if (!__any_sync(0xffffffffu, c != 0)) continue;
                     ncand += c;
                     int total;
-                    const int off = warp_excl_scan<8>(c, lane, total);
+                    const int off = warp_excl_scan<6>(c, lane, total);
                     if (total <= kNodeCap) {
                         if (nq_cnt + total > kNodeCap) run_nodes();
                         int pos = nq_cnt + off;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            unsigned mm = m[i][q];
-                            while (mm) {
-                                const int gi = __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                nq[pos++] = (lrel << 22) | (unsigned)((group0 + w0 + gi) * 4 + q);
-                            }
+                        unsigned mm = m[i];
+                        while (mm) {
+                            const int bp = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            nq[pos++] = (lrel << 22) | (node0 + (unsigned)bp);
                         }
                         nq_cnt += total;
                     } else {                                       // rare: more than a queue-full from one window
+                        constexpr int kPart = kNodeCap / 32;       // bits per part: 32 lanes x kPart entries always fit
 #pragma unroll 1
-                        for (int q = 0; q < 4; ++q)
-#pragma unroll 1
-                            for (int half = 0; half < 2; ++half) {
-                                unsigned mh = half ? (m[i][q] >> 16) : (m[i][q] & 0xFFFFu);
-                                int tot2;
-                                const int off2 = warp_excl_scan<5>(__popc(mh), lane, tot2);      // <= 32 x 16 = kNodeCap
-                                if (nq_cnt + tot2 > kNodeCap) run_nodes();
-                                int pos = nq_cnt + off2;
-                                while (mh) {
-                                    const int gi = __ffs(mh) - 1 + half * 16;
-                                    mh &= mh - 1;
-                                    nq[pos++] = (lrel << 22) | (unsigned)((group0 + w0 + gi) * 4 + q);
-                                }
-                                nq_cnt += tot2;
+                        for (int part = 0; part < 32; part += kPart) {
+                            unsigned mh = (m[i] >> part) & ((1u << kPart) - 1u);
+                            int tot2;
+                            const int off2 = warp_excl_scan<5>(__popc(mh), lane, tot2);
+                            if (nq_cnt + tot2 > kNodeCap) run_nodes();
+                            int pos = nq_cnt + off2;
+                            while (mh) {
+                                const int bp = __ffs(mh) - 1 + part;
+                                mh &= mh - 1;
+                                nq[pos++] = (lrel << 22) | (node0 + (unsigned)bp);
                             }
+                            nq_cnt += tot2;
+                        }
                     }
-                } else {
-                    const unsigned mi = m[i][0];
+                }
+            }
+        } else {
+            // window = 32 groups of 4 nodes: one mask word per line, bit = group (the OR of its four node predicates)
+            for (int w0 = 0; w0 < ngroups; w0 += 32) {
+                const int ng = min(32, ngroups - w0);
+                unsigned m[kLinesPerThread];
+#pragma unroll
+                for (int i = 0; i < kLinesPerThread; ++i) m[i] = 0u;
+#pragma unroll 2
+                for (int gi = 0; gi < ng; ++gi) {
+                    const float4 a0 = sp[(w0 + gi) * 5 + 0], a1 = sp[(w0 + gi) * 5 + 1], b0 = sp[(w0 + gi) * 5 + 2], b1 = sp[(w0 + gi) * 5 + 3];
+                    const float2 xa = make_float2(a0.x, a0.y), ya = make_float2(a0.z, a0.w), za = make_float2(a1.x, a1.y), wa = make_float2(a1.z, a1.w);
+                    const float2 xb = make_float2(b0.x, b0.y), yb = make_float2(b0.z, b0.w), zb = make_float2(b1.x, b1.y), wb = make_float2(b1.z, b1.w);
+                    const unsigned bit = 1u << gi;
+#pragma unroll
+                    for (int i = 0; i < kLinesPerThread; ++i) {
+                        const float2 u0 = make_float2(ux[i], ux[i]), u1 = make_float2(uy[i], uy[i]), u2 = make_float2(uz[i], uz[i]);
+                        const float2 m0 = make_float2(mx[i], mx[i]), m1 = make_float2(my[i], my[i]), m2 = make_float2(mz[i], mz[i]);
+                        const float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
+                        const float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
+                        const float2 qa = __ffma2_rn(ta, ta, sa);
+                        const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
+                        const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
+                        const float2 qb = __ffma2_rn(tb, tb, sb);
+                        const float qmax = fmaxf(fmaxf(qa.x, qa.y), fmaxf(qb.x, qb.y));
+                        m[i] |= (qmax > tl[i]) ? bit : 0u;
+                    }
+                }
+                // ordered push of the fired (line, group) pairs, in parts that always fit the queue
+#pragma unroll
+                for (int i = 0; i < kLinesPerThread; ++i) {
+                    const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
+                    const unsigned mi = m[i];
                     if (!__any_sync(0xffffffffu, mi != 0u)) continue;
                     ncand += __popc(mi);
-                    // two halves of 16 groups: each appends <= 32 lanes x 16 groups = kWarpQueue entries
+                    constexpr int kPart = kWarpQueue / 32;         // 16 or 8 groups per part: 32 lanes x kPart entries <= kWarpQueue
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        unsigned mh = half ? (mi >> 16) : (mi & 0xFFFFu);
+                    for (int part = 0; part < 32; part += kPart) {
+                        unsigned mh = (mi >> part) & ((1u << kPart) - 1u);
                         if (!__any_sync(0xffffffffu, mh != 0u)) continue;
                         int total;
                         const int off = warp_excl_scan<5>(__popc(mh), lane, total);
                         if (wq_cnt + total > kWarpQueue) run_groups();
                         int pos = wq_cnt + off;
                         while (mh) {
-                            const int gi = __ffs(mh) - 1 + half * 16;
+                            const int gi = __ffs(mh) - 1 + part;
                             mh &= mh - 1;
                             wq[pos++] = (lrel << 20) | (unsigned)(group0 + w0 + gi);
                         }
@@ -901,37 +938,50 @@ int launch_bruteforce(const float *tri1, const float *tri2, const float *lines, 
     return check_launch();
 }
 
-int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s) {
+template <int kNode, bool kPerNode, int LPT>
+static int launch_dense_variant(const DenseArgs &a0, const Workspace &ws, const Geometry &g, int G, cudaStream_t s) {
+    using Cfg = DenseCfg<kNode, kPerNode, LPT>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(dense_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
-        if (cudaFuncSetAttribute(dense_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
-        if (cudaFuncSetAttribute(dense_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem) != cudaSuccess) return RRL_ERR_CUDA;
+        if (cudaFuncSetAttribute(dense_kernel<kNode, kPerNode, LPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
+            return RRL_ERR_CUDA;
         attr_set = true;
     }
-    DenseArgs a;
-    a.tri[0] = tri1; a.tri[1] = tri2; a.lines = lines;
-    if (g_param[5]) return launch_bruteforce(tri1, tri2, lines, ws, g, 1, s);      // measurement / cross-check only
-    const int G = node_size(g);
-    const int line_tiles = (g.nl + kLinesPerCta - 1) / kLinesPerCta;
+    DenseArgs a = a0;
+    const int line_tiles = (g.nl + Cfg::kLines - 1) / Cfg::kLines;
     const int nn_max = (g.nf1p > g.nf2p ? g.nf1p : g.nf2p) / G;
-    // split the nodes so that the grid covers the 148 SMs (2 CTAs each) about eight times over when the line
-    // tiles alone do not; never below 64 nodes per CTA
+    // split the nodes so that the grid covers the SMs (kMinBlocks CTAs each) g_param[2] times over when the line
+    // tiles alone do not; never below g_param[3] nodes per CTA
     const long long base_ctas = (long long)line_tiles * g.B * 2;
-    const long long target = 148LL * 2 * g_param[2];
+    const long long target = 148LL * Cfg::kMinBlocks * g_param[2];
     int chunks = 1;
     if (base_ctas < target) chunks = (int)((target + base_ctas - 1) / base_ctas);
     int chunk_nodes = (nn_max + chunks - 1) / chunks;
     if (chunk_nodes < g_param[3]) chunk_nodes = g_param[3];
     chunk_nodes = ((chunk_nodes + kNodePad - 1) / kNodePad) * kNodePad;
+    // small clouds: keep the chunk's point records in shared memory (level 2 reads them once per candidate node)
+    constexpr int kFit = (Cfg::kPts / (kNode + 1)) / kNodePad * kNodePad;
+    if (kPerNode && g_param[7] == 0 && chunk_nodes > kFit) chunk_nodes = kFit;
     if (chunk_nodes / 4 >= (1 << 20) || (long long)chunk_nodes * G >= (1 << 22)) return RRL_ERR_ARG;
     chunks = (nn_max + chunk_nodes - 1) / chunk_nodes;
     a.chunk_nodes = chunk_nodes;
     dim3 grid(line_tiles, chunks, g.B * 2);
-    if (G == 8 && g_param[4] == 0) dense_kernel<8, true><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
-    else if (G == 8) dense_kernel<8, false><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
-    else dense_kernel<16, false><<<grid, kDenseThreads, kDenseSmem, s>>>(a, ws, g);
+    dense_kernel<kNode, kPerNode, LPT><<<grid, kDenseThreads, Cfg::kSmem, s>>>(a, ws, g);
     count_launch();
+    return RRL_OK;
+}
+
+int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s) {
+    DenseArgs a;
+    a.tri[0] = tri1; a.tri[1] = tri2; a.lines = lines; a.chunk_nodes = 0;
+    if (g_param[5]) return launch_bruteforce(tri1, tri2, lines, ws, g, 1, s);      // measurement / cross-check only
+    const int G = node_size(g);
+    const int lpt = g_param[6] == 2 || g_param[6] == 4 ? g_param[6] : 2;
+    int rc;
+    if (G == 8 && g_param[4] == 0) rc = lpt == 2 ? launch_dense_variant<8, true, 2>(a, ws, g, G, s) : launch_dense_variant<8, true, 4>(a, ws, g, G, s);
+    else if (G == 8) rc = lpt == 2 ? launch_dense_variant<8, false, 2>(a, ws, g, G, s) : launch_dense_variant<8, false, 4>(a, ws, g, G, s);
+    else rc = lpt == 2 ? launch_dense_variant<16, false, 2>(a, ws, g, G, s) : launch_dense_variant<16, false, 4>(a, ws, g, G, s);
+    if (rc) return rc;
     exact_kernel<<<148 * 8, 256, 0, s>>>(a, ws, g);
     count_launch();
     stage_mark(4, s);

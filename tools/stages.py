@@ -7,7 +7,11 @@ from oracle import synth
 L = rrl_b200._native.lib()
 CONFIGS = {"demo": (1, 1024, 20000), "dcp": (32, 1024, 15000), "rpm": (64, 2048, 10000), "fmr": (128, 1024, 15000), "large": (1, 500000, 100000)}
 NAMES = ["prep", "sort", "node", "dense", "select", "build", "median", "welsch", "backward", "total"]
-for name in (sys.argv[1:] or ["dcp"]):
+args = [a for a in sys.argv[1:] if "=" not in a]
+for kv in [a for a in sys.argv[1:] if "=" in a]:          # e.g. 6=4 -> rrl_debug_set_param(6, 4)
+    k, v = kv.split("=")
+    L.rrl_debug_set_param(int(k), int(v))
+for name in (args or ["dcp"]):
     B, nf, nl = CONFIGS[name]
     pairs = [synth.make_pair(1000 + i, nf, nl) for i in range(min(B, 4))]
     idx = [i % len(pairs) for i in range(B)]
