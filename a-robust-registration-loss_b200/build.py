@@ -13,6 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librrl_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("RRL_MARKS"):          # measurement builds: in-kernel phase timestamps (rrl_debug_read_marks)
+    COMMON.append("-DRRL_MARKS")
 # rrl_sampler.cu restates a floating-point knife-edge test and must not contract a*b+c into FMAs
 SOURCES = {"rrl_api.cu": [], "rrl_dense.cu": [], "rrl_sparse.cu": [], "rrl_se3.cu": [], "rrl_aux.cu": [],
            "rrl_sampler.cu": ["-fmad=false"]}

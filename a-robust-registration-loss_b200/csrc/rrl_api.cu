@@ -145,8 +145,7 @@ extern "C" int rrl_loss_forward(const float *tri1, const float *tri2, const floa
     if (rc) return rc;
     if ((rc = launch_dense(tri1, tri2, lines, ws, g, s))) return rc;
     if ((rc = launch_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, s))) return rc;
-    if ((rc = launch_median(ws, g, s))) return rc;
-    return launch_welsch_finalize(ws, g, out_loss, out_status, out_median, out_stats, s);
+    return launch_tail(ws, g, out_loss, out_status, out_median, out_stats, s);
 }
 
 extern "C" int rrl_loss_backward(const void *workspace, size_t workspace_bytes, const float *grad_out, int B, int nf1,

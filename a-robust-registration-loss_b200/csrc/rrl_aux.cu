@@ -68,6 +68,25 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, fl
     if (s == 123.456f) out[0] = s;
 }
 
+// FP64 FMA rate (mode 2 of rrl_measure_fp32_peak): sizes how much double-precision work the sparse stages can afford
+__global__ void __launch_bounds__(256) dfma_peak_kernel(float *out, int iters, double seed) {
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + i + threadIdx.x;
+    const double m = 1.0000001, c = 1e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123.456) out[0] = (float)s;
+}
+
 }  // namespace rrl
 
 using namespace rrl;
@@ -97,7 +116,8 @@ extern "C" int rrl_measure_fp32_peak(int mode, double *out_tflops, double *out_m
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0);
-        if (mode == 1) fma_peak_kernel<1><<<blocks, 256>>>(d, iters, 1.0f);
+        if (mode == 2) dfma_peak_kernel<<<blocks, 256>>>(d, iters / 16, 1.0);
+        else if (mode == 1) fma_peak_kernel<1><<<blocks, 256>>>(d, iters, 1.0f);
         else fma_peak_kernel<0><<<blocks, 256>>>(d, iters, 1.0f);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
@@ -110,7 +130,8 @@ extern "C" int rrl_measure_fp32_peak(int mode, double *out_tflops, double *out_m
     cudaEventDestroy(e1);
     cudaFree(d);
     if (cudaGetLastError() != cudaSuccess) return RRL_ERR_CUDA;
-    const double flops = (double)blocks * 256.0 * iters * 8 * 8 * 2 /*lanes of the float2*/ * 2 /*fma*/;
+    const double flops = mode == 2 ? (double)blocks * 256.0 * (iters / 16) * 8 * 8 * 2 /*fma*/
+                                   : (double)blocks * 256.0 * iters * 8 * 8 * 2 /*lanes of the float2*/ * 2 /*fma*/;
     *out_tflops = flops / (best * 1e-3) / 1e12;
     if (out_ms) *out_ms = best;
     return RRL_OK;

@@ -104,11 +104,10 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
 int launch_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                  int k_lo, int j_lo, int k_hi, int j_hi, cudaStream_t s);
 int launch_local_counts(const Workspace &ws, const Geometry &g, cudaStream_t s);
-int launch_median(const Workspace &ws, const Geometry &g, cudaStream_t s);
 int launch_welsch(const Workspace &ws, const Geometry &g, cudaStream_t s);
 int launch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
                     long long *out_stats, cudaStream_t s);
-int launch_welsch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
+int launch_tail(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
                            long long *out_stats, cudaStream_t s);
 int launch_backward(const Workspace &ws, const Geometry &g, const float *grad_out, float *g1, float *g2, cudaStream_t s);
 int launch_export_hits(const Workspace &ws, const Geometry &g, int cloud, int *out_counts, int *out_hits, cudaStream_t s);

@@ -180,85 +180,270 @@ __global__ void __launch_bounds__(256) sort_keys_kernel(const float *__restrict_
 // ------------------------------------------------------------------------------------------------------
 // nodes
 // ------------------------------------------------------------------------------------------------------
+// One bounding-sphere node, built by kNode CONSECUTIVE LANES: the lane of sorted position i = n * kNode + s loads triplet f
+// (or -1 = padding) and writes its point records; centroid, member count and radius are butterfly all-reductions inside
+// the lane group (x + y == y + x exactly, so every lane of a group holds the same bits); lane s == 0 writes the node
+// record.  Must be called by converged warps (whole groups, full mask).  Returns the node radius in lane s == 0.
 template <int kNode>
-__global__ void __launch_bounds__(128) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g) {
+__device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, float th, int f, long long i, double E,
+                                                float4 *pt_base, float4 *pt12, float4 *node4) {
+    const long long n = i / kNode;
+    const int s = (int)(i % kNode);
+    double px = 0, py = 0, pz = 0, cut = 0;
+    float4 pr = make_float4(0.f, 0.f, 0.f, -INFINITY);                // padding: never a candidate
+    float4 pr1 = pr, pr2 = pr;
+    if (f >= 0) {
+        const float *t = tri + (long long)f * 9;
+        px = __ldg(t); py = __ldg(t + 1); pz = __ldg(t + 2);
+        const double ax = __ldg(t + 3), ay = __ldg(t + 4), az = __ldg(t + 5);
+        const double bx = __ldg(t + 6), by = __ldg(t + 7), bz = __ldg(t + 8);
+        cut = (double)th * (double)th - (double)kAddEps;
+        pr = make_float4((float)px, (float)py, (float)pz, (float)(cut - (px * px + py * py + pz * pz)));
+        pr1 = make_float4((float)ax, (float)ay, (float)az, (float)(cut - (ax * ax + ay * ay + az * az)));
+        pr2 = make_float4((float)bx, (float)by, (float)bz, (float)(cut - (bx * bx + by * by + bz * bz)));
+    }
+    double cx = px, cy = py, cz = pz;                                 // 0 for padding lanes
+    int cntv = f >= 0;
+#pragma unroll
+    for (int d = 1; d < kNode; d <<= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, d);
+        cy += __shfl_xor_sync(0xffffffffu, cy, d);
+        cz += __shfl_xor_sync(0xffffffffu, cz, d);
+        cntv += __shfl_xor_sync(0xffffffffu, cntv, d);
+    }
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    double R = 0;
+    if (cntv > 0) {
+        qx = (float)(cx / cntv); qy = (float)(cy / cntv); qz = (float)(cz / cntv);   // the record's centre is the ROUNDED centroid
+        if (f >= 0) {
+            const double dx = px - qx, dy = py - qy, dz = pz - qz;
+            R = sqrt(fmax(cut + E, 0.0)) + sqrt(dx * dx + dy * dy + dz * dz);
+        }
+    }
+#pragma unroll
+    for (int d = 1; d < kNode; d <<= 1) R = fmax(R, __shfl_xor_sync(0xffffffffu, R, d));
+    pt12[i * 2] = pr1;
+    pt12[i * 2 + 1] = pr2;
+    {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB};
+        // a node occupies kNode + 1 float4 (odd stride: lanes reading different nodes hit different banks)
+        float *dp = reinterpret_cast<float *>(pt_base + n * (kNode + 1) + (s & ~1)) + (s & 1);
+        dp[0] = pr.x; dp[2] = pr.y; dp[4] = pr.z; dp[6] = pr.w;
+    }
+    float rad = 0.f;
+    if (s == 0) {
+        float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);           // empty node: never a candidate
+        if (cntv > 0) {
+            R *= 1.000002;
+            rad = (float)R * 1.000001f;
+            const double q2 = (double)qx * qx + (double)qy * qy + (double)qz * qz;
+            // round the record's slack UP: a larger w only admits more candidates
+            float w = (float)(R * R - q2);
+            w = w + fabsf(w) * 2.4e-7f + 1e-30f;
+            rec = make_float4(qx, qy, qz, w);
+        }
+        pt_base[n * (kNode + 1) + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);                  // pad slot
+        // node records: a group of 4 nodes = two interleaved pairs + one pad = 5 float4 (odd stride again)
+        float4 *grp = node4 + (n >> 2) * 5;
+        float *dst = reinterpret_cast<float *>(grp + ((n >> 1) & 1) * 2) + (n & 1);
+        dst[0] = rec.x; dst[2] = rec.y; dst[4] = rec.z; dst[6] = rec.w;
+        if ((n & 3) == 0) grp[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return rad;
+}
+
+// slack of the node radius for the rounding of the reference-order test: E = kGuardRef eps (P + Xmax)^2
+__device__ __forceinline__ double node_slack(unsigned pmax_bits, unsigned xmax_bits) {
+    const double P = sqrt((double)__uint_as_float(pmax_bits)) * 1.000001;
+    const double Xm = sqrt((double)__uint_as_float(xmax_bits)) * 1.000001;
+    return (double)kGuardRef * (double)kEps24 * (P + Xm) * (P + Xm) + 1e-12;
+}
+
+template <int kNode>
+__global__ void __launch_bounds__(256) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g) {
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
     const int nnodes = nfp / kNode;
     const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
     const float *thr = ws.thr[cloud] + (long long)b * nf;
     const int *perm = ws.perm[cloud] + (long long)b * nfp;
-    const double P = sqrt((double)__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001;
-    const double Xm = sqrt((double)__uint_as_float(ws.xmax[b * 2])) * 1.000001;
-    const double E = (double)kGuardRef * (double)kEps24 * (P + Xm) * (P + Xm) + 1e-12;
-    float4 *pt_base = ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1);
-    float4 *pt12 = ws.pt12[cloud] + (long long)b * nfp * 2;
-    for (int base = blockIdx.x * blockDim.x; base < nnodes; base += gridDim.x * blockDim.x) {   // warp-uniform trip count
-        const int n = base + threadIdx.x;
-        float rad = 0.f;
-        if (n < nnodes) {
-            double cx = 0, cy = 0, cz = 0;
-            int cntv = 0;
-            for (int s = 0; s < kNode; ++s) {
-                const int f = perm[n * kNode + s];
-                if (f >= 0) {
-                    cx += __ldg(tri + (long long)f * 9); cy += __ldg(tri + (long long)f * 9 + 1); cz += __ldg(tri + (long long)f * 9 + 2);
-                    ++cntv;
-                }
-            }
-            float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);               // empty node: never a candidate
-            if (cntv > 0) {
-                cx /= cntv; cy /= cntv; cz /= cntv;
-                const float qx = (float)cx, qy = (float)cy, qz = (float)cz;   // the record's centre is the ROUNDED centroid
-                double R = 0;
-                for (int s = 0; s < kNode; ++s) {
-                    const int f = perm[n * kNode + s];
-                    float4 pr = make_float4(0.f, 0.f, 0.f, -INFINITY);
-                    float4 pr1 = pr, pr2 = pr;
-                    if (f >= 0) {
-                        const double px = __ldg(tri + (long long)f * 9), py = __ldg(tri + (long long)f * 9 + 1), pz = __ldg(tri + (long long)f * 9 + 2);
-                        const double th = __ldg(thr + f);
-                        const double cut = th * th - (double)kAddEps;
-                        pr = make_float4((float)px, (float)py, (float)pz, (float)(cut - (px * px + py * py + pz * pz)));
-                        const double ax = __ldg(tri + (long long)f * 9 + 3), ay = __ldg(tri + (long long)f * 9 + 4), az = __ldg(tri + (long long)f * 9 + 5);
-                        const double bx = __ldg(tri + (long long)f * 9 + 6), by = __ldg(tri + (long long)f * 9 + 7), bz = __ldg(tri + (long long)f * 9 + 8);
-                        pr1 = make_float4((float)ax, (float)ay, (float)az, (float)(cut - (ax * ax + ay * ay + az * az)));
-                        pr2 = make_float4((float)bx, (float)by, (float)bz, (float)(cut - (bx * bx + by * by + bz * bz)));
-                        const double dx = px - qx, dy = py - qy, dz = pz - qz;
-                        const double reach = sqrt(fmax(cut + E, 0.0)) + sqrt(dx * dx + dy * dy + dz * dz);
-                        R = fmax(R, reach);
-                    }
-                    pt12[((long long)n * kNode + s) * 2] = pr1;
-                    pt12[((long long)n * kNode + s) * 2 + 1] = pr2;
-                    {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB};
-                        // a node occupies kNode + 1 float4 (odd stride: lanes reading different nodes hit different banks)
-                        float *dp = reinterpret_cast<float *>(pt_base + (long long)n * (kNode + 1) + (s & ~1)) + (s & 1);
-                        dp[0] = pr.x; dp[2] = pr.y; dp[4] = pr.z; dp[6] = pr.w;
-                    }
-                }
-                R *= 1.000002;
-                rad = (float)R * 1.000001f;
-                const double q2 = (double)qx * qx + (double)qy * qy + (double)qz * qz;
-                // round the record's slack UP: a larger w only admits more candidates
-                float w = (float)(R * R - q2);
-                w = w + fabsf(w) * 2.4e-7f + 1e-30f;
-                rec = make_float4(qx, qy, qz, w);
-            } else {
-                for (int s = 0; s < kNode; s += 2) {
-                    pt_base[(long long)n * (kNode + 1) + s] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    pt_base[(long long)n * (kNode + 1) + s + 1] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
-                }
-                for (int s = 0; s < 2 * kNode; ++s) pt12[(long long)n * kNode * 2 + s] = make_float4(0.f, 0.f, 0.f, -INFINITY);
-            }
-            pt_base[(long long)n * (kNode + 1) + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);            // pad slot
-            // node records: a group of 4 nodes = two interleaved pairs + one pad = 5 float4 (odd stride again)
-            float4 *grp = ws.node4[cloud] + (long long)b * (nnodes / 4) * 5 + (long long)(n >> 2) * 5;
-            float *dst = reinterpret_cast<float *>(grp + ((n >> 1) & 1) * 2) + (n & 1);
-            dst[0] = rec.x; dst[2] = rec.y; dst[4] = rec.z; dst[6] = rec.w;
-            if ((n & 3) == 0) grp[4] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    const double E = node_slack(ws.pmax[b * 2 + cloud], ws.xmax[b * 2]);
+    // one thread per sorted position; nfp is a multiple of kPointPad = 256 = blockDim.x, so every warp is full
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nfp; i += (long long)gridDim.x * blockDim.x) {
+        const int f = perm[i];
+        const float rad = make_node_coop<kNode>(tri, f >= 0 ? thr[f] : 0.f, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
+                                                ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5);
         warp_atomic_max_bits(ws.rmax + b * 2 + cloud, rad);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small clouds (<= kSortSmall padded triplets): memset + prep + sort + nodes in ONE launch
+// ------------------------------------------------------------------------------------------------------
+// grid (B, 2 + line blocks).  blockIdx.y < 2: one CTA per (pair, cloud) runs the whole chain -- thresholds and the
+// cloud's extent, the pair's line extent (each cloud CTA scans the pair's lines itself rather than wait for another
+// block), Hilbert keys, a bitonic sort in shared memory, the node records -- with block barriers instead of launch
+// boundaries.  blockIdx.y >= 2: per-line filter constants and hit counters.  The cloud-0 CTA also zeroes the pair's
+// accumulators (what the large-cloud path does with a memset).
+__device__ __forceinline__ void line_constants(const float *__restrict__ ln, float4 *lineC2, float &xm) {
+    const float u0 = __ldg(ln), u1 = __ldg(ln + 1), u2 = __ldg(ln + 2);
+    const double x = __ldg(ln + 3), y = __ldg(ln + 4), z = __ldg(ln + 5);
+    const double sd = x * u0 + y * u1 + z * u2;
+    const double xx = x * x + y * y + z * z;
+    lineC2[0] = make_float4(u0, u1, u2, (float)sqrt(xx) * 1.000001f);
+    lineC2[1] = make_float4((float)(2.0 * (x - sd * u0)), (float)(2.0 * (y - sd * u1)), (float)(2.0 * (z - sd * u2)), (float)(xx - sd * sd));
+    xm = (float)xx * 1.000001f;
+    if (!(xm == xm)) xm = INFINITY;
+}
+
+template <int kNode>
+__global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
+                                                          const float *__restrict__ lines, Workspace ws, Geometry g, int window,
+                                                          int sorted, int line_blocks) {
+    extern __shared__ unsigned long long skeys[];
+    __shared__ unsigned s_red[3];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float *lb = lines + (long long)b * g.nl * 6;
+    if (blockIdx.y >= 2) {
+        for (int l = (blockIdx.y - 2) * 1024 + tid; l < g.nl; l += line_blocks * 1024) {
+            const long long gl = (long long)b * g.nl + l;
+            float xm;
+            line_constants(lb + (long long)l * 6, ws.lineC + gl * 2, xm);
+            ws.cnt[0][gl] = 0;
+            ws.cnt[1][gl] = 0;
+        }
+        return;
+    }
+    const int cloud = blockIdx.y;
+    const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
+    const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
+    float *thr = ws.thr[cloud] + (long long)b * nf;
+    if (tid < 3) s_red[tid] = 0u;
+    if (cloud == 0) {
+        if (b == 0 && tid == 0) {
+            ws.hdr[0] = kMagic; ws.hdr[1] = g.B; ws.hdr[2] = g.nf1; ws.hdr[3] = g.nf2; ws.hdr[4] = g.nl; ws.hdr[5] = window;
+            ws.xcursor[0] = 0ull; ws.xcursor[1] = 0ull;
+        }
+        if (tid < 16) ws.n_kj[b * 16 + tid] = 0;
+        if (tid < 32) ws.sums[b * 32 + tid] = 0ull;
+        if (tid < RRL_NSTAT) ws.stats[(long long)b * RRL_NSTAT + tid] = 0;
+        if (tid < 18) ws.gcounts[b * 18 + tid] = 0;
+        if (tid < 4) ws.flags[b * 4 + tid] = 0;
+        if (tid == 0) { ws.nrec[b] = 0; ws.med[b] = 0.f; ws.xmax[b * 2 + 1] = 0u; }
+    }
+    __syncthreads();
+    // thresholds, extent of the cloud, extent of the pair's lines
+    float pm = 0.f, xm = 0.f;
+    for (int f = tid; f < nf; f += 1024) {
+        float v[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) v[q] = __ldg(tri + (long long)f * 9 + q);
+        thr[f] = triplet_thr_exact(v);
+        float m = fmaxf(fmaxf(sq3_rn(v[0], v[1], v[2]), sq3_rn(v[3], v[4], v[5])), sq3_rn(v[6], v[7], v[8]));
+        if (!(m == m)) m = INFINITY;
+        pm = fmaxf(pm, m);
+    }
+#pragma unroll 4
+    for (int l = tid; l < g.nl; l += 1024) {
+        const float *ln = lb + (long long)l * 6;
+        // float suffices: the sum is within 1.8e-7 of |x0|^2 and the factor keeps it an upper bound
+        const float x = __ldg(ln + 3), y = __ldg(ln + 4), z = __ldg(ln + 5);
+        float m = (x * x + y * y + z * z) * 1.000001f;
+        if (!(m == m)) m = INFINITY;
+        xm = fmaxf(xm, m);
+    }
+    {
+        const unsigned a = __reduce_max_sync(0xffffffffu, __float_as_uint(pm)), c = __reduce_max_sync(0xffffffffu, __float_as_uint(xm));
+        if ((tid & 31) == 0) { atomicMax(&s_red[0], a); atomicMax(&s_red[1], c); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        ws.pmax[b * 2 + cloud] = s_red[0];
+        if (cloud == 0) ws.xmax[b * 2] = s_red[1];
+    }
+    // Hilbert order: element i = e * 1024 + tid lives in register v[e]; n2 = E * 1024 >= nfp keys (sentinels sort last).
+    // Compare-exchange distances below 32 are warp shuffles, 32..512 go through shared memory (double buffered: one
+    // barrier per stage), 1024 and 2048 pair registers of the same thread.
+    const float P = sqrtf(__uint_as_float(s_red[0]));
+    const int E = nfp <= 1024 ? 1 : (nfp <= 2048 ? 2 : 4);
+    unsigned long long v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = e * 1024 + tid;
+        v[e] = 0xFFFFFFFFFFFFFFFFull;
+        if (e < E && i < nf) {
+            const float p[3] = {__ldg(tri + (long long)i * 9), __ldg(tri + (long long)i * 9 + 1), __ldg(tri + (long long)i * 9 + 2)};
+            const unsigned key = sorted ? morton_key(p, P) : 0u;
+            v[e] = ((unsigned long long)key << 32) | (unsigned)i;
+        }
+    }
+    if (sorted) {
+        auto cas = [](unsigned long long &lo_el, unsigned long long &hi_el, bool up) {      // lo_el has the lower index
+            const unsigned long long mn = lo_el < hi_el ? lo_el : hi_el, mx = lo_el < hi_el ? hi_el : lo_el;
+            lo_el = up ? mn : mx;
+            hi_el = up ? mx : mn;
+        };
+        int buf = 0;
+        const int N = E * 1024;
+        for (int k = 2; k <= N; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 1024) {
+                    // i & k for element (e, tid): k >= 2048 here, so the direction depends on e only
+                    if (j == 1024) {
+                        cas(v[0], v[1], (0 & k) == 0);
+                        if (E > 2) cas(v[2], v[3], (2048 & k) == 0);
+                    } else {
+                        cas(v[0], v[2], (0 & k) == 0);
+                        cas(v[1], v[3], (1024 & k) == 0);
+                    }
+                } else if (j >= 32) {
+                    unsigned long long *sb = skeys + buf * N;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (e < E) sb[e * 1024 + tid] = v[e];
+                    __syncthreads();
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (e < E) {
+                            const int i = e * 1024 + tid;
+                            const unsigned long long o = sb[i ^ j];
+                            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                            v[e] = (v[e] < o) == keep_min ? v[e] : o;
+                        }
+                    buf ^= 1;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (e < E) {
+                            const int i = e * 1024 + tid;
+                            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], j);
+                            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                            v[e] = (v[e] < o) == keep_min ? v[e] : o;
+                        }
+                }
+            }
+    }
+    int *perm = ws.perm[cloud] + (long long)b * nfp;
+    const int nnodes = nfp / kNode;
+    const double Eslack = node_slack(s_red[0], s_red[1]);
+    __syncthreads();                                     // thr (global) is re-read below by other threads
+    float rad = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = e * 1024 + tid;
+        if (e < E && i < nfp) {                          // nfp is a multiple of 256: whole warps
+            const unsigned idx = (unsigned)(v[e] & 0xFFFFFFFFull);
+            const int f = idx < (unsigned)nf ? (int)idx : -1;
+            perm[i] = f;
+            rad = fmaxf(rad, make_node_coop<kNode>(tri, f >= 0 ? thr[f] : 0.f, f, i, Eslack, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
+                                                   ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5));
+        }
+    }
+    {
+        const unsigned a = __reduce_max_sync(0xffffffffu, __float_as_uint(rad));
+        if ((tid & 31) == 0 && a) atomicMax(&s_red[2], a);
+    }
+    __syncthreads();
+    if (tid == 0) ws.rmax[b * 2 + cloud] = s_red[2];
 }
 
 size_t sort_scratch_bytes(int nfp_max) {
@@ -268,8 +453,8 @@ size_t sort_scratch_bytes(int nfp_max) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[8] = {0, 0, 16, 32, 0, 0, 0, 0};   // [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = chunks may exceed the shared-memory point cache
-void set_param(int id, int v) { if (id > 0 && id < 8) g_param[id] = v; }
+static int g_param[8] = {0, 0, 16, 32, 0, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = chunks may exceed the shared-memory point cache
+void set_param(int id, int v) { if (id >= 0 && id < 8) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
     return (g.nf1 > g.nf2 ? g.nf1 : g.nf2) >= 16384 ? 16 : 8;
@@ -280,6 +465,29 @@ void set_dense_variant(int v) { g_dense_variant = v; }
 
 int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                 int window, cudaStream_t s) {
+    const int sorted = g_dense_variant ? 1 : 0;
+    const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
+    const int G = node_size(g);
+    if (nfp_max <= kSortSmall && g_param[0] == 0) {
+        const int n2 = nfp_max <= 1024 ? 1024 : (nfp_max <= 2048 ? 2048 : 4096);
+        int line_blocks = (g.nl + 1023) / 1024;
+        if (line_blocks > 64) line_blocks = 64;
+        const dim3 grid(g.B, 2 + line_blocks);
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(small_prep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess ||
+                cudaFuncSetAttribute(small_prep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess)
+                return RRL_ERR_CUDA;
+            attr_set = true;
+        }
+        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks);
+        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks);
+        count_launch();
+        stage_mark(1, s);
+        stage_mark(2, s);
+        stage_mark(3, s);
+        return check_launch();
+    }
     // per-pair block {pmax ... gcounts} is contiguous, see carve()
     const size_t pair_bytes = (size_t)((char *)(ws.gcounts + (size_t)g.B * 18) - (char *)ws.xcursor);
     if (cudaMemsetAsync(ws.xcursor, 0, pair_bytes, s) != cudaSuccess) return RRL_ERR_CUDA;
@@ -291,8 +499,6 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     prep_kernel<<<dim3(bx, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, window);
     count_launch();
     stage_mark(1, s);
-    const int sorted = g_dense_variant ? 1 : 0;
-    const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
     if (nfp_max <= kSortSmall) {
         int n2 = 1;
         while (n2 < nfp_max) n2 <<= 1;
@@ -320,12 +526,10 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
             }
     }
     stage_mark(2, s);
-    const int G = node_size(g);
-    const int nn_max = nfp_max / G;
-    int nbx = (nn_max + 127) / 128;
-    if (nbx > 1024) nbx = 1024;
-    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 128, 0, s>>>(tri1, tri2, ws, g);
-    else node_kernel<16><<<dim3(nbx, g.B * 2), 128, 0, s>>>(tri1, tri2, ws, g);
+    int nbx = nfp_max / 256;
+    if (nbx > 4096) nbx = 4096;
+    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g);
+    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g);
     count_launch();
     stage_mark(3, s);
     return check_launch();

@@ -19,6 +19,20 @@
 
 namespace rrl {
 
+// ---- phase timestamps of block (0, 0) (measurement builds only: -DRRL_MARKS) ----
+#ifdef RRL_MARKS
+__device__ unsigned long long g_marks[32];
+__device__ __forceinline__ void mark(int i) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_marks[i] = t;
+    }
+}
+#else
+__device__ __forceinline__ void mark(int) {}
+#endif
+
 // weights + intersection point of ONE hit triplet
 __device__ __forceinline__ void make_point(const float *__restrict__ tri, int f, const float *ln, float *w /*[3]*/, float *q /*[3]*/) {
     const float *t = tri + (long long)f * 9;
@@ -35,66 +49,15 @@ __device__ __forceinline__ void make_point(const float *__restrict__ tri, int f,
         q[c] = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(w[0], v[c]), __fmul_rn(w[1], v[3 + c])), __fmul_rn(w[2], v[6 + c])), 3.0f);
 }
 
-__device__ __forceinline__ void cswap(int &a, int &b) {
-    const int lo = min(a, b), hi = max(a, b);
-    a = lo; b = hi;
-}
-
-// the record of one selected line, written to slot r (global record index).  Everything is fully unrolled with
-// static indices and predicated on (a < k), (c < j) so that the per-hit arrays stay in registers.
-__device__ __forceinline__ void build_record(const float *__restrict__ tri1, const float *__restrict__ tri2,
-                                             const float *__restrict__ lines, const Workspace &ws, const Geometry &g, int b,
-                                             int l, int k, int j, long long r) {
-    const long long gl = (long long)b * g.nl + l;
-    int i1[4], i2[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        i1[a] = a < k ? ws.hits[0][gl * kCap + a] : 0x7fffffff;
-        i2[a] = a < j ? ws.hits[1][gl * kCap + a] : 0x7fffffff;
-    }
-    // ascending (nonzero() order); the padding sorts to the end
-    cswap(i1[0], i1[1]); cswap(i1[2], i1[3]); cswap(i1[0], i1[2]); cswap(i1[1], i1[3]); cswap(i1[1], i1[2]);
-    cswap(i2[0], i2[1]); cswap(i2[2], i2[3]); cswap(i2[0], i2[2]); cswap(i2[1], i2[3]); cswap(i2[1], i2[2]);
-    float ln[6];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) ln[q] = __ldg(lines + gl * 6 + q);
-    float wv[24], qv[24];
-#pragma unroll
-    for (int a = 0; a < 24; ++a) { wv[a] = 0.f; qv[a] = 0.f; }
-    const float *t1 = tri1 + (long long)b * g.nf1 * 9, *t2 = tri2 + (long long)b * g.nf2 * 9;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        if (a < k) make_point(t1, i1[a], ln, wv + a * 3, qv + a * 3);
-        if (a < j) make_point(t2, i2[a], ln, wv + 12 + a * 3, qv + 12 + a * 3);
-    }
-    float4 *D4 = reinterpret_cast<float4 *>(ws.recD + r * 16);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        float d[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            d[c] = (a < k && c < j) ? sq3_rn(__fsub_rn(qv[a * 3], qv[12 + c * 3]), __fsub_rn(qv[a * 3 + 1], qv[12 + c * 3 + 1]),
-                                             __fsub_rn(qv[a * 3 + 2], qv[12 + c * 3 + 2])) : 0.f;
-        D4[a] = make_float4(d[0], d[1], d[2], d[3]);
-    }
-    reinterpret_cast<int2 *>(ws.recMeta)[r] = make_int2(l, k | (j << 8));
-    int4 *I4 = reinterpret_cast<int4 *>(ws.recIdx + r * 8);
-    I4[0] = make_int4(k > 0 ? i1[0] : -1, k > 1 ? i1[1] : -1, k > 2 ? i1[2] : -1, k > 3 ? i1[3] : -1);
-    I4[1] = make_int4(j > 0 ? i2[0] : -1, j > 1 ? i2[1] : -1, j > 2 ? i2[2] : -1, j > 3 ? i2[3] : -1);
-    float4 *W4 = reinterpret_cast<float4 *>(ws.recW + r * 24), *Q4 = reinterpret_cast<float4 *>(ws.recQ + r * 24);
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        W4[a] = make_float4(wv[4 * a], wv[4 * a + 1], wv[4 * a + 2], wv[4 * a + 3]);
-        Q4[a] = make_float4(qv[4 * a], qv[4 * a + 1], qv[4 * a + 2], qv[4 * a + 3]);
-    }
-}
-
-// One thread per line selects; the block compacts its selected lines in shared memory (ordered), claims a contiguous
-// range of record slots with ONE atomic, and builds the records with densely populated warps.
+// One thread per line selects; the block compacts its selected lines in shared memory (ordered) and claims a contiguous
+// range of record slots with ONE atomic.  The records are then built by one thread per (record, cloud, hit slot) --
+// each computes the weights and the intersection point of ONE hit triplet and drops them at the hit's rank among the
+// line's hits (ascending triplet index = nonzero() order) -- and one thread per D entry.
 __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
                                                     const float *__restrict__ lines, Workspace ws, Geometry g,
                                                     int k_lo, int j_lo, int k_hi, int j_hi) {
     __shared__ int s_line[256], s_kj[256], s_warp[8], s_hist[16], s_base;
+    __shared__ float s_q[256 * 24];            // intersection points of the block's records: q1[4][3], q2[4][3]
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int l = blockIdx.x * blockDim.x + tid;
     if (tid < 16) s_hist[tid] = 0;
@@ -124,10 +87,47 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
     if (tid == 0) s_base = atomicAdd(ws.nrec + b, total);
     __syncthreads();
     if (tid < 16 && s_hist[tid]) atomicAdd(ws.n_kj + b * 16 + tid, s_hist[tid]);
-    if (tid < total) {
-        const int kj = s_kj[tid];
-        build_record(tri1, tri2, lines, ws, g, b, s_line[tid], kj & 255, (kj >> 8) & 255, (long long)b * g.nl + s_base + tid);
+    const long long r0 = (long long)b * g.nl + s_base;
+    for (int t = tid; t < total * 8; t += 256) {
+        const int rec = t >> 3, cloud = (t >> 2) & 1, a = t & 3;
+        const int kj = s_kj[rec];
+        const int cnt = cloud ? (kj >> 8) & 255 : kj & 255;
+        const long long gl = (long long)b * g.nl + s_line[rec];
+        float w[3] = {0.f, 0.f, 0.f}, q[3] = {0.f, 0.f, 0.f};
+        int idx = -1, pos = a;                       // unused slots a >= cnt keep their place behind the hits
+        if (a < cnt) {
+            const int *h = ws.hits[cloud] + gl * kCap;
+            idx = h[a];
+            pos = 0;
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (o < cnt && o != a) pos += h[o] < idx;
+            float ln[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) ln[c] = __ldg(lines + gl * 6 + c);
+            make_point(cloud ? tri2 + (long long)b * g.nf2 * 9 : tri1 + (long long)b * g.nf1 * 9, idx, ln, w, q);
+        }
+        const long long r = r0 + rec;
+        const int o3 = cloud * 12 + pos * 3;
+        ws.recIdx[r * 8 + cloud * 4 + pos] = idx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            ws.recW[r * 24 + o3 + c] = w[c];
+            ws.recQ[r * 24 + o3 + c] = q[c];
+            s_q[rec * 24 + o3 + c] = q[c];
+        }
     }
+    __syncthreads();
+    for (int t = tid; t < total * 16; t += 256) {
+        const int rec = t >> 4, a = (t >> 2) & 3, c = t & 3;
+        const int kj = s_kj[rec];
+        const float *q1 = s_q + rec * 24 + a * 3, *q2 = s_q + rec * 24 + 12 + c * 3;
+        float d = 0.f;
+        if (a < (kj & 255) && c < ((kj >> 8) & 255))
+            d = sq3_rn(__fsub_rn(q1[0], q2[0]), __fsub_rn(q1[1], q2[1]), __fsub_rn(q1[2], q2[2]));
+        ws.recD[r0 * 16 + t] = d;
+    }
+    if (tid < total) reinterpret_cast<int2 *>(ws.recMeta)[r0 + tid] = make_int2(s_line[tid], s_kj[tid]);
 }
 
 int launch_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
@@ -160,152 +160,126 @@ int launch_local_counts(const Workspace &ws, const Geometry &g, cudaStream_t s) 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// exact lower median by radix select (non-negative floats order like their bit patterns)
+// exact lower median by range-refining selection (non-negative floats order like their bit patterns)
 // ------------------------------------------------------------------------------------------------------
-constexpr int kSelThreads = 1024;
+// Each round histograms the keys inside the current range [lo, hi] into 2^11 equal-width buckets, finds the bucket
+// that holds the wanted rank with a block-wide scan, and narrows the range to it: 31 -> 20 -> 9 -> 0 bits of width,
+// i.e. at most three or four sweeps.  Because the buckets subdivide the OCCUPIED range rather than fixed bit fields,
+// D values that share an exponent do not pile into a handful of bins, so plain shared-memory atomics suffice.
+constexpr int kSelBits = 11;
+constexpr int kSelBins = 1 << kSelBits;
+constexpr unsigned kNoKey = 0xFFFFFFFFu;     // "not a D entry" (D >= 0 never has that bit pattern)
 
-// `key(i, valid)` enumerates `slots` slots, `n` of which are valid; returns the key of rank (n-1)/2.  Block-wide.
-template <typename KeyFn>
-__device__ unsigned radix_select_lower_median(long long slots, long long n, KeyFn key, unsigned *hist /*smem[256]*/,
-                                              unsigned *s_prefix, long long *s_rank) {
-    unsigned prefix = 0, mask = 0;
+struct SelectScratch {
+    unsigned hist[kSelBins];
+    unsigned wtot[32];
+    unsigned bin, kmin, kmax;
+    long long rank;
+};
+
+// `key(i)` enumerates `slots` slots (kNoKey = not valid), n > 0 of which are valid and lie in [kmin, kmax]; returns the
+// key of rank (n-1)/2.  Block-wide (kThreads threads), every thread returns the same value.
+template <int kThreads, typename KeyFn>
+__device__ unsigned select_lower_median(long long slots, long long n, KeyFn key, unsigned kmin, unsigned kmax, SelectScratch &sc) {
+    constexpr int kPer = kSelBins / kThreads;
+    static_assert(kPer * kThreads == kSelBins && kPer >= 1 && kThreads <= 1024, "one thread owns kPer consecutive bins");
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned lo = kmin, hi = kmax;
     long long rank = (n - 1) / 2;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    for (;;) {
+        const unsigned width = hi - lo;
+        if (width == 0) return lo;
+        const int s = max(0, (32 - __clz(width)) - kSelBits);         // (width >> s) < kSelBins
+        for (int i = tid; i < kSelBins; i += kThreads) sc.hist[i] = 0;
         __syncthreads();
-        for (long long i0 = 0; i0 < slots; i0 += blockDim.x) {       // block-uniform trip count (warp collectives inside)
-            const long long i = i0 + threadIdx.x;
-            bool valid = false;
-            unsigned kbits = 0;
-            if (i < slots) kbits = key(i, valid);
-            const bool in = valid && (kbits & mask) == prefix;
-            // D values crowd a few bins (same exponent): aggregate equal bins inside the warp before the atomic
-            const unsigned bin = in ? ((kbits >> shift) & 255u) : 0xFFFFFFFFu;
-            const unsigned peers = __match_any_sync(0xffffffffu, bin);
-            if (in && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        for (long long i0 = 0; i0 < slots; i0 += 4 * kThreads) {      // four independent loads in flight per thread
+            unsigned kb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long i = i0 + u * kThreads + tid;
+                kb[u] = i < slots ? key(i) : kNoKey;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (kb[u] != kNoKey && kb[u] >= lo && kb[u] <= hi) atomicAdd(&sc.hist[(kb[u] - lo) >> s], 1u);
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            // warp 0 finds the bin holding `rank`: 8 bins per lane, exclusive warp scan of the lane totals
-            const int lane = threadIdx.x;
-            unsigned h[8], tot = 0;
+        unsigned h[kPer], tot = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { h[q] = hist[lane * 8 + q]; tot += h[q]; }
-            unsigned inc = tot;
+        for (int q = 0; q < kPer; ++q) { h[q] = sc.hist[tid * kPer + q]; tot += h[q]; }
+        unsigned inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += up;
+        }
+        if (lane == 31) sc.wtot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned v = lane < kThreads / 32 ? sc.wtot[lane] : 0u;
+            unsigned incw = v;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const unsigned up = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += up;
+                const unsigned up = __shfl_up_sync(0xffffffffu, incw, d);
+                if (lane >= d) incw += up;
             }
-            const long long before = (long long)(inc - tot);
-            if (rank >= before && rank < before + (long long)tot) {
-                long long r = rank - before;
-                int q = 0;
-                for (; q < 7; ++q) {
-                    if (r < (long long)h[q]) break;
-                    r -= h[q];
-                }
-                *s_prefix = prefix | ((unsigned)(lane * 8 + q) << shift);
-                *s_rank = r;
-            }
+            sc.wtot[lane] = incw - v;
         }
         __syncthreads();
-        prefix = *s_prefix;
-        rank = *s_rank;
-        mask |= 255u << shift;
+        const long long before = (long long)sc.wtot[wid] + (long long)(inc - tot);
+        if (tot && rank >= before && rank < before + (long long)tot) {
+            long long r = rank - before;
+            int q = 0;
+            for (; q < kPer - 1; ++q) {
+                if (r < (long long)h[q]) break;
+                r -= h[q];
+            }
+            sc.bin = (unsigned)(tid * kPer + q);
+            sc.rank = r;
+        }
         __syncthreads();
+        rank = sc.rank;
+        const unsigned long long nlo = (unsigned long long)lo + ((unsigned long long)sc.bin << s);
+        const unsigned long long nhi = nlo + ((1ull << s) - 1ull);
+        lo = (unsigned)nlo;
+        if (nhi < (unsigned long long)hi) hi = (unsigned)nhi;
+        if (s == 0) return lo;
+        __syncthreads();                               // sc.bin / sc.rank are rewritten in the next round
     }
-    return prefix;
 }
 
-constexpr int kMedCache = 48 * 1024;        // D slots cached in shared memory (192 KB); the rest is re-read through L2
-
-__global__ void __launch_bounds__(kSelThreads) median_kernel(Workspace ws, Geometry g) {
-    extern __shared__ unsigned s_keys[];     // [kMedCache]; 0xFFFFFFFF = not a D entry (D >= 0 never has that pattern)
-    __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix;
-    __shared__ long long s_rank;
-    const int b = blockIdx.x;
-    const int nrec = ws.nrec[b];
-    long long n = 0;
-    for (int c = 0; c < 16; ++c) n += (long long)ws.n_kj[b * 16 + c] * ((c >> 2) + 1) * ((c & 3) + 1);
-    if (threadIdx.x < 16) ws.gcounts[b * 18 + threadIdx.x] = ws.n_kj[b * 16 + threadIdx.x];   // single-GPU: local == global
-    if (threadIdx.x == 16) ws.gcounts[b * 18 + 16] = nrec;
-    if (threadIdx.x == 17) ws.gcounts[b * 18 + 17] = n;
-    if (n == 0) {
-        if (threadIdx.x == 0) ws.med[b] = 0.f;
-        return;
+// block-wide min / max of the valid keys a thread has seen -> sc.kmin / sc.kmax (initialised by the caller)
+__device__ __forceinline__ void block_minmax(unsigned mn, unsigned mx, SelectScratch &sc) {
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) {
+        if (mn != kNoKey) atomicMin(&sc.kmin, mn);
+        atomicMax(&sc.kmax, mx);
     }
-    const float *D = ws.recD + (long long)b * g.nl * 16;
-    const int *meta = ws.recMeta + (long long)b * g.nl * 2;
-    const long long slots = (long long)nrec * 16;
-    auto gkey = [&](long long i) -> unsigned {
-        const int kj = meta[(i >> 4) * 2 + 1];
-        const int e = (int)(i & 15);
-        const bool valid = (e >> 2) < (kj & 255) && (e & 3) < ((kj >> 8) & 255);
-        return valid ? __float_as_uint(D[i]) : 0xFFFFFFFFu;
-    };
-    // one pipelined sweep over the records fills the cache; the four select passes then run out of shared memory
-    const int ncache = (int)(slots < kMedCache ? slots : kMedCache);
-    // (both loads of a slot are issued unconditionally and eight slots are in flight per thread: with one CTA per pair
-    // the sweep is otherwise a chain of dependent L2 round trips)
-    for (int i0 = 0; i0 < ncache; i0 += 8 * kSelThreads) {
-        int kj[8];
-        unsigned kb[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * kSelThreads + threadIdx.x;
-            kj[u] = 0; kb[u] = 0;
-            if (i < ncache) { kj[u] = meta[(i >> 4) * 2 + 1]; kb[u] = __float_as_uint(D[i]); }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * kSelThreads + threadIdx.x;
-            const int e = i & 15;
-            const bool valid = (e >> 2) < (kj[u] & 255) && (e & 3) < ((kj[u] >> 8) & 255);
-            if (i < ncache) s_keys[i] = valid ? kb[u] : 0xFFFFFFFFu;
-        }
-    }
-    __syncthreads();
-    auto key = [&](long long i, bool &valid) -> unsigned {
-        const unsigned kb = i < ncache ? s_keys[i] : gkey(i);
-        valid = kb != 0xFFFFFFFFu;
-        return kb;
-    };
-    const unsigned bits = radix_select_lower_median(slots, n, key, hist, &s_prefix, &s_rank);
-    if (threadIdx.x == 0) ws.med[b] = __uint_as_float(bits);
 }
 
-int launch_median(const Workspace &ws, const Geometry &g, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMedCache * 4) != cudaSuccess) return RRL_ERR_CUDA;
-        attr_set = true;
-    }
-    median_kernel<<<g.B, kSelThreads, kMedCache * 4, s>>>(ws, g);
-    count_launch();
-    stage_mark(7, s);
-    return check_launch();
-}
-
-__global__ void __launch_bounds__(kSelThreads) select_flat_kernel(const float *__restrict__ vals, long long n, float *out) {
-    __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix;
-    __shared__ long long s_rank;
+__global__ void __launch_bounds__(1024) select_flat_kernel(const float *__restrict__ vals, long long n, float *out) {
+    __shared__ SelectScratch sc;
     if (n <= 0) {
         if (threadIdx.x == 0) *out = 0.f;
         return;
     }
-    auto key = [&](long long i, bool &valid) -> unsigned {
-        valid = true;
-        return __float_as_uint(vals[i]);
-    };
-    const unsigned bits = radix_select_lower_median(n, n, key, hist, &s_prefix, &s_rank);
+    if (threadIdx.x == 0) { sc.kmin = kNoKey; sc.kmax = 0u; }
+    __syncthreads();
+    unsigned mn = kNoKey, mx = 0u;
+    for (long long i = threadIdx.x; i < n; i += 1024) {
+        const unsigned kb = __float_as_uint(vals[i]);
+        mn = min(mn, kb); mx = max(mx, kb);
+    }
+    block_minmax(mn, mx, sc);
+    __syncthreads();
+    auto key = [&](long long i) -> unsigned { return __float_as_uint(vals[i]); };
+    const unsigned bits = select_lower_median<1024>(n, n, key, sc.kmin, sc.kmax, sc);
     if (threadIdx.x == 0) *out = __uint_as_float(bits);
 }
 
 int launch_select_median(const float *vals, long long n, float *out, cudaStream_t s) {
-    select_flat_kernel<<<1, kSelThreads, 0, s>>>(vals, n, out);
+    select_flat_kernel<<<1, 1024, 0, s>>>(vals, n, out);
     count_launch();
     return check_launch();
 }
@@ -336,37 +310,108 @@ int launch_pack_entries(const Workspace &ws, const Geometry &g, float *out, long
 // ------------------------------------------------------------------------------------------------------
 // Welsch + minima + gradient vectors
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float welsch(float D, float med) {
-    // 1 - exp(-((x / c)) / 2.0)   loss.py:21
-    // exp evaluated in double and rounded once: a well-defined (correctly rounded) float exp, so that the row/column
-    // argmin of near-tied entries does not depend on a vendor expf's last bit (the oracle does the same)
-    return __fsub_rn(1.0f, (float)exp((double)(-__fdiv_rn(__fdiv_rn(D, med), 2.0f))));
+// e^x for x <= 0 (or NaN) in double, branch free: Cody-Waite reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial
+// (truncation < 2^-57), scaling by exponent bits.  Arguments below -120 are clamped: the result is far below half the
+// smallest float subnormal either way.  Error <= 2 ulp of a double.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    x = x < -120.0 ? -120.0 : x;                                   // NaN stays NaN
+    const double t = rint(x * 1.4426950408889634074);
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821614599e-10;                          // 1/13!
+    p = fma(p, r, 2.0876756987868098979e-09);
+    p = fma(p, r, 2.5052108385441718775e-08);
+    p = fma(p, r, 2.7557319223985890653e-07);
+    p = fma(p, r, 2.7557319223985892511e-06);
+    p = fma(p, r, 2.4801587301587301566e-05);
+    p = fma(p, r, 1.9841269841269841253e-04);
+    p = fma(p, r, 1.3888888888888889419e-03);
+    p = fma(p, r, 8.3333333333333332177e-03);
+    p = fma(p, r, 4.1666666666666664354e-02);
+    p = fma(p, r, 1.6666666666666665741e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int n = __double2int_rn(t);                              // in [-174, 0]; 0 for NaN (p is NaN then)
+    return p * __longlong_as_double((long long)(1023 + n) << 52);
 }
 
-// One record: minima -> (s1, s2); the gradient vectors for a unit upstream gradient overwrite the record's
-// intersection points (recQ), which nothing reads afterwards.  cw_over_n = exp(-|k-j|/2) / C / n_kj.
-__device__ __forceinline__ void welsch_record(const Workspace &ws, long long r, float med, double cw_over_n, int k, int j,
-                                              double &s1, double &s2) {
-    float W[16], D[16];
-    const float4 *D4 = reinterpret_cast<const float4 *>(ws.recD + r * 16);
+// exp(-((x / c)) / 2.0) of loss.py:21 evaluated in double on the float argument: W = 1 - (float)e is then a well-defined
+// (correctly rounded up to the 2^-29 chance of a double-rounding tie) float exp, so that the row/column argmin of
+// near-tied entries does not depend on a vendor expf's last bit (the oracle does the same); the double e also serves
+// the gradient, dW/dD = e / (2 med).
+__device__ __forceinline__ double welsch_exp(float D, float med) {
+    return exp_nonpos((double)(-__fdiv_rn(__fdiv_rn(D, med), 2.0f)));
+}
+
+// The Welsch stage of 32 records, one per lane of a CONVERGED warp (lanes without a record pass valid = false).
+//   * a record has k*j <= 16 entries (3.3 on average) and a double-precision exp is a long dependent chain, so the exps
+//     are evaluated on a dense list: the lanes drop their valid D entries into the warp's shared-memory buffer `buf`
+//     (>= 512 floats), the warp evaluates the list 32 entries at a time, and every lane reads its (float) exps back.
+//     (One thread per record running its own k*j exps measured 4x slower: 16 predicated sites per warp.)
+//   * minima with first-index tie breaking (torch.min) -> v1 = sum_a min_b W, v2 = sum_b min_a W as 2^-40 fixed point
+//     (W * 2^40 is an exact float product; integer sums are exact and order independent);
+//   * gradient vectors for a unit upstream gradient, in float (relative error ~1e-7, bar 1e-5): they overwrite the
+//     record's intersection points (recQ), which nothing reads afterwards.
+// cw_over_n = exp(-|k-j|/2) / C / n_kj.
+__device__ __forceinline__ void welsch_warp(const Workspace &ws, bool valid, long long r, float med, float cw_over_n, int k, int j,
+                                            float *buf, unsigned long long &v1, unsigned long long &v2, bool &nan) {
+    const int lane = threadIdx.x & 31;
+    float D[16];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const float4 d = D4[a];
-        D[a * 4] = d.x; D[a * 4 + 1] = d.y; D[a * 4 + 2] = d.z; D[a * 4 + 3] = d.w;
+    for (int a = 0; a < 16; ++a) D[a] = 0.f;
+    if (valid) {
+        const float4 *D4 = reinterpret_cast<const float4 *>(ws.recD + r * 16);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float4 d = D4[a];
+            D[a * 4] = d.x; D[a * 4 + 1] = d.y; D[a * 4 + 2] = d.z; D[a * 4 + 3] = d.w;
+        }
     }
+    const int cnt = valid ? k * j : 0;
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    const int off = inc - cnt;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) W[a * 4 + c] = (a < k && c < j) ? welsch(D[a * 4 + c], med) : 0.f;
+        for (int c = 0; c < 4; ++c)
+            if (valid && a < k && c < j) buf[off + a * j + c] = D[a * 4 + c];
+    __syncwarp();
+    for (int p = lane; p < total; p += 32) buf[p] = (float)welsch_exp(buf[p], med);
+    __syncwarp();
+    float W[16], E[16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            E[a * 4 + c] = 0.f;
+            W[a * 4 + c] = 0.f;
+            if (valid && a < k && c < j) {
+                E[a * 4 + c] = buf[off + a * j + c];
+                W[a * 4 + c] = __fsub_rn(1.0f, E[a * 4 + c]);
+            }
+        }
+    __syncwarp();                                                  // buf is reused by the caller's next batch
     int arg_b[4], arg_a[4];
-    s1 = 0.0; s2 = 0.0;
+    v1 = 0ull; v2 = 0ull;
+    nan = false;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {                   // torch.min(W, 2): first index on ties
         int m = 0;
 #pragma unroll
         for (int c = 1; c < 4; ++c) if (c < j && W[a * 4 + c] < W[a * 4 + m]) m = c;
         arg_b[a] = m;
-        if (a < k) s1 += (double)W[a * 4 + m];
+        if (valid && a < k) {
+            const float w = W[a * 4 + m];
+            nan |= !(w == w);
+            v1 += (unsigned long long)__float2ll_rn(w * (float)kFixScale);
+        }
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {                   // torch.min(W, 1)
@@ -374,8 +419,15 @@ __device__ __forceinline__ void welsch_record(const Workspace &ws, long long r, 
 #pragma unroll
         for (int a = 1; a < 4; ++a) if (a < k && W[a * 4 + c] < W[m * 4 + c]) m = a;
         arg_a[c] = m;
-        if (c < j) s2 += (double)W[m * 4 + c];
+        if (valid && c < j) {
+            const float w = W[m * 4 + c];
+            nan |= !(w == w);
+            v2 += (unsigned long long)__float2ll_rn(w * (float)kFixScale);
+        }
     }
+    if (nan) { v1 = 0ull; v2 = 0ull; }
+    if (!valid) return;
+    // d loss / d D[a,c] = coef[a,c] e / (2 med); the factor 2 of d D / d q cancels the 1/2
     float4 *Q4 = reinterpret_cast<float4 *>(ws.recQ + r * 24);
     float q[24];
 #pragma unroll
@@ -383,29 +435,33 @@ __device__ __forceinline__ void welsch_record(const Workspace &ws, long long r, 
         const float4 v = Q4[a];
         q[4 * a] = v.x; q[4 * a + 1] = v.y; q[4 * a + 2] = v.z; q[4 * a + 3] = v.w;
     }
-    double G[24];
+    const float inv_med = 1.0f / med;
+    const float ck = cw_over_n / (float)k * inv_med, cj = cw_over_n / (float)j * inv_med;
+    float G[24];
 #pragma unroll
-    for (int a = 0; a < 24; ++a) G[a] = 0.0;
-    const double inv2med = 1.0 / (2.0 * (double)med);
+    for (int x = 0; x < 24; ++x) G[x] = 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            if (a >= k || c >= j) continue;
-            double coef = 0.0;
-            if (arg_b[a] == c) coef += cw_over_n / k;
-            if (arg_a[c] == a) coef += cw_over_n / j;
-            if (coef == 0.0) continue;
-            const double f = coef * exp(-(double)D[a * 4 + c] * inv2med) * inv2med * 2.0;
+            const bool live = a < k && c < j;
+            const float coef = (live && arg_b[a] == c ? ck : 0.f) + (live && arg_a[c] == a ? cj : 0.f);
+            const float f = coef * E[a * 4 + c];
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
-                const double gv = f * ((double)q[a * 3 + x] - (double)q[12 + c * 3 + x]);
+                const float gv = f * (q[a * 3 + x] - q[12 + c * 3 + x]);
                 G[a * 3 + x] += gv;
                 G[12 + c * 3 + x] -= gv;
             }
         }
 #pragma unroll
-    for (int a = 0; a < 6; ++a) Q4[a] = make_float4((float)G[4 * a], (float)G[4 * a + 1], (float)G[4 * a + 2], (float)G[4 * a + 3]);
+    for (int a = 0; a < 6; ++a) Q4[a] = make_float4(G[4 * a], G[4 * a + 1], G[4 * a + 2], G[4 * a + 3]);
+}
+
+// exp(-|k-j|/2) of loss.py:229 for |k-j| = 0..3
+__device__ __forceinline__ float combo_weight(int k, int j) {
+    const int d = abs(k - j);
+    return d == 0 ? 1.0f : d == 1 ? 0.60653065971263342f : d == 2 ? 0.36787944117144233f : 0.22313016014842982f;
 }
 
 __device__ __forceinline__ int count_combos(const long long *gc) {
@@ -414,35 +470,77 @@ __device__ __forceinline__ int count_combos(const long long *gc) {
     return C;
 }
 
+// loss = (1/C) sum_kj exp(-|k-j|/2) (S1/(n k) + S2/(n j))   (loss.py:215,227-230).  Called by ONE FULL WARP: lane c < 16
+// owns combo c (the per-lane loads would otherwise be a chain of L2 round trips in a single thread); the terms are
+// summed in a fixed butterfly order, so the result is deterministic.
 __device__ __forceinline__ void finalize_pair(const Workspace &ws, int b, float *out_loss, int *out_status, float *out_median,
                                               long long *out_stats) {
-    const long long *gc = ws.gcounts + b * 18;
-    int C = 0;
-    double loss = 0.0;
-    for (int k = 1; k <= 4; ++k)
-        for (int j = 1; j <= 4; ++j) {
-            const int c = (k - 1) * 4 + (j - 1);
-            const long long n = gc[c];
-            if (n <= 0) continue;
-            ++C;
-            const double S1 = (double)__ldcg(ws.sums + b * 32 + c) / kFixScale, S2 = (double)__ldcg(ws.sums + b * 32 + 16 + c) / kFixScale;
-            loss += exp(-0.5 * (double)abs(k - j)) * (S1 / ((double)n * k) + S2 / ((double)n * j));
-        }
+    const int lane = threadIdx.x & 31;
+    const int c = lane & 15, k = (c >> 2) + 1, j = (c & 3) + 1;
+    const long long n = __ldcg(ws.gcounts + b * 18 + c);
+    const long long extra = __ldcg(ws.gcounts + b * 18 + 16 + (lane & 1));           // lane 0: #records, lane 1: #D entries
+    const unsigned long long S1b = __ldcg(ws.sums + b * 32 + c), S2b = __ldcg(ws.sums + b * 32 + 16 + c);
+    const int nanflag = __ldcg(ws.flags + b * 4);
+    long long *st = ws.stats + (long long)b * RRL_NSTAT;
+    const long long mystat = lane < RRL_NSTAT ? __ldcg(st + lane) : 0;
+    const unsigned pm0 = __ldcg(ws.pmax + b * 2), pm1 = __ldcg(ws.pmax + b * 2 + 1);
+    const float med = __ldcg(ws.med + b);
+    double term = 0.0;
+    const bool live = lane < 16 && n > 0;
+    if (live) {
+        const double S1 = (double)S1b / kFixScale, S2 = (double)S2b / kFixScale;
+        term = exp(-0.5 * (double)abs(k - j)) * (S1 / ((double)n * k) + S2 / ((double)n * j));
+    }
+    const int C = __popc(__ballot_sync(0xffffffffu, live));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
+    double loss = term;
+    const long long nrec = __shfl_sync(0xffffffffu, extra, 0), nD = __shfl_sync(0xffffffffu, extra, 1);
+    const long long nan_count = __shfl_sync(0xffffffffu, mystat, 6);
     int status = 0;
     if (C == 0) status |= RRL_STATUS_EMPTY; else loss /= (double)C;
-    long long *st = ws.stats + (long long)b * RRL_NSTAT;
-    st[0] = gc[16]; st[1] = gc[17]; st[2] = C;
-    if (st[6] > 0) status |= RRL_STATUS_NAN;
-    if (ws.flags[b * 4]) { status |= RRL_STATUS_NAN; loss = __longlong_as_double(0x7ff8000000000000LL); }
+    if (nan_count > 0) status |= RRL_STATUS_NAN;
+    if (nanflag) { status |= RRL_STATUS_NAN; loss = __longlong_as_double(0x7ff8000000000000LL); }
     // |AC|^2 <= (P + X)^2: flag clouds whose own extent already makes the 2e-4 offset smaller than a few ulps of
     // |p|^2 (|AC|^2 >~ 1e3)
-    const float pm = fmaxf(__uint_as_float(ws.pmax[b * 2]), __uint_as_float(ws.pmax[b * 2 + 1]));
-    if (pm > 250.0f) status |= RRL_STATUS_NAN_RISK;
-    out_loss[b] = (float)loss;
-    if (out_status) out_status[b] = status;
-    if (out_median) out_median[b] = ws.med[b];
-    if (out_stats)
-        for (int q = 0; q < RRL_NSTAT; ++q) out_stats[(long long)b * RRL_NSTAT + q] = st[q];
+    if (fmaxf(__uint_as_float(pm0), __uint_as_float(pm1)) > 250.0f) status |= RRL_STATUS_NAN_RISK;
+    const long long outstat = lane == 0 ? nrec : lane == 1 ? nD : lane == 2 ? (long long)C : mystat;
+    if (lane < 3) st[lane] = outstat;
+    if (out_stats && lane < RRL_NSTAT) out_stats[(long long)b * RRL_NSTAT + lane] = outstat;
+    if (lane == 0) {
+        out_loss[b] = (float)loss;
+        if (out_status) out_status[b] = status;
+        if (out_median) out_median[b] = med;
+    }
+}
+
+// Adds the (s1, s2) of every valid lane to the block's per-combo fixed-point sums with ONE shared atomic per (warp,
+// combo): a 64-bit shared atomicAdd is a compare-and-swap loop, and hundreds of threads hammering sixteen addresses
+// serialise badly.  Lanes of equal combo are summed with warp reductions on 21-bit limbs (32 * 2^21 < 2^32).
+// Must be called by converged warps.  Integer sums: exact and order independent.
+__device__ __forceinline__ void warp_combo_add(unsigned long long *s_sum, bool valid, int combo, unsigned long long v1,
+                                               unsigned long long v2) {
+    if (!valid) { v1 = 0ull; v2 = 0ull; }                            // each <= 4 * 2^40
+    const int lane = threadIdx.x & 31;
+    unsigned remaining = __ballot_sync(0xffffffffu, valid);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int cb = __shfl_sync(0xffffffffu, combo, leader);
+        const bool mine = valid && combo == cb;
+        unsigned long long t1 = 0ull, t2 = 0ull;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const unsigned a1 = mine ? (unsigned)((v1 >> (21 * q)) & 0x1FFFFFu) : 0u;
+            const unsigned a2 = mine ? (unsigned)((v2 >> (21 * q)) & 0x1FFFFFu) : 0u;
+            t1 += (unsigned long long)__reduce_add_sync(0xffffffffu, a1) << (21 * q);
+            t2 += (unsigned long long)__reduce_add_sync(0xffffffffu, a2) << (21 * q);
+        }
+        if (lane == leader) {
+            atomicAdd(&s_sum[cb], t1);
+            atomicAdd(&s_sum[16 + cb], t2);
+        }
+        remaining &= ~__ballot_sync(0xffffffffu, mine);
+    }
 }
 
 // gcounts / med hold the GLOBAL values (rrl_shard_stage2) in the line-sharded path.  With out_loss != nullptr
@@ -450,6 +548,7 @@ __device__ __forceinline__ void finalize_pair(const Workspace &ws, int b, float 
 __global__ void __launch_bounds__(256) welsch_kernel(Workspace ws, Geometry g, float *out_loss, int *out_status, float *out_median,
                                                      long long *out_stats) {
     __shared__ unsigned long long s_sum[32];
+    __shared__ float s_buf[8 * 512];
     __shared__ int s_last;
     const int b = blockIdx.y;
     if (threadIdx.x < 32) s_sum[threadIdx.x] = 0ull;
@@ -457,18 +556,23 @@ __global__ void __launch_bounds__(256) welsch_kernel(Workspace ws, Geometry g, f
     const long long nrec = ws.nrec[b];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if ((long long)blockIdx.x * blockDim.x >= nrec && blockIdx.x != 0) return;      // whole block beyond the records
-    if (i < nrec) {
+    {
+        const bool valid = i < nrec;
         const long long r = (long long)b * g.nl + i;
-        const long long *gc = ws.gcounts + b * 18;
-        const int C = count_combos(gc);
-        const int kj = ws.recMeta[r * 2 + 1];
-        const int k = kj & 255, j = (kj >> 8) & 255;
-        const int combo = (k - 1) * 4 + (j - 1);
-        double s1, s2;
-        welsch_record(ws, r, ws.med[b], exp(-0.5 * (double)abs(k - j)) / (double)C / (double)gc[combo], k, j, s1, s2);
-        if (!(s1 == s1) || !(s2 == s2)) { ws.flags[b * 4] = 1; s1 = s2 = 0.0; }    // e.g. median 0: the reference's loss is NaN too
-        atomicAdd(&s_sum[combo], (unsigned long long)__double2ll_rn(s1 * kFixScale));
-        atomicAdd(&s_sum[16 + combo], (unsigned long long)__double2ll_rn(s2 * kFixScale));
+        int combo = 0, k = 1, j = 1;
+        float cw = 0.f;
+        if (valid) {
+            const long long *gc = ws.gcounts + b * 18;
+            const int kj = ws.recMeta[r * 2 + 1];
+            k = kj & 255; j = (kj >> 8) & 255;
+            combo = (k - 1) * 4 + (j - 1);
+            cw = combo_weight(k, j) / (float)count_combos(gc) / (float)gc[combo];
+        }
+        unsigned long long v1, v2;
+        bool nan;
+        welsch_warp(ws, valid, r, ws.med[b], cw, k, j, s_buf + (threadIdx.x >> 5) * 512, v1, v2, nan);
+        if (nan) ws.flags[b * 4] = 1;                               // e.g. median 0: the reference's loss is NaN too
+        warp_combo_add(s_sum, valid, combo, v1, v2);
     }
     __syncthreads();
     if (threadIdx.x < 32 && s_sum[threadIdx.x]) atomicAdd(ws.sums + b * 32 + threadIdx.x, s_sum[threadIdx.x]);
@@ -479,7 +583,7 @@ __global__ void __launch_bounds__(256) welsch_kernel(Workspace ws, Geometry g, f
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(ws.flags + b * 4 + 1, 1) == nblocks - 1);
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last && threadIdx.x < 32) {
         __threadfence();
         finalize_pair(ws, b, out_loss, out_status, out_median, out_stats);
     }
@@ -492,25 +596,180 @@ int launch_welsch(const Workspace &ws, const Geometry &g, cudaStream_t s) {
     return check_launch();
 }
 
-int launch_welsch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
-                           long long *out_stats, cudaStream_t s) {
-    dim3 grid((g.nl + 255) / 256, g.B);
-    welsch_kernel<<<grid, 256, 0, s>>>(ws, g, out_loss, out_status, out_median, out_stats);
+// Single-GPU tail of the forward: median -> Welsch -> loss in ONE launch.  grid (S, B): every one of the S blocks of a
+// pair recomputes the pair's median from the D entries (a few sweeps over <= 192 KB of shared memory; cheaper than a
+// second launch and a grid-wide dependency), then takes every S-th slice of the records through the Welsch stage; the
+// last block to finish writes the loss (ticket in flags[b*4+1]).
+constexpr int kTailThreads = 512;
+constexpr int kMedCache = 48 * 1024;        // D slots cached in shared memory (192 KB); the rest is re-read through L2
+
+__global__ void __launch_bounds__(kTailThreads) tail_kernel(Workspace ws, Geometry g, float *out_loss, int *out_status,
+                                                             float *out_median, long long *out_stats) {
+    extern __shared__ unsigned s_keys[];     // [kMedCache]
+    __shared__ SelectScratch sc;
+    __shared__ unsigned long long s_sum[32];
+    __shared__ long long s_gc[16];
+    __shared__ int s_last, s_count;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    mark(0);
+    const int nrec = ws.nrec[b];
+    if (tid < 16) s_gc[tid] = ws.n_kj[b * 16 + tid];
+    if (tid < 32) s_sum[tid] = 0ull;
+    if (tid == 0) { sc.kmin = kNoKey; sc.kmax = 0u; s_count = 0; }
+    __syncthreads();
+    long long n = 0;
+    int C = 0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        n += s_gc[c] * ((c >> 2) + 1) * ((c & 3) + 1);
+        C += s_gc[c] > 0;
+    }
+    if (blockIdx.x == 0) {                                     // single GPU: the local counts ARE the global counts
+        if (tid < 16) ws.gcounts[b * 18 + tid] = s_gc[tid];
+        if (tid == 16) ws.gcounts[b * 18 + 16] = nrec;
+        if (tid == 17) ws.gcounts[b * 18 + 17] = n;
+    }
+    float med = 0.f;
+    if (n > 0) {
+        const float *D = ws.recD + (long long)b * g.nl * 16;
+        const int *meta = ws.recMeta + (long long)b * g.nl * 2;
+        const long long slots = (long long)nrec * 16;
+        auto gkey = [&](long long i) -> unsigned {
+            const int kj = meta[(i >> 4) * 2 + 1];
+            const int e = (int)(i & 15);
+            const bool valid = (e >> 2) < (kj & 255) && (e & 3) < ((kj >> 8) & 255);
+            return valid ? __float_as_uint(D[i]) : kNoKey;
+        };
+        unsigned mn = kNoKey, mx = 0u;
+        if (n <= kMedCache) {
+            // the valid D entries of the pair are compacted into shared memory (their order is irrelevant to a median):
+            // one thread per record, two records in flight, one shared atomic per warp and record batch
+            const float4 *D4 = reinterpret_cast<const float4 *>(D);
+            for (int i0 = 0; i0 < nrec; i0 += 2 * kTailThreads) {                  // block-uniform trip count
+                int kj[2];
+                float4 d[2][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = i0 + u * kTailThreads + tid;
+                    kj[u] = 0;
+                    if (i < nrec) {
+                        kj[u] = meta[i * 2 + 1];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) d[u][a] = D4[(long long)i * 4 + a];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int k = kj[u] & 255, j = (kj[u] >> 8) & 255;
+                    const int cnt = k * j;
+                    int inc = cnt;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffffu, inc, dd);
+                        if ((tid & 31) >= dd) inc += up;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, inc, 31);
+                    int base = 0;
+                    if ((tid & 31) == 0 && total) base = atomicAdd(&s_count, total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    int pos = base + inc - cnt;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const float dv[4] = {d[u][a].x, d[u][a].y, d[u][a].z, d[u][a].w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (a < k && c < j) {
+                                const unsigned kb = __float_as_uint(dv[c]);
+                                s_keys[pos++] = kb;
+                                mn = min(mn, kb); mx = max(mx, kb);
+                            }
+                    }
+                }
+            }
+            block_minmax(mn, mx, sc);
+            __syncthreads();
+            mark(1);
+            auto key = [&](long long i) -> unsigned { return s_keys[i]; };
+            med = __uint_as_float(select_lower_median<kTailThreads>(n, n, key, sc.kmin, sc.kmax, sc));
+        } else {
+            // more entries than the cache holds: every sweep re-reads the records through L2
+            for (long long i = tid; i < slots; i += kTailThreads) {
+                const unsigned kb = gkey(i);
+                if (kb != kNoKey) { mn = min(mn, kb); mx = max(mx, kb); }
+            }
+            block_minmax(mn, mx, sc);
+            __syncthreads();
+            mark(1);
+            med = __uint_as_float(select_lower_median<kTailThreads>(slots, n, gkey, sc.kmin, sc.kmax, sc));
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) ws.med[b] = med;
+    mark(2);
+    float *wbuf = reinterpret_cast<float *>(s_keys) + (tid >> 5) * 512;          // the key cache is free after the select
+    for (long long i0 = (long long)blockIdx.x * kTailThreads; i0 < nrec; i0 += (long long)gridDim.x * kTailThreads) {   // block-uniform
+        const long long i = i0 + tid;
+        const bool valid = i < nrec;
+        const long long r = (long long)b * g.nl + i;
+        int combo = 0, k = 1, j = 1;
+        float cw = 0.f;
+        if (valid) {
+            const int kj = ws.recMeta[r * 2 + 1];
+            k = kj & 255; j = (kj >> 8) & 255;
+            combo = (k - 1) * 4 + (j - 1);
+            cw = combo_weight(k, j) / (float)C / (float)s_gc[combo];
+        }
+        unsigned long long v1, v2;
+        bool nan;
+        welsch_warp(ws, valid, r, med, cw, k, j, wbuf, v1, v2, nan);
+        if (nan) ws.flags[b * 4] = 1;                               // e.g. median 0: the reference's loss is NaN too
+        warp_combo_add(s_sum, valid, combo, v1, v2);
+    }
+    __syncthreads();
+    mark(3);
+    if (gridDim.x == 1) {                                      // the pair's only block: no cross-block hand-off
+        if (tid < 32) ws.sums[b * 32 + tid] = s_sum[tid];
+        if (tid == 0) s_last = 1;
+    } else {
+        if (tid < 32 && s_sum[tid]) atomicAdd(ws.sums + b * 32 + tid, s_sum[tid]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(ws.flags + b * 4 + 1, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && tid < 32) {
+        __threadfence();
+        finalize_pair(ws, b, out_loss, out_status, out_median, out_stats);
+    }
+    mark(4);
+}
+
+int launch_tail(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
+                long long *out_stats, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMedCache * 4) != cudaSuccess) return RRL_ERR_CUDA;
+        attr_set = true;
+    }
+    stage_mark(7, s);
+    int S = 148 / g.B;                       // one block per SM at most; small batches spread a pair's records wider
+    if (S < 1) S = 1;
+    if (S > 16) S = 16;
+    tail_kernel<<<dim3(S, g.B), kTailThreads, kMedCache * 4, s>>>(ws, g, out_loss, out_status, out_median, out_stats);
     count_launch();
     stage_mark(8, s);
     return check_launch();
 }
 
-__global__ void finalize_kernel(Workspace ws, Geometry g, float *out_loss, int *out_status, float *out_median,
-                                long long *out_stats) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) finalize_kernel(Workspace ws, Geometry g, float *out_loss, int *out_status, float *out_median,
+                                                        long long *out_stats) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);           // one warp per pair
     if (b >= g.B) return;
     finalize_pair(ws, b, out_loss, out_status, out_median, out_stats);
 }
 
 int launch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
                     long long *out_stats, cudaStream_t s) {
-    finalize_kernel<<<(g.B + 127) / 128, 128, 0, s>>>(ws, g, out_loss, out_status, out_median, out_stats);
+    finalize_kernel<<<(g.B + 3) / 4, 128, 0, s>>>(ws, g, out_loss, out_status, out_median, out_stats);
     count_launch();
     return check_launch();
 }
@@ -596,3 +855,9 @@ int launch_export_hits(const Workspace &ws, const Geometry &g, int cloud, int *o
 }
 
 }  // namespace rrl
+
+#ifdef RRL_MARKS
+extern "C" int rrl_debug_read_marks(unsigned long long *out32) {
+    return cudaMemcpyFromSymbol(out32, rrl::g_marks, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -3;
+}
+#endif

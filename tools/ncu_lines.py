@@ -14,7 +14,8 @@ from collections import defaultdict
 rep, obj, pattern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# NCU_ARGS='-k regex:tail_kernel' selects one kernel of a multi-kernel report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + os.environ.get("NCU_ARGS", "").split(), capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]
 body = [r for r in rows[2:] if len(r) == len(hdr)]
