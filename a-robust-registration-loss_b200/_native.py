@@ -57,6 +57,9 @@ def lib():
         "rrl_host_pinned_lines": (vp, [vp]),
         "rrl_host_subbatches": (ci, [vp]),
         "rrl_host_loss_fwd_bwd": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
+        "rrl_host_slots": (ci, [vp]),
+        "rrl_host_submit": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, C.POINTER(ci)]),
+        "rrl_host_wait": (ci, [vp, ci, vp, vp, vp]),
         "rrl_measure_fp32_peak": (ci, [ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "rrl_measure_dense": (ci, [vp, vp, vp, ci, ci, ci, ci, vp, cz, ci, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]),
         "rrl_measure_stages": (ci, [vp, vp, vp, ci, ci, ci, ci, vp, cz, ci, C.POINTER(C.c_float), vp]),
@@ -77,6 +80,7 @@ EXPORTED = ["rrl_version", "rrl_error_string", "rrl_launch_count", "rrl_workspac
             "rrl_se3_exp", "rrl_se3_apply", "rrl_se3_apply_backward", "rrl_rigid_apply", "rrl_rigid_apply_backward",
             "rrl_sampler_workspace_bytes", "rrl_sample_lines", "rrl_chamfer", "rrl_host_create", "rrl_host_destroy",
             "rrl_host_pinned_tri1", "rrl_host_pinned_tri2", "rrl_host_pinned_lines", "rrl_host_subbatches", "rrl_host_loss_fwd_bwd",
+            "rrl_host_slots", "rrl_host_submit", "rrl_host_wait",
             "rrl_measure_fp32_peak", "rrl_measure_dense", "rrl_measure_stages", "rrl_debug_set_dense_variant",
             "rrl_debug_set_param"]
 

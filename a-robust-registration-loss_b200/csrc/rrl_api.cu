@@ -224,25 +224,35 @@ extern "C" int rrl_shard_stage3(void *workspace, size_t workspace_bytes, int nf1
 }
 
 // ---- host-buffer context ---------------------------------------------------------------------------------
-// The batch is cut into up to kMaxSub sub-batches of whole pairs (pairs are independent), each with its own stream
-// and workspace: the H2D copy of sub-batch s+1 runs under the kernels of sub-batch s, and the latency-bound sparse
-// stages of one sub-batch run under the dense stage of the next.
+// Two levels of overlap.  (1) The batch is cut into up to kMaxSub sub-batches of whole pairs (pairs are independent),
+// each with its own stream and workspace: the H2D copy of sub-batch s+1 runs under the kernels of sub-batch s, and the
+// latency-bound sparse stages of one sub-batch run under the dense stage of the next.  (2) The context owns kSlots
+// complete sets of device buffers: rrl_host_submit() queues a whole evaluation on the next slot and returns, so the
+// copies of evaluation i+1 run under the kernels of evaluation i (a double-buffered input pipeline);
+// rrl_host_wait() drains one slot and hands out its results.  rrl_host_loss_fwd_bwd = submit + wait.
 constexpr int kMaxSub = 8;
+constexpr int kSlots = 2;
+struct HostSlot {
+    float *d_tri1, *d_tri2, *d_lines, *d_loss, *d_grad1;
+    int *d_status;
+    void *d_ws[kMaxSub];
+    float *p_loss, *p_grad1;
+    int *p_status;
+    cudaStream_t stream[kMaxSub];
+    bool busy, want_grad;
+};
 struct rrl_host_ctx {
-    int B, nf1, nf2, nl, device, S;
+    int B, nf1, nf2, nl, device, S, next;
     int first[kMaxSub + 1];                      // pairs [first[s], first[s+1]) form sub-batch s
     size_t n_tri1, n_tri2, n_lines;
     size_t ws_bytes[kMaxSub];
-    float *d_tri1, *d_tri2, *d_lines, *d_loss, *d_gout, *d_grad1;
-    int *d_status;
-    void *d_ws[kMaxSub];
-    float *p_tri1, *p_tri2, *p_lines, *p_loss, *p_grad1;
-    int *p_status;
-    cudaStream_t stream[kMaxSub];
+    float *d_gout;
+    float *p_tri1, *p_tri2, *p_lines;            // optional staging handed out to the caller
+    HostSlot slot[kSlots];
 };
 
 static int host_subbatches(int B) {
-    int S = B / 8;                               // >= 8 pairs per sub-batch keep the dense grids full
+    int S = B / 16;                              // >= 16 pairs per sub-batch keep the grids full (measured: 2 x 16 beats 4 x 8 and 1 x 32 at B = 32)
     if (const char *e = getenv("RRL_HOST_SUBBATCHES")) S = atoi(e);
     if (S > kMaxSub) S = kMaxSub;
     if (S > B) S = B;
@@ -253,15 +263,18 @@ static int host_subbatches(int B) {
 extern "C" void rrl_host_destroy(rrl_host_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (int s = 0; s < c->S; ++s)
-        if (c->stream[s]) cudaStreamSynchronize(c->stream[s]);
-    cudaFree(c->d_tri1); cudaFree(c->d_tri2); cudaFree(c->d_lines); cudaFree(c->d_loss); cudaFree(c->d_gout);
-    cudaFree(c->d_grad1); cudaFree(c->d_status);
-    for (int s = 0; s < c->S; ++s) cudaFree(c->d_ws[s]);
-    cudaFreeHost(c->p_tri1); cudaFreeHost(c->p_tri2); cudaFreeHost(c->p_lines); cudaFreeHost(c->p_loss);
-    cudaFreeHost(c->p_grad1); cudaFreeHost(c->p_status);
-    for (int s = 0; s < c->S; ++s)
-        if (c->stream[s]) cudaStreamDestroy(c->stream[s]);
+    for (int q = 0; q < kSlots; ++q) {
+        HostSlot &t = c->slot[q];
+        for (int s = 0; s < c->S; ++s)
+            if (t.stream[s]) cudaStreamSynchronize(t.stream[s]);
+        cudaFree(t.d_tri1); cudaFree(t.d_tri2); cudaFree(t.d_lines); cudaFree(t.d_loss); cudaFree(t.d_grad1); cudaFree(t.d_status);
+        for (int s = 0; s < c->S; ++s) cudaFree(t.d_ws[s]);
+        cudaFreeHost(t.p_loss); cudaFreeHost(t.p_grad1); cudaFreeHost(t.p_status);
+        for (int s = 0; s < c->S; ++s)
+            if (t.stream[s]) cudaStreamDestroy(t.stream[s]);
+    }
+    cudaFree(c->d_gout);
+    cudaFreeHost(c->p_tri1); cudaFreeHost(c->p_tri2); cudaFreeHost(c->p_lines);
     delete c;
 }
 
@@ -276,21 +289,25 @@ extern "C" int rrl_host_create(int B, int nf1, int nf2, int nl, int device, rrl_
     for (int s = 0; s <= c->S; ++s) c->first[s] = (int)((long long)B * s / c->S);
     c->n_tri1 = (size_t)B * nf1 * 9; c->n_tri2 = (size_t)B * nf2 * 9; c->n_lines = (size_t)B * nl * 6;
     bool ok = true;
-    for (int s = 0; s < c->S && ok; ++s) {
-        c->ws_bytes[s] = rrl_workspace_bytes(c->first[s + 1] - c->first[s], nf1, nf2, nl);
-        ok = cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaMalloc(&c->d_ws[s], c->ws_bytes[s]) == cudaSuccess;
+    for (int s = 0; s < c->S; ++s) c->ws_bytes[s] = rrl_workspace_bytes(c->first[s + 1] - c->first[s], nf1, nf2, nl);
+    for (int q = 0; q < kSlots && ok; ++q) {
+        HostSlot &t = c->slot[q];
+        for (int s = 0; s < c->S && ok; ++s)
+            ok = cudaStreamCreateWithFlags(&t.stream[s], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaMalloc(&t.d_ws[s], c->ws_bytes[s]) == cudaSuccess;
+        ok = ok && cudaMalloc(&t.d_tri1, c->n_tri1 * 4) == cudaSuccess && cudaMalloc(&t.d_tri2, c->n_tri2 * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&t.d_lines, c->n_lines * 4) == cudaSuccess && cudaMalloc(&t.d_loss, (size_t)B * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&t.d_grad1, c->n_tri1 * 4) == cudaSuccess && cudaMalloc(&t.d_status, (size_t)B * 4) == cudaSuccess;
+        ok = ok && cudaMallocHost(&t.p_loss, (size_t)B * 4) == cudaSuccess && cudaMallocHost(&t.p_status, (size_t)B * 4) == cudaSuccess;
+        ok = ok && cudaMallocHost(&t.p_grad1, c->n_tri1 * 4) == cudaSuccess;
     }
-    ok = ok && cudaMalloc(&c->d_tri1, c->n_tri1 * 4) == cudaSuccess && cudaMalloc(&c->d_tri2, c->n_tri2 * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_lines, c->n_lines * 4) == cudaSuccess && cudaMalloc(&c->d_loss, (size_t)B * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_gout, (size_t)B * 4) == cudaSuccess && cudaMalloc(&c->d_grad1, c->n_tri1 * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_status, (size_t)B * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_gout, (size_t)B * 4) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->p_tri1, c->n_tri1 * 4) == cudaSuccess && cudaMallocHost(&c->p_tri2, c->n_tri2 * 4) == cudaSuccess;
-    ok = ok && cudaMallocHost(&c->p_lines, c->n_lines * 4) == cudaSuccess && cudaMallocHost(&c->p_loss, (size_t)B * 4) == cudaSuccess;
-    ok = ok && cudaMallocHost(&c->p_grad1, c->n_tri1 * 4) == cudaSuccess && cudaMallocHost(&c->p_status, (size_t)B * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->p_lines, c->n_lines * 4) == cudaSuccess;
     if (ok) {
-        for (int b = 0; b < B; ++b) c->p_loss[b] = 1.0f;
-        ok = cudaMemcpy(c->d_gout, c->p_loss, (size_t)B * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        float *ones = c->slot[0].p_loss;
+        for (int b = 0; b < B; ++b) ones[b] = 1.0f;
+        ok = cudaMemcpy(c->d_gout, ones, (size_t)B * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) {
         rrl_host_destroy(c);
@@ -304,10 +321,14 @@ extern "C" float *rrl_host_pinned_tri1(rrl_host_ctx *c) { return c ? c->p_tri1 :
 extern "C" float *rrl_host_pinned_tri2(rrl_host_ctx *c) { return c ? c->p_tri2 : nullptr; }
 extern "C" float *rrl_host_pinned_lines(rrl_host_ctx *c) { return c ? c->p_lines : nullptr; }
 extern "C" int rrl_host_subbatches(rrl_host_ctx *c) { return c ? c->S : 0; }
+extern "C" int rrl_host_slots(rrl_host_ctx *c) { return c ? kSlots : 0; }
 
-extern "C" int rrl_host_loss_fwd_bwd(rrl_host_ctx *c, const float *h_tri1, const float *h_tri2, const float *h_lines,
-                                     int k_lo, int j_lo, int k_hi, int j_hi, float *h_loss, int *h_status, float *h_grad_tri1) {
-    if (!c || !h_tri1 || !h_tri2 || !h_lines || !h_loss) return RRL_ERR_ARG;
+extern "C" int rrl_host_submit(rrl_host_ctx *c, const float *h_tri1, const float *h_tri2, const float *h_lines,
+                               int k_lo, int j_lo, int k_hi, int j_hi, int want_grad_tri1, int *out_ticket) {
+    if (!c || !h_tri1 || !h_tri2 || !h_lines || !out_ticket) return RRL_ERR_ARG;
+    if (!window_ok(k_lo, j_lo, k_hi, j_hi)) return RRL_ERR_ARG;
+    HostSlot &t = c->slot[c->next];
+    if (t.busy) return RRL_ERR_STATE;                  // every slot in flight: rrl_host_wait() one first
     if (cudaSetDevice(c->device) != cudaSuccess) return RRL_ERR_CUDA;
     const size_t t1 = (size_t)c->nf1 * 9, t2 = (size_t)c->nf2 * 9, tl = (size_t)c->nl * 6;
     // straight from the caller's memory: asynchronous when it is pinned (the context's own buffers or any
@@ -316,35 +337,62 @@ extern "C" int rrl_host_loss_fwd_bwd(rrl_host_ctx *c, const float *h_tri1, const
     bool ok = true;
     for (int s = 0; s < c->S && ok; ++s) {
         const size_t b0 = (size_t)c->first[s], nb = (size_t)(c->first[s + 1] - c->first[s]);
-        cudaStream_t st = c->stream[s];
-        ok = cudaMemcpyAsync(c->d_tri1 + b0 * t1, h_tri1 + b0 * t1, nb * t1 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(c->d_tri2 + b0 * t2, h_tri2 + b0 * t2, nb * t2 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(c->d_lines + b0 * tl, h_lines + b0 * tl, nb * tl * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        cudaStream_t st = t.stream[s];
+        ok = cudaMemcpyAsync(t.d_tri1 + b0 * t1, h_tri1 + b0 * t1, nb * t1 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(t.d_tri2 + b0 * t2, h_tri2 + b0 * t2, nb * t2 * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(t.d_lines + b0 * tl, h_lines + b0 * tl, nb * tl * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
     }
     if (!ok) return RRL_ERR_CUDA;
+    t.busy = true;                                     // work is queued from here on: the slot must be drained
+    t.want_grad = want_grad_tri1 != 0;
+    *out_ticket = c->next;
+    c->next = (c->next + 1) % kSlots;
     for (int s = 0; s < c->S; ++s) {
         const size_t b0 = (size_t)c->first[s];
         const int nb = c->first[s + 1] - c->first[s];
-        cudaStream_t st = c->stream[s];
-        int rc = rrl_loss_forward(c->d_tri1 + b0 * t1, c->d_tri2 + b0 * t2, c->d_lines + b0 * tl, nb, c->nf1, c->nf2, c->nl,
-                                  k_lo, j_lo, k_hi, j_hi, c->d_ws[s], c->ws_bytes[s], c->d_loss + b0, c->d_status + b0, nullptr,
+        cudaStream_t st = t.stream[s];
+        int rc = rrl_loss_forward(t.d_tri1 + b0 * t1, t.d_tri2 + b0 * t2, t.d_lines + b0 * tl, nb, c->nf1, c->nf2, c->nl,
+                                  k_lo, j_lo, k_hi, j_hi, t.d_ws[s], c->ws_bytes[s], t.d_loss + b0, t.d_status + b0, nullptr,
                                   nullptr, st);
         if (rc) return rc;
-        rc = rrl_loss_backward(c->d_ws[s], c->ws_bytes[s], c->d_gout + b0, nb, c->nf1, c->nf2, c->nl, c->d_grad1 + b0 * t1,
+        rc = rrl_loss_backward(t.d_ws[s], c->ws_bytes[s], c->d_gout + b0, nb, c->nf1, c->nf2, c->nl, t.d_grad1 + b0 * t1,
                                nullptr, st);
         if (rc) return rc;
-        ok = cudaMemcpyAsync(c->p_loss + b0, c->d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(c->p_status + b0, c->d_status + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-        if (h_grad_tri1)
-            ok = ok && cudaMemcpyAsync(c->p_grad1 + b0 * t1, c->d_grad1 + b0 * t1, (size_t)nb * t1 * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = cudaMemcpyAsync(t.p_loss + b0, t.d_loss + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(t.p_status + b0, t.d_status + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        if (t.want_grad)
+            ok = ok && cudaMemcpyAsync(t.p_grad1 + b0 * t1, t.d_grad1 + b0 * t1, (size_t)nb * t1 * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
         if (!ok) return RRL_ERR_CUDA;
     }
-    for (int s = 0; s < c->S; ++s) ok = (cudaStreamSynchronize(c->stream[s]) == cudaSuccess) && ok;
-    if (!ok) return RRL_ERR_CUDA;
-    std::memcpy(h_loss, c->p_loss, (size_t)c->B * 4);
-    if (h_status) std::memcpy(h_status, c->p_status, (size_t)c->B * 4);
-    if (h_grad_tri1) std::memcpy(h_grad_tri1, c->p_grad1, c->n_tri1 * 4);
     return RRL_OK;
+}
+
+extern "C" int rrl_host_wait(rrl_host_ctx *c, int ticket, float *h_loss, int *h_status, float *h_grad_tri1) {
+    if (!c || ticket < 0 || ticket >= kSlots || !h_loss) return RRL_ERR_ARG;
+    HostSlot &t = c->slot[ticket];
+    if (!t.busy) return RRL_ERR_STATE;
+    if (h_grad_tri1 && !t.want_grad) return RRL_ERR_ARG;
+    if (cudaSetDevice(c->device) != cudaSuccess) return RRL_ERR_CUDA;
+    bool ok = true;
+    for (int s = 0; s < c->S; ++s) ok = (cudaStreamSynchronize(t.stream[s]) == cudaSuccess) && ok;
+    t.busy = false;
+    if (!ok) return RRL_ERR_CUDA;
+    std::memcpy(h_loss, t.p_loss, (size_t)c->B * 4);
+    if (h_status) std::memcpy(h_status, t.p_status, (size_t)c->B * 4);
+    if (h_grad_tri1) std::memcpy(h_grad_tri1, t.p_grad1, c->n_tri1 * 4);
+    return RRL_OK;
+}
+
+extern "C" int rrl_host_loss_fwd_bwd(rrl_host_ctx *c, const float *h_tri1, const float *h_tri2, const float *h_lines,
+                                     int k_lo, int j_lo, int k_hi, int j_hi, float *h_loss, int *h_status, float *h_grad_tri1) {
+    if (!h_loss) return RRL_ERR_ARG;
+    int ticket = -1;
+    const int rc = rrl_host_submit(c, h_tri1, h_tri2, h_lines, k_lo, j_lo, k_hi, j_hi, h_grad_tri1 != nullptr, &ticket);
+    if (rc) {
+        if (ticket >= 0) rrl_host_wait(c, ticket, h_loss, nullptr, nullptr);
+        return rc;
+    }
+    return rrl_host_wait(c, ticket, h_loss, h_status, h_grad_tri1);
 }
 
 // ---- measurement ---------------------------------------------------------------------------------------------

@@ -340,29 +340,52 @@ def run_gpu(args):
         h_loss = np.zeros(B, np.float32)
         h_status = np.zeros(B, np.int32)
 
-        def e2e_step(i):
+        n_slots = int(L.rrl_host_slots(ctx))
+        tickets = [C.c_int(-1) for _ in range(n_slots)]
+
+        def submit(i):
             p = pinned[i % n_sets]
             base = p.data_ptr()
-            rrl_b200._native.check(L.rrl_host_loss_fwd_bwd(ctx, base, base + 4 * n1, base + 4 * (n1 + n2), 1, 1, 5, 5,
-                                                           h_loss.ctypes.data, h_status.ctypes.data, None),
-                                   "rrl_host_loss_fwd_bwd")
-        for i in range(3):
-            e2e_step(i)
+            rrl_b200._native.check(L.rrl_host_submit(ctx, base, base + 4 * n1, base + 4 * (n1 + n2), 1, 1, 5, 5, 0,
+                                                     C.byref(tickets[i % n_slots])), "rrl_host_submit")
+
+        def wait(i):
+            rrl_b200._native.check(L.rrl_host_wait(ctx, tickets[i % n_slots].value, h_loss.ctypes.data, h_status.ctypes.data, None),
+                                   "rrl_host_wait")
+
+        def run(n):
+            # the input pipeline of a training loop: the copies of step i+1 are queued before step i's result is awaited,
+            # so they run under its kernels; every step still copies its own inputs in and its loss + status out
+            submit(0)
+            for i in range(n):
+                if i + 1 < n:
+                    submit(i + 1)
+                wait(i)
+        run(3)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            e2e_step(i)
+        run(args.steps)
         dt = time.perf_counter() - t0
+        # the same steps through the blocking call (no overlap between consecutive steps), reported beside it
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            p = pinned[i % n_sets]
+            rrl_b200._native.check(L.rrl_host_loss_fwd_bwd(ctx, p.data_ptr(), p.data_ptr() + 4 * n1, p.data_ptr() + 4 * (n1 + n2),
+                                                           1, 1, 5, 5, h_loss.ctypes.data, h_status.ctypes.data, None),
+                                   "rrl_host_loss_fwd_bwd")
+        dt_sync = time.perf_counter() - t0
         L.rrl_host_destroy(ctx)
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * nl / (float(t.item()) / args.steps), "unit": "pairs*lines/s",
                "h2d_bytes_per_step": bytes_per_set, "d2h_bytes_per_step": 8 * B,
-               "api": "rrl_host_loss_fwd_bwd (C ABI, host pointers; per step: H2D of the three inputs from pinned memory, "
-                      "forward, backward to points1, D2H of loss+status, sync; pipelined over %d sub-batches of pairs so "
-                      "that copies run under the kernels of the previous sub-batch)" % n_sub,
-               "ms_per_step": float(t.item()) / args.steps * 1e3}
+               "api": "rrl_host_submit + rrl_host_wait (C ABI, host pointers; per step: H2D of the three inputs from pinned "
+                      "memory, forward, backward to points1, D2H of loss+status; %d buffer sets in flight, so the copies of "
+                      "step i+1 run under the kernels of step i, and each step is cut into %d sub-batches of pairs on "
+                      "their own streams)" % (n_slots, n_sub),
+               "ms_per_step": float(t.item()) / args.steps * 1e3,
+               "blocking_call_ms_per_step": dt_sync / args.steps * 1e3}
 
     if rank != 0:
         if world > 1:

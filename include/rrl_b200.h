@@ -183,6 +183,17 @@ int rrl_host_loss_fwd_bwd(rrl_host_ctx *ctx, const float *h_tri1, const float *h
                           int k_lo, int j_lo, int k_hi, int j_hi,
                           float *h_loss, int *h_status, float *h_grad_tri1);
 
+/* Double-buffered form of the same evaluation (a training loop's input pipeline): rrl_host_submit() queues copies and
+ * kernels on the next of rrl_host_slots() buffer sets and returns a ticket without waiting, so the H2D copies of
+ * evaluation i+1 run under the kernels of evaluation i; rrl_host_wait() drains that ticket and copies out loss [B],
+ * status [B] (may be NULL) and, if requested at submit time, the (B,nf1,9) gradient.  The h_* inputs must stay valid and
+ * unchanged until the wait returns.  RRL_ERR_STATE: every slot is in flight (submit) / the ticket is not (wait).
+ * rrl_host_loss_fwd_bwd == submit + wait. */
+int rrl_host_slots(rrl_host_ctx *ctx);
+int rrl_host_submit(rrl_host_ctx *ctx, const float *h_tri1, const float *h_tri2, const float *h_lines,
+                    int k_lo, int j_lo, int k_hi, int j_hi, int want_grad_tri1, int *out_ticket);
+int rrl_host_wait(rrl_host_ctx *ctx, int ticket, float *h_loss, int *h_status, float *h_grad_tri1);
+
 /* ---------------------------------------------------------------------------------------------------
  * Measurement helpers used by bench.py (not part of the reference's interface).
  * ------------------------------------------------------------------------------------------------- */

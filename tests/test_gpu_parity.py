@@ -290,6 +290,41 @@ def test_host_buffer_entry(rrl, subbatches, monkeypatch):
         assert _rel(g1[i], orc.grad1) <= REL_TOL
 
 
+def test_host_buffer_pipelined_submit_wait(rrl):
+    """double-buffered form: two evaluations in flight, results come back per ticket; a third submit is refused"""
+    L = rrl._native.lib()
+    sets = []
+    for s in range(3):
+        pairs = [synth.make_pair(900 + 10 * s + i, 256, 800) for i in range(4)]
+        sets.append((pairs,) + tuple(np.ascontiguousarray(np.stack([p[k] for p in pairs])) for k in ("tri1", "tri2", "lines")))
+    ctx = C.c_void_p()
+    assert L.rrl_host_create(4, 256, 256, 800, 0, C.byref(ctx)) == 0
+    try:
+        assert L.rrl_host_slots(ctx) == 2
+        tk = [C.c_int(-1) for _ in sets]
+        out = [(np.zeros(4, np.float32), np.zeros(4, np.int32), np.zeros_like(s[1])) for s in sets]
+        sub = lambda i, grad: L.rrl_host_submit(ctx, sets[i][1].ctypes.data, sets[i][2].ctypes.data, sets[i][3].ctypes.data,
+                                                1, 1, 5, 5, grad, C.byref(tk[i]))
+        wait = lambda i, grad: L.rrl_host_wait(ctx, tk[i].value, out[i][0].ctypes.data, out[i][1].ctypes.data,
+                                               out[i][2].ctypes.data if grad else None)
+        assert sub(0, 1) == 0 and sub(1, 1) == 0
+        assert sub(2, 1) == -4                                   # RRL_ERR_STATE: both slots in flight
+        assert wait(0, True) == 0
+        assert L.rrl_host_wait(ctx, tk[0].value, out[0][0].ctypes.data, None, None) == -4      # already drained
+        assert sub(2, 0) == 0                                    # reuses slot 0 while evaluation 1 is still in flight
+        assert wait(1, True) == 0
+        assert L.rrl_host_wait(ctx, tk[2].value, out[2][0].ctypes.data, None, out[2][2].ctypes.data) == -1   # no gradient requested
+        assert wait(2, False) == 0
+    finally:
+        L.rrl_host_destroy(ctx)
+    for i, s in enumerate(sets):
+        for b, p in enumerate(s[0]):
+            orc = co.loss(p["tri1"], p["tri2"], p["lines"])
+            assert abs(out[i][0][b] - orc.loss) <= REL_TOL * orc.loss
+            if i < 2:
+                assert _rel(out[i][2][b], orc.grad1) <= REL_TOL
+
+
 def test_full_size_dcp_batch_properties(rrl):
     """BASELINE config 2 at full size (32 x 1024 triplets x 15000 lines): the oracle checks a few pairs completely,
     every pair through size-independent properties."""

@@ -27,4 +27,15 @@ for S in [int(x) for x in (sys.argv[2:] or ["1", "2", "4", "8"])]:
     dt = (time.perf_counter() - t0) / n
     print("%s S=%d (actual %d): %.1f us per call, %.1f M pair*lines/s, loss sum %.6f" %
           (name, S, L.rrl_host_subbatches(ctx), dt * 1e6, B * nl / dt / 1e6, float(loss.sum())), flush=True)
+    tk = [C.c_int(-1), C.c_int(-1)]
+    sub = lambda i: L.rrl_host_submit(ctx, host[0].data_ptr(), host[1].data_ptr(), host[2].data_ptr(), 1, 1, 5, 5, 0, C.byref(tk[i % 2]))
+    wt = lambda i: L.rrl_host_wait(ctx, tk[i % 2].value, loss.ctypes.data, status.ctypes.data, None)
+    def run(n):
+        assert sub(0) == 0
+        for i in range(n):
+            if i + 1 < n: assert sub(i + 1) == 0
+            assert wt(i) == 0
+    run(5)
+    t0 = time.perf_counter(); run(n); dt = (time.perf_counter() - t0) / n
+    print("%s S=%d pipelined submit/wait: %.1f us per step, %.1f M pair*lines/s" % (name, S, dt * 1e6, B * nl / dt / 1e6), flush=True)
     L.rrl_host_destroy(ctx)
