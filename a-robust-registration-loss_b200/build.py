@@ -16,7 +16,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relax
 if os.environ.get("RRL_MARKS"):          # measurement builds: in-kernel phase timestamps (rrl_debug_read_marks)
     COMMON.append("-DRRL_MARKS")
 # rrl_sampler.cu restates a floating-point knife-edge test and must not contract a*b+c into FMAs
-SOURCES = {"rrl_api.cu": [], "rrl_dense.cu": [], "rrl_sparse.cu": [], "rrl_se3.cu": [], "rrl_aux.cu": [],
+SOURCES = {"rrl_api.cu": [], "rrl_dense.cu": [], "rrl_sparse.cu": [], "rrl_se3.cu": [], "rrl_aux.cu": [], "rrl_neigh.cu": [],
            "rrl_sampler.cu": ["-fmad=false"]}
 
 

@@ -163,6 +163,21 @@ int rrl_sample_lines(const float *radius, const float *centers, const float *ver
 int rrl_chamfer(const float *x, const float *y, int B, int M, int N, float *out, float *scratch, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Pre-processing: replaces Sample_neighs (loss.py:473-485) = utils.farthest_point_sample (utils.py:275-296) followed by
+ * a 3-nearest-neighbour query (sklearn KDTree, loss.py:479-480).  `xyz` is one cloud (N,3), float32 (is_double = 0, what
+ * every caller of the reference passes) or float64 (is_double = 1).
+ *   rrl_fps  out_idx[npoint] int32: the reference recurrence from centroid `start` (the reference draws it with
+ *            torch.randint on the CPU generator; the caller supplies it), first index on equal distances like
+ *            torch.max; the running minimum is float32 as in the reference (torch.ones(B,N)*1e10).
+ *   rrl_knn  out_idx (M,k) int32: the k <= 8 nearest points (squared distance in double, ties: smaller index) of
+ *            every query point xyz[query_idx[q]], nearest first -- the query point itself comes first.
+ * ------------------------------------------------------------------------------------------------- */
+size_t rrl_fps_workspace_bytes(int N);
+int rrl_fps(const void *xyz, int is_double, int N, int npoint, int start, int *out_idx, void *workspace,
+            size_t workspace_bytes, void *stream);
+int rrl_knn(const void *xyz, int is_double, int N, const int *query_idx, int M, int k, int *out_idx, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Host-buffer convenience path (what an FFI caller without device memory uses; bench.py's e2e leg).
  * The context owns device buffers, pinned staging and a stream for one geometry.
  * ------------------------------------------------------------------------------------------------- */

@@ -145,3 +145,46 @@ def test_reference_named_module_runs_the_demo_step(rrl):
     assert lines.shape == (1, 20000, 6)
     cd = M.chamfer_dist(moved.detach().reshape(1, -1, 3), torch.from_numpy(g0["tgt"]).cuda().reshape(1, -1, 3))
     assert abs(cd.item() - float(g0["ref_chamfer"][0])) <= 1e-4 * float(g0["ref_chamfer"][0])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_sample_neighs_against_reference_vectors(rrl, tag):
+    """Sample_neighs through the CUDA FPS + kNN kernels, bit-exact against the unmodified reference's output; the
+    start index comes from torch's CPU generator exactly like the reference's torch.randint (utils.py:288)"""
+    g = golden("sample_neighs")
+    pts, ns = g[tag + "_points"], int(g[tag + "_num_sample"])
+    torch.manual_seed(int(g[tag + "_seed"]))
+    out = rrl.loss.Sample_neighs(pts, num_sample=ns, num_neigh=3)
+    assert out.dtype == pts.dtype and np.array_equal(out, g[tag + "_ref_neighs"])
+    idx = rrl.prep.farthest_point_sample(torch.from_numpy(pts).cuda(), ns, start=int(g[tag + "_ref_fps_idx"][0]))
+    assert np.array_equal(idx.cpu().numpy(), g[tag + "_ref_fps_idx"])
+
+
+@pytest.mark.parametrize("n,npoint,dtype", [(5, 5, np.float32), (1000, 37, np.float64), (70001, 300, np.float32),
+                                            (300000, 64, np.float32)])
+def test_fps_and_knn_against_oracle(rrl, n, npoint, dtype):
+    """single- and multi-block grids (the cooperative kernel adds a block per 4096 points), float64 input, npoint = N"""
+    from oracle import neigh_oracle as no
+    rng = np.random.default_rng(n)
+    pts = (rng.standard_normal((n, 3)) * np.array([2.0, 1.0, 0.5])).astype(dtype)
+    pts[n // 2] = pts[0]                                          # a duplicated point: equal distances -> first index wins
+    start = int(rng.integers(0, n))
+    want = no.fps(pts, npoint, start)
+    p = torch.from_numpy(pts).cuda()
+    got = rrl.prep.farthest_point_sample(p, npoint, start=start)
+    assert np.array_equal(got.cpu().numpy(), want)
+    k = min(3, n)
+    q = got[: min(npoint, 50)]
+    nn = rrl.prep.knn(p, q, k).cpu().numpy()
+    assert np.array_equal(nn, no.knn(pts, pts[q.cpu().numpy()], k))
+
+
+def test_fps_rejects_bad_arguments(rrl):
+    p = torch.zeros(10, 3, device="cuda")
+    with pytest.raises(ValueError):
+        rrl.prep.farthest_point_sample(p, 11)
+    with pytest.raises(rrl.NativeError):
+        rrl.prep.farthest_point_sample(p.cpu(), 3)
+    L = rrl._native.lib()
+    assert L.rrl_fps(p.data_ptr(), 0, 10, 3, 10, p.data_ptr(), p.data_ptr(), 1 << 20, None) == -1     # start out of range
+    assert L.rrl_knn(p.data_ptr(), 0, 10, p.data_ptr(), 2, 9, p.data_ptr(), None) == -1               # k > 8

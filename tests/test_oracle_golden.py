@@ -144,3 +144,14 @@ def test_demo_trajectory_with_port_sampler():
     assert abs(r.loss - float(g["ref_loss"][0])) <= REL_TOL * float(g["ref_loss"][0])
     gt = co.se3_backward(g["twist0"], g["tri1_raw"].reshape(-1, 3), r.grad1.reshape(-1, 3))
     assert _rel(gt, g["ref_twist_grad"][0]) <= 2e-5
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_neigh_oracle_matches_reference_sample_neighs(tag):
+    """FPS + 3-NN restatement (oracle/neigh_oracle.py) against the unmodified reference's Sample_neighs and
+    utils.farthest_point_sample outputs (oracle/make_golden_neigh.py): index- and bit-exact"""
+    from oracle import neigh_oracle as no
+    g = golden("sample_neighs")
+    pts, ns, ref_idx = g[tag + "_points"], int(g[tag + "_num_sample"]), g[tag + "_ref_fps_idx"]
+    assert np.array_equal(no.fps(pts, ns, int(ref_idx[0])), ref_idx)
+    assert np.array_equal(no.sample_neighs(pts, ns, 3, int(ref_idx[0])), g[tag + "_ref_neighs"])
