@@ -40,6 +40,8 @@ def lib():
         "rrl_shard_counts": (ci, [vp, cz, ci, ci, ci, vp, vp]),
         "rrl_shard_pack_entries": (ci, [vp, cz, ci, ci, ci, vp, cl, vp]),
         "rrl_select_lower_median": (ci, [vp, cl, vp, vp]),
+        "rrl_shard_select_hist": (ci, [vp, cz, ci, ci, ci, ci, vp, vp, vp]),
+        "rrl_shard_select_pick": (ci, [ci, vp, vp, vp, vp, vp]),
         "rrl_shard_stage2": (ci, [vp, cz, ci, ci, ci, vp, vp, vp, vp]),
         "rrl_shard_stage3": (ci, [vp, cz, ci, ci, ci, vp, vp, vp, vp]),
         "rrl_se3_exp": (ci, [vp, ci, vp, vp, vp]),
@@ -79,7 +81,8 @@ def lib():
 
 EXPORTED = ["rrl_version", "rrl_error_string", "rrl_launch_count", "rrl_workspace_bytes", "rrl_loss_forward",
             "rrl_loss_backward", "rrl_loss_export_hits", "rrl_shard_stage1", "rrl_shard_counts",
-            "rrl_shard_pack_entries", "rrl_select_lower_median", "rrl_shard_stage2", "rrl_shard_stage3",
+            "rrl_shard_pack_entries", "rrl_select_lower_median", "rrl_shard_select_hist", "rrl_shard_select_pick",
+            "rrl_shard_stage2", "rrl_shard_stage3",
             "rrl_se3_exp", "rrl_se3_apply", "rrl_se3_apply_backward", "rrl_rigid_apply", "rrl_rigid_apply_backward",
             "rrl_sampler_workspace_bytes", "rrl_sample_lines", "rrl_chamfer", "rrl_fps_workspace_bytes", "rrl_fps", "rrl_knn", "rrl_host_create", "rrl_host_destroy",
             "rrl_host_pinned_tri1", "rrl_host_pinned_tri2", "rrl_host_pinned_lines", "rrl_host_subbatches", "rrl_host_loss_fwd_bwd",

@@ -199,6 +199,20 @@ extern "C" int rrl_select_lower_median(const float *values, long long n, float *
     return launch_select_median(values, n, out_median, (cudaStream_t)stream);
 }
 
+extern "C" int rrl_shard_select_hist(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl, int round,
+                                     const long long *state2, int *out_hist65536, void *stream) {
+    if (!workspace || !state2 || !out_hist65536 || (round != 0 && round != 1) || !geometry_ok(1, nf1, nf2, nl)) return RRL_ERR_ARG;
+    const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    return launch_shard_hist(ws, make_geometry(1, nf1, nf2, nl), round, state2, out_hist65536, (cudaStream_t)stream);
+}
+
+extern "C" int rrl_shard_select_pick(int round, const int *global_hist65536, const long long *global_counts18, long long *state2,
+                                     float *out_median, void *stream) {
+    if (!global_hist65536 || !global_counts18 || !state2 || !out_median || (round != 0 && round != 1)) return RRL_ERR_ARG;
+    return launch_shard_pick(round, global_hist65536, global_counts18, state2, out_median, (cudaStream_t)stream);
+}
+
 extern "C" int rrl_shard_stage2(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,
                                 const long long *global_counts18, const float *global_median, long long *sums32, void *stream) {
     if (!workspace || !global_counts18 || !global_median || !sums32 || !geometry_ok(1, nf1, nf2, nl)) return RRL_ERR_ARG;

@@ -113,6 +113,8 @@ int launch_backward(const Workspace &ws, const Geometry &g, const float *grad_ou
 int launch_export_hits(const Workspace &ws, const Geometry &g, int cloud, int *out_counts, int *out_hits, cudaStream_t s);
 int launch_pack_entries(const Workspace &ws, const Geometry &g, float *out, long long cap, cudaStream_t s);
 int launch_select_median(const float *vals, long long n, float *out, cudaStream_t s);
+int launch_shard_hist(const Workspace &ws, const Geometry &g, int round, const long long *state, int *hist, cudaStream_t s);
+int launch_shard_pick(int round, const int *hist, const long long *gcounts18, long long *state, float *out_median, cudaStream_t s);
 
 #ifdef __CUDACC__
 // ---- exact reference-order arithmetic (never contracted into FMA) -----------------------------------

@@ -284,6 +284,91 @@ int launch_select_median(const float *vals, long long n, float *out, cudaStream_
     return check_launch();
 }
 
+// ---- distributed lower median (line-sharded path): two rounds of 16-bit histograms ------------------------------
+// Every rank histograms the keys of ITS records (round 0: the high 16 bits of the float's bit pattern; round 1: the low
+// 16 bits of the keys that fall into the bin round 0 chose), the histograms are summed across ranks by the caller
+// (all-reduce), and every rank picks the bin that holds the global rank from the summed histogram -- identical inputs,
+// identical decision, no host round trip and no variable-length exchange.
+// state[0] = key prefix chosen so far, state[1] = rank of the median inside that prefix.
+constexpr int kShardBins = 65536;
+
+__global__ void __launch_bounds__(256) shard_hist_kernel(Workspace ws, Geometry g, int round, const long long *__restrict__ state,
+                                                          int *__restrict__ hist) {
+    const long long slots = (long long)ws.nrec[0] * 16;
+    const unsigned hi = (unsigned)state[0] >> 16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (long long)gridDim.x * blockDim.x) {
+        const int kj = ws.recMeta[(i >> 4) * 2 + 1];
+        const int e = (int)(i & 15);
+        if ((e >> 2) < (kj & 255) && (e & 3) < ((kj >> 8) & 255)) {
+            const unsigned key = __float_as_uint(ws.recD[i]);
+            if (round == 0) atomicAdd(hist + (key >> 16), 1);
+            else if ((key >> 16) == hi) atomicAdd(hist + (key & 0xFFFFu), 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) shard_pick_kernel(int round, const int *__restrict__ hist, const long long *__restrict__ gcounts18,
+                                                           long long *state, float *out_median) {
+    __shared__ long long s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long n = gcounts18[17];
+    if (n <= 0) {                                                // no entry anywhere: median 0, like the single-GPU path
+        if (tid == 0) { state[0] = 0; state[1] = 0; if (round == 1) *out_median = 0.f; }
+        return;
+    }
+    const long long rank = round == 0 ? (n - 1) / 2 : state[1];
+    constexpr int kPer = kShardBins / 1024;
+    long long tot = 0;
+    for (int q = 0; q < kPer; ++q) tot += hist[tid * kPer + q];
+    long long inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += up;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const long long v = s_w[lane];
+        long long incw = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, incw, d);
+            if (lane >= d) incw += up;
+        }
+        s_w[lane] = incw - v;
+    }
+    __syncthreads();
+    const long long before = s_w[wid] + inc - tot;
+    if (tot > 0 && rank >= before && rank < before + tot) {      // exactly one thread
+        long long r = rank - before;
+        int q = 0;
+        for (; q < kPer - 1; ++q) {
+            const long long h = hist[tid * kPer + q];
+            if (r < h) break;
+            r -= h;
+        }
+        const unsigned bin = (unsigned)(tid * kPer + q);
+        const unsigned prefix = round == 0 ? bin << 16 : (((unsigned)state[0] & 0xFFFF0000u) | bin);
+        state[0] = prefix;
+        state[1] = r;
+        if (round == 1) *out_median = __uint_as_float(prefix);
+    }
+}
+
+int launch_shard_hist(const Workspace &ws, const Geometry &g, int round, const long long *state, int *hist, cudaStream_t s) {
+    if (cudaMemsetAsync(hist, 0, sizeof(int) * kShardBins, s) != cudaSuccess) return RRL_ERR_CUDA;
+    shard_hist_kernel<<<148 * 2, 256, 0, s>>>(ws, g, round, state, hist);
+    count_launch();
+    return check_launch();
+}
+
+int launch_shard_pick(int round, const int *hist, const long long *gcounts18, long long *state, float *out_median, cudaStream_t s) {
+    shard_pick_kernel<<<1, 1024, 0, s>>>(round, hist, gcounts18, state, out_median);
+    count_launch();
+    return check_launch();
+}
+
 // compact the valid D entries of pair 0 (line-sharded path)
 __global__ void pack_entries_kernel(Workspace ws, Geometry g, float *out, long long cap) {
     const int nrec = ws.nrec[0];

@@ -4,9 +4,11 @@ host logic).  SURVEY 8(e):
   batch shard  pairs are independent -> each rank evaluates its own pairs; the only exchange is an all-reduce of the
                scalar loss (and whatever the caller logs).
   line shard   one pair, lines split across ranks; the global lower median and the 1/(n_kj k) normalisers couple
-               all lines, so there is exactly one exchange step between the dense and the Welsch stage and one
-               all-reduce of the fixed-point partial sums; the point gradient (or the 12 pose-gradient floats)
-               is all-reduced in backward.
+               all lines, so there is one exchange step between the dense and the Welsch stage -- an all-reduce of
+               the 18 counts and two all-reduces of 16-bit key histograms from which every rank picks the same
+               median (no host round trip, no variable-length gather) -- and one all-reduce of the fixed-point
+               partial sums; in backward the point gradient is all-reduced, or, with reduce_grad=False, left
+               local so that the caller reduces it in pose space (line_sharded_twist_loss: 6 floats).
 """
 from typing import List, Optional, Tuple
 
@@ -97,6 +99,16 @@ class NativeShardBackend:
                                                med.data_ptr(), self._stream()), "rrl_select_lower_median")
         return med
 
+    def select_hist(self, rnd, state):
+        hist = torch.empty(65536, dtype=torch.int32, device=self.dev)
+        N.check(self.L.rrl_shard_select_hist(*self._geom(), int(rnd), state.data_ptr(), hist.data_ptr(), self._stream()),
+                "rrl_shard_select_hist")
+        return hist
+
+    def select_pick(self, rnd, ghist, gcounts, state, med):
+        N.check(self.L.rrl_shard_select_pick(int(rnd), ghist.data_ptr(), gcounts.data_ptr(), state.data_ptr(), med.data_ptr(),
+                                             self._stream()), "rrl_shard_select_pick")
+
     def stage2_sums(self, gcounts, med):
         sums = torch.empty(32, dtype=torch.int64, device=self.dev)
         N.check(self.L.rrl_shard_stage2(*self._geom(), gcounts.data_ptr(), med.data_ptr(), sums.data_ptr(),
@@ -113,17 +125,17 @@ class NativeShardBackend:
 
 def line_shard_forward(backend, group=None):
     """The exchange protocol of SURVEY 8(e), independent of where the stages run (the CPU tests drive it with an
-    oracle-backed backend over gloo).  Exactly three collectives: all-gather of the 18 per-rank counts, all-gather
-    of the D entries, all-reduce of the 32 fixed-point partial sums."""
-    counts = backend.stage1_counts()
-    world = dist_.get_world_size(group)
-    all_counts = [torch.empty_like(counts) for _ in range(world)]
-    dist_.all_gather(all_counts, counts, group=group)
-    per_rank_entries = [int(c[17].item()) for c in all_counts]             # one host read: sizes of the exchange
-    gcounts = torch.stack(all_counts).sum(0)
-    n_local = per_rank_entries[dist_.get_rank(group)]
-    entries = gather_entries(backend.pack_entries(n_local), n_local, per_rank_entries, group)
-    med = backend.median(entries)
+    oracle-backed backend over gloo).  Four small all-reduces, nothing read by the host, nothing of variable length:
+    the 18 counts, two 65536-bin key histograms (distributed lower median: high then low 16 bits of the float bit
+    pattern), the 32 fixed-point partial sums."""
+    gcounts = backend.stage1_counts()
+    dist_.all_reduce(gcounts, op=dist_.ReduceOp.SUM, group=group)
+    state = torch.zeros(2, dtype=torch.int64, device=gcounts.device)
+    med = torch.zeros(1, dtype=torch.float32, device=gcounts.device)
+    for rnd in (0, 1):
+        hist = backend.select_hist(rnd, state)
+        dist_.all_reduce(hist, op=dist_.ReduceOp.SUM, group=group)
+        backend.select_pick(rnd, hist, gcounts, state, med)
     sums = backend.stage2_sums(gcounts, med)
     dist_.all_reduce(sums, op=dist_.ReduceOp.SUM, group=group)
     loss, status = backend.stage3_loss(sums)
@@ -132,10 +144,10 @@ def line_shard_forward(backend, group=None):
 
 class _LineShardedLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tri1, tri2, lines_local, window, group):
+    def forward(ctx, tri1, tri2, lines_local, window, group, reduce_grad):
         backend = NativeShardBackend(tri1, tri2, lines_local, window)
         loss, status, med = line_shard_forward(backend, group)
-        ctx.ws, ctx.geom, ctx.group = backend.ws, (backend.nf1, backend.nf2, backend.nl), group
+        ctx.ws, ctx.geom, ctx.group, ctx.reduce_grad = backend.ws, (backend.nf1, backend.nf2, backend.nl), group, reduce_grad
         ctx.mark_non_differentiable(status, med)
         return loss, status, med
 
@@ -152,18 +164,45 @@ class _LineShardedLoss(torch.autograd.Function):
                                           g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None,
                                           torch.cuda.current_stream(dev).cuda_stream), "rrl_loss_backward")
         # every rank holds the replicated clouds, so the point gradient is summed over the line shards
-        for t in (g1, g2):
-            if t is not None:
-                dist_.all_reduce(t, op=dist_.ReduceOp.SUM, group=ctx.group)
-        return g1, g2, None, None, None
+        if ctx.reduce_grad:
+            for t in (g1, g2):
+                if t is not None:
+                    dist_.all_reduce(t, op=dist_.ReduceOp.SUM, group=ctx.group)
+        return g1, g2, None, None, None, None
 
 
-def line_sharded_loss(tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None):
+class _AllReduceGrad(torch.autograd.Function):
+    """identity whose gradient is summed over the ranks"""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist_.all_reduce(g, op=dist_.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def line_sharded_twist_loss(twist, raw_tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None):
+    """The demo's / large-scan configuration: cloud 1 = se(3) transform of `raw_tri1` (nf1,9) by `twist` (6,), one pair,
+    lines sharded.  The sparse point gradient of every rank's line shard is reduced to pose space locally (closed-form
+    se(3) backward) and only the 6 twist-gradient floats cross NVLink.  Returns (loss (1,), status, median)."""
+    from . import ops
+    tw = _AllReduceGrad.apply(twist.reshape(1, 6), group)
+    tri1 = ops.se3_apply(tw, raw_tri1.reshape(1, -1, 3)).reshape(-1, 9)
+    return line_sharded_loss(tri1, tri2, lines_local, window, group, reduce_grad=False)
+
+
+def line_sharded_loss(tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, reduce_grad=True):
     """ONE pair: tri1 (nf1,9) and tri2 (nf2,9) replicated on every rank, lines_local (nl_r,6) = this rank's shard.
-    Returns (loss (1,), status (1,), median (1,)) -- identical on all ranks; gradients are all-reduced."""
+    Returns (loss (1,), status (1,), median (1,)) -- identical on all ranks; the point gradients are all-reduced unless
+    reduce_grad=False (then each rank keeps the gradient of its own line shard)."""
     from .ops import _cuda_f32
     if not (dist_.is_available() and dist_.is_initialized()):
         raise RuntimeError("line_sharded_loss needs an initialised torch.distributed process group")
     w = tuple(int(v) for v in window)
     return _LineShardedLoss.apply(_cuda_f32(tri1, "points1"), _cuda_f32(tri2, "points2"),
-                                  _cuda_f32(lines_local.detach(), "line"), w, group)
+                                  _cuda_f32(lines_local.detach(), "line"), w, group, bool(reduce_grad))

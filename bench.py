@@ -285,17 +285,26 @@ def run_gpu(args):
     dev_sets = [tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in s) for s in host_sets]
     nl_local = dev_sets[0][2].shape[1]
 
+    twist_mode = args.workload == "large"          # the scan pair is evaluated through the se(3) twist
+    twist0 = torch.tensor([0.01, -0.02, 0.015, 0.03, -0.01, 0.02], device=dev)
+
     def step(i):
         t1, t2, ln = dev_sets[i % n_sets]
+        if twist_mode:
+            tw = twist0.clone().requires_grad_(True)
+            if line_sharded:
+                loss, _, _ = rrl_b200.dist.line_sharded_twist_loss(tw, t1[0], t2[0], ln[0])
+            else:
+                tri1 = rrl_b200.se3_apply(tw.reshape(1, 6), t1.reshape(1, -1, 3)).reshape(1, -1, 9)
+                loss = rrl_b200.intersected_line_loss(tri1, t2, ln)
+            total = loss.sum()
+            total.backward()
+            return total.detach(), tw.grad
         t1 = t1.detach().requires_grad_(True)
-        if line_sharded:
-            loss, _, _ = rrl_b200.dist.line_sharded_loss(t1[0], t2[0], ln[0])
-            total = loss.sum()
-        else:
-            loss = rrl_b200.intersected_line_loss(t1, t2, ln)
-            total = loss.sum()
+        loss = rrl_b200.intersected_line_loss(t1, t2, ln)
+        total = loss.sum()
         total.backward()
-        if world > 1 and not line_sharded:
+        if world > 1:
             red = total.detach().clone()
             dist.all_reduce(red)                      # the only exchange of the batch-sharded path
             return red, t1.grad
@@ -429,7 +438,9 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": desc, "name": args.workload, "pairs_per_gpu": B, "triplets_per_cloud": nf,
                        "lines_per_pair": nl, "sharding": "lines" if line_sharded else "pairs (batch)",
-                       "window": [1, 1, 5, 5], "backward": "d loss / d points1 (B, nf, 9)",
+                       "window": [1, 1, 5, 5],
+                       "backward": "d loss / d twist (6) through the fused se(3) transform of cloud 1" if twist_mode
+                                   else "d loss / d points1 (B, nf, 9)",
                        "l2": "inputs rotate over %d distinct sets (%.0f MB > 126 MB L2), no flush needed" %
                              (n_sets, n_sets * bytes_per_set / 2 ** 20)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

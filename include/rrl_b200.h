@@ -118,6 +118,15 @@ int rrl_shard_pack_entries(void *workspace, size_t workspace_bytes, int nf1, int
                            float *out_entries, long long capacity, void *stream);
 /* lower median of a flat device array of n non-negative floats (n read from the host argument) */
 int rrl_select_lower_median(const float *values, long long n, float *out_median, void *stream);
+/* Distributed lower median without a host round trip or a variable-length exchange: for round = 0, 1 every rank
+ * histograms its D entries (round 0: high 16 bits of the float bit pattern; round 1: low 16 bits inside the bin chosen
+ * in round 0) into out_hist65536 (int32), the caller sums the histograms over the ranks (all-reduce), and
+ * rrl_shard_select_pick narrows state2 = {prefix, rank} from the summed histogram and the summed counts; after round 1
+ * out_median holds the global lower median on every rank (0 when no rank has an entry). */
+int rrl_shard_select_hist(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl, int round,
+                          const long long *state2, int *out_hist65536, void *stream);
+int rrl_shard_select_pick(int round, const int *global_hist65536, const long long *global_counts18, long long *state2,
+                          float *out_median, void *stream);
 int rrl_shard_stage2(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,
                      const long long *global_counts18, const float *global_median, long long *sums32, void *stream);
 int rrl_shard_stage3(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,

@@ -47,6 +47,29 @@ class OracleShardBackend:
         v = np.sort(entries.numpy())
         return torch.tensor([v[(len(v) - 1) // 2] if len(v) else 0.0], dtype=torch.float32)
 
+    # distributed lower median: the semantics of rrl_shard_select_hist / rrl_shard_select_pick in numpy
+    def select_hist(self, rnd, state):
+        keys = self._entries().astype(np.float32).view(np.uint32)
+        if rnd == 1:
+            keys = keys[(keys >> 16) == (np.uint32(int(state[0])) >> 16)] & np.uint32(0xFFFF)
+        else:
+            keys = keys >> 16
+        return torch.from_numpy(np.bincount(keys.astype(np.int64), minlength=65536).astype(np.int32))
+
+    def select_pick(self, rnd, ghist, gcounts, state, med):
+        n = int(gcounts[17])
+        if n <= 0:
+            state[:] = 0
+            med[0] = 0.0
+            return
+        rank = (n - 1) // 2 if rnd == 0 else int(state[1])
+        cum = np.cumsum(ghist.numpy().astype(np.int64))
+        b = int(np.searchsorted(cum, rank, side="right"))
+        state[1] = rank - (int(cum[b - 1]) if b else 0)
+        state[0] = (b << 16) if rnd == 0 else ((int(state[0]) & 0xFFFF0000) | b)
+        if rnd == 1:
+            med[0] = float(np.array([int(state[0])], np.uint32).view(np.float32)[0])
+
     def stage2_sums(self, gcounts, med):
         m = np.float32(med.item())
         sums = np.zeros(32, np.int64)

@@ -28,6 +28,16 @@ assert abs(float(loss) - orc.loss) <= 1e-5 * orc.loss, (float(loss), orc.loss)
 g = t1.grad.cpu().numpy()
 err = np.linalg.norm(g - orc.grad1) / np.linalg.norm(orc.grad1)
 assert err <= 1e-5, err
+# ---- line shard through the se(3) twist: only 6 gradient floats are exchanged ----
+tw = torch.tensor([0.02, -0.01, 0.03, 0.05, -0.02, 0.01], device=dev, requires_grad=True)
+raw = torch.from_numpy(p["tri1"]).to(dev)
+loss_t, _, _ = rrl_b200.dist.line_sharded_twist_loss(tw, raw, t2, torch.from_numpy(p["lines"][lo:hi]).to(dev))
+loss_t.sum().backward()
+tri1_moved = rrl_b200.se3_apply(tw.detach().reshape(1, 6), raw.reshape(1, -1, 3)).reshape(-1, 9).cpu().numpy()
+orc_t = co.loss(tri1_moved, p["tri2"], p["lines"])
+gt = co.se3_backward(tw.detach().cpu().numpy(), p["tri1"].reshape(-1, 3), orc_t.grad1.reshape(-1, 3))
+err_t = np.linalg.norm(tw.grad.cpu().numpy() - gt) / np.linalg.norm(gt)
+assert abs(float(loss_t) - orc_t.loss) <= 1e-5 * orc_t.loss and err_t <= 1e-5, (float(loss_t), orc_t.loss, err_t)
 # ---- batch shard: each rank its own pairs ----
 pairs = [synth.make_pair(5000 + 10 * rank + i, 512, 2000) for i in range(3)]
 a = torch.from_numpy(np.stack([q["tri1"] for q in pairs])).to(dev).requires_grad_(True)
@@ -43,6 +53,6 @@ for i, w in enumerate(want_local):
     assert np.linalg.norm(a.grad[i].cpu().numpy() - w.grad1) <= 1e-5 * np.linalg.norm(w.grad1)
 dist.barrier()
 if rank == 0:
-    print("dist_check ok: world %d, line-shard loss %.6f (oracle %.6f), grad err %.2e, batch total %.6f" %
-          (world, float(loss), orc.loss, err, float(total)))
+    print("dist_check ok: world %d, line-shard loss %.6f (oracle %.6f), grad err %.2e, twist-grad err %.2e, batch total %.6f" %
+          (world, float(loss), orc.loss, err, err_t, float(total)))
 dist.destroy_process_group()
