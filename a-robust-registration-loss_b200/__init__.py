@@ -9,6 +9,7 @@ The directory name carries a hyphen, so import it through the repo-root shim:  `
     rrl_b200.loss                                          drop-in module with the reference's names (code/loss.py)
     rrl_b200.dist                                          batch-/line-sharded multi-GPU evaluation
     rrl_b200.prep                                          farthest-point sampling + kNN triplets (Sample_neighs)
+    rrl_b200.io                                            dataset file formats of the reference's DL loaders
 """
 from . import _native
 from ._native import NativeError, launch_count
@@ -16,6 +17,7 @@ from .ops import (LossInfo, chamfer, intersected_line_loss, rigid_apply, sample_
 from . import loss  # noqa: E402  (reference-compatible names)
 from . import dist  # noqa: E402
 from . import prep  # noqa: E402
+from . import io  # noqa: E402
 
 __all__ = ["NativeError", "launch_count", "LossInfo", "chamfer", "intersected_line_loss", "rigid_apply",
-           "sample_lines", "se3_apply", "se3_exp", "loss", "dist", "prep"]
+           "sample_lines", "se3_apply", "se3_exp", "loss", "dist", "prep", "io"]

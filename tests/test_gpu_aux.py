@@ -188,3 +188,26 @@ def test_fps_rejects_bad_arguments(rrl):
     L = rrl._native.lib()
     assert L.rrl_fps(p.data_ptr(), 0, 10, 3, 10, p.data_ptr(), p.data_ptr(), 1 << 20, None) == -1     # start out of range
     assert L.rrl_knn(p.data_ptr(), 0, 10, p.data_ptr(), 2, 9, p.data_ptr(), None) == -1               # k > 8
+
+
+def test_demo_flow_with_the_reference_names(rrl):
+    """examples/demo_lie_algebra.py = test_demo_optimized_Lie_Algebra.py with `loss` shadowed by the B200 module:
+    Sample_neighs -> Reconstruction_point -> per epoch sampler + loss + Adam + chamfer.  A 12-degree misalignment of a
+    synthetic ellipsoid must shrink."""
+    import argparse
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_demo", os.path.join(root, "examples", "demo_lie_algebra.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    torch.manual_seed(5); np.random.seed(5); rrl.loss.manual_seed(5)
+    args = argparse.Namespace(synthetic=1500, seed=5, angle=12.0, data_path="", label1="0")
+    data = demo.load_case(args, "cuda")
+    assert data["vertics1_faces_tensor"].shape == (1, 3 * 1500, 3)
+    model, hist = demo.test_one_case(data, n_epoch=60, n_sample_line=8000, device="cuda", log=None)
+    assert len(hist) >= 50
+    first, last = np.mean([h[0] for h in hist[:3]]), np.mean([h[0] for h in hist[-3:]])
+    assert last < 0.5 * first, (first, last)
+    R, T = model.Transform()
+    assert R.shape == (1, 3, 3) and T.shape == (1, 3) and "parameters_" in model.state_dict()
