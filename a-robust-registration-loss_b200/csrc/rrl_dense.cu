@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) sort_keys_kernel(const float *__restrict_
 // record.  Must be called by converged warps (whole groups, full mask).  Returns the node radius in lane s == 0.
 template <int kNode>
 __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, float th, int f, long long i, double E,
-                                                float4 *pt_base, float4 *pt12, float4 *node4) {
+                                                float4 *pt_base, float4 *pt12, float4 *node4, int ball_iters) {
     const long long n = i / kNode;
     const int s = (int)(i % kNode);
     double px = 0, py = 0, pz = 0, cut = 0;
@@ -214,7 +214,35 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     float qx = 0.f, qy = 0.f, qz = 0.f;
     double R = 0;
     if (cntv > 0) {
-        qx = (float)(cx / cntv); qy = (float)(cy / cntv); qz = (float)(cz / cntv);   // the record's centre is the ROUNDED centroid
+        qx = (float)(cx / cntv); qy = (float)(cy / cntv); qz = (float)(cz / cntv);   // start: the ROUNDED centroid
+    }
+    // Shrink the sphere: the centre that minimises max_f (|p0_f - q| + r_f) instead of the centroid (Badoiu-Clarkson
+    // steps q += (p_far - q) / (k + 1) towards the member that currently defines the radius; the best centre seen is
+    // kept).  About a quarter fewer (line, node) candidates on surface clouds.  Only a heuristic for WHERE the centre
+    // goes: the radius below is computed for whatever centre comes out, so the superset property is untouched.  Every
+    // lane of the group computes the same bits (same operations on the same shuffled values).
+    if (ball_iters > 0) {
+        const float fx = (float)px, fy = (float)py, fz = (float)pz;
+        const float rf = f >= 0 ? sqrtf(fmaxf((float)(cut + E), 0.f)) : 0.f;
+        const unsigned gmask = (kNode >= 32 ? 0xffffffffu : ((1u << kNode) - 1u)) << ((threadIdx.x & 31) & ~(kNode - 1));
+        float bx = qx, by = qy, bz = qz, bestR = INFINITY;
+        float ccx = qx, ccy = qy, ccz = qz;
+        for (int k = 1; k <= ball_iters + 1; ++k) {
+            const float dx = fx - ccx, dy = fy - ccy, dz = fz - ccz;
+            const float d = f >= 0 ? sqrtf(dx * dx + dy * dy + dz * dz) + rf : -INFINITY;
+            float m = d;
+#pragma unroll
+            for (int dd = 1; dd < kNode; dd <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, dd));
+            if (m < bestR) { bestR = m; bx = ccx; by = ccy; bz = ccz; }
+            const unsigned bal = __ballot_sync(0xffffffffu, d == m) & gmask;
+            const int far = bal ? __ffs(bal) - 1 : (int)(threadIdx.x & 31);
+            const float gx = __shfl_sync(0xffffffffu, fx, far), gy = __shfl_sync(0xffffffffu, fy, far), gz = __shfl_sync(0xffffffffu, fz, far);
+            const float step = 1.0f / (float)(k + 1);
+            ccx += (gx - ccx) * step; ccy += (gy - ccy) * step; ccz += (gz - ccz) * step;
+        }
+        if (cntv > 0 && bestR < INFINITY) { qx = bx; qy = by; qz = bz; }
+    }
+    if (cntv > 0) {
         if (f >= 0) {
             const double dx = px - qx, dy = py - qy, dz = pz - qz;
             R = sqrt(fmax(cut + E, 0.0)) + sqrt(dx * dx + dy * dy + dz * dz);
@@ -259,7 +287,7 @@ __device__ __forceinline__ double node_slack(unsigned pmax_bits, unsigned xmax_b
 }
 
 template <int kNode>
-__global__ void __launch_bounds__(256) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g) {
+__global__ void __launch_bounds__(256) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g, int ball_iters) {
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
     const int nnodes = nfp / kNode;
@@ -271,7 +299,7 @@ __global__ void __launch_bounds__(256) node_kernel(const float *__restrict__ tri
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nfp; i += (long long)gridDim.x * blockDim.x) {
         const int f = perm[i];
         const float rad = make_node_coop<kNode>(tri, f >= 0 ? thr[f] : 0.f, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
-                                                ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5);
+                                                ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters);
         warp_atomic_max_bits(ws.rmax + b * 2 + cloud, rad);
     }
 }
@@ -298,7 +326,7 @@ __device__ __forceinline__ void line_constants(const float *__restrict__ ln, flo
 template <int kNode>
 __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
                                                           const float *__restrict__ lines, Workspace ws, Geometry g, int window,
-                                                          int sorted, int line_blocks) {
+                                                          int sorted, int line_blocks, int ball_iters) {
     extern __shared__ unsigned long long skeys[];
     __shared__ unsigned s_red[3];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -435,7 +463,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
             const int f = idx < (unsigned)nf ? (int)idx : -1;
             perm[i] = f;
             rad = fmaxf(rad, make_node_coop<kNode>(tri, f >= 0 ? thr[f] : 0.f, f, i, Eslack, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
-                                                   ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5));
+                                                   ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters));
         }
     }
     {
@@ -453,8 +481,8 @@ size_t sort_scratch_bytes(int nfp_max) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[8] = {0, 0, 16, 32, 0, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = chunks may exceed the shared-memory point cache
-void set_param(int id, int v) { if (id >= 0 && id < 8) g_param[id] = v; }
+static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = chunks may exceed the shared-memory point cache, [8] enclosing-ball refinement steps of the node centres (0 = centroid)
+void set_param(int id, int v) { if (id >= 0 && id < 12) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
     return (g.nf1 > g.nf2 ? g.nf1 : g.nf2) >= 16384 ? 16 : 8;
@@ -480,8 +508,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
                 return RRL_ERR_CUDA;
             attr_set = true;
         }
-        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks);
-        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks);
+        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8]);
+        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8]);
         count_launch();
         stage_mark(1, s);
         stage_mark(2, s);
@@ -528,8 +556,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     stage_mark(2, s);
     int nbx = nfp_max / 256;
     if (nbx > 4096) nbx = 4096;
-    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g);
-    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g);
+    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8]);
+    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8]);
     count_launch();
     stage_mark(3, s);
     return check_launch();

@@ -352,3 +352,50 @@ def test_full_size_dcp_batch_properties(rrl):
         ok = (c > s + 1)
         assert np.all(h[..., s][ok] < h[..., s + 1][ok])
     assert h.max() < nf and int(info.stats[:, 6].sum()) == 0
+
+
+def test_large_cloud_path_vs_oracle(rrl):
+    """clouds above 16384 triplets take the other launch plan (radix sort, 16-triplet nodes, group -> node -> triplet
+    queues): complete oracle comparison at a size the oracle still finishes in seconds"""
+    p = synth.make_pair(141, 40000, 3000, nf2=33000, zero_frac=0.05)
+    out = _run(rrl, p["tri1"], p["tri2"], p["lines"])
+    _check_against_oracle(out, co.loss(p["tri1"], p["tri2"], p["lines"]))
+
+
+def test_full_size_large_pair_properties(rrl):
+    """BASELINE config 5 at full size (500k triplets x 100k lines): the oracle checks a sample of the lines completely,
+    the on-device brute-force kernel (every (line, triplet) tested exactly, the reference's formulation) checks all of
+    them, and the loss must not depend on the order of the lines"""
+    nf, nl = 500000, 100000
+    p = synth.make_pair(5000, nf, nl)
+    t1 = torch.from_numpy(p["tri1"]).cuda()[None]
+    t2 = torch.from_numpy(p["tri2"]).cuda()[None]
+    ln = torch.from_numpy(p["lines"]).cuda()[None]
+    loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True)
+    c1, h1 = (x[0].cpu().numpy() for x in info.hits(1))
+    c2, h2 = (x[0].cpu().numpy() for x in info.hits(2))
+    assert int(info.stats[0, 6]) == 0 and np.isfinite(loss.item()) and loss.item() > 0
+    # (a) a sample of the lines against the C oracle (hit lists only: the loss couples all lines through the median)
+    sample = np.random.default_rng(1).choice(nl, 1024, replace=False)
+    orc = co.loss(p["tri1"], p["tri2"], p["lines"][sample], want_grad=False)
+    assert np.array_equal(c1[sample], orc.counts1) and np.array_equal(c2[sample], orc.counts2)
+    for cnt, mine, ref in ((orc.counts1, h1[sample], orc.hits1), (orc.counts2, h2[sample], orc.hits2)):
+        keep = cnt <= co.CAP
+        assert np.array_equal(mine[keep], ref[keep])
+    # (b) every line against the brute-force kernel
+    L = rrl._native.lib()
+    try:
+        L.rrl_debug_set_param(5, 1)
+        loss_bf, info_bf = rrl.intersected_line_loss(t1, t2, ln, return_info=True)
+        b1, g1 = (x[0].cpu().numpy() for x in info_bf.hits(1))
+        b2, g2 = (x[0].cpu().numpy() for x in info_bf.hits(2))
+    finally:
+        L.rrl_debug_set_param(5, 0)
+    assert np.array_equal(c1, b1) and np.array_equal(c2, b2)
+    assert np.array_equal(h1[c1 <= co.CAP], g1[c1 <= co.CAP]) and np.array_equal(h2[c2 <= co.CAP], g2[c2 <= co.CAP])
+    assert loss_bf.item() == loss.item() and float(info_bf.median[0]) == float(info.median[0])
+    # (c) permuting the lines permutes the hit lists and leaves median and loss bit-identical (fixed-point sums)
+    perm = torch.randperm(nl, generator=torch.Generator().manual_seed(3)).cuda()
+    loss_p, info_p = rrl.intersected_line_loss(t1, t2, ln[:, perm], return_info=True)
+    assert float(info_p.median[0]) == float(info.median[0]) and loss_p.item() == loss.item()
+    assert np.array_equal(info_p.hits(1)[0][0].cpu().numpy(), c1[perm.cpu().numpy()])

@@ -15,7 +15,10 @@ CONFIGS = {"demo": (1, 1024, 20000), "dcp": (32, 1024, 15000), "rpm": (64, 2048,
            "large": (1, 500000, 100000)}
 DEFAULTS = {1: 0, 2: 16, 3: 32, 4: 0}
 variants = sys.argv[1:] or [""]
+import os
 for name, (B, nf, nl) in CONFIGS.items():
+    if os.environ.get("ONLY") and name not in os.environ["ONLY"].split(","):
+        continue
     pairs = [synth.make_pair(1000 + i, nf, nl) for i in range(min(B, 4))]
     idx = [i % len(pairs) for i in range(B)]
     t1, t2, ln = (torch.from_numpy(np.stack([pairs[i][k] for i in idx])).cuda() for k in ("tri1", "tri2", "lines"))
@@ -32,5 +35,5 @@ for name, (B, nf, nl) in CONFIGS.items():
             md, mp = C.c_float(), C.c_float()
             assert L.rrl_measure_dense(t1.data_ptr(), t2.data_ptr(), ln.data_ptr(), B, nf, nf, nl, ws.data_ptr(), wsb, 10,
                                        C.byref(md), C.byref(mp), None) == 0
-            res.setdefault(v or "default", []).append(round(md.value, 4))
+            res.setdefault(v or "default", []).append((round(md.value, 4), round(mp.value, 4)))
     print(name, json.dumps(res), flush=True)

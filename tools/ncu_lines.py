@@ -90,3 +90,31 @@ for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print("%-22s %6.2f%% %6.2f%% %5d  %-34s %s" % ("%s:%d" % key if key else "?", 100.0 * a[0] / max(tot_inst, 1),
                                                  100.0 * a[1] / max(tot_samp, 1), a[2],
                                                  " ".join("%s:%d" % (k, v) for k, v in st), src(key)))
+
+# REGIONS="name:lo-hi,name:lo-hi,..." (line ranges of the kernel's own file): executed instructions and samples per
+# region; rows whose line info points into an intrinsic header inherit the last own-file line seen before them
+if os.environ.get("REGIONS"):
+    own = os.environ.get("REGION_FILE", "rrl_dense.cu")
+    regs = []
+    for part in os.environ["REGIONS"].split(","):
+        name, rng = part.split(":")
+        lo, hi = rng.split("-")
+        regs.append((name, int(lo), int(hi)))
+    acc = defaultdict(lambda: [0, 0, 0])
+    last = None
+    for i in range(n):
+        key = lines[i][0]
+        if key and key[0] == own:
+            last = key[1]
+        name = "?"
+        for nm, lo, hi in regs:
+            if last is not None and lo <= last <= hi:
+                name = nm
+                break
+        r = body[i]
+        acc[name][0] += int(r[col["Instructions Executed"]] or 0)
+        acc[name][1] += int(r[col["# Samples"]] or 0)
+        acc[name][2] += 1
+    print("\nregion            inst%   samp%  sass")
+    for nm, a in sorted(acc.items(), key=lambda kv: -kv[1][0]):
+        print("%-16s %6.2f%% %6.2f%% %5d" % (nm, 100.0 * a[0] / max(tot_inst, 1), 100.0 * a[1] / max(tot_samp, 1), a[2]))
