@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librrl_b200.so")
+# RRL_LIB_PATH: an A/B build of the same library (build.py, RRL_VARIANT) for the measurement tools
+LIB_PATH = os.environ.get("RRL_LIB_PATH") or os.path.join(_HERE, "librrl_b200.so")
 
 HIT_CAP = 5
 NSTAT = 8

@@ -10,9 +10,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "librrl_b200.so")
+# A/B builds: RRL_VARIANT=name RRL_DEFS="-DFOO=1 ..." writes build/variants/librrl_b200_<name>.so next to the product
+# library; tools load it with RRL_LIB_PATH.  The product build never sets either.
+VARIANT = os.environ.get("RRL_VARIANT", "")
+OUT = os.path.join(HERE, "build", "variants", "librrl_b200_%s.so" % VARIANT) if VARIANT else os.path.join(HERE, "librrl_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+COMMON += os.environ.get("RRL_DEFS", "").split()
 if os.environ.get("RRL_MARKS"):          # measurement builds: in-kernel phase timestamps (rrl_debug_read_marks)
     COMMON.append("-DRRL_MARKS")
 # rrl_sampler.cu restates a floating-point knife-edge test and must not contract a*b+c into FMAs
@@ -32,7 +36,7 @@ def build(force=False, verbose=False):
     newest = max(os.path.getmtime(d) for d in deps)
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", "variants", VARIANT) if VARIANT else os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []
     for src, extra in SOURCES.items():

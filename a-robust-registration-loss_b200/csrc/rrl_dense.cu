@@ -481,7 +481,7 @@ size_t sort_scratch_bytes(int nfp_max) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = chunks may exceed the shared-memory point cache, [8] enclosing-ball refinement steps of the node centres (0 = centroid)
+static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] unused, [8] enclosing-ball refinement steps of the node centres (0 = centroid)
 void set_param(int id, int v) { if (id >= 0 && id < 12) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -632,8 +632,11 @@ struct DenseCfg {
     static constexpr int kWq = LPT >= 4 ? 512 : 256;                   // per warp: (line, group) entries, or (line, node) when kPerNode
     static constexpr int kNq = 256;                                    // per warp: (line, node) entries of the 3-level pipeline
     static constexpr int kXq = 32 * kNode + 64;                        // per warp: (line, triplet); one level-2 pass appends <= 32 * kNode
-    static constexpr int kPts = LPT >= 4 ? 576 : 288;                  // point-0 records (float4, incl. pads) staged when the chunk fits
-    static constexpr int kPts12 = LPT >= 4 ? 1024 : 512;               // point-1/2 records of the chunk
+    // kPerNode (small clouds): the chunk's point records are staged in shared memory -- the launch sizes the chunks to
+    // fit -- and read with LDS; otherwise they are read through L1/L2 with LDG.  Compile-time either way: a pointer that
+    // may be shared or global turns every access into a generic load (4 % of the kernel on the DCP batch).
+    static constexpr int kPts = !kPerNode ? 0 : (LPT >= 4 ? 576 : 288);    // point-0 records (float4, incl. pads)
+    static constexpr int kPts12 = !kPerNode ? 0 : (LPT >= 4 ? 1024 : 512); // point-1/2 records of the chunk
     static constexpr int kOffLine = 2 * kStage * 16;
     static constexpr int kOffWq = kOffLine + kLines * 32;
     static constexpr int kOffNq = kOffWq + kNumWarps * kWq * 4;
@@ -647,8 +650,22 @@ struct DenseCfg {
 
 // exclusive prefix sum over the lanes of a (converged) warp of a count c < 2^kBits, by bit planes: kBits independent
 // ballots instead of a dependent chain of five shuffles (the queue levels are latency bound, not issue bound)
+#ifndef RRL_SCAN_SHFL
+#define RRL_SCAN_SHFL 0
+#endif
+
 template <int kBits>
 __device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
+#if RRL_SCAN_SHFL
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - c;
+#endif
     const unsigned lt = (1u << lane) - 1u;
     int off = 0;
     total = 0;
@@ -753,12 +770,13 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
     };
     // the chunk's triplet records (level 2) go to shared memory when they fit, else they are read through L2
     const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + n_begin) * (kNode + 1);   // chunk start
-    const bool pts_in_smem = (n_end - n_begin) * (kNode + 1) <= kSmemPtsF4;
-    const float4 *pts = pts_in_smem ? spts : pt4_c;
+    constexpr bool pts_in_smem = kPerNode, pts12_in_smem = kPerNode;
+    const float4 *pts = spts;
+    if constexpr (!kPerNode) pts = pt4_c;
     // point-1/2 records of the chunk (refine pass before the hand-off to the exact kernel)
     const float4 *pt12_c = ws.pt12[cloud] + ((long long)b * nfp + (long long)n_begin * kNode) * 2;
-    const bool pts12_in_smem = (n_end - n_begin) * kNode * 2 <= kSmemPts12F4;
-    const float4 *pts12 = pts12_in_smem ? spts12 : pt12_c;
+    const float4 *pts12 = spts12;
+    if constexpr (!kPerNode) pts12 = pt12_c;
     if (tid == 0) {
         issue(0);
         if (ntiles > 1) issue(1);
@@ -778,8 +796,9 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
 
     int ncand = 0;
     const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)n_begin * kNode;   // from the chunk start
-    // node records for level 1: a single-tile chunk stays resident in stage 0, otherwise re-read through L2
-    const float4 *node_src = (ntiles == 1) ? stage : src;                                  // from the chunk start
+    // node records for level 1: re-read through L1/L2 (a pointer that is sometimes the resident stage would make
+    // every access a generic load)
+    const float4 *node_src = src;                                                          // from the chunk start
     int wq_cnt = 0, nq_cnt = 0, xq_cnt = 0;                      // warp-uniform fill levels
 
     // level 3 hand-off: (line, triplet) entries that passed both filters go to the launch-wide queue of the exact
@@ -1192,8 +1211,9 @@ static int launch_dense_variant(const DenseArgs &a0, const Workspace &ws, const 
     if (chunk_nodes < g_param[3]) chunk_nodes = g_param[3];
     chunk_nodes = ((chunk_nodes + kNodePad - 1) / kNodePad) * kNodePad;
     // small clouds: keep the chunk's point records in shared memory (level 2 reads them once per candidate node)
-    constexpr int kFit = (Cfg::kPts / (kNode + 1)) / kNodePad * kNodePad;
-    if (kPerNode && g_param[7] == 0 && chunk_nodes > kFit) chunk_nodes = kFit;
+    constexpr int kFit = kPerNode ? (Cfg::kPts / (kNode + 1)) / kNodePad * kNodePad : 0;
+    static_assert(!kPerNode || kFit * kNode * 2 <= Cfg::kPts12, "point-1/2 cache must hold what the point-0 cache holds");
+    if (kPerNode && chunk_nodes > kFit) chunk_nodes = kFit;
     if (chunk_nodes / 4 >= (1 << 20) || (long long)chunk_nodes * G >= (1 << 22)) return RRL_ERR_ARG;
     chunks = (nn_max + chunk_nodes - 1) / chunk_nodes;
     a.chunk_nodes = chunk_nodes;
