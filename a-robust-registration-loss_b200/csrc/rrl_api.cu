@@ -39,11 +39,12 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     const int nf1p = pad_points(nf1), nf2p = pad_points(nf2);
     w.hdr = reinterpret_cast<int *>(take(8 * sizeof(int)));
     // ---- per-pair block, contiguous and zeroed by one memset in launch_prep (order matters) ----
-    char *pair = take(16 + sB * (3 * 2 * 4 + 4 + 16 * 4 + 4 + 4 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
+    char *pair = take(16 + sB * (4 * 2 * 4 + 4 + 16 * 4 + 4 + 4 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
     w.xcursor = reinterpret_cast<unsigned long long *>(pair);         pair += 16;
     w.pmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.xmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.rmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
+    w.smax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.nrec = reinterpret_cast<int *>(pair);                           pair += sB * 4;
     w.n_kj = reinterpret_cast<int *>(pair);                           pair += sB * 16 * 4;
     w.med = reinterpret_cast<float *>(pair);                          pair += sB * 4;
@@ -63,7 +64,9 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.pt12[1] = reinterpret_cast<float4 *>(take(sB * nf2p * 2 * sizeof(float4)));
     w.node4[0] = reinterpret_cast<float4 *>(take(sB * (nf1p / kMinNode / 4) * 5 * sizeof(float4)));
     w.node4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kMinNode / 4) * 5 * sizeof(float4)));
-    w.sortbuf_bytes = sort_scratch_bytes(nf1p > nf2p ? nf1p : nf2p);
+    w.super4[0] = reinterpret_cast<float4 *>(take(sB * (pad_supers(nf1p) / 4) * 5 * sizeof(float4)));
+    w.super4[1] = reinterpret_cast<float4 *>(take(sB * (pad_supers(nf2p) / 4) * 5 * sizeof(float4)));
+    w.sortbuf_bytes = sort_scratch_bytes(nf1p > nf2p ? nf1p : nf2p, B);
     w.sortbuf = reinterpret_cast<unsigned long long *>(take(w.sortbuf_bytes));
     // ---- per line ----
     w.lineC = reinterpret_cast<float4 *>(take(lines * 2 * sizeof(float4)));

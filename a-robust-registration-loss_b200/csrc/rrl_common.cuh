@@ -34,6 +34,8 @@ constexpr int kPointPad = 256;                                  // triplet array
 constexpr int kMinNode = 8;                                     // smallest node size (sizes the node arrays)
 constexpr int kExactPerLine = 12;                               // capacity of the exact-candidate queue, entries per line
 constexpr int kSortSmall = 4096;                                // clouds up to this many (padded) triplets sort in one CTA
+constexpr int kSuperPts = 256;                                  // triplets per super node (= kPointPad: one node_kernel CTA builds one)
+constexpr int kSuperMin = 16384;                                // clouds from this many triplets get the super-node level
 
 // ---- fixed-point accumulation of Welsch sums (order-independent, hence run-to-run deterministic) ---
 constexpr double kFixScale = 1099511627776.0;                   // 2^40
@@ -51,6 +53,7 @@ struct Workspace {
     unsigned int *pmax;      // (B,2): bits of max |p|^2 over all 3 points of all triplets of the cloud
     unsigned int *xmax;      // (B,2): [0] bits of max |x0|^2 over the pair's lines, [1] reserved
     unsigned int *rmax;      // (B,2): bits of the largest node radius of the cloud
+    unsigned int *smax;      // (B,2): bits of the largest super-node radius of the cloud (large clouds only)
     int *nrec;               // (B)
     int *n_kj;               // (B,16)
     float *med;              // (B)
@@ -65,6 +68,7 @@ struct Workspace {
     float4 *pt4[2];          // (B, nnodes, node_size + 1): sorted order, pair-interleaved {p0.xyz, cut - |p0|^2}, 1 pad per node
     float4 *pt12[2];         // (B, nfp, 2): sorted order, {p1.xyz, cut - |p1|^2}, {p2.xyz, cut - |p2|^2}
     float4 *node4[2];        // (B, nnodes/4, 5): pair-interleaved {xA,xB,yA,yB}{zA,zB,wA,wB} x2 + 1 pad; w = R^2 - |q|^2
+    float4 *super4[2];       // (B, nsuperp/4, 5): same layout, one record per kSuperPts sorted triplets (large clouds only)
     unsigned long long *sortbuf; // scratch for the large-cloud sort (keys/values double buffers + cub temp)
     size_t sortbuf_bytes;
     // per line
@@ -85,7 +89,8 @@ struct Workspace {
 constexpr int kMagic = 0x52524c31;   // "RRL1"
 
 inline int pad_points(int nf) { return ((nf + kPointPad - 1) / kPointPad) * kPointPad; }
-size_t sort_scratch_bytes(int nfp_max);
+inline int pad_supers(int nfp) { return ((nfp / kSuperPts + 3) / 4) * 4; }      // super records come in groups of 4
+size_t sort_scratch_bytes(int nfp_max, int B);
 int node_size(const Geometry &g);       // triplets per bounding-sphere node for this geometry (8 or 16)
 
 Workspace carve(void *base, int B, int nf1, int nf2, int nl);

@@ -39,26 +39,29 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
     if (b == 0 && t0 == 0) {
         ws.hdr[0] = kMagic; ws.hdr[1] = g.B; ws.hdr[2] = g.nf1; ws.hdr[3] = g.nf2; ws.hdr[4] = g.nl; ws.hdr[5] = window;
     }
-#pragma unroll 1
+    float block_max[3];
+#pragma unroll
     for (int cloud = 0; cloud < 2; ++cloud) {
         const int nf = cloud ? g.nf2 : g.nf1;
         const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
         float *thr = ws.thr[cloud] + (long long)b * nf;
+        float pm = 0.f;                                                           // running maximum: ONE atomic per warp
         for (int base = blockIdx.x * blockDim.x; base < nf; base += stride) {      // warp-uniform trip count
             const int f = base + threadIdx.x;
-            float pm = 0.f;
             if (f < nf) {
                 float v[9];
 #pragma unroll
                 for (int q = 0; q < 9; ++q) v[q] = __ldg(tri + (long long)f * 9 + q);
                 thr[f] = triplet_thr_exact(v);
-                pm = fmaxf(fmaxf(sq3_rn(v[0], v[1], v[2]), sq3_rn(v[3], v[4], v[5])), sq3_rn(v[6], v[7], v[8]));
-                if (!(pm == pm)) pm = INFINITY;
+                float m = fmaxf(fmaxf(sq3_rn(v[0], v[1], v[2]), sq3_rn(v[3], v[4], v[5])), sq3_rn(v[6], v[7], v[8]));
+                if (!(m == m)) m = INFINITY;
+                pm = fmaxf(pm, m);
             }
-            warp_atomic_max_bits(ws.pmax + b * 2 + cloud, pm);
         }
+        block_max[cloud] = pm;
     }
     const float *lb = lines + (long long)b * g.nl * 6;
+    float xmw = 0.f;
     for (int base = blockIdx.x * blockDim.x; base < g.nl; base += stride) {
         const int l = base + threadIdx.x;
         float xm = 0.f;
@@ -77,8 +80,21 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
             xm = (float)xx * 1.000001f;
             if (!(xm == xm)) xm = INFINITY;
         }
-        warp_atomic_max_bits(ws.xmax + b * 2, xm);
+        xmw = fmaxf(xmw, xm);
     }
+    block_max[2] = xmw;
+    // one atomic per CTA and array: thousands of same-address atomics would serialise in L2
+    __shared__ unsigned s_max[3];
+    if (threadIdx.x < 3) s_max[threadIdx.x] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(block_max[q]));
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max[q], m);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && s_max[threadIdx.x])
+        atomicMax(threadIdx.x < 2 ? ws.pmax + b * 2 + threadIdx.x : ws.xmax + b * 2, s_max[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -159,33 +175,66 @@ __global__ void __launch_bounds__(1024) sort_small_kernel(const float *__restric
     }
 }
 
-// large clouds: keys for the CUB radix sort
-__global__ void __launch_bounds__(256) sort_keys_kernel(const float *__restrict__ tri, int nf, int nfp, float P, const unsigned int *pmax_bits,
-                                                        unsigned *keys, int *vals, int sorted) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nfp) return;
-    const float Pm = sqrtf(__uint_as_float(*pmax_bits));
-    (void)P;
-    unsigned key = 0xFFFFFFFFu;
+// large clouds: keys for ONE CUB radix sort over both clouds of up to kSortPairs pairs.  Segment = cloud * nb + pair;
+// key = segment << (32 - segbits) | padding << (31 - segbits) | the leading 31 - segbits bits of the 30-bit Hilbert index
+// (any prefix of a Hilbert index is the index on a coarser grid): the clouds of all pairs sort into place in one go,
+// cloud 0 of every pair first (the layout of perm[0], perm[1]), paddings last in each segment.
+constexpr int kSortPairs = 512;
+__global__ void __launch_bounds__(256) sort_keys_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, int nb, int nf1, int nf1p,
+                                                        int nf2, int nf2p, const unsigned int *pmax_bits, int segbits, unsigned *keys, int *vals,
+                                                        int sorted) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n1 = (long long)nb * nf1p;
+    if (t >= n1 + (long long)nb * nf2p) return;
+    const int cloud = t >= n1;
+    const long long r = cloud ? t - n1 : t;
+    const int nfp = cloud ? nf2p : nf1p, nf = cloud ? nf2 : nf1;
+    const int b = (int)(r / nfp), i = (int)(r % nfp);
+    const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
+    const float Pm = sqrtf(__uint_as_float(pmax_bits[b * 2 + cloud]));
+    const int hbits = 31 - segbits < 30 ? 31 - segbits : 30;
+    unsigned key = (1u << hbits);                                 // padding flag: after every real key of the segment
     int val = -1;
     if (i < nf) {
         const float p[3] = {__ldg(tri + (long long)i * 9), __ldg(tri + (long long)i * 9 + 1), __ldg(tri + (long long)i * 9 + 2)};
-        key = sorted ? morton_key(p, Pm) : 0u;
+        key = sorted ? morton_key(p, Pm) >> (30 - hbits) : 0u;
         val = i;
     }
-    keys[i] = key;
-    vals[i] = val;
+    keys[t] = key | ((unsigned)(cloud * nb + b) << (hbits + 1));
+    vals[t] = val;
 }
 
 // ------------------------------------------------------------------------------------------------------
 // nodes
 // ------------------------------------------------------------------------------------------------------
+// Upper bound, in float with directed rounding, of  sqrt(cut_f + E) + |p0_f - q|  (cut_f = thr_f^2 - 2e-4): the radius a
+// sphere centred at q needs to cover triplet f's hit cylinder.  (The double-precision version of this cost more than
+// everything else in the node build: FP64 issue is slow on this part.)
+__device__ __forceinline__ float cover_radius_up(float th, float E_up, float px, float py, float pz, float qx, float qy, float qz) {
+    const float cut_up = __fadd_ru(__fmul_ru(th, th), -kAddEps);
+    const float a = __fsqrt_ru(fmaxf(__fadd_ru(cut_up, E_up), 0.f));
+    const float dx = fmaxf(fabsf(__fsub_ru(px, qx)), fabsf(__fsub_rd(px, qx)));
+    const float dy = fmaxf(fabsf(__fsub_ru(py, qy)), fabsf(__fsub_rd(py, qy)));
+    const float dz = fmaxf(fabsf(__fsub_ru(pz, qz)), fabsf(__fsub_rd(pz, qz)));
+    const float d2 = __fmaf_ru(dz, dz, __fmaf_ru(dy, dy, __fmul_ru(dx, dx)));
+    return __fadd_ru(a, __fsqrt_ru(d2));
+}
+// sphere record {q, w = R^2 - |q|^2}, w rounded up (a larger w only admits more candidates); also returns the radius
+__device__ __forceinline__ float4 sphere_record_up(float R, float qx, float qy, float qz, float &rad) {
+    R = __fmul_ru(R, 1.000002f);
+    rad = __fmul_ru(R, 1.000001f);
+    const float q2_dn = __fmaf_rd(qz, qz, __fmaf_rd(qy, qy, __fmul_rd(qx, qx)));
+    float w = __fsub_ru(__fmul_ru(R, R), q2_dn);
+    w = w + fabsf(w) * 2.4e-7f + 1e-30f;
+    return make_float4(qx, qy, qz, w);
+}
+
 // One bounding-sphere node, built by kNode CONSECUTIVE LANES: the lane of sorted position i = n * kNode + s loads triplet f
 // (or -1 = padding) and writes its point records; centroid, member count and radius are butterfly all-reductions inside
 // the lane group (x + y == y + x exactly, so every lane of a group holds the same bits); lane s == 0 writes the node
 // record.  Must be called by converged warps (whole groups, full mask).  Returns the node radius in lane s == 0.
 template <int kNode>
-__device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, float th, int f, long long i, double E,
+__device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, float th, int f, long long i, float E_up,
                                                 float4 *pt_base, float4 *pt12, float4 *node4, int ball_iters) {
     const long long n = i / kNode;
     const int s = (int)(i % kNode);
@@ -202,7 +251,8 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
         pr1 = make_float4((float)ax, (float)ay, (float)az, (float)(cut - (ax * ax + ay * ay + az * az)));
         pr2 = make_float4((float)bx, (float)by, (float)bz, (float)(cut - (bx * bx + by * by + bz * bz)));
     }
-    double cx = px, cy = py, cz = pz;                                 // 0 for padding lanes
+    // centroid in float: WHERE the centre goes is a heuristic, the radius below is an upper bound for whatever centre
+    float cx = (float)px, cy = (float)py, cz = (float)pz;            // 0 for padding lanes
     int cntv = f >= 0;
 #pragma unroll
     for (int d = 1; d < kNode; d <<= 1) {
@@ -212,9 +262,10 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
         cntv += __shfl_xor_sync(0xffffffffu, cntv, d);
     }
     float qx = 0.f, qy = 0.f, qz = 0.f;
-    double R = 0;
+    float R = 0.f;
     if (cntv > 0) {
-        qx = (float)(cx / cntv); qy = (float)(cy / cntv); qz = (float)(cz / cntv);   // start: the ROUNDED centroid
+        const float inv = 1.0f / (float)cntv;
+        qx = cx * inv; qy = cy * inv; qz = cz * inv;
     }
     // Shrink the sphere: the centre that minimises max_f (|p0_f - q| + r_f) instead of the centroid (Badoiu-Clarkson
     // steps q += (p_far - q) / (k + 1) towards the member that currently defines the radius; the best centre seen is
@@ -223,7 +274,7 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     // lane of the group computes the same bits (same operations on the same shuffled values).
     if (ball_iters > 0) {
         const float fx = (float)px, fy = (float)py, fz = (float)pz;
-        const float rf = f >= 0 ? sqrtf(fmaxf((float)(cut + E), 0.f)) : 0.f;
+        const float rf = f >= 0 ? sqrtf(fmaxf((float)cut + E_up, 0.f)) : 0.f;
         const unsigned gmask = (kNode >= 32 ? 0xffffffffu : ((1u << kNode) - 1u)) << ((threadIdx.x & 31) & ~(kNode - 1));
         float bx = qx, by = qy, bz = qz, bestR = INFINITY;
         float ccx = qx, ccy = qy, ccz = qz;
@@ -242,14 +293,9 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
         }
         if (cntv > 0 && bestR < INFINITY) { qx = bx; qy = by; qz = bz; }
     }
-    if (cntv > 0) {
-        if (f >= 0) {
-            const double dx = px - qx, dy = py - qy, dz = pz - qz;
-            R = sqrt(fmax(cut + E, 0.0)) + sqrt(dx * dx + dy * dy + dz * dz);
-        }
-    }
+    if (cntv > 0 && f >= 0) R = cover_radius_up(th, E_up, (float)px, (float)py, (float)pz, qx, qy, qz);
 #pragma unroll
-    for (int d = 1; d < kNode; d <<= 1) R = fmax(R, __shfl_xor_sync(0xffffffffu, R, d));
+    for (int d = 1; d < kNode; d <<= 1) R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, d));
     pt12[i * 2] = pr1;
     pt12[i * 2 + 1] = pr2;
     {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB};
@@ -260,15 +306,7 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     float rad = 0.f;
     if (s == 0) {
         float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);           // empty node: never a candidate
-        if (cntv > 0) {
-            R *= 1.000002;
-            rad = (float)R * 1.000001f;
-            const double q2 = (double)qx * qx + (double)qy * qy + (double)qz * qz;
-            // round the record's slack UP: a larger w only admits more candidates
-            float w = (float)(R * R - q2);
-            w = w + fabsf(w) * 2.4e-7f + 1e-30f;
-            rec = make_float4(qx, qy, qz, w);
-        }
+        if (cntv > 0) rec = sphere_record_up(R, qx, qy, qz, rad);
         pt_base[n * (kNode + 1) + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);                  // pad slot
         // node records: a group of 4 nodes = two interleaved pairs + one pad = 5 float4 (odd stride again)
         float4 *grp = node4 + (n >> 2) * 5;
@@ -279,28 +317,133 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     return rad;
 }
 
+__device__ __forceinline__ int pad_supers_dev(int nfp) { return ((nfp / kSuperPts + 3) / 4) * 4; }
+
 // slack of the node radius for the rounding of the reference-order test: E = kGuardRef eps (P + Xmax)^2
-__device__ __forceinline__ double node_slack(unsigned pmax_bits, unsigned xmax_bits) {
-    const double P = sqrt((double)__uint_as_float(pmax_bits)) * 1.000001;
-    const double Xm = sqrt((double)__uint_as_float(xmax_bits)) * 1.000001;
-    return (double)kGuardRef * (double)kEps24 * (P + Xm) * (P + Xm) + 1e-12;
+__device__ __forceinline__ float node_slack(unsigned pmax_bits, unsigned xmax_bits) {   // rounded up throughout
+    const float P = __fmul_ru(__fsqrt_ru(__uint_as_float(pmax_bits)), 1.000001f);
+    const float Xm = __fmul_ru(__fsqrt_ru(__uint_as_float(xmax_bits)), 1.000001f);
+    const float PX = __fadd_ru(P, Xm);
+    return __fadd_ru(__fmul_ru(__fmul_ru(kGuardRef * kEps24, PX), PX), 1e-12f);
+}
+
+// Super node = bounding sphere of the kSuperPts = 256 sorted triplets one node_kernel CTA handles per trip (16 nodes of
+// 16): the same construction as a node -- centre refined towards the minimum enclosing ball, radius
+// R >= sqrt(cut_f + E) + |p0_f - q| for every member, so "member passes => super node passes" holds by the same
+// argument -- with block-wide instead of lane-group reductions.  Every thread computes the same centre
+// (the partial results are combined in the same order by all).  Thread 0 writes the record.
+__device__ __forceinline__ float make_super_block(const float *__restrict__ tri, float th, int f, long long i, float E_up,
+                                                  float4 *super4, int nsuper, int nsuperp, int ball_iters) {
+    __shared__ float s_sum[8][4];
+    __shared__ float s_far[2][8][4];
+    __shared__ float s_rad[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double px = 0, py = 0, pz = 0, cut = 0;
+    if (f >= 0) {
+        const float *t = tri + (long long)f * 9;
+        px = __ldg(t); py = __ldg(t + 1); pz = __ldg(t + 2);
+        cut = (double)th * (double)th - (double)kAddEps;
+    }
+    float cx = (float)px, cy = (float)py, cz = (float)pz, cn = f >= 0 ? 1.f : 0.f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, d);
+        cy += __shfl_xor_sync(0xffffffffu, cy, d);
+        cz += __shfl_xor_sync(0xffffffffu, cz, d);
+        cn += __shfl_xor_sync(0xffffffffu, cn, d);
+    }
+    if (lane == 0) { s_sum[wid][0] = cx; s_sum[wid][1] = cy; s_sum[wid][2] = cz; s_sum[wid][3] = cn; }
+    __syncthreads();
+    cx = cy = cz = cn = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { cx += s_sum[w][0]; cy += s_sum[w][1]; cz += s_sum[w][2]; cn += s_sum[w][3]; }
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (cn > 0) { qx = cx / cn; qy = cy / cn; qz = cz / cn; }
+    if (ball_iters > 0 && cn > 0) {                              // block-uniform condition
+        const float fx = (float)px, fy = (float)py, fz = (float)pz;
+        const float rf = f >= 0 ? sqrtf(fmaxf((float)cut + E_up, 0.f)) : 0.f;
+        float bx = qx, by = qy, bz = qz, bestR = INFINITY;
+        float ccx = qx, ccy = qy, ccz = qz;
+        for (int k = 1; k <= ball_iters + 1; ++k) {
+            const float dx = fx - ccx, dy = fy - ccy, dz = fz - ccz;
+            const float d = f >= 0 ? sqrtf(dx * dx + dy * dy + dz * dz) + rf : -INFINITY;
+            float m = d;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, dd));
+            const unsigned bal = __ballot_sync(0xffffffffu, d == m);
+            const int far = bal ? __ffs(bal) - 1 : 0;
+            float (*sf)[4] = s_far[k & 1];                        // double buffered: one barrier per step
+            if (lane == far) { sf[wid][0] = m; sf[wid][1] = fx; sf[wid][2] = fy; sf[wid][3] = fz; }
+            __syncthreads();
+            float gm = sf[0][0];
+            int gw = 0;
+#pragma unroll
+            for (int w = 1; w < 8; ++w)
+                if (sf[w][0] > gm) { gm = sf[w][0]; gw = w; }
+            if (gm < bestR) { bestR = gm; bx = ccx; by = ccy; bz = ccz; }
+            const float step = 1.0f / (float)(k + 1);
+            ccx += (sf[gw][1] - ccx) * step; ccy += (sf[gw][2] - ccy) * step; ccz += (sf[gw][3] - ccz) * step;
+        }
+        if (bestR < INFINITY) { qx = bx; qy = by; qz = bz; }
+    }
+    float R = 0.f;
+    if (f >= 0) R = cover_radius_up(th, E_up, (float)px, (float)py, (float)pz, qx, qy, qz);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, d));
+    if (lane == 0) s_rad[wid] = R;
+    __syncthreads();
+    float rad = 0.f;
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) R = fmaxf(R, s_rad[w]);
+        const long long n = i / kSuperPts;
+        float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);      // empty: never a candidate
+        if (cn > 0) rec = sphere_record_up(R, qx, qy, qz, rad);
+        auto put = [&](long long m, const float4 &r) {
+            float4 *grp = super4 + (m >> 2) * 5;
+            float *dst = reinterpret_cast<float *>(grp + ((m >> 1) & 1) * 2) + (m & 1);
+            dst[0] = r.x; dst[2] = r.y; dst[4] = r.z; dst[6] = r.w;
+            if ((m & 3) == 0) grp[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        put(n, rec);
+        if (n == nsuper - 1)                                     // sentinels up to the multiple of 4
+            for (long long m = nsuper; m < nsuperp; ++m) put(m, make_float4(0.f, 0.f, 0.f, -INFINITY));
+    }
+    __syncthreads();                                             // shared buffers are reused by the next trip
+    return rad;
 }
 
 template <int kNode>
-__global__ void __launch_bounds__(256) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g, int ball_iters) {
+__global__ void __launch_bounds__(256) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g, int ball_iters,
+                                                   int supers) {
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
     const int nnodes = nfp / kNode;
     const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
     const float *thr = ws.thr[cloud] + (long long)b * nf;
     const int *perm = ws.perm[cloud] + (long long)b * nfp;
-    const double E = node_slack(ws.pmax[b * 2 + cloud], ws.xmax[b * 2]);
+    const float E = node_slack(ws.pmax[b * 2 + cloud], ws.xmax[b * 2]);
     // one thread per sorted position; nfp is a multiple of kPointPad = 256 = blockDim.x, so every warp is full
+    float rad = 0.f, srad = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nfp; i += (long long)gridDim.x * blockDim.x) {
         const int f = perm[i];
-        const float rad = make_node_coop<kNode>(tri, f >= 0 ? thr[f] : 0.f, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
-                                                ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters);
-        warp_atomic_max_bits(ws.rmax + b * 2 + cloud, rad);
+        const float th = f >= 0 ? thr[f] : 0.f;
+        rad = fmaxf(rad, make_node_coop<kNode>(tri, th, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
+                                               ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters));
+        if (supers)
+            srad = fmaxf(srad, make_super_block(tri, th, f, i, E, ws.super4[cloud] + (long long)b * (pad_supers_dev(nfp) / 4) * 5,
+                                                nfp / kSuperPts, pad_supers_dev(nfp), ball_iters));
+    }
+    // one block-level maximum and one atomic per CTA (thousands of same-address atomics serialise in L2)
+    __shared__ unsigned s_radm;
+    if (threadIdx.x == 0) s_radm = 0u;
+    __syncthreads();
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(rad));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_radm, m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_radm) atomicMax(ws.rmax + b * 2 + cloud, s_radm);
+        if (srad > 0.f) atomicMax(ws.smax + b * 2 + cloud, __float_as_uint(srad));     // thread 0 holds the super radii
     }
 }
 
@@ -452,7 +595,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     }
     int *perm = ws.perm[cloud] + (long long)b * nfp;
     const int nnodes = nfp / kNode;
-    const double Eslack = node_slack(s_red[0], s_red[1]);
+    const float Eslack = node_slack(s_red[0], s_red[1]);
     __syncthreads();                                     // thr (global) is re-read below by other threads
     float rad = 0.f;
 #pragma unroll
@@ -474,18 +617,27 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     if (tid == 0) ws.rmax[b * 2 + cloud] = s_red[2];
 }
 
-size_t sort_scratch_bytes(int nfp_max) {
+size_t sort_scratch_bytes(int nfp_max, int B) {
     if (nfp_max <= kSortSmall) return 0;
-    // keys_in, keys_out, vals_in (vals_out is perm) + CUB temp: CUB's requirement is checked at launch time
-    return (size_t)nfp_max * 4 * 3 + 768 + (size_t)nfp_max * 8 + (4u << 20);
+    // keys in/out, values in/out of every cloud of up to kSortPairs pairs + CUB temp (CUB's requirement is checked at
+    // launch time)
+    const size_t nb = B < kSortPairs ? B : kSortPairs;
+    return nb * nfp_max * 2 * 4 * 4 + 1024 + nb * nfp_max * 16 + (4u << 20);
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] unused, [8] enclosing-ball refinement steps of the node centres (0 = centroid)
+static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 16, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode
 void set_param(int id, int v) { if (id >= 0 && id < 12) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
     return (g.nf1 > g.nf2 ? g.nf1 : g.nf2) >= 16384 ? 16 : 8;
+}
+
+// the super-node level (one more bounding-sphere level above the nodes) for clouds of kSuperMin triplets and more
+int use_supers(const Geometry &g) {
+    // measured: pays from about 16k triplets per cloud (node size 16); below, the per-node kernel with its shared-memory
+    // point cache is as fast and the node build is cheaper without the extra level
+    return g_param[7] == 0 && node_size(g) == 16 && (g.nf1p > g.nf2p ? g.nf1p : g.nf2p) > kSortSmall;
 }
 
 static int g_dense_variant = 1;        // 1 = Morton-sorted nodes (default), 0 = nodes in input order (A/B measurement)
@@ -533,31 +685,49 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
         sort_small_kernel<<<dim3(g.B, 2), 1024, (size_t)n2 * 8, s>>>(tri1, tri2, ws, g, sorted);
         count_launch();
     } else {
+        // every cloud of (up to kSortPairs) pairs in ONE sort: the passes are latency bound at these sizes, so a sort of
+        // many segments costs little more than a sort of one.  When a single sort covers the batch, perm[0] and perm[1]
+        // are adjacent and the sort writes them directly.
+        const int nbmax = g.B < kSortPairs ? g.B : kSortPairs;
+        const size_t cap = (size_t)nbmax * ((size_t)g.nf1p + g.nf2p);
         unsigned *keys_in = reinterpret_cast<unsigned *>(ws.sortbuf);
-        unsigned *keys_out = keys_in + nfp_max;
-        int *vals_in = reinterpret_cast<int *>(keys_out + nfp_max);
-        char *temp = reinterpret_cast<char *>(vals_in + nfp_max);
+        unsigned *keys_out = keys_in + cap;
+        int *vals_in = reinterpret_cast<int *>(keys_out + cap);
+        int *vals_tmp = vals_in + cap;
+        char *temp = reinterpret_cast<char *>(vals_tmp + cap);
         temp = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(temp) + 255) / 256 * 256);
+        if ((size_t)(temp - reinterpret_cast<char *>(ws.sortbuf)) > ws.sortbuf_bytes) return RRL_ERR_WORKSPACE;
         const size_t temp_avail = ws.sortbuf_bytes - (size_t)(temp - reinterpret_cast<char *>(ws.sortbuf));
-        for (int b = 0; b < g.B; ++b)
-            for (int cloud = 0; cloud < 2; ++cloud) {
-                const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
-                const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
-                sort_keys_kernel<<<(nfp + 255) / 256, 256, 0, s>>>(tri, nf, nfp, 0.f, ws.pmax + b * 2 + cloud, keys_in, vals_in, sorted);
-                count_launch();
-                size_t need = 0;
-                cub::DeviceRadixSort::SortPairs(nullptr, need, keys_in, keys_out, vals_in, ws.perm[cloud] + (long long)b * nfp, nfp, 0, 32, s);
-                if (need > temp_avail) return RRL_ERR_WORKSPACE;
-                if (cub::DeviceRadixSort::SortPairs(temp, need, keys_in, keys_out, vals_in, ws.perm[cloud] + (long long)b * nfp, nfp, 0, 32, s) != cudaSuccess)
+        for (int b0 = 0; b0 < g.B; b0 += nbmax) {
+            const int nb = g.B - b0 < nbmax ? g.B - b0 : nbmax;
+            int segbits = 1;
+            while ((1 << segbits) < 2 * nb) ++segbits;
+            const size_t ntot = (size_t)nb * ((size_t)g.nf1p + g.nf2p);
+            if (ntot >= (1ull << 31)) return RRL_ERR_ARG;
+            int *perm0 = ws.perm[0] + (long long)b0 * g.nf1p, *perm1 = ws.perm[1] + (long long)b0 * g.nf2p;
+            const bool adjacent = perm1 == perm0 + (long long)nb * g.nf1p;
+            int *vals_out = adjacent ? perm0 : vals_tmp;
+            sort_keys_kernel<<<(unsigned)((ntot + 255) / 256), 256, 0, s>>>(tri1 + (long long)b0 * g.nf1 * 9, tri2 + (long long)b0 * g.nf2 * 9, nb, g.nf1,
+                                                                          g.nf1p, g.nf2, g.nf2p, ws.pmax + b0 * 2, segbits, keys_in, vals_in, sorted);
+            count_launch();
+            size_t need = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, need, keys_in, keys_out, vals_in, vals_out, (int)ntot, 0, 32, s);
+            if (need > temp_avail) return RRL_ERR_WORKSPACE;
+            if (cub::DeviceRadixSort::SortPairs(temp, need, keys_in, keys_out, vals_in, vals_out, (int)ntot, 0, 32, s) != cudaSuccess)
+                return RRL_ERR_CUDA;
+            count_launch(4);
+            if (!adjacent) {
+                if (cudaMemcpyAsync(perm0, vals_tmp, (size_t)nb * g.nf1p * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+                    cudaMemcpyAsync(perm1, vals_tmp + (size_t)nb * g.nf1p, (size_t)nb * g.nf2p * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
                     return RRL_ERR_CUDA;
-                count_launch(4);
             }
+        }
     }
     stage_mark(2, s);
     int nbx = nfp_max / 256;
     if (nbx > 4096) nbx = 4096;
-    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8]);
-    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8]);
+    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g));
+    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g));
     count_launch();
     stage_mark(3, s);
     return check_launch();
@@ -624,12 +794,13 @@ constexpr int kNumWarps = kDenseThreads / 32;
 // Shared-memory plan of one dense CTA.  LPT = lines per thread: 4 lines amortise every broadcast node read over more
 // arithmetic (2 CTAs per SM, 128 registers), 2 lines halve the register and shared-memory footprint so that 4 CTAs
 // (32 warps) fit an SM and cover the latency of the queue levels.
-template <int kNode, bool kPerNode, int LPT>
+template <int kNode, bool kPerNode, int LPT, bool kSuper = false>
 struct DenseCfg {
+    static_assert(!kSuper || !kPerNode, "super nodes feed the (line, group) queue");
     static constexpr int kLines = kDenseThreads * LPT;                 // lines per CTA
     static constexpr int kTile = LPT >= 4 ? 256 : 128;                 // nodes per TMA stage
     static constexpr int kStage = (kTile / 4) * 5;                     // float4 per stage: 5 per group of 4 nodes
-    static constexpr int kWq = LPT >= 4 ? 512 : 256;                   // per warp: (line, group) entries, or (line, node) when kPerNode
+    static constexpr int kWq = LPT >= 4 || kSuper ? 512 : 256;         // per warp: (line, group) entries, or (line, node) when kPerNode
     static constexpr int kNq = 256;                                    // per warp: (line, node) entries of the 3-level pipeline
     static constexpr int kXq = 32 * kNode + 64;                        // per warp: (line, triplet); one level-2 pass appends <= 32 * kNode
     // kPerNode (small clouds): the chunk's point records are staged in shared memory -- the launch sizes the chunks to
@@ -687,9 +858,12 @@ __device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
 // kPerNode (small, hit-dense clouds): the main loop keeps one mask per node of a group and feeds (line, node) entries
 // straight to level 2 -- level 1 would otherwise re-evaluate nearly every group (half of all (line, group) pairs
 // fire on a 1024-triplet cloud).
-template <int kNode, bool kPerNode, int LPT>
-__global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>::kMinBlocks) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
-    using Cfg = DenseCfg<kNode, kPerNode, LPT>;
+// kSuper (large clouds): the main loop streams SUPER-node records (bounding spheres of 16 nodes = 256 triplets) instead
+// of node records and expands every fired (line, super node) pair into its four (line, group) entries; the node
+// predicates then run in level 1 only where a line comes near, instead of for all nodes x lines.
+template <int kNode, bool kPerNode, int LPT, bool kSuper = false>
+__global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, kSuper>::kMinBlocks) dense_kernel(DenseArgs a, Workspace ws, Geometry g) {
+    using Cfg = DenseCfg<kNode, kPerNode, LPT, kSuper>;
     constexpr int kLinesPerThread = LPT, kLinesPerCta = Cfg::kLines, kTileNodes = Cfg::kTile, kStageF4 = Cfg::kStage;
     constexpr int kWarpQueue = Cfg::kWq, kNodeQueue = Cfg::kNq, kExactQueue = Cfg::kXq;
     constexpr int kSmemPtsF4 = Cfg::kPts, kSmemPts12F4 = Cfg::kPts12;
@@ -706,9 +880,13 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
     const int b = blockIdx.z >> 1, cloud = blockIdx.z & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
     const int nnodes = nfp / kNode;
+    // records streamed by the main loop: nodes, or super nodes (kSuperNodes nodes each); chunk bounds are in records
+    constexpr int kSuperNodes = kSuper ? kSuperPts / kNode : 1;
+    const int nrecs = kSuper ? pad_supers_dev(nfp) : nnodes;
     const int n_begin = blockIdx.y * a.chunk_nodes;
-    if (n_begin >= nnodes) return;
-    const int n_end = min(nnodes, n_begin + a.chunk_nodes);
+    if (n_begin >= nrecs) return;
+    const int n_end = min(nrecs, n_begin + a.chunk_nodes);
+    const int node_begin = n_begin * kSuperNodes;                  // first NODE of the chunk
     const int line_base = blockIdx.x * kLinesPerCta;
     unsigned *wq = reinterpret_cast<unsigned *>(dsm + Cfg::kOffWq) + wid * kWarpQueue;
     // the (line, node) queue: in kPerNode mode the main loop fills it directly and it takes over the larger region
@@ -728,11 +906,12 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
     // ---- per-thread lines -> filter thresholds ------------------------------------------------------------
     const float P = sqrtf(__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001f;
     const float Rmax = __uint_as_float(ws.rmax[b * 2 + cloud]);
+    const float Smax = kSuper ? __uint_as_float(ws.smax[b * 2 + cloud]) : 0.f;
     const float4 *lineC = ws.lineC + (long long)b * g.nl * 2;
     float ux[kLinesPerThread], uy[kLinesPerThread], uz[kLinesPerThread];
     float mx[kLinesPerThread], my[kLinesPerThread], mz[kLinesPerThread], tl[kLinesPerThread];
     // threshold of the triplet-level predicate and of the node-level predicate for a line
-    auto thresholds = [&](const float4 &c0, const float4 &c1, float &tl_point, float &tl_node) {
+    auto thresholds = [&](const float4 &c0, const float4 &c1, float &tl_point, float &tl_node, float &tl_super) {
         const float PX = P + c0.w;
         const float guard = kGuardFast * kEps24 * PX * PX + 1e-12f;
         tl_point = c1.w - guard - fabsf(c1.w) * 1.2e-7f;                    // rounded down: admits more
@@ -741,6 +920,8 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
         const float e = fmaxf(s2 - 1.0f, 0.f) * PX * PX;
         const float slack = (2.0f * Rmax * sqrtf(e) + 2.0f * e) * 1.00001f;
         tl_node = tl_point - slack - fabsf(tl_point) * 1.2e-7f;
+        const float sslack = (2.0f * Smax * sqrtf(e) + 2.0f * e) * 1.00001f;
+        tl_super = tl_point - sslack - fabsf(tl_point) * 1.2e-7f;
     };
 #pragma unroll
     for (int i = 0; i < kLinesPerThread; ++i) {
@@ -751,16 +932,18 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
             const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
             ux[i] = c0.x; uy[i] = c0.y; uz[i] = c0.z;
             mx[i] = c1.x; my[i] = c1.y; mz[i] = c1.z;
-            float tp;
-            thresholds(c0, c1, tp, tl[i]);
+            float tp, tn, ts;
+            thresholds(c0, c1, tp, tn, ts);
+            tl[i] = kSuper ? ts : tn;                              // threshold of the records the main loop streams
             // only ever re-read by this warp's queue levels, which need the thresholds rather than |x0| and c
-            slineU[tid + i * kDenseThreads] = make_float4(c0.x, c0.y, c0.z, tl[i]);
+            slineU[tid + i * kDenseThreads] = make_float4(c0.x, c0.y, c0.z, tn);
             slineM[tid + i * kDenseThreads] = make_float4(c1.x, c1.y, c1.z, tp);
         }
     }
     __syncthreads();
 
-    const float4 *src = ws.node4[cloud] + (long long)b * (nnodes / 4) * 5 + (long long)(n_begin / 4) * 5;   // chunk start
+    const float4 *src = (kSuper ? ws.super4[cloud] + (long long)b * (nrecs / 4) * 5 : ws.node4[cloud] + (long long)b * (nnodes / 4) * 5) +
+                        (long long)(n_begin / 4) * 5;                                                          // chunk start
     const int ntiles = (n_end - n_begin + kTileNodes - 1) / kTileNodes;
     auto issue = [&](int t) {
         const int n = min(kTileNodes, n_end - (n_begin + t * kTileNodes));
@@ -769,12 +952,12 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
         tma_bulk_load(stage + (t & 1) * kStageF4, src + (long long)t * kStageF4, bytes, &mbar[t & 1]);
     };
     // the chunk's triplet records (level 2) go to shared memory when they fit, else they are read through L2
-    const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + n_begin) * (kNode + 1);   // chunk start
+    const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + node_begin) * (kNode + 1);   // chunk start
     constexpr bool pts_in_smem = kPerNode, pts12_in_smem = kPerNode;
     const float4 *pts = spts;
     if constexpr (!kPerNode) pts = pt4_c;
     // point-1/2 records of the chunk (refine pass before the hand-off to the exact kernel)
-    const float4 *pt12_c = ws.pt12[cloud] + ((long long)b * nfp + (long long)n_begin * kNode) * 2;
+    const float4 *pt12_c = ws.pt12[cloud] + ((long long)b * nfp + (long long)node_begin * kNode) * 2;
     const float4 *pts12 = spts12;
     if constexpr (!kPerNode) pts12 = pt12_c;
     if (tid == 0) {
@@ -795,10 +978,10 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
     if (pts12_in_smem) mbar_wait(&mbar[3], 0);
 
     int ncand = 0;
-    const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)n_begin * kNode;   // from the chunk start
+    const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)node_begin * kNode;   // from the chunk start
     // node records for level 1: re-read through L1/L2 (a pointer that is sometimes the resident stage would make
     // every access a generic load)
-    const float4 *node_src = src;                                                          // from the chunk start
+    const float4 *node_src = ws.node4[cloud] + (long long)b * (nnodes / 4) * 5 + (long long)(node_begin / 4) * 5;   // from the chunk start
     int wq_cnt = 0, nq_cnt = 0, xq_cnt = 0;                      // warp-uniform fill levels
 
     // level 3 hand-off: (line, triplet) entries that passed both filters go to the launch-wide queue of the exact
@@ -942,8 +1125,8 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
         const float4 *sp = stage + (t & 1) * kStageF4;
         const int ngroups = nn / 4;
         const int group0 = t * (kTileNodes / 4);
-        if constexpr (kPerNode) {
-            // window = 8 groups = 32 nodes: ONE mask word per line, bit = node index inside the window
+        if constexpr (kPerNode || kSuper) {
+            // window = 8 groups = 32 records: ONE mask word per line, bit = record index inside the window
             for (int w0 = 0; w0 < ngroups; w0 += 8) {
                 const int ng = min(8, ngroups - w0);
                 unsigned m[kLinesPerThread];
@@ -974,6 +1157,52 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
                 }
                 // ordered push of the fired (line, node) pairs: one scan and one bit loop per line
                 const unsigned node0 = (unsigned)((group0 + w0) * 4);
+                if constexpr (kSuper) {
+                    // every fired (line, super node) pair -> the (line, group) entries of its kSuperNodes / 4 node groups
+                    constexpr int kGroupsPer = kSuperNodes / 4;
+                    constexpr int kPart = kWarpQueue / (32 * kGroupsPer);      // bits per part: 32 lanes x kPart x kGroupsPer entries fit
+                    static_assert(kPart >= 1 && (kPart & (kPart - 1)) == 0, "part size");
+#pragma unroll
+                    for (int i = 0; i < kLinesPerThread; ++i) {
+                        const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
+                        const unsigned mi = m[i];
+                        if (!__any_sync(0xffffffffu, mi != 0u)) continue;
+                        ncand += __popc(mi);
+                        // fired bits are sparse (a line comes near a handful of super nodes): one scan over the whole
+                        // word; the part loop only when a window fills more than a queue
+                        int total;
+                        const int off = warp_excl_scan<6>(__popc(mi), lane, total);
+                        if (total * kGroupsPer <= kWarpQueue) {
+                            if (wq_cnt + total * kGroupsPer > kWarpQueue) run_groups();
+                            int pos = wq_cnt + off * kGroupsPer;
+                            unsigned mh = mi;
+                            while (mh) {
+                                const unsigned rec = node0 + (unsigned)(__ffs(mh) - 1);              // super node, chunk relative
+                                mh &= mh - 1;
+#pragma unroll
+                                for (int q = 0; q < kGroupsPer; ++q) wq[pos++] = (lrel << 20) | (rec * kGroupsPer + (unsigned)q);
+                            }
+                            wq_cnt += total * kGroupsPer;
+                            continue;
+                        }
+#pragma unroll 1
+                        for (int part = 0; part < 32; part += kPart) {
+                            unsigned mh = (mi >> part) & ((1u << kPart) - 1u);
+                            if (!__any_sync(0xffffffffu, mh != 0u)) continue;
+                            int tot2;
+                            const int off2 = warp_excl_scan<3>(__popc(mh), lane, tot2);
+                            if (wq_cnt + tot2 * kGroupsPer > kWarpQueue) run_groups();
+                            int pos = wq_cnt + off2 * kGroupsPer;
+                            while (mh) {
+                                const unsigned rec = node0 + (unsigned)(__ffs(mh) - 1 + part);      // super node, chunk relative
+                                mh &= mh - 1;
+#pragma unroll
+                                for (int q = 0; q < kGroupsPer; ++q) wq[pos++] = (lrel << 20) | (rec * kGroupsPer + (unsigned)q);
+                            }
+                            wq_cnt += tot2 * kGroupsPer;
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int i = 0; i < kLinesPerThread; ++i) {
                     const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
@@ -1010,6 +1239,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT>:
                         }
                     }
                 }
+                }   // !kSuper
             }
         } else {
             // window = 32 groups of 4 nodes: one mask word per line, bit = group (the OR of its four node predicates)
@@ -1189,36 +1419,40 @@ int launch_bruteforce(const float *tri1, const float *tri2, const float *lines, 
     return check_launch();
 }
 
-template <int kNode, bool kPerNode, int LPT>
+template <int kNode, bool kPerNode, int LPT, bool kSuper = false>
 static int launch_dense_variant(const DenseArgs &a0, const Workspace &ws, const Geometry &g, int G, cudaStream_t s) {
-    using Cfg = DenseCfg<kNode, kPerNode, LPT>;
+    using Cfg = DenseCfg<kNode, kPerNode, LPT, kSuper>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(dense_kernel<kNode, kPerNode, LPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
+        if (cudaFuncSetAttribute(dense_kernel<kNode, kPerNode, LPT, kSuper>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
             return RRL_ERR_CUDA;
         attr_set = true;
     }
     DenseArgs a = a0;
     const int line_tiles = (g.nl + Cfg::kLines - 1) / Cfg::kLines;
-    const int nn_max = (g.nf1p > g.nf2p ? g.nf1p : g.nf2p) / G;
-    // split the nodes so that the grid covers the SMs (kMinBlocks CTAs each) g_param[2] times over when the line
-    // tiles alone do not; never below g_param[3] nodes per CTA
+    // records the main loop streams: nodes, or super nodes
+    const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
+    const int nn_max = kSuper ? pad_supers(nfp_max) : nfp_max / G;
+    const int rec_pad = kSuper ? 4 : kNodePad;
+    // split the records so that the grid covers the SMs (kMinBlocks CTAs each) g_param[2] times over when the line
+    // tiles alone do not; never below g_param[3] records per CTA
     const long long base_ctas = (long long)line_tiles * g.B * 2;
-    const long long target = 148LL * Cfg::kMinBlocks * g_param[2];
+    const long long target = 148LL * Cfg::kMinBlocks * g_param[kSuper ? 9 : 2];
     int chunks = 1;
     if (base_ctas < target) chunks = (int)((target + base_ctas - 1) / base_ctas);
     int chunk_nodes = (nn_max + chunks - 1) / chunks;
     if (chunk_nodes < g_param[3]) chunk_nodes = g_param[3];
-    chunk_nodes = ((chunk_nodes + kNodePad - 1) / kNodePad) * kNodePad;
+    chunk_nodes = ((chunk_nodes + rec_pad - 1) / rec_pad) * rec_pad;
     // small clouds: keep the chunk's point records in shared memory (level 2 reads them once per candidate node)
     constexpr int kFit = kPerNode ? (Cfg::kPts / (kNode + 1)) / kNodePad * kNodePad : 0;
     static_assert(!kPerNode || kFit * kNode * 2 <= Cfg::kPts12, "point-1/2 cache must hold what the point-0 cache holds");
     if (kPerNode && chunk_nodes > kFit) chunk_nodes = kFit;
-    if (chunk_nodes / 4 >= (1 << 20) || (long long)chunk_nodes * G >= (1 << 22)) return RRL_ERR_ARG;
+    const long long chunk_real_nodes = (long long)chunk_nodes * (kSuper ? kSuperPts / kNode : 1);
+    if (chunk_real_nodes / 4 >= (1 << 20) || chunk_real_nodes * G >= (1 << 22)) return RRL_ERR_ARG;
     chunks = (nn_max + chunk_nodes - 1) / chunk_nodes;
     a.chunk_nodes = chunk_nodes;
     dim3 grid(line_tiles, chunks, g.B * 2);
-    dense_kernel<kNode, kPerNode, LPT><<<grid, kDenseThreads, Cfg::kSmem, s>>>(a, ws, g);
+    dense_kernel<kNode, kPerNode, LPT, kSuper><<<grid, kDenseThreads, Cfg::kSmem, s>>>(a, ws, g);
     count_launch();
     return RRL_OK;
 }
@@ -1230,7 +1464,10 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     const int G = node_size(g);
     const int lpt = g_param[6] == 2 || g_param[6] == 4 ? g_param[6] : 2;
     int rc;
-    if (G == 8 && g_param[4] == 0) rc = lpt == 2 ? launch_dense_variant<8, true, 2>(a, ws, g, G, s) : launch_dense_variant<8, true, 4>(a, ws, g, G, s);
+    if (use_supers(g)) {
+        if (G == 8) rc = lpt == 2 ? launch_dense_variant<8, false, 2, true>(a, ws, g, G, s) : launch_dense_variant<8, false, 4, true>(a, ws, g, G, s);
+        else rc = lpt == 2 ? launch_dense_variant<16, false, 2, true>(a, ws, g, G, s) : launch_dense_variant<16, false, 4, true>(a, ws, g, G, s);
+    } else if (G == 8 && g_param[4] == 0) rc = lpt == 2 ? launch_dense_variant<8, true, 2>(a, ws, g, G, s) : launch_dense_variant<8, true, 4>(a, ws, g, G, s);
     else if (G == 8) rc = lpt == 2 ? launch_dense_variant<8, false, 2>(a, ws, g, G, s) : launch_dense_variant<8, false, 4>(a, ws, g, G, s);
     else rc = lpt == 2 ? launch_dense_variant<16, false, 2>(a, ws, g, G, s) : launch_dense_variant<16, false, 4>(a, ws, g, G, s);
     if (rc) return rc;

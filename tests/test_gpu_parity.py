@@ -362,6 +362,55 @@ def test_large_cloud_path_vs_oracle(rrl):
     _check_against_oracle(out, co.loss(p["tri1"], p["tri2"], p["lines"]))
 
 
+def test_batched_mid_and_large_clouds_share_one_sort(rrl):
+    """clouds above 4096 triplets are Hilbert-sorted by ONE radix sort over every cloud of every pair (segment bits above
+    a shortened curve index): three ragged pairs per batch, each compared completely with the oracle -- once below
+    16384 triplets (per-node kernel) and once above (super-node level)"""
+    for nf1, nf2, nl in ((6000, 4500, 1500), (20000, 17000, 1200)):
+        pairs = [synth.make_pair(300 + i, nf1, nl, nf2=nf2, zero_frac=0.03) for i in range(3)]
+        t1 = torch.from_numpy(np.stack([p["tri1"] for p in pairs])).cuda().requires_grad_(True)
+        t2 = torch.from_numpy(np.stack([p["tri2"] for p in pairs])).cuda()
+        ln = torch.from_numpy(np.stack([p["lines"] for p in pairs])).cuda()
+        loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True)
+        loss.sum().backward()
+        c1, h1 = info.hits(1)
+        c2, h2 = info.hits(2)
+        for i, p in enumerate(pairs):
+            orc = co.loss(p["tri1"], p["tri2"], p["lines"])
+            assert np.array_equal(c1[i].cpu().numpy(), orc.counts1) and np.array_equal(c2[i].cpu().numpy(), orc.counts2)
+            for cnt, mine, ref in ((orc.counts1, h1[i], orc.hits1), (orc.counts2, h2[i], orc.hits2)):
+                keep = cnt <= co.CAP
+                assert np.array_equal(mine.cpu().numpy()[keep], ref[keep])
+            assert float(info.median[i]) == orc.median
+            assert abs(loss[i].item() - orc.loss) <= REL_TOL * orc.loss
+            assert _rel(t1.grad[i].cpu().numpy(), orc.grad1) <= REL_TOL
+
+
+def test_super_node_level_with_degenerate_lines_and_without(rrl):
+    """the super-node level (clouds from 16384 triplets) must stay a superset filter for |u| != 1, all-zero rows and
+    duplicates, and switching it off must not change a single index"""
+    p = synth.make_pair(151, 18000, 2500, nf2=16500, zero_frac=0.15)
+    lines = p["lines"].copy()
+    rng = np.random.default_rng(6)
+    lines[:400, :3] *= rng.uniform(1.0, 1.01, size=(400, 1)).astype(np.float32)
+    lines[400:700, :3] *= rng.uniform(0.3, 1.0, size=(300, 1)).astype(np.float32)
+    lines[700:730, :3] *= 3.0
+    lines[730:780] = lines[1]
+    out = _run(rrl, p["tri1"], p["tri2"], lines)
+    _check_against_oracle(out, co.loss(p["tri1"], p["tri2"], lines))
+    L = rrl._native.lib()
+    try:
+        L.rrl_debug_set_param(7, 1)
+        flat = _run(rrl, p["tri1"], p["tri2"], lines)
+    finally:
+        L.rrl_debug_set_param(7, 0)
+    for c, h in (("counts1", "hits1"), ("counts2", "hits2")):
+        assert np.array_equal(out[c], flat[c])
+        keep = out[c] <= co.CAP                   # beyond the cap only the count is defined
+        assert np.array_equal(out[h][keep], flat[h][keep])
+    assert out["loss"] == flat["loss"] and out["median"] == flat["median"]
+
+
 def test_full_size_large_pair_properties(rrl):
     """BASELINE config 5 at full size (500k triplets x 100k lines): the oracle checks a sample of the lines completely,
     the on-device brute-force kernel (every (line, triplet) tested exactly, the reference's formulation) checks all of

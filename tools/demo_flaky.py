@@ -1,0 +1,18 @@
+"""Spread of the demo-flow convergence check over repeated runs (same seeds): python tools/demo_flaky.py [runs] [epochs]"""
+import argparse, importlib.util, os, sys
+import numpy as np, torch
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, root)
+import rrl_b200 as rrl
+spec = importlib.util.spec_from_file_location("_demo", os.path.join(root, "examples", "demo_lie_algebra.py"))
+demo = importlib.util.module_from_spec(spec); spec.loader.exec_module(demo)
+runs = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+for r in range(runs):
+    torch.manual_seed(5); np.random.seed(5); rrl.loss.manual_seed(5)
+    args = argparse.Namespace(synthetic=1500, seed=5, angle=12.0, data_path="", label1="0")
+    data = demo.load_case(args, "cuda")
+    model, hist = demo.test_one_case(data, n_epoch=epochs, n_sample_line=8000, device="cuda", log=None)
+    cf = [h[0] for h in hist]
+    print(r, len(hist), "chamfer first3 %.5f last3 %.5f min %.5f | at 20/40/60/80/100: %s" % (
+        np.mean(cf[:3]), np.mean(cf[-3:]), min(cf), " ".join("%.5f" % cf[i] for i in range(19, len(cf), 20))), flush=True)
