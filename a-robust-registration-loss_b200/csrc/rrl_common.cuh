@@ -89,7 +89,7 @@ struct Workspace {
 constexpr int kMagic = 0x52524c31;   // "RRL1"
 
 inline int pad_points(int nf) { return ((nf + kPointPad - 1) / kPointPad) * kPointPad; }
-inline int pad_supers(int nfp) { return ((nfp / kSuperPts + 3) / 4) * 4; }      // super records come in groups of 4
+inline int pad_supers(int nfp) { return ((nfp / kSuperPts + kNodePad - 1) / kNodePad) * kNodePad; }   // like the node arrays: multiples of 16 records
 size_t sort_scratch_bytes(int nfp_max, int B);
 int node_size(const Geometry &g);       // triplets per bounding-sphere node for this geometry (8 or 16)
 

@@ -205,6 +205,103 @@ __global__ void __launch_bounds__(256) sort_keys_kernel(const float *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// local k-d refinement of the Hilbert order
+// ------------------------------------------------------------------------------------------------------
+// kNode consecutive points of a space-filling curve through a SURFACE are a strip, or two patches when the curve
+// leaves the surface in between: bounding spheres several times the area of a compact cluster of kNode points.  One
+// warp re-partitions a window of 64 consecutive sorted triplets into k-d leaves of kNode (median splits along the
+// longest axis of the segment's bounding box, 64 -> 32 -> 16 (-> 8)): about a third fewer (line, node) candidates.
+// Only the ORDER inside the window changes (perm); nothing downstream depends on how the order was made.
+//   slot s = lane + 32 e holds element e of the lane.  Per level every element gets the key
+//   segment << 29 | 23 leading bits of its order-preserving coordinate | slot  (unique), its rank among the 64 keys IS
+//   its new slot; elements move through a per-warp shared-memory scratch.  Paddings and NaNs sort last.
+template <int kNode>
+__device__ __forceinline__ void kd_refine64(const float *__restrict__ tri, int &f0, int &f1, int lane, float4 *scratch) {
+    float x[2], y[2], z[2];
+    int f[2] = {f0, f1};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        x[e] = y[e] = z[e] = __int_as_float(0x7fc00000);         // padding: NaN = "not there"
+        if (f[e] >= 0) {
+            const float *t = tri + (long long)f[e] * 9;
+            x[e] = __ldg(t); y[e] = __ldg(t + 1); z[e] = __ldg(t + 2);
+        }
+    }
+#pragma unroll
+    for (int m = 64; m > kNode; m >>= 1) {
+        // bounding box of the element's segment (fminf / fmaxf drop NaNs); lanes of one segment end up with equal bits
+        float lo[2][3], hi[2][3];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            lo[e][0] = hi[e][0] = x[e]; lo[e][1] = hi[e][1] = y[e]; lo[e][2] = hi[e][2] = z[e];
+        }
+        if (m == 64) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                lo[0][a] = lo[1][a] = fminf(lo[0][a], lo[1][a]);
+                hi[0][a] = hi[1][a] = fmaxf(hi[0][a], hi[1][a]);
+            }
+        }
+        const int span = m >= 32 ? 32 : m;                       // lanes per segment
+#pragma unroll
+        for (int d = 1; d < span; d <<= 1)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    lo[e][a] = fminf(lo[e][a], __shfl_xor_sync(0xffffffffu, lo[e][a], d));
+                    hi[e][a] = fmaxf(hi[e][a], __shfl_xor_sync(0xffffffffu, hi[e][a], d));
+                }
+        unsigned key[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float ex = hi[e][0] - lo[e][0], ey = hi[e][1] - lo[e][1], ez = hi[e][2] - lo[e][2];
+            const float c = (ex >= ey && ex >= ez) ? x[e] : (ey >= ez ? y[e] : z[e]);
+            const unsigned u = __float_as_uint(c);
+            unsigned ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            if (!(c == c)) ord = 0xFFFFFFFFu;
+            const unsigned slot = (unsigned)(lane + 32 * e);
+            key[e] = ((slot / (unsigned)m) << 29) | ((ord >> 9) << 6) | slot;
+        }
+        int rank[2] = {0, 0};
+#pragma unroll 8
+        for (int t = 0; t < 32; ++t) {
+            const unsigned k0 = __shfl_sync(0xffffffffu, key[0], t), k1 = __shfl_sync(0xffffffffu, key[1], t);
+            rank[0] += (k0 < key[0]) + (k1 < key[0]);
+            rank[1] += (k0 < key[1]) + (k1 < key[1]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 2; ++e) scratch[rank[e]] = make_float4(x[e], y[e], z[e], __int_as_float(f[e]));
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float4 q = scratch[lane + 32 * e];
+            x[e] = q.x; y[e] = q.y; z[e] = q.z; f[e] = __float_as_int(q.w);
+        }
+    }
+    f0 = f[0];
+    f1 = f[1];
+}
+
+// large clouds: one warp per window of 64 sorted positions, in place on perm
+template <int kNode>
+__global__ void __launch_bounds__(256) refine_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g) {
+    __shared__ float4 s_kd[8][64];
+    const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
+    const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
+    const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
+    int *perm = ws.perm[cloud] + (long long)b * nfp;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int w = blockIdx.x * 8 + wid; w < nfp / 64; w += gridDim.x * 8) {
+        int f0 = perm[w * 64 + lane], f1 = perm[w * 64 + 32 + lane];
+        kd_refine64<kNode>(tri, f0, f1, lane, s_kd[wid]);
+        perm[w * 64 + lane] = f0;
+        perm[w * 64 + 32 + lane] = f1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // nodes
 // ------------------------------------------------------------------------------------------------------
 // Upper bound, in float with directed rounding, of  sqrt(cut_f + E) + |p0_f - q|  (cut_f = thr_f^2 - 2e-4): the radius a
@@ -317,7 +414,7 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     return rad;
 }
 
-__device__ __forceinline__ int pad_supers_dev(int nfp) { return ((nfp / kSuperPts + 3) / 4) * 4; }
+__device__ __forceinline__ int pad_supers_dev(int nfp) { return ((nfp / kSuperPts + kNodePad - 1) / kNodePad) * kNodePad; }
 
 // slack of the node radius for the rounding of the reference-order test: E = kGuardRef eps (P + Xmax)^2
 __device__ __forceinline__ float node_slack(unsigned pmax_bits, unsigned xmax_bits) {   // rounded up throughout
@@ -469,7 +566,7 @@ __device__ __forceinline__ void line_constants(const float *__restrict__ ln, flo
 template <int kNode>
 __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
                                                           const float *__restrict__ lines, Workspace ws, Geometry g, int window,
-                                                          int sorted, int line_blocks, int ball_iters) {
+                                                          int sorted, int line_blocks, int ball_iters, int refine) {
     extern __shared__ unsigned long long skeys[];
     __shared__ unsigned s_red[3];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -596,14 +693,35 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     int *perm = ws.perm[cloud] + (long long)b * nfp;
     const int nnodes = nfp / kNode;
     const float Eslack = node_slack(s_red[0], s_red[1]);
-    __syncthreads();                                     // thr (global) is re-read below by other threads
+    __syncthreads();                                     // thr (global) is re-read below by other threads; sort buffers are dead
+    // sorted indices -> shared memory, k-d refinement of every window of 64 (one warp each), then the records
+    int *sidx = reinterpret_cast<int *>(skeys);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = e * 1024 + tid;
+        if (e < E && i < nfp) {
+            const unsigned idx = (unsigned)(v[e] & 0xFFFFFFFFull);
+            sidx[i] = idx < (unsigned)nf ? (int)idx : -1;
+        }
+    }
+    __syncthreads();
+    if (sorted && refine) {
+        __shared__ float4 s_kd[32][64];
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int w = wid; w < nfp / 64; w += 32) {
+            int f0 = sidx[w * 64 + lane], f1 = sidx[w * 64 + 32 + lane];
+            kd_refine64<kNode>(tri, f0, f1, lane, s_kd[wid]);
+            sidx[w * 64 + lane] = f0;
+            sidx[w * 64 + 32 + lane] = f1;
+        }
+    }
+    __syncthreads();
     float rad = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int i = e * 1024 + tid;
         if (e < E && i < nfp) {                          // nfp is a multiple of 256: whole warps
-            const unsigned idx = (unsigned)(v[e] & 0xFFFFFFFFull);
-            const int f = idx < (unsigned)nf ? (int)idx : -1;
+            const int f = sidx[i];
             perm[i] = f;
             rad = fmaxf(rad, make_node_coop<kNode>(tri, f >= 0 ? thr[f] : 0.f, f, i, Eslack, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
                                                    ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters));
@@ -626,7 +744,7 @@ size_t sort_scratch_bytes(int nfp_max, int B) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 16, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode
+static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 16, 1, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode, [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path)
 void set_param(int id, int v) { if (id >= 0 && id < 12) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -660,8 +778,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
                 return RRL_ERR_CUDA;
             attr_set = true;
         }
-        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8]);
-        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8]);
+        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10]);
+        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10]);
         count_launch();
         stage_mark(1, s);
         stage_mark(2, s);
@@ -722,6 +840,14 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
                     return RRL_ERR_CUDA;
             }
         }
+    }
+    if (sorted && g_param[10] == 2) {              // measured on the large path: costs more (33 us) than it saves; A/B only
+        int rbx = nfp_max / 64 / 8;
+        if (rbx > 2048) rbx = 2048;
+        if (rbx < 1) rbx = 1;
+        if (G == 8) refine_kernel<8><<<dim3(rbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g);
+        else refine_kernel<16><<<dim3(rbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g);
+        count_launch();
     }
     stage_mark(2, s);
     int nbx = nfp_max / 256;
@@ -840,8 +966,11 @@ __device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
     const unsigned lt = (1u << lane) - 1u;
     int off = 0;
     total = 0;
+    // only the bit planes some lane uses (counts are mostly 0..3: two or three ballots instead of kBits)
+    const unsigned used = __reduce_or_sync(0xffffffffu, (unsigned)c);
 #pragma unroll
     for (int bit = 0; bit < kBits; ++bit) {
+        if ((used >> bit) == 0u) break;
         const unsigned bal = __ballot_sync(0xffffffffu, (c >> bit) & 1);
         off += __popc(bal & lt) << bit;
         total += __popc(bal) << bit;
@@ -903,6 +1032,40 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         tile_done[0] = 0; tile_done[1] = 0;
     }
 
+    const float4 *src = (kSuper ? ws.super4[cloud] + (long long)b * (nrecs / 4) * 5 : ws.node4[cloud] + (long long)b * (nnodes / 4) * 5) +
+                        (long long)(n_begin / 4) * 5;                                                          // chunk start
+    const int ntiles = (n_end - n_begin + kTileNodes - 1) / kTileNodes;
+    auto issue = [&](int t) {
+        const int n = min(kTileNodes, n_end - (n_begin + t * kTileNodes));
+        const unsigned bytes = (unsigned)(n / 4) * 5u * 16u;
+        mbar_expect_tx(&mbar[t & 1], bytes);
+        tma_bulk_load(stage + (t & 1) * kStageF4, src + (long long)t * kStageF4, bytes, &mbar[t & 1]);
+    };
+    // the chunk's triplet records (level 2) go to shared memory when they fit, else they are read through L2
+    const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + node_begin) * (kNode + 1);   // chunk start
+    constexpr bool pts_in_smem = kPerNode, pts12_in_smem = kPerNode;
+    const float4 *pts = spts;
+    if constexpr (!kPerNode) pts = pt4_c;
+    // point-1/2 records of the chunk (refine pass before the hand-off to the exact kernel)
+    const float4 *pt12_c = ws.pt12[cloud] + ((long long)b * nfp + (long long)node_begin * kNode) * 2;
+    const float4 *pts12 = spts12;
+    if constexpr (!kPerNode) pts12 = pt12_c;
+    // tid 0 initialised the barriers itself, so it issues the copies BEFORE the line set-up below: the TMA latency runs
+    // under the loads and threshold arithmetic of the lines instead of after them
+    if (tid == 0) {
+        issue(0);
+        if (ntiles > 1) issue(1);
+        if (pts_in_smem) {
+            const unsigned bytes = (unsigned)(n_end - n_begin) * (kNode + 1) * 16u;
+            mbar_expect_tx(&mbar[2], bytes);
+            tma_bulk_load(spts, pt4_c, bytes, &mbar[2]);
+        }
+        if (pts12_in_smem) {
+            const unsigned bytes = (unsigned)(n_end - n_begin) * kNode * 2u * 16u;
+            mbar_expect_tx(&mbar[3], bytes);
+            tma_bulk_load(spts12, pt12_c, bytes, &mbar[3]);
+        }
+    }
     // ---- per-thread lines -> filter thresholds ------------------------------------------------------------
     const float P = sqrtf(__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001f;
     const float Rmax = __uint_as_float(ws.rmax[b * 2 + cloud]);
@@ -942,38 +1105,6 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     }
     __syncthreads();
 
-    const float4 *src = (kSuper ? ws.super4[cloud] + (long long)b * (nrecs / 4) * 5 : ws.node4[cloud] + (long long)b * (nnodes / 4) * 5) +
-                        (long long)(n_begin / 4) * 5;                                                          // chunk start
-    const int ntiles = (n_end - n_begin + kTileNodes - 1) / kTileNodes;
-    auto issue = [&](int t) {
-        const int n = min(kTileNodes, n_end - (n_begin + t * kTileNodes));
-        const unsigned bytes = (unsigned)(n / 4) * 5u * 16u;
-        mbar_expect_tx(&mbar[t & 1], bytes);
-        tma_bulk_load(stage + (t & 1) * kStageF4, src + (long long)t * kStageF4, bytes, &mbar[t & 1]);
-    };
-    // the chunk's triplet records (level 2) go to shared memory when they fit, else they are read through L2
-    const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + node_begin) * (kNode + 1);   // chunk start
-    constexpr bool pts_in_smem = kPerNode, pts12_in_smem = kPerNode;
-    const float4 *pts = spts;
-    if constexpr (!kPerNode) pts = pt4_c;
-    // point-1/2 records of the chunk (refine pass before the hand-off to the exact kernel)
-    const float4 *pt12_c = ws.pt12[cloud] + ((long long)b * nfp + (long long)node_begin * kNode) * 2;
-    const float4 *pts12 = spts12;
-    if constexpr (!kPerNode) pts12 = pt12_c;
-    if (tid == 0) {
-        issue(0);
-        if (ntiles > 1) issue(1);
-        if (pts_in_smem) {
-            const unsigned bytes = (unsigned)(n_end - n_begin) * (kNode + 1) * 16u;
-            mbar_expect_tx(&mbar[2], bytes);
-            tma_bulk_load(spts, pt4_c, bytes, &mbar[2]);
-        }
-        if (pts12_in_smem) {
-            const unsigned bytes = (unsigned)(n_end - n_begin) * kNode * 2u * 16u;
-            mbar_expect_tx(&mbar[3], bytes);
-            tma_bulk_load(spts12, pt12_c, bytes, &mbar[3]);
-        }
-    }
     if (pts_in_smem) mbar_wait(&mbar[2], 0);
     if (pts12_in_smem) mbar_wait(&mbar[3], 0);
 
@@ -1132,27 +1263,36 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 unsigned m[kLinesPerThread];
 #pragma unroll
                 for (int i = 0; i < kLinesPerThread; ++i) m[i] = 0u;
-#pragma unroll 2
-                for (int gi = 0; gi < ng; ++gi) {
-                    // 4 nodes = two interleaved pairs: {xA,xB,yA,yB} {zA,zB,wA,wB}
-                    const float4 a0 = sp[(w0 + gi) * 5 + 0], a1 = sp[(w0 + gi) * 5 + 1], b0 = sp[(w0 + gi) * 5 + 2], b1 = sp[(w0 + gi) * 5 + 3];
-                    const float2 xa = make_float2(a0.x, a0.y), ya = make_float2(a0.z, a0.w), za = make_float2(a1.x, a1.y), wa = make_float2(a1.z, a1.w);
-                    const float2 xb = make_float2(b0.x, b0.y), yb = make_float2(b0.z, b0.w), zb = make_float2(b1.x, b1.y), wb = make_float2(b1.z, b1.w);
-                    const unsigned bit = 1u << (gi * 4);
+                // record counts are multiples of kNodePad = 16 = 4 groups: a window is one or two halves of 4 groups,
+                // fully unrolled so that every mask bit is an immediate (a bit position computed from a loop counter
+                // cost a MOV + SHF per test)
 #pragma unroll
-                    for (int i = 0; i < kLinesPerThread; ++i) {
-                        const float2 u0 = make_float2(ux[i], ux[i]), u1 = make_float2(uy[i], uy[i]), u2 = make_float2(uz[i], uz[i]);
-                        const float2 m0 = make_float2(mx[i], mx[i]), m1 = make_float2(my[i], my[i]), m2 = make_float2(mz[i], mz[i]);
-                        const float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
-                        const float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
-                        const float2 qa = __ffma2_rn(ta, ta, sa);
-                        const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
-                        const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
-                        const float2 qb = __ffma2_rn(tb, tb, sb);
-                        m[i] |= (qa.x > tl[i]) ? bit : 0u;
-                        m[i] |= (qa.y > tl[i]) ? (bit << 1) : 0u;
-                        m[i] |= (qb.x > tl[i]) ? (bit << 2) : 0u;
-                        m[i] |= (qb.y > tl[i]) ? (bit << 3) : 0u;
+                for (int h = 0; h < 2; ++h) {
+                    if (h * 4 >= ng) break;
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        const int gi = h * 4 + gq;
+                        // 4 records = two interleaved pairs: {xA,xB,yA,yB} {zA,zB,wA,wB}
+                        const float4 a0 = sp[(w0 + gi) * 5 + 0], a1 = sp[(w0 + gi) * 5 + 1], b0 = sp[(w0 + gi) * 5 + 2], b1 = sp[(w0 + gi) * 5 + 3];
+                        const float2 xa = make_float2(a0.x, a0.y), ya = make_float2(a0.z, a0.w), za = make_float2(a1.x, a1.y), wa = make_float2(a1.z, a1.w);
+                        const float2 xb = make_float2(b0.x, b0.y), yb = make_float2(b0.z, b0.w), zb = make_float2(b1.x, b1.y), wb = make_float2(b1.z, b1.w);
+                        constexpr unsigned one = 1u;
+                        const unsigned bit = one << (gi * 4);
+#pragma unroll
+                        for (int i = 0; i < kLinesPerThread; ++i) {
+                            const float2 u0 = make_float2(ux[i], ux[i]), u1 = make_float2(uy[i], uy[i]), u2 = make_float2(uz[i], uz[i]);
+                            const float2 m0 = make_float2(mx[i], mx[i]), m1 = make_float2(my[i], my[i]), m2 = make_float2(mz[i], mz[i]);
+                            const float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
+                            const float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
+                            const float2 qa = __ffma2_rn(ta, ta, sa);
+                            const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
+                            const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
+                            const float2 qb = __ffma2_rn(tb, tb, sb);
+                            m[i] |= (qa.x > tl[i]) ? bit : 0u;
+                            m[i] |= (qa.y > tl[i]) ? (bit << 1) : 0u;
+                            m[i] |= (qb.x > tl[i]) ? (bit << 2) : 0u;
+                            m[i] |= (qb.y > tl[i]) ? (bit << 3) : 0u;
+                        }
                     }
                 }
                 // ordered push of the fired (line, node) pairs: one scan and one bit loop per line
@@ -1433,7 +1573,7 @@ static int launch_dense_variant(const DenseArgs &a0, const Workspace &ws, const 
     // records the main loop streams: nodes, or super nodes
     const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
     const int nn_max = kSuper ? pad_supers(nfp_max) : nfp_max / G;
-    const int rec_pad = kSuper ? 4 : kNodePad;
+    const int rec_pad = kNodePad;
     // split the records so that the grid covers the SMs (kMinBlocks CTAs each) g_param[2] times over when the line
     // tiles alone do not; never below g_param[3] records per CTA
     const long long base_ctas = (long long)line_tiles * g.B * 2;
