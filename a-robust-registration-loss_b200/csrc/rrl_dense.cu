@@ -461,7 +461,8 @@ __device__ __forceinline__ float make_super_block(const float *__restrict__ tri,
         const float rf = f >= 0 ? sqrtf(fmaxf((float)cut + E_up, 0.f)) : 0.f;
         float bx = qx, by = qy, bz = qz, bestR = INFINITY;
         float ccx = qx, ccy = qy, ccz = qz;
-        for (int k = 1; k <= ball_iters + 1; ++k) {
+        const int steps = ball_iters / 2 + 1;                      // block-wide steps cost a barrier each: half of the nodes' count
+        for (int k = 1; k <= steps; ++k) {
             const float dx = fx - ccx, dy = fy - ccy, dz = fz - ccz;
             const float d = f >= 0 ? sqrtf(dx * dx + dy * dy + dz * dz) + rf : -INFINITY;
             float m = d;
@@ -472,11 +473,13 @@ __device__ __forceinline__ float make_super_block(const float *__restrict__ tri,
             float (*sf)[4] = s_far[k & 1];                        // double buffered: one barrier per step
             if (lane == far) { sf[wid][0] = m; sf[wid][1] = fx; sf[wid][2] = fy; sf[wid][3] = fz; }
             __syncthreads();
-            float gm = sf[0][0];
-            int gw = 0;
-#pragma unroll
-            for (int w = 1; w < 8; ++w)
-                if (sf[w][0] > gm) { gm = sf[w][0]; gw = w; }
+            // block maximum of the 8 warp maxima (distances are >= 0 or -inf: as unsigned bits they order like floats
+            // once -inf is mapped to 0), first warp on ties: one load, one REDUX, one ballot per thread
+            const float mw = sf[lane & 7][0];
+            const unsigned mb = mw > 0.f ? __float_as_uint(mw) : 0u;
+            const unsigned gb = __reduce_max_sync(0xffffffffu, mb);
+            const int gw = __ffs(__ballot_sync(0xffffffffu, mb == gb) & 0xffu) - 1;
+            const float gm = __uint_as_float(gb);
             if (gm < bestR) { bestR = gm; bx = ccx; by = ccy; bz = ccz; }
             const float step = 1.0f / (float)(k + 1);
             ccx += (sf[gw][1] - ccx) * step; ccy += (sf[gw][2] - ccy) * step; ccz += (sf[gw][3] - ccz) * step;

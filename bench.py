@@ -71,9 +71,10 @@ def rigid_variants(base, n_out, seed, keep_first=True):
     return np.stack(tri1), np.stack(tri2), np.stack(lines)
 
 
-def make_inputs(workload, rank, n_sets, n_base=None):
+def make_inputs(workload, rank, n_sets, n_base=None, nl=None):
     from oracle import synth
-    B, nf, nl, kw, _ = WORKLOADS[workload]
+    B, nf, nl0, kw, _ = WORKLOADS[workload]
+    nl = nl or nl0
     n_base = n_base or min(B, 8 if nf <= 4096 else 1)
     cfg_id = list(WORKLOADS).index(workload) + 2
     base = [synth.make_pair(1000 * cfg_id + 97 * rank + i, nf, nl, **kw) for i in range(n_base)]
@@ -276,11 +277,13 @@ def run_gpu(args):
 
     B, nf, nl, kw, desc = WORKLOADS[args.workload]
     line_sharded = args.workload == "large" and world > 1
+    weak_lines = line_sharded and args.large_scaling == "weak"     # every rank keeps nl lines: world * nl lines in total
     bytes_per_set = 4 * (2 * B * nf * 9 + B * nl * 6)
     n_sets = max(2, min(16, math.ceil(1.5 * L2_BYTES / bytes_per_set)))
-    host_sets = make_inputs(args.workload, 0 if line_sharded else rank, n_sets)
+    nl_total = nl * world if weak_lines else nl                    # lines of the ONE pair all ranks share
+    host_sets = make_inputs(args.workload, 0 if line_sharded else rank, n_sets, nl=nl_total)
     if line_sharded:
-        lo, hi = rrl_b200.dist.shard_range(nl, rank, world)
+        lo, hi = rrl_b200.dist.shard_range(nl_total, rank, world)
         host_sets = [(a, b_, c[:, lo:hi]) for a, b_, c in host_sets]
     dev_sets = [tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in s) for s in host_sets]
     nl_local = dev_sets[0][2].shape[1]
@@ -305,15 +308,55 @@ def run_gpu(args):
         total = loss.sum()
         total.backward()
         if world > 1:
+            # the only exchange of the batch-sharded path: the global loss, a logged scalar that nothing on
+            # the device waits for.  It is reduced asynchronously (NCCL's own stream) and collected one step later, so
+            # its latency (tens of microseconds at 8 ranks) runs under the next step's kernels; the last one is awaited
+            # inside the timed region.
             red = total.detach().clone()
-            dist.all_reduce(red)                      # the only exchange of the batch-sharded path
+            if pending:
+                pending.pop().wait()
+            pending.append(dist.all_reduce(red, async_op=True))
             return red, t1.grad
         return total.detach(), t1.grad
+
+    pending = []
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # Twist-mode steps are short (the exchange of the line shard is five tiny collectives between kernels of tens of
+    # microseconds): capture one CUDA graph per input set -- transform, forward, exchange, backward, se(3) backward --
+    # so that the step is not bound by the host's launch rate.  Same kernels, same collectives, same inputs.
+    graphs = None
+    if twist_mode and args.graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for i in range(max(3, n_sets)):
+                    step(i)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            barrier()
+            graphs = []
+            for i in range(n_sets):
+                gph = torch.cuda.CUDAGraph()
+                n0 = rrl_b200.launch_count()
+                with torch.cuda.graph(gph):
+                    out = step(i)
+                graphs.append((gph, out, rrl_b200.launch_count() - n0))     # kernels of OURS inside this graph
+            barrier()
+            eager_step = step
+
+            def step(i):                                   # noqa: F811
+                gph, out, _ = graphs[i % n_sets]
+                gph.replay()
+                return out
+        except Exception as exc:                           # capture not available: keep the eager step, say so
+            graphs = None
+            sys.stderr.write("bench: CUDA graph capture failed (%s: %s); running eagerly\n" % (type(exc).__name__, exc))
+            torch.cuda.synchronize()
 
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -325,16 +368,20 @@ def run_gpu(args):
     e0.record()
     for i in range(args.steps):
         last = step(i)
+    while pending:
+        pending.pop().wait()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = rrl_b200.launch_count() - launches0
+    if graphs:                                            # replayed, not re-issued by the host: count what each graph holds
+        launches = sum(graphs[i % n_sets][2] for i in range(args.steps))
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    pairs_lines_per_step = (1 * nl) if line_sharded else (world * B * nl)
+    pairs_lines_per_step = (1 * nl_total) if line_sharded else (world * B * nl)
     value = pairs_lines_per_step / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through the C ABI (H2D of the step's inputs from pinned memory, D2H of loss + status) ----
@@ -434,13 +481,14 @@ def run_gpu(args):
     cpu = cpu_baseline(args.workload, inputs=host_sets[0]) if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": "loss fwd+bwd evaluations/s (pairs x lines per second)", "value": value, "unit": "pairs*lines/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong" if line_sharded else "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong" if (line_sharded and not weak_lines) else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "name": args.workload, "pairs_per_gpu": B, "triplets_per_cloud": nf,
-                       "lines_per_pair": nl, "sharding": "lines" if line_sharded else "pairs (batch)",
+                       "lines_per_pair": nl_total, "sharding": "lines" if line_sharded else "pairs (batch)",
                        "window": [1, 1, 5, 5],
                        "backward": "d loss / d twist (6) through the fused se(3) transform of cloud 1" if twist_mode
                                    else "d loss / d points1 (B, nf, 9)",
+                       "launch": ("one CUDA graph per input set (kernels + collectives)" if graphs else "eager launches"),
                        "l2": "inputs rotate over %d distinct sets (%.0f MB > 126 MB L2), no flush needed" %
                              (n_sets, n_sets * bytes_per_set / 2 ** 20)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -459,6 +507,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dcp", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="twist-mode workloads: replay the step as a CUDA graph (0 = eager launches)")
+    ap.add_argument("--large-scaling", default="strong", choices=["strong", "weak"],
+                    help="workload large at N > 1: strong = the 100k lines of the pair are split over the ranks (BASELINE "
+                         "configs[4]); weak = every rank keeps 100k lines of a pair with N x 100k lines")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

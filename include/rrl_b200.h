@@ -238,7 +238,9 @@ int rrl_measure_stages(const float *tri1, const float *tri2, const float *lines,
  * Results are identical; measurement / A-B testing only. */
 int rrl_debug_set_dense_variant(int variant);
 /* launch-geometry knobs for A/B measurements: id 1 = triplets per node (0 auto, 8, 16), 2 = target waves of CTAs,
- * 3 = minimum nodes per CTA chunk.  Results never depend on them. */
+ * 3 = minimum nodes per CTA chunk, 5 = brute-force cross-check kernel, 6 = lines per thread, 7 = 1: no super-node level,
+ * 8 = enclosing-ball steps of the node centres, 9 = target waves in super-node mode, 10 = k-d refinement of the Hilbert
+ * order (0 off, 1 small clouds, 2 everywhere).  Results never depend on them. */
 int rrl_debug_set_param(int id, int value);
 
 #ifdef __cplusplus

@@ -207,7 +207,9 @@ def test_demo_flow_with_the_reference_names(rrl):
     assert data["vertics1_faces_tensor"].shape == (1, 3 * 1500, 3)
     model, hist = demo.test_one_case(data, n_epoch=60, n_sample_line=8000, device="cuda", log=None)
     assert len(hist) >= 50
-    first, last = np.mean([h[0] for h in hist[:3]]), np.mean([h[0] for h in hist[-3:]])
+    # the Chamfer distance of single epochs is noisy (fresh random lines every epoch, float atomics in the backward):
+    # compare the start with the MEDIAN of the last 15 epochs (measured spread over repeated runs: ratio 0.01 .. 0.26)
+    first, last = np.mean([h[0] for h in hist[:3]]), np.median([h[0] for h in hist[-15:]])
     assert last < 0.5 * first, (first, last)
     R, T = model.Transform()
     assert R.shape == (1, 3, 3) and T.shape == (1, 3) and "parameters_" in model.state_dict()
