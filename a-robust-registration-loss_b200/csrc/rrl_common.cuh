@@ -54,6 +54,7 @@ struct Workspace {
     unsigned int *xmax;      // (B,2): [0] bits of max |x0|^2 over the pair's lines, [1] reserved
     unsigned int *rmax;      // (B,2): bits of the largest node radius of the cloud
     unsigned int *smax;      // (B,2): bits of the largest super-node radius of the cloud (large clouds only)
+    unsigned int *bad;       // (B,2): non-zero when the cloud (or, in either slot, a line of the pair) holds a NaN / infinite value
     int *nrec;               // (B)
     int *n_kj;               // (B,16)
     float *med;              // (B)

@@ -28,6 +28,18 @@
 
 namespace rrl {
 
+// max |p|^2 over the FINITE points of a triplet; a NaN / infinite coordinate (such a point can never pass the test: its
+// distance is NaN) stays out of the extent -- it would turn every filter threshold into -inf or NaN -- and raises `bad`
+__device__ __forceinline__ float finite_extent(const float *v, int &bad) {
+    float m = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float s = sq3_rn(v[3 * q], v[3 * q + 1], v[3 * q + 2]);
+        if (s < INFINITY) m = fmaxf(m, s); else bad = 1;
+    }
+    return m;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // prep: thresholds, line constants, extents
 // ------------------------------------------------------------------------------------------------------
@@ -40,6 +52,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
         ws.hdr[0] = kMagic; ws.hdr[1] = g.B; ws.hdr[2] = g.nf1; ws.hdr[3] = g.nf2; ws.hdr[4] = g.nl; ws.hdr[5] = window;
     }
     float block_max[3];
+    int badv = 0;
 #pragma unroll
     for (int cloud = 0; cloud < 2; ++cloud) {
         const int nf = cloud ? g.nf2 : g.nf1;
@@ -53,12 +66,12 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
 #pragma unroll
                 for (int q = 0; q < 9; ++q) v[q] = __ldg(tri + (long long)f * 9 + q);
                 thr[f] = triplet_thr_exact(v);
-                float m = fmaxf(fmaxf(sq3_rn(v[0], v[1], v[2]), sq3_rn(v[3], v[4], v[5])), sq3_rn(v[6], v[7], v[8]));
-                if (!(m == m)) m = INFINITY;
-                pm = fmaxf(pm, m);
+                pm = fmaxf(pm, finite_extent(v, badv));
             }
         }
         block_max[cloud] = pm;
+        if (__any_sync(0xffffffffu, badv) && (threadIdx.x & 31) == 0) atomicOr(ws.bad + b * 2 + cloud, 1u);
+        badv = 0;
     }
     const float *lb = lines + (long long)b * g.nl * 6;
     float xmw = 0.f;
@@ -77,12 +90,13 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
                                                (float)(2.0 * (z - sd * u2)), (float)(xx - sd * sd));
             ws.cnt[0][gl] = 0;
             ws.cnt[1][gl] = 0;
-            xm = (float)xx * 1.000001f;
-            if (!(xm == xm)) xm = INFINITY;
+            xm = (float)xx * 1.000001f + 0.f * (u0 + u1 + u2);       // NaN for a NaN / infinite position OR direction
+            if (!(xm < INFINITY)) { xm = 0.f; badv = 1; }            // such a line never hits: it stays out of the extent
         }
         xmw = fmaxf(xmw, xm);
     }
     block_max[2] = xmw;
+    if (__any_sync(0xffffffffu, badv) && (threadIdx.x & 31) == 0) atomicOr(ws.bad + b * 2, 1u);
     // one atomic per CTA and array: thousands of same-address atomics would serialise in L2
     __shared__ unsigned s_max[3];
     if (threadIdx.x < 3) s_max[threadIdx.x] = 0u;
@@ -338,6 +352,7 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     double px = 0, py = 0, pz = 0, cut = 0;
     float4 pr = make_float4(0.f, 0.f, 0.f, -INFINITY);                // padding: never a candidate
     float4 pr1 = pr, pr2 = pr;
+    const int f_in = f;
     if (f >= 0) {
         const float *t = tri + (long long)f * 9;
         px = __ldg(t); py = __ldg(t + 1); pz = __ldg(t + 2);
@@ -347,7 +362,11 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
         pr = make_float4((float)px, (float)py, (float)pz, (float)(cut - (px * px + py * py + pz * pz)));
         pr1 = make_float4((float)ax, (float)ay, (float)az, (float)(cut - (ax * ax + ay * ay + az * az)));
         pr2 = make_float4((float)bx, (float)by, (float)bz, (float)(cut - (bx * bx + by * by + bz * bz)));
+        // a triplet whose point 0 or threshold is NaN / infinite can never hit: it keeps its (inert) records but stays
+        // out of the sphere, which would otherwise become NaN and hide the node's other triplets
+        if (!(fabs(px) + fabs(py) + fabs(pz) + fabs(cut) < (double)INFINITY)) { f = -1; px = py = pz = cut = 0; }
     }
+    (void)f_in;
     // centroid in float: WHERE the centre goes is a heuristic, the radius below is an upper bound for whatever centre
     float cx = (float)px, cy = (float)py, cz = (float)pz;            // 0 for padding lanes
     int cntv = f >= 0;
@@ -440,6 +459,7 @@ __device__ __forceinline__ float make_super_block(const float *__restrict__ tri,
         const float *t = tri + (long long)f * 9;
         px = __ldg(t); py = __ldg(t + 1); pz = __ldg(t + 2);
         cut = (double)th * (double)th - (double)kAddEps;
+        if (!(fabs(px) + fabs(py) + fabs(pz) + fabs(cut) < (double)INFINITY)) { f = -1; px = py = pz = cut = 0; }   // as in make_node_coop
     }
     float cx = (float)px, cy = (float)py, cz = (float)pz, cn = f >= 0 ? 1.f : 0.f;
 #pragma unroll
@@ -604,14 +624,13 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     __syncthreads();
     // thresholds, extent of the cloud, extent of the pair's lines
     float pm = 0.f, xm = 0.f;
+    int badv = 0;
     for (int f = tid; f < nf; f += 1024) {
         float v[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) v[q] = __ldg(tri + (long long)f * 9 + q);
         thr[f] = triplet_thr_exact(v);
-        float m = fmaxf(fmaxf(sq3_rn(v[0], v[1], v[2]), sq3_rn(v[3], v[4], v[5])), sq3_rn(v[6], v[7], v[8]));
-        if (!(m == m)) m = INFINITY;
-        pm = fmaxf(pm, m);
+        pm = fmaxf(pm, finite_extent(v, badv));
     }
 #pragma unroll 4
     for (int l = tid; l < g.nl; l += 1024) {
@@ -619,17 +638,19 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         // float suffices: the sum is within 1.8e-7 of |x0|^2 and the factor keeps it an upper bound
         const float x = __ldg(ln + 3), y = __ldg(ln + 4), z = __ldg(ln + 5);
         float m = (x * x + y * y + z * z) * 1.000001f;
-        if (!(m == m)) m = INFINITY;
+        m += 0.f * (__ldg(ln) + __ldg(ln + 1) + __ldg(ln + 2));      // NaN for a NaN / infinite position OR direction
+        if (!(m < INFINITY)) { m = 0.f; badv = 1; }                  // such a line never hits: it stays out of the extent
         xm = fmaxf(xm, m);
     }
     {
         const unsigned a = __reduce_max_sync(0xffffffffu, __float_as_uint(pm)), c = __reduce_max_sync(0xffffffffu, __float_as_uint(xm));
         if ((tid & 31) == 0) { atomicMax(&s_red[0], a); atomicMax(&s_red[1], c); }
     }
-    __syncthreads();
+    const int bad_any = __syncthreads_or(badv);          // (also the barrier the reductions above need)
     if (tid == 0) {
         ws.pmax[b * 2 + cloud] = s_red[0];
         if (cloud == 0) ws.xmax[b * 2] = s_red[1];
+        ws.bad[b * 2 + cloud] = bad_any ? 1u : 0u;       // this cloud's points, or any line of the pair (both CTAs scan them)
     }
     // Hilbert order: element i = e * 1024 + tid lives in register v[e]; n2 = E * 1024 >= nfp keys (sentinels sort last).
     // Compare-exchange distances below 32 are warp shuffles, 32..512 go through shared memory (double buffered: one
@@ -1083,7 +1104,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         tl_point = c1.w - guard - fabsf(c1.w) * 1.2e-7f;                    // rounded down: admits more
         // |u| > 1 makes F slightly indefinite; e bounds the deficit, 0 for |u| <= 1 (incl. all-zero lines)
         const float s2 = (c0.x * c0.x + c0.y * c0.y + c0.z * c0.z) * 1.0000004f;
-        const float e = fmaxf(s2 - 1.0f, 0.f) * PX * PX;
+        const float e = s2 > 1.0f ? (s2 - 1.0f) * PX * PX : 0.f;
         const float slack = (2.0f * Rmax * sqrtf(e) + 2.0f * e) * 1.00001f;
         tl_node = tl_point - slack - fabsf(tl_point) * 1.2e-7f;
         const float sslack = (2.0f * Smax * sqrtf(e) + 2.0f * e) * 1.00001f;

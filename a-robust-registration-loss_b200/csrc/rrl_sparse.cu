@@ -589,6 +589,10 @@ __device__ __forceinline__ void finalize_pair(const Workspace &ws, int b, float 
     // |AC|^2 <= (P + X)^2: flag clouds whose own extent already makes the 2e-4 offset smaller than a few ulps of
     // |p|^2 (|AC|^2 >~ 1e3)
     if (fmaxf(__uint_as_float(pm0), __uint_as_float(pm1)) > 250.0f) status |= RRL_STATUS_NAN_RISK;
+    // a NaN or infinite coordinate in a cloud or a line (prep records it as an infinite extent) gives NaN distances in the
+    // reference's dense tensor, which is what makes it exit (loss.py:89-91).  Here such triplets and lines never hit
+    // (comparisons with NaN are false) and may never reach the exact test, so the inputs themselves raise the flag.
+    if (__ldcg(ws.bad + b * 2) | __ldcg(ws.bad + b * 2 + 1)) status |= RRL_STATUS_NAN;
     const long long outstat = lane == 0 ? nrec : lane == 1 ? nD : lane == 2 ? (long long)C : mystat;
     if (lane < 3) st[lane] = outstat;
     if (out_stats && lane < RRL_NSTAT) out_stats[(long long)b * RRL_NSTAT + lane] = outstat;

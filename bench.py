@@ -330,7 +330,7 @@ def run_gpu(args):
     # microseconds): capture one CUDA graph per input set -- transform, forward, exchange, backward, se(3) backward --
     # so that the step is not bound by the host's launch rate.  Same kernels, same collectives, same inputs.
     graphs = None
-    if twist_mode and args.graph:
+    if (twist_mode and args.graph) or args.graph >= 2:
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -507,7 +507,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dcp", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=1, help="twist-mode workloads: replay the step as a CUDA graph (0 = eager launches)")
+    ap.add_argument("--graph", type=int, default=1, help="1: twist-mode workloads replay the step as a CUDA graph; 2: every workload does; 0: eager launches")
     ap.add_argument("--large-scaling", default="strong", choices=["strong", "weak"],
                     help="workload large at N > 1: strong = the 100k lines of the pair are split over the ranks (BASELINE "
                          "configs[4]); weak = every rank keeps 100k lines of a pair with N x 100k lines")

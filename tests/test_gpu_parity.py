@@ -124,6 +124,27 @@ def test_unnormalised_and_degenerate_lines(rrl):
     _check_against_oracle(out, co.loss(p["tri1"], p["tri2"], lines))
 
 
+def test_nan_points_and_lines_are_flagged_not_fatal(rrl):
+    """the reference prints "Exit the systerm" and exit(0)s on a NaN distance (loss.py:89-91); here NaN triplets and NaN
+    lines simply never hit (every comparison with NaN is false, as in the oracle), the status carries RRL_STATUS_NAN,
+    and the rest of the pair is evaluated as usual"""
+    p = synth.make_pair(113, 400, 700)
+    tri1, lines = p["tri1"].copy(), p["lines"].copy()
+    tri1[5, 0] = np.nan                      # point 0 of a triplet
+    tri1[77, 4] = np.nan                     # point 1 of another
+    lines[10, 3] = np.nan                    # a line through nowhere
+    lines[11, 1] = np.nan
+    out = _run(rrl, tri1, p["tri2"], lines)
+    orc = co.loss(tri1, p["tri2"], lines)
+    assert np.array_equal(out["counts1"], orc.counts1) and np.array_equal(out["counts2"], orc.counts2)
+    keep = orc.counts1 <= co.CAP
+    assert np.array_equal(out["hits1"][keep], orc.hits1[keep])
+    assert out["counts1"][10] == 0 and out["counts1"][11] == 0 and not np.isin([5, 77], out["hits1"]).any()
+    assert out["status"] & 2                                           # RRL_STATUS_NAN
+    assert np.isfinite(out["loss"]) and abs(out["loss"] - orc.loss) <= REL_TOL * abs(orc.loss)
+    assert np.isfinite(out["grad1"]).all()
+
+
 def test_clustered_cloud_with_duplicate_points(rrl):
     """many coincident triplets (zero-radius nodes, zero thresholds) and a tight cluster next to a sparse shell"""
     rng = np.random.default_rng(11)
