@@ -768,7 +768,7 @@ size_t sort_scratch_bytes(int nfp_max, int B) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 16, 1, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode, [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path)
+static int g_param[12] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 16, 1, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode, [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2)
 void set_param(int id, int v) { if (id >= 0 && id < 12) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -1482,7 +1482,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
 
 // Level 3: the EXACT reference-order test of every queued (line, triplet) pair.  The chain entry -> line/triplet ->
 // counter -> slot is four dependent memory round trips, so every thread keeps kExactIlp entries in flight.
-constexpr int kExactIlp = 2;
+template <int kExactIlp>
 __global__ void __launch_bounds__(256) exact_kernel(DenseArgs a, Workspace ws, Geometry g) {
     const unsigned long long reserved = *ws.xcursor;
     const long long n = reserved < (unsigned long long)ws.xcap ? (long long)reserved : ws.xcap;
@@ -1635,7 +1635,9 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     else if (G == 8) rc = lpt == 2 ? launch_dense_variant<8, false, 2>(a, ws, g, G, s) : launch_dense_variant<8, false, 4>(a, ws, g, G, s);
     else rc = lpt == 2 ? launch_dense_variant<16, false, 2>(a, ws, g, G, s) : launch_dense_variant<16, false, 4>(a, ws, g, G, s);
     if (rc) return rc;
-    exact_kernel<<<148 * 8, 256, 0, s>>>(a, ws, g);
+    if (g_param[11] == 4) exact_kernel<4><<<148 * 8, 256, 0, s>>>(a, ws, g);
+    else if (g_param[11] == 1) exact_kernel<1><<<148 * 8, 256, 0, s>>>(a, ws, g);
+    else exact_kernel<2><<<148 * 8, 256, 0, s>>>(a, ws, g);
     count_launch();
     stage_mark(4, s);
     return check_launch();

@@ -291,7 +291,8 @@ def run_gpu(args):
     twist_mode = args.workload == "large"          # the scan pair is evaluated through the se(3) twist
     twist0 = torch.tensor([0.01, -0.02, 0.015, 0.03, -0.01, 0.02], device=dev)
 
-    def step(i):
+    def compute(i):
+        """the device work of one step on input set i: forward + backward (for the line shard: with its exchange)"""
         t1, t2, ln = dev_sets[i % n_sets]
         if twist_mode:
             tw = twist0.clone().requires_grad_(True)
@@ -307,17 +308,23 @@ def run_gpu(args):
         loss = rrl_b200.intersected_line_loss(t1, t2, ln)
         total = loss.sum()
         total.backward()
-        if world > 1:
+        return total.detach(), t1.grad
+
+    def exchange(out):
+        if world > 1 and not line_sharded:
             # the only exchange of the batch-sharded path: the global loss, a logged scalar that nothing on
             # the device waits for.  It is reduced asynchronously (NCCL's own stream) and collected one step later, so
             # its latency (tens of microseconds at 8 ranks) runs under the next step's kernels; the last one is awaited
             # inside the timed region.
-            red = total.detach().clone()
+            red = out[0].clone()
             if pending:
                 pending.pop().wait()
             pending.append(dist.all_reduce(red, async_op=True))
-            return red, t1.grad
-        return total.detach(), t1.grad
+            return red, out[1]
+        return out
+
+    def step(i):
+        return exchange(compute(i))
 
     pending = []
 
@@ -326,17 +333,18 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Twist-mode steps are short (the exchange of the line shard is five tiny collectives between kernels of tens of
-    # microseconds): capture one CUDA graph per input set -- transform, forward, exchange, backward, se(3) backward --
-    # so that the step is not bound by the host's launch rate.  Same kernels, same collectives, same inputs.
+    # One CUDA graph per input set holds the device work of a step -- (transform,) forward, backward, and for the line shard
+    # its five tiny collectives -- so that the host's launch rate (Python + autograd: ~0.25 ms per step, as long as the DCP
+    # step itself) does not bound the measurement.  Same kernels, same collectives, same inputs; `--graph 0` issues them
+    # eagerly.  The asynchronous all-reduce of the batch shard stays outside the graphs.
     graphs = None
-    if (twist_mode and args.graph) or args.graph >= 2:
+    if args.graph:
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for i in range(max(3, n_sets)):
-                    step(i)
+                    compute(i)
             torch.cuda.current_stream(dev).wait_stream(side)
             barrier()
             graphs = []
@@ -344,15 +352,14 @@ def run_gpu(args):
                 gph = torch.cuda.CUDAGraph()
                 n0 = rrl_b200.launch_count()
                 with torch.cuda.graph(gph):
-                    out = step(i)
+                    out = compute(i)
                 graphs.append((gph, out, rrl_b200.launch_count() - n0))     # kernels of OURS inside this graph
             barrier()
-            eager_step = step
 
             def step(i):                                   # noqa: F811
                 gph, out, _ = graphs[i % n_sets]
                 gph.replay()
-                return out
+                return exchange(out)
         except Exception as exc:                           # capture not available: keep the eager step, say so
             graphs = None
             sys.stderr.write("bench: CUDA graph capture failed (%s: %s); running eagerly\n" % (type(exc).__name__, exc))
@@ -488,7 +495,7 @@ def run_gpu(args):
                        "window": [1, 1, 5, 5],
                        "backward": "d loss / d twist (6) through the fused se(3) transform of cloud 1" if twist_mode
                                    else "d loss / d points1 (B, nf, 9)",
-                       "launch": ("one CUDA graph per input set (kernels + collectives)" if graphs else "eager launches"),
+                       "launch": ("one CUDA graph per input set" if graphs else "eager launches"),
                        "l2": "inputs rotate over %d distinct sets (%.0f MB > 126 MB L2), no flush needed" %
                              (n_sets, n_sets * bytes_per_set / 2 ** 20)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -507,7 +514,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dcp", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=1, help="1: twist-mode workloads replay the step as a CUDA graph; 2: every workload does; 0: eager launches")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the device work of a step as a CUDA graph (one per input set); 0: eager launches")
     ap.add_argument("--large-scaling", default="strong", choices=["strong", "weak"],
                     help="workload large at N > 1: strong = the 100k lines of the pair are split over the ranks (BASELINE "
                          "configs[4]); weak = every rank keeps 100k lines of a pair with N x 100k lines")
