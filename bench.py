@@ -484,6 +484,18 @@ def run_gpu(args):
                         "kernel decides most (line, triplet) pairs with a conservative bounding-sphere + FMA predicate and "
                         "runs the exact reference-order test only on candidates, so frac can exceed 1 (DESIGN.md)",
                 "algorithmic_hbm_bytes_per_launch": 4.0 * t1.shape[0] * (9 * 2 * nf + 6 * nl_local)}
+    # the memory side of the same kernel, for the record (north star: "as a fraction of FP32 and HBM peak"): the
+    # algorithmic bytes (both clouds and the lines once per launch) against the measured copy bandwidth
+    hbm_peak = None
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    hbm_achieved = roofline["algorithmic_hbm_bytes_per_launch"] / (md.value * 1e-3) / 1e9
+    roofline["hbm"] = {"achieved": hbm_achieved, "peak": hbm_peak or 6552.3, "unit": "GB/s",
+                       "frac": hbm_achieved / (hbm_peak or 6552.3),
+                       "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback: the pool's measured 6552.3 GB/s",
+                       "traffic": traffic}
 
     cpu = cpu_baseline(args.workload, inputs=host_sets[0]) if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": "loss fwd+bwd evaluations/s (pairs x lines per second)", "value": value, "unit": "pairs*lines/s",
