@@ -60,7 +60,7 @@ def _check_against_oracle(out, orc, check_grad=True):
         assert _rel(out["grad2"], orc.grad2) <= REL_TOL
 
 
-@pytest.mark.parametrize("name", ["demo_step0", "synth_sphere", "synth_ragged", "synth_rpm_like", "synth_window"])
+@pytest.mark.parametrize("name", ["demo_step0", "synth_sphere", "synth_ragged", "synth_rpm_like", "synth_window", "synth_short_dirs"])
 def test_golden_cases(rrl, name):
     g = golden(name)
     w = tuple(int(v) for v in g["krange"])

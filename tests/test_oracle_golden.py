@@ -8,7 +8,7 @@ from conftest import golden, hits_to_lists
 from oracle import c_oracle as co
 from oracle import torch_port as tp
 
-LOSS_CASES = ["demo_step0", "synth_sphere", "synth_ragged", "synth_rpm_like", "synth_window"]
+LOSS_CASES = ["demo_step0", "synth_sphere", "synth_ragged", "synth_rpm_like", "synth_window", "synth_short_dirs"]
 REL_TOL = 1e-5          # north-star tolerance for loss and gradients (relative, Frobenius for tensors)
 
 
