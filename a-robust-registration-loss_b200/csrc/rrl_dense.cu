@@ -352,7 +352,6 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     double px = 0, py = 0, pz = 0, cut = 0;
     float4 pr = make_float4(0.f, 0.f, 0.f, -INFINITY);                // padding: never a candidate
     float4 pr1 = pr, pr2 = pr;
-    const int f_in = f;
     if (f >= 0) {
         const float *t = tri + (long long)f * 9;
         px = __ldg(t); py = __ldg(t + 1); pz = __ldg(t + 2);
@@ -366,7 +365,6 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
         // out of the sphere, which would otherwise become NaN and hide the node's other triplets
         if (!(fabs(px) + fabs(py) + fabs(pz) + fabs(cut) < (double)INFINITY)) { f = -1; px = py = pz = cut = 0; }
     }
-    (void)f_in;
     // centroid in float: WHERE the centre goes is a heuristic, the radius below is an upper bound for whatever centre
     float cx = (float)px, cy = (float)py, cz = (float)pz;            // 0 for padding lanes
     int cntv = f >= 0;
