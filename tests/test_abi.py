@@ -39,6 +39,14 @@ def test_version_errors_and_workspace_sizing(native):
     assert L.rrl_workspace_bytes(0, 1, 1, 1) == 0 and L.rrl_workspace_bytes(1, 0, 1, 1) == 0
     small, big = L.rrl_workspace_bytes(1, 1024, 1024, 20000), L.rrl_workspace_bytes(32, 1024, 1024, 15000)
     assert 0 < small < big < 4 << 30
+    # the radix-sort scratch of clouds above 4096 triplets covers every cloud of up to 512 pairs (one sort per batch):
+    # it grows with the batch up to that cap and the whole workspace stays linear in triplets and lines
+    one, eight = L.rrl_workspace_bytes(1, 8192, 8192, 1000), L.rrl_workspace_bytes(8, 8192, 8192, 1000)
+    fixed = 4 << 20                                                           # CUB's temporary storage allowance
+    assert 7 * (one - fixed) < eight - fixed < 9 * (one - fixed)
+    large = L.rrl_workspace_bytes(1, 500000, 500000, 100000)
+    assert 100 << 20 < large < 200 << 20
+    assert L.rrl_workspace_bytes(1, 500000, 300, 100000) < large              # ragged pair: sized per cloud
     assert L.rrl_sampler_workspace_bytes(1, 20000, 10) >= 200000
     # null pointers / bad windows are rejected before anything touches a device
     assert L.rrl_loss_forward(None, None, None, 1, 8, 8, 8, 1, 1, 5, 5, None, 0, None, None, None, None, None) == -1
