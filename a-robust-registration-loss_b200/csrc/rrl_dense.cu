@@ -6,19 +6,24 @@
 //
 //   prep_kernel    per triplet: exact threshold thr_f (reference op order, IEEE sqrt) and the cloud's max |p|^2;
 //                  per line: the filter constants {u, |x0|, M, c} in double precision, the pair's max |x0|^2;
-//                  zeroes the per-line hit counters.
-//   sort kernels   Hilbert-curve order of every cloud's points (one CTA bitonic sort up to 4096 triplets, CUB radix sort
-//                  above) so that kNode consecutive triplets are spatial neighbours.
+//                  zeroes the per-line hit counters.  NaN / infinite inputs stay out of the extents and raise a flag.
+//   sort kernels   Hilbert-curve order of every cloud's points (a register bitonic sort inside small_prep_kernel up
+//                  to 4096 triplets; above, ONE CUB radix sort over every cloud of every pair) so that kNode
+//                  consecutive triplets are spatial neighbours; kd_refine64 re-partitions windows of 64 sorted
+//                  triplets into k-d leaves of kNode (small clouds).
 //   node_kernel    per node of kNode sorted triplets: bounding sphere (centre q, radius R covering every
-//                  triplet's hit cylinder) -> node record float4(q, R^2 - |q|^2); per triplet the point record
-//                  float4(p0, cut_f - |p0|^2) in sorted order.
-//   dense_kernel   streams tiles of NODE records through shared memory with 1-D TMA bulk copies
+//                  triplet's hit cylinder, upper bounds in float with directed rounding) -> node record
+//                  float4(q, R^2 - |q|^2); per triplet the point record float4(p0, cut_f - |p0|^2) in sorted
+//                  order; from 16384 triplets on also one SUPER-node record per 256 sorted triplets.
+//   small_prep_kernel  all of the above in one launch for clouds up to 4096 triplets.
+//   dense_kernel   streams tiles of node (or super-node) records through shared memory with 1-D TMA bulk copies
 //                  (cp.async.bulk + mbarrier, double buffered) against register-resident lines.  7 packed FP32
-//                  ops (FFMA2) decide per (line, node) whether the line can touch the node's sphere; results
-//                  are accumulated branch-free into per-line bit masks and pushed (ordered, by warp scans) to
-//                  warp-private queues; three further levels -- node predicate, triplet predicate, EXACT
-//                  reference-order test of all three points -- each run one queue entry per lane with converged
-//                  warps.  Confirmed hits go to fixed-capacity per-line slots.
+//                  ops (FFMA2) decide per (line, record) whether the line can touch the sphere; results are
+//                  accumulated branch-free into per-line bit masks and pushed (ordered, by warp scans) to
+//                  warp-private queues; further levels -- node predicate, triplet predicate, refine on points 1
+//                  and 2 -- each run one queue entry per lane with converged warps.
+//   exact_kernel   the EXACT reference-order test of all three points of every surviving (line, triplet) pair;
+//                  confirmed hits go to fixed-capacity per-line slots.
 //
 // Both filters are superset tests ("filtered predicate"); the decision itself is always taken by the
 // literal arithmetic of loss.py:84-110, so the selected indices are bit-exact against the oracle.
