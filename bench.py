@@ -497,6 +497,32 @@ def run_gpu(args):
                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback: the pool's measured 6552.3 GB/s",
                        "traffic": traffic}
 
+    # ---- lines sampled on the device instead of supplied (SURVEY 8(d) asks for both; the sampler stays out of the
+    # roofline figure): device time of rrl_sample_lines for one batch of the workload, and the step rate with it ----
+    sampled = None
+    try:
+        v1 = t1.reshape(t1.shape[0], -1, 9)[:, :, :3].contiguous()           # the clouds = point 0 of every triplet
+        v2 = t2.reshape(t2.shape[0], -1, 9)[:, :, :3].contiguous()
+        lo2, hi2 = v2.min(1)[0], v2.max(1)[0]
+        rad = (hi2 - lo2).norm(dim=1, keepdim=True) * float(kw.get("radius_scale", 0.5))
+        cen = v2.mean(1)
+        for _ in range(3):
+            lines_s, filled = rrl_b200.sample_lines(rad, cen, nl_local, v1, v2, seed=11, offset=0)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s0.record()
+        for it in range(20):
+            lines_s, filled = rrl_b200.sample_lines(rad, cen, nl_local, v1, v2, seed=11, offset=it + 1)
+        s1.record()
+        torch.cuda.synchronize()
+        smp_ms = s0.elapsed_time(s1) / 20
+        sampled = {"sampler_ms_per_batch": smp_ms, "filled_fraction": float(filled.float().mean().item()) / nl_local,
+                   "value_with_sampling": pairs_lines_per_step / ((ms_per_step + smp_ms) * 1e-3), "unit": "pairs*lines/s",
+                   "note": "rrl_sample_lines (Philox4x32-10, 10 rounds, 12-triangle AABB test of loss.py:265-432) timed alone on "
+                           "this rank's batch; value_with_sampling = the step with the sampler in front of it"}
+    except Exception as exc:
+        sampled = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     cpu = cpu_baseline(args.workload, inputs=host_sets[0]) if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": "loss fwd+bwd evaluations/s (pairs x lines per second)", "value": value, "unit": "pairs*lines/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -511,6 +537,7 @@ def run_gpu(args):
                        "l2": "inputs rotate over %d distinct sets (%.0f MB > 126 MB L2), no flush needed" %
                              (n_sets, n_sets * bytes_per_set / 2 ** 20)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "lines_sampled_on_device": sampled,
             "loss_checksum": float(last[0].item())}
     print(json.dumps(line), flush=True)
     if world > 1:
