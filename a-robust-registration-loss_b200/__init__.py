@@ -13,7 +13,7 @@ The directory name carries a hyphen, so import it through the repo-root shim:  `
 """
 from . import _native
 from ._native import NativeError, launch_count
-from .ops import (LossInfo, chamfer, intersected_line_loss, rigid_apply, sample_lines, se3_apply, se3_exp)
+from .ops import (LossInfo, LossSession, chamfer, intersected_line_loss, rigid_apply, sample_lines, se3_apply, se3_exp)
 from . import loss  # noqa: E402  (reference-compatible names)
 from . import dist  # noqa: E402
 from . import prep  # noqa: E402

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("RRL_LIB_PATH") or os.path.join(_HERE, "librrl_b200.so
 HIT_CAP = 5
 NSTAT = 8
 STATUS_EMPTY, STATUS_NAN, STATUS_NAN_RISK = 1, 2, 4
+REUSE_ORDER = 1                  # RRL_REUSE_ORDER flag of rrl_loss_forward_ex / rrl_shard_stage1_ex
 
 _lib = None
 
@@ -35,6 +36,8 @@ def lib():
         "rrl_launch_count": (cl, []),
         "rrl_workspace_bytes": (cz, [ci, ci, ci, ci]),
         "rrl_loss_forward": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, cz, vp, vp, vp, vp, vp]),
+        "rrl_loss_forward_ex": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, cz, vp, vp, vp, vp, ci, vp]),
+        "rrl_shard_stage1_ex": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, cz, ci, vp]),
         "rrl_loss_backward": (ci, [vp, cz, vp, ci, ci, ci, ci, vp, vp, vp]),
         "rrl_loss_export_hits": (ci, [vp, cz, ci, ci, ci, ci, ci, vp, vp, vp]),
         "rrl_shard_stage1": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, cz, vp]),
@@ -81,6 +84,7 @@ def lib():
 
 
 EXPORTED = ["rrl_version", "rrl_error_string", "rrl_launch_count", "rrl_workspace_bytes", "rrl_loss_forward",
+            "rrl_loss_forward_ex", "rrl_shard_stage1_ex",
             "rrl_loss_backward", "rrl_loss_export_hits", "rrl_shard_stage1", "rrl_shard_counts",
             "rrl_shard_pack_entries", "rrl_select_lower_median", "rrl_shard_select_hist", "rrl_shard_select_pick",
             "rrl_shard_stage2", "rrl_shard_stage3",

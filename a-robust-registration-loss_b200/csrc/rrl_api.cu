@@ -101,9 +101,9 @@ static Geometry make_geometry(int B, int nf1, int nf2, int nl) {
 }
 
 static int stage_dense_and_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws,
-                                 const Geometry &g, int k_lo, int j_lo, int k_hi, int j_hi, cudaStream_t s) {
+                                 const Geometry &g, int k_lo, int j_lo, int k_hi, int j_hi, int flags, cudaStream_t s) {
     const int window = k_lo | (j_lo << 8) | (k_hi << 16) | (j_hi << 24);
-    int rc = launch_prep(tri1, tri2, lines, ws, g, window, s);
+    int rc = launch_prep(tri1, tri2, lines, ws, g, window, (flags & RRL_REUSE_ORDER) != 0, s);
     if (rc) return rc;
     rc = launch_dense(tri1, tri2, lines, ws, g, s);
     if (rc) return rc;
@@ -134,22 +134,28 @@ extern "C" size_t rrl_workspace_bytes(int B, int nf1, int nf2, int nl) {
     return carve(nullptr, B, nf1, nf2, nl).bytes;
 }
 
-extern "C" int rrl_loss_forward(const float *tri1, const float *tri2, const float *lines, int B, int nf1, int nf2, int nl,
-                                int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes,
-                                float *out_loss, int *out_status, float *out_median, long long *out_stats, void *stream) {
+extern "C" int rrl_loss_forward_ex(const float *tri1, const float *tri2, const float *lines, int B, int nf1, int nf2, int nl,
+                                   int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes,
+                                   float *out_loss, int *out_status, float *out_median, long long *out_stats, int flags,
+                                   void *stream) {
     if (!tri1 || !tri2 || !lines || !workspace || !out_loss) return RRL_ERR_ARG;
     if (!geometry_ok(B, nf1, nf2, nl) || !window_ok(k_lo, j_lo, k_hi, j_hi)) return RRL_ERR_ARG;
+    if (flags & ~RRL_REUSE_ORDER) return RRL_ERR_ARG;
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return RRL_ERR_ARG;
     const Workspace ws = carve(workspace, B, nf1, nf2, nl);
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
     const Geometry g = make_geometry(B, nf1, nf2, nl);
     cudaStream_t s = (cudaStream_t)stream;
-    const int window = k_lo | (j_lo << 8) | (k_hi << 16) | (j_hi << 24);
-    int rc = launch_prep(tri1, tri2, lines, ws, g, window, s);
+    int rc = stage_dense_and_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, flags, s);
     if (rc) return rc;
-    if ((rc = launch_dense(tri1, tri2, lines, ws, g, s))) return rc;
-    if ((rc = launch_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, s))) return rc;
     return launch_tail(ws, g, out_loss, out_status, out_median, out_stats, s);
+}
+
+extern "C" int rrl_loss_forward(const float *tri1, const float *tri2, const float *lines, int B, int nf1, int nf2, int nl,
+                                int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes,
+                                float *out_loss, int *out_status, float *out_median, long long *out_stats, void *stream) {
+    return rrl_loss_forward_ex(tri1, tri2, lines, B, nf1, nf2, nl, k_lo, j_lo, k_hi, j_hi, workspace, workspace_bytes, out_loss,
+                               out_status, out_median, out_stats, 0, stream);
 }
 
 extern "C" int rrl_loss_backward(const void *workspace, size_t workspace_bytes, const float *grad_out, int B, int nf1,
@@ -170,14 +176,22 @@ extern "C" int rrl_loss_export_hits(const void *workspace, size_t workspace_byte
 }
 
 // ---- line-shard stages (B = 1) -------------------------------------------------------------------------
-extern "C" int rrl_shard_stage1(const float *tri1, const float *tri2, const float *lines, int nf1, int nf2, int nl,
-                                int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int rrl_shard_stage1_ex(const float *tri1, const float *tri2, const float *lines, int nf1, int nf2, int nl,
+                                   int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes, int flags,
+                                   void *stream) {
     if (!tri1 || !tri2 || !lines || !workspace) return RRL_ERR_ARG;
     if (!geometry_ok(1, nf1, nf2, nl) || !window_ok(k_lo, j_lo, k_hi, j_hi)) return RRL_ERR_ARG;
+    if (flags & ~RRL_REUSE_ORDER) return RRL_ERR_ARG;
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return RRL_ERR_ARG;
     const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
-    return stage_dense_and_build(tri1, tri2, lines, ws, make_geometry(1, nf1, nf2, nl), k_lo, j_lo, k_hi, j_hi, (cudaStream_t)stream);
+    return stage_dense_and_build(tri1, tri2, lines, ws, make_geometry(1, nf1, nf2, nl), k_lo, j_lo, k_hi, j_hi, flags,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int rrl_shard_stage1(const float *tri1, const float *tri2, const float *lines, int nf1, int nf2, int nl,
+                                int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes, void *stream) {
+    return rrl_shard_stage1_ex(tri1, tri2, lines, nf1, nf2, nl, k_lo, j_lo, k_hi, j_hi, workspace, workspace_bytes, 0, stream);
 }
 
 extern "C" int rrl_shard_counts(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl, long long *counts18, void *stream) {
@@ -428,7 +442,7 @@ extern "C" int rrl_measure_dense(const float *tri1, const float *tri2, const flo
     int rc = RRL_OK;
     for (int it = 0; it < iters + 1 && rc == RRL_OK; ++it) {
         cudaEventRecord(e0, s);
-        rc = launch_prep(tri1, tri2, lines, ws, g, 1 | (1 << 8) | (5 << 16) | (5 << 24), s);
+        rc = launch_prep(tri1, tri2, lines, ws, g, 1 | (1 << 8) | (5 << 16) | (5 << 24), 0, s);
         cudaEventRecord(e1, s);
         if (rc == RRL_OK) rc = launch_dense(tri1, tri2, lines, ws, g, s);
         cudaEventRecord(e2, s);

@@ -103,7 +103,7 @@ void stage_mark(int stage, cudaStream_t s);   // measurement hook: records an ev
 
 // ---- stage launchers (rrl_dense.cu, rrl_sparse.cu) ------------------------------------------------------
 int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
-                int window, cudaStream_t s);
+                int window, int reuse_order, cudaStream_t s);
 int launch_bruteforce(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                       int force, cudaStream_t s);
 int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s);

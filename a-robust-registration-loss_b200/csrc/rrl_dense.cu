@@ -592,7 +592,7 @@ __device__ __forceinline__ void line_constants(const float *__restrict__ ln, flo
 template <int kNode>
 __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
                                                           const float *__restrict__ lines, Workspace ws, Geometry g, int window,
-                                                          int sorted, int line_blocks, int ball_iters, int refine) {
+                                                          int sorted, int line_blocks, int ball_iters, int refine, int reuse) {
     extern __shared__ unsigned long long skeys[];
     __shared__ unsigned s_red[3];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -661,6 +661,16 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     const float P = sqrtf(__uint_as_float(s_red[0]));
     const int E = nfp <= 1024 ? 1 : (nfp <= 2048 ? 2 : 4);
     unsigned long long v[4];
+    int *perm = ws.perm[cloud] + (long long)b * nfp;
+    if (reuse) {
+        // RRL_REUSE_ORDER: the workspace holds the order of a previous forward of this geometry.  ANY permutation is a
+        // valid order (it only decides which triplets share a node); a rigidly moved cloud keeps a good one.
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = e * 1024 + tid;
+            v[e] = (e < E && i < nfp) ? (unsigned long long)(unsigned)perm[i] : 0xFFFFFFFFull;
+        }
+    } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int i = e * 1024 + tid;
@@ -671,7 +681,8 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
             v[e] = ((unsigned long long)key << 32) | (unsigned)i;
         }
     }
-    if (sorted) {
+    }
+    if (sorted && !reuse) {
         auto cas = [](unsigned long long &lo_el, unsigned long long &hi_el, bool up) {      // lo_el has the lower index
             const unsigned long long mn = lo_el < hi_el ? lo_el : hi_el, mx = lo_el < hi_el ? hi_el : lo_el;
             lo_el = up ? mn : mx;
@@ -717,7 +728,6 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
                 }
             }
     }
-    int *perm = ws.perm[cloud] + (long long)b * nfp;
     const int nnodes = nfp / kNode;
     const float Eslack = node_slack(s_red[0], s_red[1]);
     __syncthreads();                                     // thr (global) is re-read below by other threads; sort buffers are dead
@@ -732,7 +742,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         }
     }
     __syncthreads();
-    if (sorted && refine) {
+    if (sorted && refine && !reuse) {
         __shared__ float4 s_kd[32][64];
         const int lane = tid & 31, wid = tid >> 5;
         for (int w = wid; w < nfp / 64; w += 32) {
@@ -789,7 +799,7 @@ static int g_dense_variant = 1;        // 1 = Morton-sorted nodes (default), 0 =
 void set_dense_variant(int v) { g_dense_variant = v; }
 
 int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
-                int window, cudaStream_t s) {
+                int window, int reuse_order, cudaStream_t s) {
     const int sorted = g_dense_variant ? 1 : 0;
     const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
     const int G = node_size(g);
@@ -805,8 +815,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
                 return RRL_ERR_CUDA;
             attr_set = true;
         }
-        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10]);
-        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10]);
+        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order);
+        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order);
         count_launch();
         stage_mark(1, s);
         stage_mark(2, s);
@@ -824,7 +834,9 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     prep_kernel<<<dim3(bx, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, window);
     count_launch();
     stage_mark(1, s);
-    if (nfp_max <= kSortSmall) {
+    if (reuse_order) {
+        // RRL_REUSE_ORDER: perm[] of the previous forward of this geometry stays as it is (see small_prep_kernel)
+    } else if (nfp_max <= kSortSmall) {
         int n2 = 1;
         while (n2 < nfp_max) n2 <<= 1;
         sort_small_kernel<<<dim3(g.B, 2), 1024, (size_t)n2 * 8, s>>>(tri1, tri2, ws, g, sorted);
@@ -868,7 +880,7 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
             }
         }
     }
-    if (sorted && g_param[10] == 2) {              // measured on the large path: costs more (33 us) than it saves; A/B only
+    if (sorted && g_param[10] == 2 && !reuse_order) {   // measured on the large path: costs more (33 us) than it saves; A/B only
         int rbx = nfp_max / 64 / 8;
         if (rbx > 2048) rbx = 2048;
         if (rbx < 1) rbx = 1;

@@ -64,13 +64,16 @@ def gather_entries(local: torch.Tensor, n_local: int, counts: List[int], group=N
 class NativeShardBackend:
     """The per-rank stages of the line-sharded evaluation on the C ABI (include/rrl_b200.h, rrl_shard_*)."""
 
-    def __init__(self, tri1, tri2, lines_local, window):
+    def __init__(self, tri1, tri2, lines_local, window, session=None):
         self.L = N.lib()
         self.dev = tri1.device
         self.nf1, self.nf2, self.nl = tri1.shape[0], tri2.shape[0], lines_local.shape[0]
         self.tri1, self.tri2, self.lines, self.window = tri1, tri2, lines_local, window
         self.wsb = self.L.rrl_workspace_bytes(1, self.nf1, self.nf2, self.nl)
-        self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=self.dev)
+        if session is not None:                 # ops.LossSession: the clouds' spatial order survives from call to call
+            self.ws, self.flags = session.acquire((1, self.nf1, self.nf2, self.nl), self.dev, self.wsb)
+        else:
+            self.ws, self.flags = torch.empty(self.wsb, dtype=torch.uint8, device=self.dev), 0
 
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
@@ -80,9 +83,9 @@ class NativeShardBackend:
 
     def stage1_counts(self):
         w = self.window
-        N.check(self.L.rrl_shard_stage1(self.tri1.data_ptr(), self.tri2.data_ptr(), self.lines.data_ptr(), self.nf1,
-                                        self.nf2, self.nl, w[0], w[1], w[2], w[3], self.ws.data_ptr(), self.wsb,
-                                        self._stream()), "rrl_shard_stage1")
+        N.check(self.L.rrl_shard_stage1_ex(self.tri1.data_ptr(), self.tri2.data_ptr(), self.lines.data_ptr(), self.nf1,
+                                           self.nf2, self.nl, w[0], w[1], w[2], w[3], self.ws.data_ptr(), self.wsb,
+                                           self.flags, self._stream()), "rrl_shard_stage1_ex")
         counts = torch.empty(18, dtype=torch.int64, device=self.dev)
         N.check(self.L.rrl_shard_counts(*self._geom(), counts.data_ptr(), self._stream()), "rrl_shard_counts")
         return counts
@@ -144,8 +147,8 @@ def line_shard_forward(backend, group=None):
 
 class _LineShardedLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tri1, tri2, lines_local, window, group, reduce_grad):
-        backend = NativeShardBackend(tri1, tri2, lines_local, window)
+    def forward(ctx, tri1, tri2, lines_local, window, group, reduce_grad, session=None):
+        backend = NativeShardBackend(tri1, tri2, lines_local, window, session)
         loss, status, med = line_shard_forward(backend, group)
         ctx.ws, ctx.geom, ctx.group, ctx.reduce_grad = backend.ws, (backend.nf1, backend.nf2, backend.nl), group, reduce_grad
         ctx.mark_non_differentiable(status, med)
@@ -168,7 +171,7 @@ class _LineShardedLoss(torch.autograd.Function):
             for t in (g1, g2):
                 if t is not None:
                     dist_.all_reduce(t, op=dist_.ReduceOp.SUM, group=ctx.group)
-        return g1, g2, None, None, None, None
+        return g1, g2, None, None, None, None, None
 
 
 class _AllReduceGrad(torch.autograd.Function):
@@ -186,17 +189,17 @@ class _AllReduceGrad(torch.autograd.Function):
         return g, None
 
 
-def line_sharded_twist_loss(twist, raw_tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None):
+def line_sharded_twist_loss(twist, raw_tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, session=None):
     """The demo's / large-scan configuration: cloud 1 = se(3) transform of `raw_tri1` (nf1,9) by `twist` (6,), one pair,
     lines sharded.  The sparse point gradient of every rank's line shard is reduced to pose space locally (closed-form
     se(3) backward) and only the 6 twist-gradient floats cross NVLink.  Returns (loss (1,), status, median)."""
     from . import ops
     tw = _AllReduceGrad.apply(twist.reshape(1, 6), group)
     tri1 = ops.se3_apply(tw, raw_tri1.reshape(1, -1, 3)).reshape(-1, 9)
-    return line_sharded_loss(tri1, tri2, lines_local, window, group, reduce_grad=False)
+    return line_sharded_loss(tri1, tri2, lines_local, window, group, reduce_grad=False, session=session)
 
 
-def line_sharded_loss(tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, reduce_grad=True):
+def line_sharded_loss(tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, reduce_grad=True, session=None):
     """ONE pair: tri1 (nf1,9) and tri2 (nf2,9) replicated on every rank, lines_local (nl_r,6) = this rank's shard.
     Returns (loss (1,), status (1,), median (1,)) -- identical on all ranks; the point gradients are all-reduced unless
     reduce_grad=False (then each rank keeps the gradient of its own line shard)."""
@@ -205,4 +208,4 @@ def line_sharded_loss(tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, 
         raise RuntimeError("line_sharded_loss needs an initialised torch.distributed process group")
     w = tuple(int(v) for v in window)
     return _LineShardedLoss.apply(_cuda_f32(tri1, "points1"), _cuda_f32(tri2, "points2"),
-                                  _cuda_f32(lines_local.detach(), "line"), w, group, bool(reduce_grad))
+                                  _cuda_f32(lines_local.detach(), "line"), w, group, bool(reduce_grad), session)

@@ -54,11 +54,34 @@ class LossInfo:
         return counts, hits
 
 
+class LossSession:
+    """Keeps the workspace of ONE geometry alive across calls, so that the spatial order of both clouds computed by
+    one forward is reused by the next (RRL_REUSE_ORDER, include/rrl_b200.h): the steps of a registration loop, the
+    iterations of RPM-Net / FMR on one batch.  Any order gives the same results; a cloud that moved rigidly keeps a good
+    one.  The backward of a call must run before the next forward on the same session (they share the workspace).
+    `reset()` forces a fresh sort (e.g. when the clouds were replaced by different ones)."""
+
+    def __init__(self):
+        self._ws, self._key, self._ready = None, None, False
+
+    def reset(self):
+        self._ready = False
+
+    def acquire(self, geom, dev, nbytes):
+        key = (tuple(geom), str(dev), int(nbytes))
+        if self._ws is None or self._key != key:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._key, self._ready = key, False
+        flags = N.REUSE_ORDER if self._ready else 0
+        self._ready = True                      # the forward about to be queued leaves a complete order behind
+        return self._ws, flags
+
+
 class _IntersectedLineLoss(torch.autograd.Function):
     """loss[b] = reference loss of pair b (loss.py:170-232 on the B=1 slice); lines carry no gradient."""
 
     @staticmethod
-    def forward(ctx, tri1, tri2, lines, window, holder):
+    def forward(ctx, tri1, tri2, lines, window, holder, session=None):
         B, nf1, _ = tri1.shape
         nf2, nl = tri2.shape[1], lines.shape[1]
         dev = tri1.device
@@ -66,15 +89,18 @@ class _IntersectedLineLoss(torch.autograd.Function):
         ws_bytes = L.rrl_workspace_bytes(B, nf1, nf2, nl)
         if ws_bytes == 0:
             raise ValueError("unsupported geometry B=%d nf1=%d nf2=%d nl=%d" % (B, nf1, nf2, nl))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if session is not None:
+            ws, flags = session.acquire((B, nf1, nf2, nl), dev, ws_bytes)
+        else:
+            ws, flags = torch.empty(ws_bytes, dtype=torch.uint8, device=dev), 0
         loss = torch.empty(B, dtype=torch.float32, device=dev)
         status = torch.empty(B, dtype=torch.int32, device=dev)
         median = torch.empty(B, dtype=torch.float32, device=dev)
         stats = torch.empty(B, N.NSTAT, dtype=torch.int64, device=dev)
-        N.check(L.rrl_loss_forward(tri1.data_ptr(), tri2.data_ptr(), lines.data_ptr(), B, nf1, nf2, nl,
-                                   window[0], window[1], window[2], window[3], ws.data_ptr(), ws_bytes,
-                                   loss.data_ptr(), status.data_ptr(), median.data_ptr(), stats.data_ptr(),
-                                   _stream(tri1)), "rrl_loss_forward")
+        N.check(L.rrl_loss_forward_ex(tri1.data_ptr(), tri2.data_ptr(), lines.data_ptr(), B, nf1, nf2, nl,
+                                      window[0], window[1], window[2], window[3], ws.data_ptr(), ws_bytes,
+                                      loss.data_ptr(), status.data_ptr(), median.data_ptr(), stats.data_ptr(), flags,
+                                      _stream(tri1)), "rrl_loss_forward_ex")
         ctx.ws = ws
         ctx.geom = (B, nf1, nf2, nl)
         ctx.mark_non_differentiable(status, median, stats)
@@ -93,15 +119,16 @@ class _IntersectedLineLoss(torch.autograd.Function):
         N.check(N.lib().rrl_loss_backward(ws.data_ptr(), ws.numel(), g.data_ptr(), B, nf1, nf2, nl,
                                           g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None,
                                           _stream(ws)), "rrl_loss_backward")
-        return g1, g2, None, None, None
+        return g1, g2, None, None, None, None
 
 
 def intersected_line_loss(tri1: torch.Tensor, tri2: torch.Tensor, lines: torch.Tensor,
-                          window=(1, 1, 5, 5), return_info: bool = False):
+                          window=(1, 1, 5, 5), return_info: bool = False, session: Optional[LossSession] = None):
     """Batched native API: tri1 (B,nf1,9), tri2 (B,nf2,9), lines (B,nl,6) -> per-pair losses (B,).
 
     `window` = the reference's (s_m, s_n, e_m, e_n).  Differentiable w.r.t. tri1 and tri2.
     A pair with no populated (k,j) combo yields loss 0 with zero gradient and status bit RRL_STATUS_EMPTY.
+    `session`: a LossSession that carries the clouds' spatial order from call to call (see there).
     """
     for name, t, last in (("points1", tri1, 9), ("points2", tri2, 9), ("line", lines, 6)):
         if t.dim() != 3 or t.shape[-1] != last:
@@ -114,7 +141,7 @@ def intersected_line_loss(tri1: torch.Tensor, tri2: torch.Tensor, lines: torch.T
     tri1, tri2 = _cuda_f32(tri1, "points1"), _cuda_f32(tri2, "points2")
     lines = _cuda_f32(lines.detach(), "line")
     holder = [] if return_info else None
-    loss, _, _, _ = _IntersectedLineLoss.apply(tri1, tri2, lines, w, holder)
+    loss, _, _, _ = _IntersectedLineLoss.apply(tri1, tri2, lines, w, holder, session)
     return (loss, holder[0]) if return_info else loss
 
 

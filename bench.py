@@ -291,16 +291,21 @@ def run_gpu(args):
     twist_mode = args.workload == "large"          # the scan pair is evaluated through the se(3) twist
     twist0 = torch.tensor([0.01, -0.02, 0.015, 0.03, -0.01, 0.02], device=dev)
 
+    # --reuse-order (twist-mode workloads = registration loops on a fixed pair): every input set keeps a LossSession, so
+    # each step after the first reuses the spatial order of both clouds left by the previous step on that pair
+    sessions = [rrl_b200.LossSession() for _ in range(n_sets)] if (twist_mode and args.reuse_order) else None
+
     def compute(i):
         """the device work of one step on input set i: forward + backward (for the line shard: with its exchange)"""
         t1, t2, ln = dev_sets[i % n_sets]
         if twist_mode:
             tw = twist0.clone().requires_grad_(True)
+            sess = sessions[i % n_sets] if sessions else None
             if line_sharded:
-                loss, _, _ = rrl_b200.dist.line_sharded_twist_loss(tw, t1[0], t2[0], ln[0])
+                loss, _, _ = rrl_b200.dist.line_sharded_twist_loss(tw, t1[0], t2[0], ln[0], session=sess)
             else:
                 tri1 = rrl_b200.se3_apply(tw.reshape(1, 6), t1.reshape(1, -1, 3)).reshape(1, -1, 9)
-                loss = rrl_b200.intersected_line_loss(tri1, t2, ln)
+                loss = rrl_b200.intersected_line_loss(tri1, t2, ln, session=sess)
             total = loss.sum()
             total.backward()
             return total.detach(), tw.grad
@@ -534,6 +539,7 @@ def run_gpu(args):
                        "backward": "d loss / d twist (6) through the fused se(3) transform of cloud 1" if twist_mode
                                    else "d loss / d points1 (B, nf, 9)",
                        "launch": ("one CUDA graph per input set" if graphs else "eager launches"),
+                       "reuse_order": bool(sessions),
                        "l2": "inputs rotate over %d distinct sets (%.0f MB > 126 MB L2), no flush needed" %
                              (n_sets, n_sets * bytes_per_set / 2 ** 20)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -554,6 +560,8 @@ def main():
     ap.add_argument("--workload", default="dcp", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the device work of a step as a CUDA graph (one per input set); 0: eager launches")
+    ap.add_argument("--reuse-order", type=int, default=0,
+                    help="twist-mode workloads: 1 = keep the clouds' spatial order from step to step (RRL_REUSE_ORDER)")
     ap.add_argument("--large-scaling", default="strong", choices=["strong", "weak"],
                     help="workload large at N > 1: strong = the 100k lines of the pair are split over the ranks (BASELINE "
                          "configs[4]); weak = every rank keeps 100k lines of a pair with N x 100k lines")

@@ -82,6 +82,21 @@ int rrl_loss_forward(const float *tri1, const float *tri2, const float *lines,
                      void *stream);
 
 /*
+ * Forward with flags.  RRL_REUSE_ORDER: `workspace` holds a completed forward of the SAME geometry (B, nf1, nf2, nl);
+ * the spatial order of both clouds computed then is kept and the sort stage is skipped.  Any order gives the same
+ * results (it only decides which triplets share a bounding sphere), so this is safe for clouds that changed -- and
+ * pays when they changed little: the steps of a registration loop (the target is fixed, the source moves rigidly:
+ * test_demo_optimized_Lie_Algebra.py:46-66) or the iterations of RPM-Net / FMR on one batch.
+ */
+#define RRL_REUSE_ORDER 1
+int rrl_loss_forward_ex(const float *tri1, const float *tri2, const float *lines,
+                        int B, int nf1, int nf2, int nl,
+                        int k_lo, int j_lo, int k_hi, int j_hi,
+                        void *workspace, size_t workspace_bytes,
+                        float *out_loss, int *out_status, float *out_median, long long *out_stats,
+                        int flags, void *stream);
+
+/*
  * Backward of the forward held in `workspace` (autograd of loss.py:170-232; closed form SURVEY 9.1).
  * grad_out [B] is d(total)/d(out_loss[b]).  grad_tri1 (B,nf1,9) / grad_tri2 (B,nf2,9) are overwritten
  * (zero where no selected line touches a triplet); either may be NULL when not needed.
@@ -112,6 +127,10 @@ int rrl_loss_export_hits(const void *workspace, size_t workspace_bytes, int B, i
  */
 int rrl_shard_stage1(const float *tri1, const float *tri2, const float *lines, int nf1, int nf2, int nl,
                      int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes, void *stream);
+/* stage 1 with the flags of rrl_loss_forward_ex (RRL_REUSE_ORDER) */
+int rrl_shard_stage1_ex(const float *tri1, const float *tri2, const float *lines, int nf1, int nf2, int nl,
+                        int k_lo, int j_lo, int k_hi, int j_hi, void *workspace, size_t workspace_bytes, int flags,
+                        void *stream);
 int rrl_shard_counts(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl, long long *counts18,
                      void *stream);
 int rrl_shard_pack_entries(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,

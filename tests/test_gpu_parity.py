@@ -432,6 +432,34 @@ def test_super_node_level_with_degenerate_lines_and_without(rrl):
     assert out["loss"] == flat["loss"] and out["median"] == flat["median"]
 
 
+@pytest.mark.parametrize("nf,nl", [(900, 1500), (20000, 1200)])
+def test_reused_order_gives_identical_results(rrl, nf, nl):
+    """RRL_REUSE_ORDER (LossSession): the second call keeps the spatial order of the first.  Any order must give the
+    same indices, median and loss -- for the same clouds, for a rigidly moved source, and even for a different pair of
+    the same geometry (the order is then merely a bad one); small-cloud and large-cloud launch plans."""
+    p = synth.make_pair(171, nf, nl)
+    q = synth.make_pair(172, nf, nl)
+    rng = np.random.default_rng(7)
+    Rm = synth.random_rotation(rng, 5.0)
+    moved = (p["tri1"].reshape(-1, 3).astype(np.float64) @ Rm.T + 0.02).astype(np.float32).reshape(-1, 9)
+    sess = rrl.LossSession()
+    for tri1, tri2, lines in ((p["tri1"], p["tri2"], p["lines"]), (p["tri1"], p["tri2"], p["lines"]),
+                              (moved, p["tri2"], p["lines"]), (q["tri1"], q["tri2"], q["lines"])):
+        t1 = torch.from_numpy(tri1).cuda()[None].requires_grad_(True)
+        t2 = torch.from_numpy(tri2).cuda()[None]
+        ln = torch.from_numpy(lines).cuda()[None]
+        loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True, session=sess)
+        loss.sum().backward()
+        c1, h1 = (x[0].cpu().numpy() for x in info.hits(1))
+        c2, h2 = (x[0].cpu().numpy() for x in info.hits(2))
+        orc = co.loss(tri1, tri2, lines)
+        assert np.array_equal(c1, orc.counts1) and np.array_equal(c2, orc.counts2)
+        assert np.array_equal(h1[orc.counts1 <= co.CAP], orc.hits1[orc.counts1 <= co.CAP])
+        assert float(info.median[0]) == orc.median
+        assert abs(loss.item() - orc.loss) <= REL_TOL * orc.loss
+        assert _rel(t1.grad[0].cpu().numpy(), orc.grad1) <= REL_TOL
+
+
 def test_full_size_large_pair_properties(rrl):
     """BASELINE config 5 at full size (500k triplets x 100k lines): the oracle checks a sample of the lines completely,
     the on-device brute-force kernel (every (line, triplet) tested exactly, the reference's formulation) checks all of
