@@ -128,17 +128,24 @@ class NativeShardBackend:
 
 def line_shard_forward(backend, group=None):
     """The exchange protocol of SURVEY 8(e), independent of where the stages run (the CPU tests drive it with an
-    oracle-backed backend over gloo).  Four small all-reduces, nothing read by the host, nothing of variable length:
+    oracle-backed backend over gloo).  Three small all-reduces, nothing read by the host, nothing of variable length:
     the 18 counts, two 65536-bin key histograms (distributed lower median: high then low 16 bits of the float bit
     pattern), the 32 fixed-point partial sums."""
-    gcounts = backend.stage1_counts()
-    dist_.all_reduce(gcounts, op=dist_.ReduceOp.SUM, group=group)
-    state = torch.zeros(2, dtype=torch.int64, device=gcounts.device)
-    med = torch.zeros(1, dtype=torch.float32, device=gcounts.device)
-    for rnd in (0, 1):
-        hist = backend.select_hist(rnd, state)
-        dist_.all_reduce(hist, op=dist_.ReduceOp.SUM, group=group)
-        backend.select_pick(rnd, hist, gcounts, state, med)
+    lcounts = backend.stage1_counts()
+    state = torch.zeros(2, dtype=torch.int64, device=lcounts.device)
+    med = torch.zeros(1, dtype=torch.float32, device=lcounts.device)
+    # the first histogram does not depend on the global counts (only the pick does): counts and histogram share ONE
+    # all-reduce (int64 payload: the 18 counts behind the 65536 bins)
+    hist0 = backend.select_hist(0, state)
+    buf = torch.empty(65536 + 18, dtype=torch.int64, device=lcounts.device)
+    buf[:65536] = hist0
+    buf[65536:] = lcounts
+    dist_.all_reduce(buf, op=dist_.ReduceOp.SUM, group=group)
+    gcounts = buf[65536:].clone()
+    backend.select_pick(0, buf[:65536].to(torch.int32), gcounts, state, med)
+    hist = backend.select_hist(1, state)
+    dist_.all_reduce(hist, op=dist_.ReduceOp.SUM, group=group)
+    backend.select_pick(1, hist, gcounts, state, med)
     sums = backend.stage2_sums(gcounts, med)
     dist_.all_reduce(sums, op=dist_.ReduceOp.SUM, group=group)
     loss, status = backend.stage3_loss(sums)

@@ -7,7 +7,8 @@ sys.path.insert(0, ".")
 import rrl_b200
 from oracle import synth
 L = rrl_b200._native.lib()
-for name, (B, nf, nl, rs) in {"dcp": (32, 1024, 15000, 0.5), "large-lines": (1, 100000, 100000, 0.5)}.items():
+for name, (B, nf, nl, rs) in {"dcp": (32, 1024, 15000, 0.5), "dcp-wide-sphere": (32, 1024, 15000, 2.0),
+                              "large-lines": (1, 20000, 100000, 0.5)}.items():
     pairs = [synth.make_pair(1000 + i, nf, 256, radius_scale=rs) for i in range(min(B, 4))]
     idx = [i % len(pairs) for i in range(B)]
     v1 = torch.from_numpy(np.stack([pairs[i]["tri1"][:, :3] for i in idx])).cuda().contiguous()
