@@ -10,14 +10,16 @@ The directory name carries a hyphen, so import it through the repo-root shim:  `
     rrl_b200.dist                                          batch-/line-sharded multi-GPU evaluation
     rrl_b200.prep                                          farthest-point sampling + kNN triplets (Sample_neighs)
     rrl_b200.io                                            dataset file formats of the reference's DL loaders
+    rrl_b200.hooks                                         batched DCP / RPM-Net / FMR hook losses, FMR's se3.Exp
 """
 from . import _native
 from ._native import NativeError, launch_count
-from .ops import (LossInfo, LossSession, chamfer, intersected_line_loss, rigid_apply, sample_lines, se3_apply, se3_exp)
+from .ops import (LossInfo, LossSession, chamfer, intersected_line_loss, rigid_apply, sample_lines, se3_apply, se3_exp, se3_Exp)
 from . import loss  # noqa: E402  (reference-compatible names)
 from . import dist  # noqa: E402
 from . import prep  # noqa: E402
 from . import io  # noqa: E402
+from . import hooks  # noqa: E402
 
 __all__ = ["NativeError", "launch_count", "LossInfo", "chamfer", "intersected_line_loss", "rigid_apply",
-           "sample_lines", "se3_apply", "se3_exp", "loss", "dist", "prep", "io"]
+           "sample_lines", "se3_apply", "se3_exp", "se3_Exp", "loss", "dist", "prep", "io", "hooks"]

@@ -49,6 +49,8 @@ def lib():
         "rrl_shard_stage2": (ci, [vp, cz, ci, ci, ci, vp, vp, vp, vp]),
         "rrl_shard_stage3": (ci, [vp, cz, ci, ci, ci, vp, vp, vp, vp]),
         "rrl_se3_exp": (ci, [vp, ci, vp, vp, vp]),
+        "rrl_se3_exp4": (ci, [vp, ci, vp, vp]),
+        "rrl_se3_expmap_backward": (ci, [vp, vp, ci, vp, vp]),
         "rrl_se3_apply": (ci, [vp, vp, ci, ci, vp, vp]),
         "rrl_se3_apply_backward": (ci, [vp, vp, vp, ci, ci, vp, vp, vp]),
         "rrl_rigid_apply": (ci, [vp, vp, vp, ci, ci, vp, vp]),
@@ -56,6 +58,8 @@ def lib():
         "rrl_sampler_workspace_bytes": (cz, [ci, ci, ci]),
         "rrl_sample_lines": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, cull, cull, vp, vp, vp, vp, cz, vp]),
         "rrl_chamfer": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),
+        "rrl_chamfer_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp]),
+        "rrl_chamfer_backward": (ci, [vp, vp, vp, vp, ci, ci, ci, vp, vp, vp]),
         "rrl_fps_workspace_bytes": (cz, [ci]),
         "rrl_fps": (ci, [vp, ci, ci, ci, ci, vp, vp, cz, vp]),
         "rrl_knn": (ci, [vp, ci, ci, vp, ci, ci, vp, vp]),
@@ -88,8 +92,8 @@ EXPORTED = ["rrl_version", "rrl_error_string", "rrl_launch_count", "rrl_workspac
             "rrl_loss_backward", "rrl_loss_export_hits", "rrl_shard_stage1", "rrl_shard_counts",
             "rrl_shard_pack_entries", "rrl_select_lower_median", "rrl_shard_select_hist", "rrl_shard_select_pick",
             "rrl_shard_stage2", "rrl_shard_stage3",
-            "rrl_se3_exp", "rrl_se3_apply", "rrl_se3_apply_backward", "rrl_rigid_apply", "rrl_rigid_apply_backward",
-            "rrl_sampler_workspace_bytes", "rrl_sample_lines", "rrl_chamfer", "rrl_fps_workspace_bytes", "rrl_fps", "rrl_knn", "rrl_host_create", "rrl_host_destroy",
+            "rrl_se3_exp", "rrl_se3_exp4", "rrl_se3_expmap_backward", "rrl_se3_apply", "rrl_se3_apply_backward", "rrl_rigid_apply", "rrl_rigid_apply_backward",
+            "rrl_sampler_workspace_bytes", "rrl_sample_lines", "rrl_chamfer", "rrl_chamfer_forward", "rrl_chamfer_backward", "rrl_fps_workspace_bytes", "rrl_fps", "rrl_knn", "rrl_host_create", "rrl_host_destroy",
             "rrl_host_pinned_tri1", "rrl_host_pinned_tri2", "rrl_host_pinned_lines", "rrl_host_subbatches", "rrl_host_loss_fwd_bwd",
             "rrl_host_slots", "rrl_host_submit", "rrl_host_wait",
             "rrl_measure_fp32_peak", "rrl_measure_dense", "rrl_measure_stages", "rrl_debug_set_dense_variant",

@@ -13,6 +13,19 @@ namespace rrl {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int check_launch() { return cudaGetLastError() == cudaSuccess ? RRL_OK : RRL_ERR_CUDA; }
+int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64) {
+        const int c = cached[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
 void set_dense_variant(int v);
 
 // ---- per-stage timing hook (rrl_measure_stages) ----
@@ -83,6 +96,7 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.recIdx = reinterpret_cast<int *>(take(lines * 8 * sizeof(int)));
     w.recW = reinterpret_cast<float *>(take(lines * 24 * sizeof(float)));
     w.recQ = reinterpret_cast<float *>(take(lines * 24 * sizeof(float)));
+    w.recG = reinterpret_cast<float *>(take(lines * 24 * sizeof(float)));
     w.bytes = off;
     return w;
 }
@@ -264,6 +278,17 @@ extern "C" int rrl_shard_stage3(void *workspace, size_t workspace_bytes, int nf1
 // rrl_host_wait() drains one slot and hands out its results.  rrl_host_loss_fwd_bwd = submit + wait.
 constexpr int kMaxSub = 8;
 constexpr int kSlots = 2;
+// the host-buffer entry points work on the context's device and hand the caller's current device back on return
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (prev == device) || cudaSetDevice(device) == cudaSuccess;
+        if (prev == device) prev = -1;                       // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 struct HostSlot {
     float *d_tri1, *d_tri2, *d_lines, *d_loss, *d_grad1;
     int *d_status;
@@ -294,7 +319,7 @@ static int host_subbatches(int B) {
 
 extern "C" void rrl_host_destroy(rrl_host_ctx *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     for (int q = 0; q < kSlots; ++q) {
         HostSlot &t = c->slot[q];
         for (int s = 0; s < c->S; ++s)
@@ -312,7 +337,8 @@ extern "C" void rrl_host_destroy(rrl_host_ctx *c) {
 
 extern "C" int rrl_host_create(int B, int nf1, int nf2, int nl, int device, rrl_host_ctx **out_ctx) {
     if (!out_ctx || !geometry_ok(B, nf1, nf2, nl)) return RRL_ERR_ARG;
-    if (cudaSetDevice(device) != cudaSuccess) return RRL_ERR_CUDA;
+    DeviceGuard guard(device);
+    if (!guard.ok) return RRL_ERR_CUDA;
     rrl_host_ctx *c = new (std::nothrow) rrl_host_ctx();
     if (!c) return RRL_ERR_CUDA;
     std::memset(c, 0, sizeof(*c));
@@ -361,7 +387,8 @@ extern "C" int rrl_host_submit(rrl_host_ctx *c, const float *h_tri1, const float
     if (!window_ok(k_lo, j_lo, k_hi, j_hi)) return RRL_ERR_ARG;
     HostSlot &t = c->slot[c->next];
     if (t.busy) return RRL_ERR_STATE;                  // every slot in flight: rrl_host_wait() one first
-    if (cudaSetDevice(c->device) != cudaSuccess) return RRL_ERR_CUDA;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return RRL_ERR_CUDA;
     const size_t t1 = (size_t)c->nf1 * 9, t2 = (size_t)c->nf2 * 9, tl = (size_t)c->nl * 6;
     // straight from the caller's memory: asynchronous when it is pinned (the context's own buffers or any
     // cudaHostAlloc/cudaHostRegister'ed range), staged by the driver when it is pageable.  All copies are queued
@@ -404,7 +431,8 @@ extern "C" int rrl_host_wait(rrl_host_ctx *c, int ticket, float *h_loss, int *h_
     HostSlot &t = c->slot[ticket];
     if (!t.busy) return RRL_ERR_STATE;
     if (h_grad_tri1 && !t.want_grad) return RRL_ERR_ARG;
-    if (cudaSetDevice(c->device) != cudaSuccess) return RRL_ERR_CUDA;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return RRL_ERR_CUDA;
     bool ok = true;
     for (int s = 0; s < c->S; ++s) ok = (cudaStreamSynchronize(t.stream[s]) == cudaSuccess) && ok;
     t.busy = false;

@@ -5,7 +5,7 @@ namespace rrl {
 
 // directed min squared distance: for every point of `x` the minimum over all points of `y` (loss.py:38-52, 244-245)
 __global__ void __launch_bounds__(256) chamfer_min_kernel(const float *__restrict__ x, const float *__restrict__ y, int M, int N,
-                                                          float *__restrict__ out) {
+                                                          float *__restrict__ out, int *__restrict__ out_idx) {
     __shared__ float4 tile[512];
     const int b = blockIdx.y;
     const float *xb = x + (long long)b * M * 3, *yb = y + (long long)b * N * 3;
@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) chamfer_min_kernel(const float *__restric
     float px = 0.f, py = 0.f, pz = 0.f;
     if (i < M) { px = xb[3 * i]; py = xb[3 * i + 1]; pz = xb[3 * i + 2]; }
     float best = INFINITY;
+    int arg = 0;
     for (int t0 = 0; t0 < N; t0 += 512) {
         const int cnt = min(512, N - t0);
         __syncthreads();
@@ -21,10 +22,35 @@ __global__ void __launch_bounds__(256) chamfer_min_kernel(const float *__restric
         __syncthreads();
         for (int q = 0; q < cnt; ++q) {
             const float4 v = tile[q];
-            best = fminf(best, sq3_rn(__fsub_rn(px, v.x), __fsub_rn(py, v.y), __fsub_rn(pz, v.z)));
+            const float d = sq3_rn(__fsub_rn(px, v.x), __fsub_rn(py, v.y), __fsub_rn(pz, v.z));
+            if (d < best) { best = d; arg = t0 + q; }          // first index on ties (torch.min)
         }
     }
-    if (i < M) out[(long long)b * M + i] = best;
+    if (i < M) {
+        out[(long long)b * M + i] = best;
+        if (out_idx) out_idx[(long long)b * M + i] = arg;
+    }
+}
+
+// autograd of chamfer_dist (loss.py:236-252; the reference's is differentiable: DCP returns it in its loss tuple):
+// every directed minimum d = |a_i - c_arg|^2 contributes go / (B (M + N)) * 2 (a_i - c_arg) to a_i and the negative to c_arg
+__global__ void __launch_bounds__(256) chamfer_backward_kernel(const float *__restrict__ a, const float *__restrict__ c,
+                                                               const int *__restrict__ idx, const float *__restrict__ grad_out,
+                                                               float scale, int Ma, int Nc, float *__restrict__ ga,
+                                                               float *__restrict__ gc) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ma) return;
+    const float *ab = a + ((long long)b * Ma + i) * 3;
+    const int j = idx[(long long)b * Ma + i];
+    const float *cb = c + ((long long)b * Nc + j) * 3;
+    const float s = 2.0f * scale * grad_out[0];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float gq = s * (ab[q] - cb[q]);
+        if (ga) atomicAdd(ga + ((long long)b * Ma + i) * 3 + q, gq);
+        if (gc) atomicAdd(gc + ((long long)b * Nc + j) * 3 + q, -gq);
+    }
 }
 
 __global__ void __launch_bounds__(1024) mean_kernel(const float *__restrict__ v, long long n, float *out) {
@@ -94,10 +120,35 @@ using namespace rrl;
 extern "C" int rrl_chamfer(const float *x, const float *y, int B, int M, int N, float *out, float *scratch, void *stream) {
     if (!x || !y || !out || !scratch || B <= 0 || M <= 0 || N <= 0) return RRL_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    chamfer_min_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(x, y, M, N, scratch);
-    chamfer_min_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(y, x, N, M, scratch + (size_t)B * M);
+    chamfer_min_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(x, y, M, N, scratch, nullptr);
+    chamfer_min_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(y, x, N, M, scratch + (size_t)B * M, nullptr);
     mean_kernel<<<1, 1024, 0, s>>>(scratch, (long long)B * (M + N), out);
     count_launch(3);
+    return check_launch();
+}
+
+extern "C" int rrl_chamfer_forward(const float *x, const float *y, int B, int M, int N, float *out, float *scratch, int *argmin,
+                                   void *stream) {
+    if (!x || !y || !out || !scratch || !argmin || B <= 0 || M <= 0 || N <= 0) return RRL_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    chamfer_min_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(x, y, M, N, scratch, argmin);
+    chamfer_min_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(y, x, N, M, scratch + (size_t)B * M, argmin + (size_t)B * M);
+    mean_kernel<<<1, 1024, 0, s>>>(scratch, (long long)B * (M + N), out);
+    count_launch(3);
+    return check_launch();
+}
+
+extern "C" int rrl_chamfer_backward(const float *x, const float *y, const int *argmin, const float *grad_out, int B, int M, int N,
+                                    float *grad_x, float *grad_y, void *stream) {
+    if (!x || !y || !argmin || !grad_out || B <= 0 || M <= 0 || N <= 0) return RRL_ERR_ARG;
+    if (!grad_x && !grad_y) return RRL_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (grad_x && cudaMemsetAsync(grad_x, 0, sizeof(float) * 3 * (size_t)B * M, s) != cudaSuccess) return RRL_ERR_CUDA;
+    if (grad_y && cudaMemsetAsync(grad_y, 0, sizeof(float) * 3 * (size_t)B * N, s) != cudaSuccess) return RRL_ERR_CUDA;
+    const float scale = 1.0f / ((float)B * (float)(M + N));
+    chamfer_backward_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(x, y, argmin, grad_out, scale, M, N, grad_x, grad_y);
+    chamfer_backward_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(y, x, argmin + (size_t)B * M, grad_out, scale, N, M, grad_y, grad_x);
+    count_launch(2);
     return check_launch();
 }
 

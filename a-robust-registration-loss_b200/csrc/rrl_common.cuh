@@ -47,7 +47,7 @@ struct Geometry {
 
 // One forward's scratch, carved out of the caller's workspace.  All pointers are device pointers.
 struct Workspace {
-    int *hdr;                // [8]: {magic, B, nf1, nf2, nl, window, 0, 0}
+    int *hdr;                // [8]: {magic, B, nf1, nf2, nl, window, Welsch stage done, 0}; checked by hdr_ok() on the device
     // launch-wide + per pair (one contiguous block, zeroed by a single memset)
     unsigned long long *xcursor; // [2]: {entries reserved in xcand, reserved}
     unsigned int *pmax;      // (B,2): bits of max |p|^2 over all 3 points of all triplets of the cloud
@@ -83,7 +83,9 @@ struct Workspace {
     int *recMeta;            // (cap,2): {line, k | j<<8 | argmins<<16}
     int *recIdx;             // (cap,8)
     float *recW;             // (cap,24): w1[4][3], w2[4][3]
-    float *recQ;             // (cap,24): q1[4][3], q2[4][3]; overwritten by the gradient vectors G1, G2 in the Welsch stage
+    float *recQ;             // (cap,24): intersection points q1[4][3], q2[4][3]
+    float *recG;             // (cap,24): gradient vectors G1[4][3], G2[4][3] written by the Welsch stage (its own buffer, so the
+                             //           stage can be re-run on one forward, e.g. rrl_shard_stage2 with other global counts)
     size_t bytes;
 };
 
@@ -97,6 +99,19 @@ int node_size(const Geometry &g);       // triplets per bounding-sphere node for
 Workspace carve(void *base, int B, int nf1, int nf2, int nl);
 
 // ---- launch bookkeeping -------------------------------------------------------------------------------
+int sm_count();              // multiprocessors of the CURRENT device (cached per device; 148 on a B200)
+// opt-in to more than 48 KB of dynamic shared memory: a per-DEVICE attribute of the function, so it is tracked per device
+// (a process-wide flag left every device after the first without it)
+template <typename K>
+inline int ensure_dyn_smem(K kernel, int bytes, unsigned long long &done_mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RRL_ERR_CUDA;
+    if (dev >= 64 || !((done_mask >> dev) & 1ull)) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return RRL_ERR_CUDA;
+        if (dev < 64) done_mask |= 1ull << dev;      // benign race: two threads may both set the same attribute
+    }
+    return RRL_OK;
+}
 void count_launch(int n = 1);
 int check_launch();          // cudaGetLastError -> RRL_OK / RRL_ERR_CUDA
 void stage_mark(int stage, cudaStream_t s);   // measurement hook: records an event after stage `stage` when enabled
@@ -123,6 +138,22 @@ int launch_shard_hist(const Workspace &ws, const Geometry &g, int round, const l
 int launch_shard_pick(int round, const int *hist, const long long *gcounts18, long long *state, float *out_median, cudaStream_t s);
 
 #ifdef __CUDACC__
+// Does `ws` hold a forward of this geometry?  Kernels that consume a forward (backward, export, the shard stages) return
+// early when it does not -- a fresh, stale or differently shaped workspace would otherwise be read as records and the
+// backward would scatter to arbitrary triplet indices.  Outputs then keep their initial state (zero gradients).
+__device__ __forceinline__ bool hdr_ok(const Workspace &ws, const Geometry &g) {
+    const int *h = ws.hdr;
+    return h[0] == kMagic && h[1] == g.B && h[2] == g.nf1 && h[3] == g.nf2 && h[4] == g.nl;
+}
+
+// hdr[7] of a workspace whose LAST forward of geometry g ran to its end (tail / finalize): the order in perm[] is complete
+__host__ __device__ __forceinline__ int order_token(const Geometry &g) {
+    unsigned h = 0x9E3779B9u;
+    h = (h ^ (unsigned)g.B) * 0x85EBCA6Bu; h = (h ^ (unsigned)g.nf1) * 0xC2B2AE35u;
+    h = (h ^ (unsigned)g.nf2) * 0x27D4EB2Fu; h = (h ^ (unsigned)g.nl) * 0x165667B1u;
+    return (int)(h | 1u);
+}
+
 // ---- exact reference-order arithmetic (never contracted into FMA) -----------------------------------
 __device__ __forceinline__ float sq3_rn(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));

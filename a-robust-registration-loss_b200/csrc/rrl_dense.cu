@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0 && t0 == 0) {
         ws.hdr[0] = kMagic; ws.hdr[1] = g.B; ws.hdr[2] = g.nf1; ws.hdr[3] = g.nf2; ws.hdr[4] = g.nl; ws.hdr[5] = window;
+        ws.hdr[6] = 0;
     }
     float block_max[3];
     int badv = 0;
@@ -549,7 +550,8 @@ __global__ void __launch_bounds__(256) node_kernel(const float *__restrict__ tri
     // one thread per sorted position; nfp is a multiple of kPointPad = 256 = blockDim.x, so every warp is full
     float rad = 0.f, srad = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nfp; i += (long long)gridDim.x * blockDim.x) {
-        const int f = perm[i];
+        int f = perm[i];
+        if ((unsigned)f >= (unsigned)nf) f = -1;      // padding; also keeps a violated RRL_REUSE_ORDER contract memory-safe
         const float th = f >= 0 ? thr[f] : 0.f;
         rad = fmaxf(rad, make_node_coop<kNode>(tri, th, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
                                                ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters));
@@ -596,6 +598,10 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     extern __shared__ unsigned long long skeys[];
     __shared__ unsigned s_red[3];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius
     const int b = blockIdx.x, tid = threadIdx.x;
+    // RRL_REUSE_ORDER is honoured only when an earlier forward of this very geometry completed in this workspace (hdr[7]
+    // is written by that forward's LAST kernel and by nobody in this launch, so every CTA reads the same value); on a
+    // fresh or differently shaped workspace the cloud is simply sorted
+    reuse = reuse && ws.hdr[7] == order_token(g);
     const float *lb = lines + (long long)b * g.nl * 6;
     if (blockIdx.y >= 2) {
         for (int l = (blockIdx.y - 2) * 1024 + tid; l < g.nl; l += line_blocks * 1024) {
@@ -615,6 +621,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     if (cloud == 0) {
         if (b == 0 && tid == 0) {
             ws.hdr[0] = kMagic; ws.hdr[1] = g.B; ws.hdr[2] = g.nf1; ws.hdr[3] = g.nf2; ws.hdr[4] = g.nl; ws.hdr[5] = window;
+            ws.hdr[6] = 0;
             ws.xcursor[0] = 0ull; ws.xcursor[1] = 0ull;
         }
         if (tid < 16) ws.n_kj[b * 16 + tid] = 0;
@@ -668,7 +675,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int i = e * 1024 + tid;
-            v[e] = (e < E && i < nfp) ? (unsigned long long)(unsigned)perm[i] : 0xFFFFFFFFull;
+            v[e] = (e < E && i < nfp) ? (unsigned long long)(unsigned)perm[i] : 0xFFFFFFFFull;      // -1 (padding) = 0xFFFFFFFF >= nf
         }
     } else {
 #pragma unroll
@@ -808,13 +815,9 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
         int line_blocks = (g.nl + 1023) / 1024;
         if (line_blocks > 64) line_blocks = 64;
         const dim3 grid(g.B, 2 + line_blocks);
-        static bool attr_set = false;
-        if (!attr_set) {
-            if (cudaFuncSetAttribute(small_prep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess ||
-                cudaFuncSetAttribute(small_prep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess)
-                return RRL_ERR_CUDA;
-            attr_set = true;
-        }
+        static unsigned long long attr_mask8 = 0ull, attr_mask16 = 0ull;
+        if (ensure_dyn_smem(small_prep_kernel<8>, 65536, attr_mask8) || ensure_dyn_smem(small_prep_kernel<16>, 65536, attr_mask16))
+            return RRL_ERR_CUDA;
         if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order);
         else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order);
         count_launch();
@@ -828,7 +831,7 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     if (cudaMemsetAsync(ws.xcursor, 0, pair_bytes, s) != cudaSuccess) return RRL_ERR_CUDA;
     const int most = g.nl > g.nf1 ? (g.nl > g.nf2 ? g.nl : g.nf2) : (g.nf1 > g.nf2 ? g.nf1 : g.nf2);
     int bx = (most + 255) / 256;
-    const int cap = (148 * 8 + g.B - 1) / g.B;
+    const int cap = (sm_count() * 8 + g.B - 1) / g.B;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     prep_kernel<<<dim3(bx, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, window);
@@ -1601,12 +1604,8 @@ int launch_bruteforce(const float *tri1, const float *tri2, const float *lines, 
 template <int kNode, bool kPerNode, int LPT, bool kSuper = false>
 static int launch_dense_variant(const DenseArgs &a0, const Workspace &ws, const Geometry &g, int G, cudaStream_t s) {
     using Cfg = DenseCfg<kNode, kPerNode, LPT, kSuper>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(dense_kernel<kNode, kPerNode, LPT, kSuper>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
-            return RRL_ERR_CUDA;
-        attr_set = true;
-    }
+    static unsigned long long attr_mask = 0ull;
+    if (ensure_dyn_smem(dense_kernel<kNode, kPerNode, LPT, kSuper>, Cfg::kSmem, attr_mask)) return RRL_ERR_CUDA;
     DenseArgs a = a0;
     const int line_tiles = (g.nl + Cfg::kLines - 1) / Cfg::kLines;
     // records the main loop streams: nodes, or super nodes
@@ -1616,7 +1615,7 @@ static int launch_dense_variant(const DenseArgs &a0, const Workspace &ws, const 
     // split the records so that the grid covers the SMs (kMinBlocks CTAs each) g_param[2] times over when the line
     // tiles alone do not; never below g_param[3] records per CTA
     const long long base_ctas = (long long)line_tiles * g.B * 2;
-    const long long target = 148LL * Cfg::kMinBlocks * g_param[kSuper ? 9 : 2];
+    const long long target = (long long)sm_count() * Cfg::kMinBlocks * g_param[kSuper ? 9 : 2];
     int chunks = 1;
     if (base_ctas < target) chunks = (int)((target + base_ctas - 1) / base_ctas);
     int chunk_nodes = (nn_max + chunks - 1) / chunks;
@@ -1650,9 +1649,10 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     else if (G == 8) rc = lpt == 2 ? launch_dense_variant<8, false, 2>(a, ws, g, G, s) : launch_dense_variant<8, false, 4>(a, ws, g, G, s);
     else rc = lpt == 2 ? launch_dense_variant<16, false, 2>(a, ws, g, G, s) : launch_dense_variant<16, false, 4>(a, ws, g, G, s);
     if (rc) return rc;
-    if (g_param[11] == 4) exact_kernel<4><<<148 * 8, 256, 0, s>>>(a, ws, g);
-    else if (g_param[11] == 1) exact_kernel<1><<<148 * 8, 256, 0, s>>>(a, ws, g);
-    else exact_kernel<2><<<148 * 8, 256, 0, s>>>(a, ws, g);
+    const int xgrid = sm_count() * 8;
+    if (g_param[11] == 4) exact_kernel<4><<<xgrid, 256, 0, s>>>(a, ws, g);
+    else if (g_param[11] == 1) exact_kernel<1><<<xgrid, 256, 0, s>>>(a, ws, g);
+    else exact_kernel<2><<<xgrid, 256, 0, s>>>(a, ws, g);
     count_launch();
     stage_mark(4, s);
     return check_launch();

@@ -331,7 +331,7 @@ extern "C" int rrl_sample_lines(const float *radius, const float *centers, const
     a.acc = a.chunk + (size_t)B * a.nchunks;
     if (cudaMemsetAsync(a.chunk, 0, (size_t)B * (a.nchunks + kPhases + 1) * sizeof(int), s) != cudaSuccess) return RRL_ERR_CUDA;
     bbox_kernel<<<dim3(B, 2), 256, 0, s>>>(verts1, verts2, n1, n2, a.bbox);
-    const int cap = (148 * 8 + B - 1) / B;
+    const int cap = (sm_count() * 8 + B - 1) / B;
     // a chunk belongs to the phase of rounds that holds its first candidate
     const int edge[kPhases + 1] = {0, 1 < rounds ? 1 : rounds, 2 < rounds ? 2 : rounds, 4 < rounds ? 4 : rounds, rounds};
     int bx_all = 1;

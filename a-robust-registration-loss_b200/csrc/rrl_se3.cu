@@ -77,6 +77,53 @@ __global__ void se3_exp_kernel(const float *__restrict__ twist, int B, float *R,
     for (int i = 0; i < 3; ++i) T[b * 3 + i] = t[i];
 }
 
+// FMR's se3.Exp (fmr/se_math/se3.py:60-84): the same R and p = V v as exp3, packed as g = [R p; 0 0 0 1] (B,4,4)
+__global__ void se3_exp4_kernel(const float *__restrict__ twist, int B, float *__restrict__ g) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float r[9], t[3];
+    exp3(twist + b * 6, r, t);
+    float *o = g + (long long)b * 16;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[4 * i + j] = r[3 * i + j];
+        o[4 * i + 3] = t[i];
+    }
+    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+}
+
+// Backward of FMR's ExpMap (fmr/se_math/se3.py:133-165) -- NOT the derivative of exp: the reference propagates
+//   grad_x[k] = sum_ij grad_g[i][j] * (gen_k g)[i][j],   gen_k = mat(e_k)  (se3.py:27-55), g = exp(x),
+// i.e. the left-trivialised tangent.  gen_k g = [hat(e_k) R, hat(e_k) p; 0] for k < 3 and [0, e_{k-3}; 0] for k >= 3.
+__global__ void se3_expmap_backward_kernel(const float *__restrict__ twist, const float *__restrict__ grad_g, int B,
+                                           float *__restrict__ grad_twist) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float r[9], t[3];
+    exp3(twist + b * 6, r, t);
+    const float *go = grad_g + (long long)b * 16;
+    double G[3][4], M[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { G[i][j] = go[4 * i + j]; M[i][j] = r[3 * i + j]; }
+        G[i][3] = go[4 * i + 3];
+        M[i][3] = t[i];
+    }
+    // (hat(e_k) M)[i][j] = sum_m hat(e_k)[i][m] M[m][j];  hat(e_0) = [0 0 0; 0 0 -1; 0 1 0], etc.
+    double gx[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        gx[0] += -G[1][j] * M[2][j] + G[2][j] * M[1][j];
+        gx[1] += G[0][j] * M[2][j] - G[2][j] * M[0][j];
+        gx[2] += -G[0][j] * M[1][j] + G[1][j] * M[0][j];
+    }
+    float *o = grad_twist + (long long)b * 6;
+    o[0] = (float)gx[0]; o[1] = (float)gx[1]; o[2] = (float)gx[2];
+    o[3] = go[3]; o[4] = go[7]; o[5] = go[11];
+}
+
 // out = p @ R + T with R,T either recomputed from the twist (kFromTwist) or read (column convention: R^T applied)
 template <bool kFromTwist>
 __global__ void __launch_bounds__(256) apply_kernel(const float *__restrict__ twist_or_R, const float *__restrict__ t_in,
@@ -209,6 +256,20 @@ using namespace rrl;
 extern "C" int rrl_se3_exp(const float *twist, int B, float *R, float *T, void *stream) {
     if (!twist || !R || !T || B <= 0) return RRL_ERR_ARG;
     se3_exp_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(twist, B, R, T);
+    count_launch();
+    return check_launch();
+}
+
+extern "C" int rrl_se3_exp4(const float *twist, int B, float *g, void *stream) {
+    if (!twist || !g || B <= 0) return RRL_ERR_ARG;
+    se3_exp4_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(twist, B, g);
+    count_launch();
+    return check_launch();
+}
+
+extern "C" int rrl_se3_expmap_backward(const float *twist, const float *grad_g, int B, float *grad_twist, void *stream) {
+    if (!twist || !grad_g || !grad_twist || B <= 0) return RRL_ERR_ARG;
+    se3_expmap_backward_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(twist, grad_g, B, grad_twist);
     count_launch();
     return check_launch();
 }

@@ -140,9 +140,13 @@ int launch_build(const float *tri1, const float *tri2, const float *lines, const
 }
 
 // local counts -> gcounts (B,18): n_kj[16], #records, #D entries.  In the single-GPU path these ARE the global counts.
-__global__ void local_counts_kernel(Workspace ws, int B) {
+__global__ void local_counts_kernel(Workspace ws, Geometry g) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    if (b >= g.B) return;
+    if (!hdr_ok(ws, g)) {                                     // no forward of this geometry here: nothing selected
+        for (int c = 0; c < 18; ++c) ws.gcounts[b * 18 + c] = 0;
+        return;
+    }
     long long nD = 0;
     for (int c = 0; c < 16; ++c) {
         const long long n = ws.n_kj[b * 16 + c];
@@ -154,7 +158,7 @@ __global__ void local_counts_kernel(Workspace ws, int B) {
 }
 
 int launch_local_counts(const Workspace &ws, const Geometry &g, cudaStream_t s) {
-    local_counts_kernel<<<(g.B + 127) / 128, 128, 0, s>>>(ws, g.B);
+    local_counts_kernel<<<(g.B + 127) / 128, 128, 0, s>>>(ws, g);
     count_launch();
     return check_launch();
 }
@@ -294,6 +298,7 @@ constexpr int kShardBins = 65536;
 
 __global__ void __launch_bounds__(256) shard_hist_kernel(Workspace ws, Geometry g, int round, const long long *__restrict__ state,
                                                           int *__restrict__ hist) {
+    if (!hdr_ok(ws, g)) return;
     const long long slots = (long long)ws.nrec[0] * 16;
     const unsigned hi = (unsigned)state[0] >> 16;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (long long)gridDim.x * blockDim.x) {
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(1024) shard_pick_kernel(int round, const int *
 
 int launch_shard_hist(const Workspace &ws, const Geometry &g, int round, const long long *state, int *hist, cudaStream_t s) {
     if (cudaMemsetAsync(hist, 0, sizeof(int) * kShardBins, s) != cudaSuccess) return RRL_ERR_CUDA;
-    shard_hist_kernel<<<148 * 2, 256, 0, s>>>(ws, g, round, state, hist);
+    shard_hist_kernel<<<sm_count() * 2, 256, 0, s>>>(ws, g, round, state, hist);
     count_launch();
     return check_launch();
 }
@@ -371,6 +376,7 @@ int launch_shard_pick(int round, const int *hist, const long long *gcounts18, lo
 
 // compact the valid D entries of pair 0 (line-sharded path)
 __global__ void pack_entries_kernel(Workspace ws, Geometry g, float *out, long long cap) {
+    if (!hdr_ok(ws, g)) return;
     const int nrec = ws.nrec[0];
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrec) return;
@@ -436,8 +442,7 @@ __device__ __forceinline__ double welsch_exp(float D, float med) {
 //     (One thread per record running its own k*j exps measured 4x slower: 16 predicated sites per warp.)
 //   * minima with first-index tie breaking (torch.min) -> v1 = sum_a min_b W, v2 = sum_b min_a W as 2^-40 fixed point
 //     (W * 2^40 is an exact float product; integer sums are exact and order independent);
-//   * gradient vectors for a unit upstream gradient, in float (relative error ~1e-7, bar 1e-5): they overwrite the
-//     record's intersection points (recQ), which nothing reads afterwards.
+//   * gradient vectors for a unit upstream gradient, in float (relative error ~1e-7, bar 1e-5): written to recG.
 // cw_over_n = exp(-|k-j|/2) / C / n_kj.
 __device__ __forceinline__ void welsch_warp(const Workspace &ws, bool valid, long long r, float med, float cw_over_n, int k, int j,
                                             float *buf, unsigned long long &v1, unsigned long long &v2, bool &nan) {
@@ -513,7 +518,8 @@ __device__ __forceinline__ void welsch_warp(const Workspace &ws, bool valid, lon
     if (nan) { v1 = 0ull; v2 = 0ull; }
     if (!valid) return;
     // d loss / d D[a,c] = coef[a,c] e / (2 med); the factor 2 of d D / d q cancels the 1/2
-    float4 *Q4 = reinterpret_cast<float4 *>(ws.recQ + r * 24);
+    const float4 *Q4 = reinterpret_cast<const float4 *>(ws.recQ + r * 24);
+    float4 *G4 = reinterpret_cast<float4 *>(ws.recG + r * 24);
     float q[24];
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
@@ -540,7 +546,7 @@ __device__ __forceinline__ void welsch_warp(const Workspace &ws, bool valid, lon
             }
         }
 #pragma unroll
-    for (int a = 0; a < 6; ++a) Q4[a] = make_float4(G[4 * a], G[4 * a + 1], G[4 * a + 2], G[4 * a + 3]);
+    for (int a = 0; a < 6; ++a) G4[a] = make_float4(G[4 * a], G[4 * a + 1], G[4 * a + 2], G[4 * a + 3]);
 }
 
 // exp(-|k-j|/2) of loss.py:229 for |k-j| = 0..3
@@ -640,7 +646,9 @@ __global__ void __launch_bounds__(256) welsch_kernel(Workspace ws, Geometry g, f
     __shared__ float s_buf[8 * 512];
     __shared__ int s_last;
     const int b = blockIdx.y;
+    if (!hdr_ok(ws, g)) return;
     if (threadIdx.x < 32) s_sum[threadIdx.x] = 0ull;
+    if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) { ws.hdr[6] = 1; ws.hdr[7] = order_token(g); }   // gradient vectors in place; order complete
     __syncthreads();
     const long long nrec = ws.nrec[b];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -701,6 +709,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(Workspace ws, Geomet
     __shared__ int s_last, s_count;
     const int b = blockIdx.y, tid = threadIdx.x;
     mark(0);
+    if (blockIdx.x == 0 && b == 0 && tid == 0) { ws.hdr[6] = 1; ws.hdr[7] = order_token(g); }   // gradient vectors in place; order complete
     const int nrec = ws.nrec[b];
     if (tid < 16) s_gc[tid] = ws.n_kj[b * 16 + tid];
     if (tid < 32) s_sum[tid] = 0ull;
@@ -834,13 +843,10 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(Workspace ws, Geomet
 
 int launch_tail(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
                 long long *out_stats, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMedCache * 4) != cudaSuccess) return RRL_ERR_CUDA;
-        attr_set = true;
-    }
+    static unsigned long long attr_mask = 0ull;
+    if (ensure_dyn_smem(tail_kernel, kMedCache * 4, attr_mask)) return RRL_ERR_CUDA;
     stage_mark(7, s);
-    int S = 148 / g.B;                       // one block per SM at most; small batches spread a pair's records wider
+    int S = sm_count() / g.B;                       // one block per SM at most; small batches spread a pair's records wider
     if (S < 1) S = 1;
     if (S > 16) S = 16;
     tail_kernel<<<dim3(S, g.B), kTailThreads, kMedCache * 4, s>>>(ws, g, out_loss, out_status, out_median, out_stats);
@@ -852,7 +858,7 @@ int launch_tail(const Workspace &ws, const Geometry &g, float *out_loss, int *ou
 __global__ void __launch_bounds__(128) finalize_kernel(Workspace ws, Geometry g, float *out_loss, int *out_status, float *out_median,
                                                         long long *out_stats) {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);           // one warp per pair
-    if (b >= g.B) return;
+    if (b >= g.B || !hdr_ok(ws, g)) return;
     finalize_pair(ws, b, out_loss, out_status, out_median, out_stats);
 }
 
@@ -870,12 +876,13 @@ __global__ void __launch_bounds__(128) backward_kernel(Workspace ws, Geometry g,
                                                        float *__restrict__ g1, float *__restrict__ g2) {
     const int b = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!hdr_ok(ws, g) || ws.hdr[6] != 1) return;           // no completed forward of this geometry here: gradients stay zero
     if (i >= ws.nrec[b]) return;
     const long long r = (long long)b * g.nl + i;
     const int meta = ws.recMeta[r * 2 + 1];
     const int k = meta & 255, j = (meta >> 8) & 255;
     const float go = grad_out[b] * (1.0f / 3.0f);
-    const float *G = ws.recQ + r * 24, *Wt = ws.recW + r * 24;
+    const float *G = ws.recG + r * 24, *Wt = ws.recW + r * 24;
     const int *idx = ws.recIdx + r * 8;
     if (g1) {
         float *O = g1 + (long long)b * g.nf1 * 9;
@@ -923,6 +930,11 @@ int launch_backward(const Workspace &ws, const Geometry &g, const float *grad_ou
 __global__ void export_hits_kernel(Workspace ws, Geometry g, int cloud, int *out_counts, int *out_hits) {
     const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gl >= (long long)g.B * g.nl) return;
+    if (!hdr_ok(ws, g)) {                                     // no forward of this geometry here: report "no hits"
+        out_counts[gl] = 0;
+        for (int a = 0; a < kCap; ++a) out_hits[gl * kCap + a] = -1;
+        return;
+    }
     const int c = ws.cnt[cloud][gl];
     out_counts[gl] = c;
     int v[kCap];

@@ -12,6 +12,19 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _on(t: torch.Tensor):
+    """Context that makes t's device current for the native call: the C entry points launch on the current device with
+    the stream they are handed, so a tensor on cuda:1 while cuda:0 is current would otherwise meet a foreign stream."""
+    return torch.cuda.device(t.device)
+
+
+def _same_device(*ts):
+    dev = ts[0].device
+    for t in ts[1:]:
+        if t is not None and t.device != dev:
+            raise ValueError("all inputs must live on one device, got %s and %s" % (dev, t.device))
+
+
 def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise N.NativeError("%s must live on a CUDA device: the B200 kernels are the only implementation "
@@ -49,8 +62,9 @@ class LossInfo:
         B, nf1, nf2, nl = self._geom
         counts = torch.empty(B, nl, dtype=torch.int32, device=self._ws.device)
         hits = torch.empty(B, nl, N.HIT_CAP, dtype=torch.int32, device=self._ws.device)
-        N.check(N.lib().rrl_loss_export_hits(self._ws.data_ptr(), self._ws.numel(), B, nf1, nf2, nl, cloud,
-                                             counts.data_ptr(), hits.data_ptr(), _stream(self._ws)), "rrl_loss_export_hits")
+        with _on(self._ws):
+            N.check(N.lib().rrl_loss_export_hits(self._ws.data_ptr(), self._ws.numel(), B, nf1, nf2, nl, cloud,
+                                                 counts.data_ptr(), hits.data_ptr(), _stream(self._ws)), "rrl_loss_export_hits")
         return counts, hits
 
 
@@ -97,10 +111,11 @@ class _IntersectedLineLoss(torch.autograd.Function):
         status = torch.empty(B, dtype=torch.int32, device=dev)
         median = torch.empty(B, dtype=torch.float32, device=dev)
         stats = torch.empty(B, N.NSTAT, dtype=torch.int64, device=dev)
-        N.check(L.rrl_loss_forward_ex(tri1.data_ptr(), tri2.data_ptr(), lines.data_ptr(), B, nf1, nf2, nl,
-                                      window[0], window[1], window[2], window[3], ws.data_ptr(), ws_bytes,
-                                      loss.data_ptr(), status.data_ptr(), median.data_ptr(), stats.data_ptr(), flags,
-                                      _stream(tri1)), "rrl_loss_forward_ex")
+        with _on(tri1):
+            N.check(L.rrl_loss_forward_ex(tri1.data_ptr(), tri2.data_ptr(), lines.data_ptr(), B, nf1, nf2, nl,
+                                          window[0], window[1], window[2], window[3], ws.data_ptr(), ws_bytes,
+                                          loss.data_ptr(), status.data_ptr(), median.data_ptr(), stats.data_ptr(), flags,
+                                          _stream(tri1)), "rrl_loss_forward_ex")
         ctx.ws = ws
         ctx.geom = (B, nf1, nf2, nl)
         ctx.mark_non_differentiable(status, median, stats)
@@ -116,9 +131,10 @@ class _IntersectedLineLoss(torch.autograd.Function):
         g = grad_loss.contiguous().float()
         g1 = torch.empty(B, nf1, 9, dtype=torch.float32, device=ws.device) if need1 else None
         g2 = torch.empty(B, nf2, 9, dtype=torch.float32, device=ws.device) if need2 else None
-        N.check(N.lib().rrl_loss_backward(ws.data_ptr(), ws.numel(), g.data_ptr(), B, nf1, nf2, nl,
-                                          g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None,
-                                          _stream(ws)), "rrl_loss_backward")
+        with _on(ws):
+            N.check(N.lib().rrl_loss_backward(ws.data_ptr(), ws.numel(), g.data_ptr(), B, nf1, nf2, nl,
+                                              g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None,
+                                              _stream(ws)), "rrl_loss_backward")
         return g1, g2, None, None, None, None
 
 
@@ -140,6 +156,7 @@ def intersected_line_loss(tri1: torch.Tensor, tri2: torch.Tensor, lines: torch.T
         raise ValueError("hit-count window must satisfy 1 <= lo < hi <= 5, got %s" % (w,))
     tri1, tri2 = _cuda_f32(tri1, "points1"), _cuda_f32(tri2, "points2")
     lines = _cuda_f32(lines.detach(), "line")
+    _same_device(tri1, tri2, lines)
     holder = [] if return_info else None
     loss, _, _, _ = _IntersectedLineLoss.apply(tri1, tri2, lines, w, holder, session)
     return (loss, holder[0]) if return_info else loss
@@ -153,8 +170,9 @@ class _Se3Apply(torch.autograd.Function):
     def forward(ctx, twist, points):
         B, n, _ = points.shape
         out = torch.empty_like(points)
-        N.check(N.lib().rrl_se3_apply(twist.data_ptr(), points.data_ptr(), B, n, out.data_ptr(), _stream(points)),
-                "rrl_se3_apply")
+        with _on(points):
+            N.check(N.lib().rrl_se3_apply(twist.data_ptr(), points.data_ptr(), B, n, out.data_ptr(), _stream(points)),
+                    "rrl_se3_apply")
         ctx.save_for_backward(twist, points)
         return out
 
@@ -165,8 +183,9 @@ class _Se3Apply(torch.autograd.Function):
         g = grad_out.contiguous().float()
         gt = torch.empty(B, 6, dtype=torch.float32, device=points.device)
         scratch = torch.empty(B * 12, dtype=torch.float64, device=points.device)
-        N.check(N.lib().rrl_se3_apply_backward(twist.data_ptr(), points.data_ptr(), g.data_ptr(), B, n, gt.data_ptr(),
-                                               scratch.data_ptr(), _stream(points)), "rrl_se3_apply_backward")
+        with _on(points):
+            N.check(N.lib().rrl_se3_apply_backward(twist.data_ptr(), points.data_ptr(), g.data_ptr(), B, n, gt.data_ptr(),
+                                                   scratch.data_ptr(), _stream(points)), "rrl_se3_apply_backward")
         return gt, None
 
 
@@ -174,7 +193,9 @@ def se3_apply(twist: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
     """twist (B,6) [w|v], points (B,n,3) -> (B,n,3); differentiable w.r.t. the twist."""
     if twist.dim() != 2 or twist.shape[1] != 6 or points.dim() != 3 or points.shape[2] != 3:
         raise ValueError("expected twist (B,6) and points (B,n,3)")
-    return _Se3Apply.apply(_cuda_f32(twist, "twist"), _cuda_f32(points.detach(), "points"))
+    twist, points = _cuda_f32(twist, "twist"), _cuda_f32(points.detach(), "points")
+    _same_device(twist, points)
+    return _Se3Apply.apply(twist, points)
 
 
 def se3_exp(twist: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -183,8 +204,40 @@ def se3_exp(twist: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     B = twist.shape[0]
     R = torch.empty(B, 3, 3, dtype=torch.float32, device=twist.device)
     T = torch.empty(B, 3, dtype=torch.float32, device=twist.device)
-    N.check(N.lib().rrl_se3_exp(twist.data_ptr(), B, R.data_ptr(), T.data_ptr(), _stream(twist)), "rrl_se3_exp")
+    with _on(twist):
+        N.check(N.lib().rrl_se3_exp(twist.data_ptr(), B, R.data_ptr(), T.data_ptr(), _stream(twist)), "rrl_se3_exp")
     return R, T
+
+
+class _Se3ExpMap(torch.autograd.Function):
+    """FMR's se3.Exp (exps_deep_learning/fmr/se_math/se3.py:133-165): x (B,6) -> g (B,4,4); the backward is the
+    reference's ExpMap.backward (sum_ij grad_g[i][j] (gen_k g)[i][j]), not the analytic derivative of exp."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B = x.shape[0]
+        g = torch.empty(B, 4, 4, dtype=torch.float32, device=x.device)
+        with _on(x):
+            N.check(N.lib().rrl_se3_exp4(x.data_ptr(), B, g.data_ptr(), _stream(x)), "rrl_se3_exp4")
+        ctx.save_for_backward(x)
+        return g
+
+    @staticmethod
+    def backward(ctx, grad_g):
+        x, = ctx.saved_tensors
+        go = grad_g.contiguous().float()
+        gx = torch.empty_like(x)
+        with _on(x):
+            N.check(N.lib().rrl_se3_expmap_backward(x.data_ptr(), go.data_ptr(), x.shape[0], gx.data_ptr(), _stream(x)),
+                    "rrl_se3_expmap_backward")
+        return gx
+
+
+def se3_Exp(x: torch.Tensor) -> torch.Tensor:
+    """Drop-in for fmr/se_math/se3.Exp: x (..., 6) -> g (..., 4, 4) with the reference's ExpMap gradient convention."""
+    lead = x.shape[:-1]
+    g = _Se3ExpMap.apply(_cuda_f32(x.reshape(-1, 6), "x"))
+    return g.reshape(*lead, 4, 4)
 
 
 class _RigidApply(torch.autograd.Function):
@@ -194,8 +247,9 @@ class _RigidApply(torch.autograd.Function):
     def forward(ctx, R, t, points):
         B, n, _ = points.shape
         out = torch.empty_like(points)
-        N.check(N.lib().rrl_rigid_apply(R.data_ptr(), t.data_ptr(), points.data_ptr(), B, n, out.data_ptr(),
-                                        _stream(points)), "rrl_rigid_apply")
+        with _on(points):
+            N.check(N.lib().rrl_rigid_apply(R.data_ptr(), t.data_ptr(), points.data_ptr(), B, n, out.data_ptr(),
+                                            _stream(points)), "rrl_rigid_apply")
         ctx.save_for_backward(R, points)
         return out
 
@@ -208,15 +262,18 @@ class _RigidApply(torch.autograd.Function):
         gt = torch.empty(B, 3, dtype=torch.float32, device=points.device)
         gp = torch.empty_like(points) if ctx.needs_input_grad[2] else None
         scratch = torch.empty(B * 12, dtype=torch.float64, device=points.device)
-        N.check(N.lib().rrl_rigid_apply_backward(R.data_ptr(), points.data_ptr(), g.data_ptr(), B, n, gR.data_ptr(),
-                                                 gt.data_ptr(), gp.data_ptr() if gp is not None else None,
-                                                 scratch.data_ptr(), _stream(points)), "rrl_rigid_apply_backward")
+        with _on(points):
+            N.check(N.lib().rrl_rigid_apply_backward(R.data_ptr(), points.data_ptr(), g.data_ptr(), B, n, gR.data_ptr(),
+                                                     gt.data_ptr(), gp.data_ptr() if gp is not None else None,
+                                                     scratch.data_ptr(), _stream(points)), "rrl_rigid_apply_backward")
         return gR, gt, gp
 
 
 def rigid_apply(R: torch.Tensor, t: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
     """R (B,3,3), t (B,3), points (B,n,3) -> R p + t, differentiable w.r.t. all three."""
-    return _RigidApply.apply(_cuda_f32(R, "R"), _cuda_f32(t.reshape(-1, 3), "t"), _cuda_f32(points, "points"))
+    R, t, points = _cuda_f32(R, "R"), _cuda_f32(t.reshape(-1, 3), "t"), _cuda_f32(points, "points")
+    _same_device(R, t, points)
+    return _RigidApply.apply(R, t, points)
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -239,21 +296,62 @@ def sample_lines(radius: torch.Tensor, centers: torch.Tensor, n_lines: int, vert
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     lines = torch.empty(B, n_lines, 6, dtype=torch.float32, device=dev)
     filled = torch.empty(B, dtype=torch.int32, device=dev)
-    N.check(L.rrl_sample_lines(radius.data_ptr(), centers.data_ptr(), verts1.data_ptr(), verts2.data_ptr(), B,
-                               verts1.shape[1], verts2.shape[1], n_lines, rounds, seed & (2 ** 64 - 1),
-                               offset & (2 ** 64 - 1), uniforms.data_ptr() if uniforms is not None else None,
-                               lines.data_ptr(), filled.data_ptr(), ws.data_ptr(), wsb, _stream(verts1)),
-            "rrl_sample_lines")
+    _same_device(verts1, verts2, radius, centers, uniforms)
+    with _on(verts1):
+        N.check(L.rrl_sample_lines(radius.data_ptr(), centers.data_ptr(), verts1.data_ptr(), verts2.data_ptr(), B,
+                                   verts1.shape[1], verts2.shape[1], n_lines, rounds, seed & (2 ** 64 - 1),
+                                   offset & (2 ** 64 - 1), uniforms.data_ptr() if uniforms is not None else None,
+                                   lines.data_ptr(), filled.data_ptr(), ws.data_ptr(), wsb, _stream(verts1)),
+                "rrl_sample_lines")
     return lines, filled
 
 
+class _Chamfer(torch.autograd.Function):
+    """chamfer_dist (loss.py:236-252) with its autograd: the forward records the argmin of every directed minimum."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        B, M, _ = x.shape
+        Nn = y.shape[1]
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(B * (M + Nn), dtype=torch.float32, device=x.device)
+        arg = torch.empty(B * (M + Nn), dtype=torch.int32, device=x.device)
+        with _on(x):
+            N.check(N.lib().rrl_chamfer_forward(x.data_ptr(), y.data_ptr(), B, M, Nn, out.data_ptr(), scratch.data_ptr(),
+                                                arg.data_ptr(), _stream(x)), "rrl_chamfer_forward")
+        ctx.save_for_backward(x, y, arg)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, y, arg = ctx.saved_tensors
+        B, M, _ = x.shape
+        Nn = y.shape[1]
+        go = grad_out.reshape(1).contiguous().float()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        with _on(x):
+            N.check(N.lib().rrl_chamfer_backward(x.data_ptr(), y.data_ptr(), arg.data_ptr(), go.data_ptr(), B, M, Nn,
+                                                 gx.data_ptr() if gx is not None else None,
+                                                 gy.data_ptr() if gy is not None else None, _stream(x)),
+                    "rrl_chamfer_backward")
+        return gx, gy
+
+
 def chamfer(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """chamfer_dist (loss.py:236-252): x (B,M,3), y (B,N,3) -> 0-dim tensor.  Monitoring only (no autograd)."""
-    x, y = _cuda_f32(x.detach(), "points_x"), _cuda_f32(y.detach(), "points_y")
-    B, M, _ = x.shape
-    Nn = y.shape[1]
-    out = torch.empty(1, dtype=torch.float32, device=x.device)
-    scratch = torch.empty(B * (M + Nn), dtype=torch.float32, device=x.device)
-    N.check(N.lib().rrl_chamfer(x.data_ptr(), y.data_ptr(), B, M, Nn, out.data_ptr(), scratch.data_ptr(), _stream(x)),
-            "rrl_chamfer")
-    return out[0]
+    """chamfer_dist (loss.py:236-252): x (B,M,3), y (B,N,3) -> 0-dim tensor, differentiable w.r.t. both clouds like the
+    reference's (Train_DCP.py:248,297 returns it in the loss tuple)."""
+    x, y = _cuda_f32(x, "points_x"), _cuda_f32(y, "points_y")
+    _same_device(x, y)
+    if x.dim() != 3 or y.dim() != 3 or x.shape[2] != 3 or y.shape[2] != 3 or x.shape[0] != y.shape[0]:
+        raise ValueError("expected points_x (B,M,3) and points_y (B,N,3)")
+    if not (torch.is_grad_enabled() and (x.requires_grad or y.requires_grad)):
+        B, M, _ = x.shape
+        Nn = y.shape[1]
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(B * (M + Nn), dtype=torch.float32, device=x.device)
+        with _on(x):
+            N.check(N.lib().rrl_chamfer(x.data_ptr(), y.data_ptr(), B, M, Nn, out.data_ptr(), scratch.data_ptr(), _stream(x)),
+                    "rrl_chamfer")
+        return out[0]
+    return _Chamfer.apply(x, y)

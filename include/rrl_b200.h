@@ -38,7 +38,11 @@ enum {
     RRL_ERR_ARG = -1,              /* null pointer / non-positive size / window outside 1..4 */
     RRL_ERR_WORKSPACE = -2,        /* workspace smaller than rrl_workspace_bytes() */
     RRL_ERR_CUDA = -3,             /* a CUDA runtime call or kernel launch failed */
-    RRL_ERR_STATE = -4             /* backward called on a workspace that holds no forward */
+    RRL_ERR_STATE = -4             /* host-buffer context: every slot in flight (submit) / ticket not in flight (wait).
+                                      A workspace that holds no forward of the stated geometry cannot be seen from the host
+                                      without a synchronisation; the kernels that consume a forward (backward, export_hits,
+                                      the rrl_shard_* stages) check its header ON THE DEVICE and return early: gradients
+                                      stay zero, counts are 0, hit slots -1. */
 };
 
 /* per-pair status bits written by rrl_loss_forward into out_status[b] */
@@ -157,6 +161,11 @@ int rrl_shard_stage3(void *workspace, size_t workspace_bytes, int nf1, int nf2, 
  * twist (B,6) = [w | v];  R (B,3,3) row-major, T (B,3);  points (B,n,3);  out = points @ R + T (row vectors).
  * ------------------------------------------------------------------------------------------------- */
 int rrl_se3_exp(const float *twist, int B, float *R, float *T, void *stream);
+/* FMR's se3.Exp (exps_deep_learning/fmr/se_math/se3.py:60-84,133-165): g (B,4,4) = [R p; 0 0 0 1] with the R and
+ * p = V v of exp3.  The backward is the reference's ExpMap.backward, grad_twist[k] = sum_ij grad_g[i][j] (gen_k g)[i][j]
+ * (the left-trivialised tangent the IC solver of FMR propagates -- not the analytic derivative of exp). */
+int rrl_se3_exp4(const float *twist, int B, float *g, void *stream);
+int rrl_se3_expmap_backward(const float *twist, const float *grad_g, int B, float *grad_twist, void *stream);
 int rrl_se3_apply(const float *twist, const float *points, int B, int n, float *out, void *stream);
 /* grad_out (B,n,3) = d loss / d out  ->  grad_twist (B,6).  scratch: B*12 doubles. */
 int rrl_se3_apply_backward(const float *twist, const float *points, const float *grad_out, int B, int n,
@@ -189,6 +198,14 @@ int rrl_sample_lines(const float *radius, const float *centers, const float *ver
  * concatenation of both directed min-squared-distances of all pairs.  scratch: B*(M+N) floats.
  * ------------------------------------------------------------------------------------------------- */
 int rrl_chamfer(const float *x, const float *y, int B, int M, int N, float *out, float *scratch, void *stream);
+/* The differentiable form (the reference's chamfer_dist is plain autograd; Train_DCP.py:248,297 returns it inside the loss
+ * tuple): forward also records the argmin of every directed minimum (first index on ties, like torch.min) in
+ * argmin (B*(M+N)) int32 -- x's M minima, then y's N --; backward scatters d out / d x (B,M,3) and d out / d y (B,N,3)
+ * (either may be NULL) for the upstream gradient grad_out (1). */
+int rrl_chamfer_forward(const float *x, const float *y, int B, int M, int N, float *out, float *scratch, int *argmin,
+                        void *stream);
+int rrl_chamfer_backward(const float *x, const float *y, const int *argmin, const float *grad_out, int B, int M, int N,
+                         float *grad_x, float *grad_y, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Pre-processing: replaces Sample_neighs (loss.py:473-485) = utils.farthest_point_sample (utils.py:275-296) followed by

@@ -33,22 +33,33 @@ def test_round_trips_and_byte_layout(tmp_path):
     assert np.array_equal(io.read_transform_bin(tmp_path / "t.bin"), rt)
 
 
-def test_load_pair_recentres_the_ground_truth(tmp_path):
-    """src @ R + T must map the centred source onto the centred target when the files hold tar = R_gt src + t_gt"""
+def test_load_pair_matches_the_reference_loader(tmp_path):
+    """tests/golden/loader.npz = Dataset_2021_8_29.__getitem__ of the unmodified reference (oracle/make_golden_r2.py) on
+    one pair, for the plain / DCP / FMR layout switches; load_pair must reproduce every key bit for bit (tar_box: the two
+    corners the hooks read, pre_dataloader.py:111 + Train_DCP.py:234-236)"""
     io = _io()
-    rng = np.random.default_rng(1)
-    src = rng.standard_normal((40, 3)) + np.array([3.0, -1.0, 0.5])
-    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
-    q *= np.sign(np.linalg.det(q))
-    t = np.array([0.3, -0.2, 0.7])
-    tar = src @ q.T + t
-    p = io.write_pair(str(tmp_path), 5, src, tar, np.repeat(src, 3, 0), np.repeat(tar, 3, 0), np.concatenate([q, t[:, None]], 1))
-    assert os.path.basename(p["transform"]) == "5_transform.bin" and os.path.basename(p["src_neigh"]) == "5_src_sample_neigh.bin"
-    d = io.load_pair(p["src"], p["tar"])
-    assert abs(d["points_src_sample"].mean(0)).max() < 1e-6 and abs(d["points_tar_sample"].mean(0)).max() < 1e-6
-    # the reference stores R_inv = R_gt^T ("rotation") and applies clouds as row vectors: src @ rotation + T = tar
-    assert np.allclose(d["points_src_sample"] @ d["R_inv"] + d["T"], d["points_tar_sample"], atol=1e-5)
-    assert np.allclose(d["R"], d["R_inv"].T) and d["tar_box"].shape == (8, 3)
-    assert np.allclose(d["points_based_neighs_src"].reshape(-1, 3, 3)[:, 0], d["points_src_sample"], atol=1e-6)
-    dd = io.load_pair(p["src"], p["tar"], dcp=True, fmr=True)
-    assert dd["points_src_sample"].shape[0] == 3 and np.allclose(dd["R"], d["R"].T)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "loader.npz"))
+    d = str(tmp_path)
+    def wobj(path, v):
+        with open(path, "w") as f:
+            for p in v:
+                f.write("v %.17g %.17g %.17g\n" % tuple(p))
+    p = io.pair_paths(d, 7)
+    wobj(p["src"], g["src"]); wobj(p["tar"], g["tar"])
+    io.write_neigh_bin(p["src_neigh"], g["n_src"]); io.write_neigh_bin(p["tar_neigh"], g["n_tar"])
+    io.write_transform_bin(p["transform"], g["rt"])
+    for tag, kw in (("plain", {}), ("dcp", dict(dcp=True)), ("fmr", dict(fmr=True))):
+        out = io.load_pair(p["src"], p["tar"], **kw)
+        keys = [k[len("ref_%s_" % tag):] for k in g.files if k.startswith("ref_%s_" % tag)]
+        assert sorted(keys) == sorted(out.keys())
+        for k in keys:
+            ref = g["ref_%s_%s" % (tag, k)]
+            assert out[k].shape == ref.shape and out[k].dtype == ref.dtype, (tag, k)
+            if k == "tar_box":
+                assert np.array_equal(out[k][[0, -1]], ref[[0, -1]])
+                assert sorted(map(tuple, out[k])) == sorted(map(tuple, ref))
+            else:
+                assert np.array_equal(out[k], ref), (tag, k)
+    plain = io.load_pair(p["src"], p["tar"])
+    # the reference's numpy `.transpose(0, 1)` is the identity: R == R_inv == gt[:3, :3] outside the DCP switch
+    assert np.array_equal(plain["R"], plain["R_inv"]) and np.array_equal(plain["R"], g["rt"][:, :3].astype(np.float32))

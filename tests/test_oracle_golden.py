@@ -155,3 +155,33 @@ def test_neigh_oracle_matches_reference_sample_neighs(tag):
     pts, ns, ref_idx = g[tag + "_points"], int(g[tag + "_num_sample"]), g[tag + "_ref_fps_idx"]
     assert np.array_equal(no.fps(pts, ns, int(ref_idx[0])), ref_idx)
     assert np.array_equal(no.sample_neighs(pts, ns, 3, int(ref_idx[0])), g[tag + "_ref_neighs"])
+
+
+def test_expmap_oracle_matches_the_reference():
+    """fmr/se_math/se3.py Exp + ExpMap.backward (golden minted by oracle/make_golden_r2.py)"""
+    from oracle import aux_oracle as ao
+    g = golden("expmap")
+    assert np.abs(ao.se3_exp4(g["twist"]) - g["ref_g"]).max() <= 2e-6
+    gx = ao.expmap_backward(g["twist"], g["grad_g"])
+    assert np.linalg.norm(gx - g["ref_grad_twist"]) <= 1e-5 * np.linalg.norm(g["ref_grad_twist"])
+
+
+def test_chamfer_gradient_oracle_matches_the_reference():
+    from oracle import aux_oracle as ao
+    g = golden("chamfer_grad")
+    val, gx, gy = ao.chamfer_with_grad(g["x"], g["y"], float(g["upstream"]))
+    assert abs(val - float(g["ref"])) <= 1e-5 * float(g["ref"])
+    assert np.linalg.norm(gx - g["ref_grad_x"]) <= 1e-5 * np.linalg.norm(g["ref_grad_x"])
+    assert np.linalg.norm(gy - g["ref_grad_y"]) <= 1e-5 * np.linalg.norm(g["ref_grad_y"])
+
+
+def test_se3_log_of_the_shim_matches_the_reference():
+    """loss.se3_log (host-side float64, runs once when Reconstruction_point is given an initial (R, T)) against
+    LieAlgebra/se3.py:124-134 on exp3 outputs, incl. a near-identity rotation"""
+    import torch
+    import rrl_b200
+    g = golden("se3_log")
+    for i in range(g["twist"].shape[0]):
+        out = rrl_b200.loss.se3_log(torch.from_numpy(g["R"][i]), torch.from_numpy(g["T"][i])).numpy()
+        assert np.abs(out - g["ref_log"][i]).max() <= 2e-5 * max(1.0, np.abs(g["ref_log"][i]).max()), i
+        assert np.abs(out - g["twist"][i]).max() <= 5e-5
