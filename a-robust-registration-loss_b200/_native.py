@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("RRL_LIB_PATH") or os.path.join(_HERE, "librrl_b200.so
 
 HIT_CAP = 5
 NSTAT = 8
-STATUS_EMPTY, STATUS_NAN, STATUS_NAN_RISK = 1, 2, 4
+STATUS_EMPTY, STATUS_NAN, STATUS_NAN_RISK, STATUS_COMM = 1, 2, 4, 8
 REUSE_ORDER = 1                  # RRL_REUSE_ORDER flag of rrl_loss_forward_ex / rrl_shard_stage1_ex
 
 _lib = None
@@ -48,6 +48,16 @@ def lib():
         "rrl_shard_select_pick": (ci, [ci, vp, vp, vp, vp, vp]),
         "rrl_shard_stage2": (ci, [vp, cz, ci, ci, ci, vp, vp, vp, vp]),
         "rrl_shard_stage3": (ci, [vp, cz, ci, ci, ci, vp, vp, vp, vp]),
+        "rrl_comm_create": (ci, [ci, ci, cz, C.POINTER(vp)]),
+        "rrl_comm_destroy": (None, [vp]),
+        "rrl_comm_slot_bytes": (cz, [vp]),
+        "rrl_comm_local_base": (vp, [vp]),
+        "rrl_comm_ipc_handle": (ci, [vp, vp]),
+        "rrl_comm_connect_ipc": (ci, [vp, vp]),
+        "rrl_comm_connect_ptrs": (ci, [vp, C.POINTER(vp)]),
+        "rrl_comm_error": (ci, [vp]),
+        "rrl_comm_allreduce_f64": (ci, [vp, vp, ci, vp]),
+        "rrl_shard_tail": (ci, [vp, cz, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
         "rrl_se3_exp": (ci, [vp, ci, vp, vp, vp]),
         "rrl_se3_exp4": (ci, [vp, ci, vp, vp]),
         "rrl_se3_expmap_backward": (ci, [vp, vp, ci, vp, vp]),
@@ -91,7 +101,9 @@ EXPORTED = ["rrl_version", "rrl_error_string", "rrl_launch_count", "rrl_workspac
             "rrl_loss_forward_ex", "rrl_shard_stage1_ex",
             "rrl_loss_backward", "rrl_loss_export_hits", "rrl_shard_stage1", "rrl_shard_counts",
             "rrl_shard_pack_entries", "rrl_select_lower_median", "rrl_shard_select_hist", "rrl_shard_select_pick",
-            "rrl_shard_stage2", "rrl_shard_stage3",
+            "rrl_shard_stage2", "rrl_shard_stage3", "rrl_shard_tail",
+            "rrl_comm_create", "rrl_comm_destroy", "rrl_comm_slot_bytes", "rrl_comm_local_base", "rrl_comm_ipc_handle",
+            "rrl_comm_connect_ipc", "rrl_comm_connect_ptrs", "rrl_comm_error", "rrl_comm_allreduce_f64",
             "rrl_se3_exp", "rrl_se3_exp4", "rrl_se3_expmap_backward", "rrl_se3_apply", "rrl_se3_apply_backward", "rrl_rigid_apply", "rrl_rigid_apply_backward",
             "rrl_sampler_workspace_bytes", "rrl_sample_lines", "rrl_chamfer", "rrl_chamfer_forward", "rrl_chamfer_backward", "rrl_fps_workspace_bytes", "rrl_fps", "rrl_knn", "rrl_host_create", "rrl_host_destroy",
             "rrl_host_pinned_tri1", "rrl_host_pinned_tri2", "rrl_host_pinned_lines", "rrl_host_subbatches", "rrl_host_loss_fwd_bwd",

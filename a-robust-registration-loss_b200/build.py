@@ -20,7 +20,7 @@ COMMON += os.environ.get("RRL_DEFS", "").split()
 if os.environ.get("RRL_MARKS"):          # measurement builds: in-kernel phase timestamps (rrl_debug_read_marks)
     COMMON.append("-DRRL_MARKS")
 # rrl_sampler.cu restates a floating-point knife-edge test and must not contract a*b+c into FMAs
-SOURCES = {"rrl_api.cu": [], "rrl_dense.cu": [], "rrl_sparse.cu": [], "rrl_se3.cu": [], "rrl_aux.cu": [], "rrl_neigh.cu": [],
+SOURCES = {"rrl_api.cu": [], "rrl_dense.cu": [], "rrl_sparse.cu": [], "rrl_se3.cu": [], "rrl_aux.cu": [], "rrl_neigh.cu": [], "rrl_comm.cu": [],
            "rrl_sampler.cu": ["-fmad=false"]}
 
 

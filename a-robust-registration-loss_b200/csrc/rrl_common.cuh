@@ -91,6 +91,23 @@ struct Workspace {
 
 constexpr int kMagic = 0x52524c31;   // "RRL1"
 
+// ---- peer-memory exchange between the ranks of a line shard (rrl_comm.cu) ------------------------------------------
+// Every rank owns one buffer that all ranks of the job have mapped (CUDA IPC, NVLink peer access):
+//   [ flags: kCommMaxWorld x u64 | epoch u64 | error u32 ... pad to 1024 B | slot[parity 0..1][sender 0..world) of slot_bytes ]
+// An exchange with sequence number seq: every rank PUSHES its payload into slot[seq & 1][rank] of every peer (plain
+// stores over NVLink), fences, then stores seq into flags[rank] of every peer; a rank has everybody's payload once all
+// of ITS OWN flags (local memory) have reached seq.  Slots are double buffered by the parity of seq: a sender can only
+// be two exchanges ahead of a receiver after that receiver has signalled the exchange in between, i.e. after it has
+// finished reading the older payload.  No host involvement, no NCCL, graph-capturable; the sequence number lives on the device.
+constexpr int kCommMaxWorld = 16;
+constexpr int kCommHeader = 1024;
+constexpr int RRL_STATUS_COMM_BIT = 8;
+struct CommView {
+    int rank, world;
+    unsigned long long slot_bytes;
+    char *peer[kCommMaxWorld];       // base of every rank's buffer as mapped in this process; peer[rank] is the local one
+};
+
 inline int pad_points(int nf) { return ((nf + kPointPad - 1) / kPointPad) * kPointPad; }
 inline int pad_supers(int nfp) { return ((nfp / kSuperPts + kNodePad - 1) / kNodePad) * kNodePad; }   // like the node arrays: multiples of 16 records
 size_t sort_scratch_bytes(int nfp_max, int B);
@@ -136,6 +153,8 @@ int launch_pack_entries(const Workspace &ws, const Geometry &g, float *out, long
 int launch_select_median(const float *vals, long long n, float *out, cudaStream_t s);
 int launch_shard_hist(const Workspace &ws, const Geometry &g, int round, const long long *state, int *hist, cudaStream_t s);
 int launch_shard_pick(int round, const int *hist, const long long *gcounts18, long long *state, float *out_median, cudaStream_t s);
+int launch_shard_tail(const Workspace &ws, const Geometry &g, const CommView &comm, float *out_loss, int *out_status,
+                      float *out_median, long long *out_stats, cudaStream_t s);
 
 #ifdef __CUDACC__
 // Does `ws` hold a forward of this geometry?  Kernels that consume a forward (backward, export, the shard stages) return
@@ -144,6 +163,51 @@ int launch_shard_pick(int round, const int *hist, const long long *gcounts18, lo
 __device__ __forceinline__ bool hdr_ok(const Workspace &ws, const Geometry &g) {
     const int *h = ws.hdr;
     return h[0] == kMagic && h[1] == g.B && h[2] == g.nf1 && h[3] == g.nf2 && h[4] == g.nl;
+}
+
+// ---- device side of the peer exchange (called by ALL threads of ONE CTA) ---------------------------------------------
+__device__ __forceinline__ unsigned long long *comm_flags(char *base) { return reinterpret_cast<unsigned long long *>(base); }
+__device__ __forceinline__ unsigned long long *comm_epoch(char *base) { return reinterpret_cast<unsigned long long *>(base) + kCommMaxWorld; }
+__device__ __forceinline__ unsigned int *comm_error(char *base) { return reinterpret_cast<unsigned int *>(base + (kCommMaxWorld + 1) * 8); }
+__device__ __forceinline__ char *comm_slot(const CommView &c, char *base, unsigned long long seq, int sender) {
+    return base + kCommHeader + ((seq & 1ull) * (unsigned long long)c.world + (unsigned long long)sender) * c.slot_bytes;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// The payload of this rank already sits in ITS OWN slot[seq & 1][rank] (`bytes` of it, a multiple of 16): copy it to every
+// peer, signal, and wait for every sender.  Returns false on a timeout (a peer never arrived: ~2 s), after raising the
+// local error word.  Readers must use __ldcg on the slots (remote stores land in L2; L1 may hold the previous payload).
+__device__ __forceinline__ bool comm_exchange(const CommView &c, unsigned long long seq, unsigned bytes) {
+    char *mine = c.peer[c.rank];
+    const uint4 *src = reinterpret_cast<const uint4 *>(comm_slot(c, mine, seq, c.rank));
+    const unsigned n16 = bytes >> 4;
+    for (int p = 0; p < c.world; ++p) {
+        if (p == c.rank) continue;
+        uint4 *dst = reinterpret_cast<uint4 *>(comm_slot(c, c.peer[p], seq, c.rank));
+        for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldcg(src + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < c.world) st_release_sys(comm_flags(c.peer[threadIdx.x]) + c.rank, seq);
+    __shared__ int s_comm_ok;
+    if (threadIdx.x == 0) s_comm_ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < c.world) {
+        const unsigned long long *f = comm_flags(mine) + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > 4000000000LL) { s_comm_ok = 0; atomicExch(comm_error(mine), 1u); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    return s_comm_ok != 0;
 }
 
 // hdr[7] of a workspace whose LAST forward of geometry g ran to its end (tail / finalize): the order in perm[] is complete

@@ -565,7 +565,7 @@ __device__ __forceinline__ int count_combos(const long long *gc) {
 // owns combo c (the per-lane loads would otherwise be a chain of L2 round trips in a single thread); the terms are
 // summed in a fixed butterfly order, so the result is deterministic.
 __device__ __forceinline__ void finalize_pair(const Workspace &ws, int b, float *out_loss, int *out_status, float *out_median,
-                                              long long *out_stats) {
+                                              long long *out_stats, int extra_status = 0) {
     const int lane = threadIdx.x & 31;
     const int c = lane & 15, k = (c >> 2) + 1, j = (c & 3) + 1;
     const long long n = __ldcg(ws.gcounts + b * 18 + c);
@@ -588,7 +588,7 @@ __device__ __forceinline__ void finalize_pair(const Workspace &ws, int b, float 
     double loss = term;
     const long long nrec = __shfl_sync(0xffffffffu, extra, 0), nD = __shfl_sync(0xffffffffu, extra, 1);
     const long long nan_count = __shfl_sync(0xffffffffu, mystat, 6);
-    int status = 0;
+    int status = extra_status;
     if (C == 0) status |= RRL_STATUS_EMPTY; else loss /= (double)C;
     if (nan_count > 0) status |= RRL_STATUS_NAN;
     if (nanflag) { status |= RRL_STATUS_NAN; loss = __longlong_as_double(0x7ff8000000000000LL); }
@@ -852,6 +852,196 @@ int launch_tail(const Workspace &ws, const Geometry &g, float *out_loss, int *ou
     tail_kernel<<<dim3(S, g.B), kTailThreads, kMedCache * 4, s>>>(ws, g, out_loss, out_status, out_median, out_stats);
     count_launch();
     stage_mark(8, s);
+    return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Line shard: exchange + global median + Welsch + exchange + loss in ONE launch per rank (peer memory, no NCCL)
+// ------------------------------------------------------------------------------------------------------
+// What the NCCL protocol does with ~15 small launches and four collectives (counts, two 256 KB histograms, sums; every
+// one of them a latency-bound round trip through the host-side enqueue): one CTA per rank
+//   1. compacts the rank's valid D entries and its 18 counts into its slot and PUSHES them to every peer over NVLink
+//      (comm_exchange, rrl_common.cuh); when all flags have arrived every rank holds every rank's entries;
+//   2. selects the global lower median of ALL entries itself (same data, same deterministic selection on every rank:
+//      bit-identical medians without a second round), adds up the global counts;
+//   3. runs the Welsch stage on ITS records with the global median and normalisers;
+//   4. pushes its 32 fixed-point partial sums (+ NaN / bad-input bits), sums everybody's (integers: exact, order
+//      independent) and writes the loss -- identical on every rank.
+// The workspace ends up as after a single-GPU forward with GLOBAL med / gcounts, so rrl_loss_backward works unchanged and
+// yields the gradient share of this rank's lines.
+constexpr int kShardThreads = 1024;
+constexpr int kShardEntryOff = 160;          // payload A: 18 int64 counts, padded to a 16-byte boundary, then the float entries
+
+__global__ void __launch_bounds__(kShardThreads) shard_tail_kernel(Workspace ws, Geometry g, CommView comm, float *out_loss,
+                                                                    int *out_status, float *out_median, long long *out_stats) {
+    extern __shared__ unsigned s_keys[];     // [kMedCache]
+    __shared__ SelectScratch sc;
+    __shared__ unsigned long long s_sum[32];
+    __shared__ long long s_gc[18], s_pref[kCommMaxWorld + 1];
+    __shared__ int s_count, s_extra;
+    const int tid = threadIdx.x, lane = tid & 31;
+    char *mine = comm.peer[comm.rank];
+    const unsigned long long seq = *comm_epoch(mine) + 1ull;
+    const bool have = hdr_ok(ws, g);          // a rank without a forward still takes part (with nothing), or its peers would wait
+    const int nrec = have ? ws.nrec[0] : 0;
+    const float *D = ws.recD;
+    const int *meta = ws.recMeta;
+    if (tid < 32) s_sum[tid] = 0ull;
+    if (tid == 0) { sc.kmin = kNoKey; sc.kmax = 0u; s_count = 0; s_extra = 0; ws.hdr[6] = 1; ws.hdr[7] = order_token(g); }
+    __syncthreads();
+    // ---- 1. payload A: counts + compacted entries -> own slot ------------------------------------------------------
+    char *slotA = comm_slot(comm, mine, seq, comm.rank);
+    float *ent = reinterpret_cast<float *>(slotA + kShardEntryOff);
+    const float4 *D4 = reinterpret_cast<const float4 *>(D);
+    for (int i0 = 0; i0 < nrec; i0 += kShardThreads) {                       // block-uniform trip count
+        const int i = i0 + tid;
+        int kj = 0;
+        float4 d[4];
+        if (i < nrec) {
+            kj = meta[i * 2 + 1];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) d[a] = D4[(long long)i * 4 + a];
+        }
+        const int k = kj & 255, j = (kj >> 8) & 255;
+        const int cnt = k * j;
+        int inc = cnt;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, inc, dd);
+            if (lane >= dd) inc += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        int base = 0;
+        if (lane == 0 && total) base = atomicAdd(&s_count, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        int pos = base + inc - cnt;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float dv[4] = {d[a].x, d[a].y, d[a].z, d[a].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (a < k && c < j) ent[pos++] = dv[c];
+        }
+    }
+    __syncthreads();
+    const int nD_local = s_count;
+    if (tid < 18) {
+        long long v = 0;
+        if (tid < 16) v = have ? ws.n_kj[tid] : 0;
+        else if (tid == 16) v = nrec;
+        else v = nD_local;
+        reinterpret_cast<long long *>(slotA)[tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    bool ok = comm_exchange(comm, seq, (unsigned)((kShardEntryOff + 4 * nD_local + 15) & ~15));
+    // ---- 2. global counts, global lower median ----------------------------------------------------------------------
+    if (tid < 18) {
+        long long v = 0;
+        for (int r = 0; r < comm.world; ++r) v += __ldcg(reinterpret_cast<const long long *>(comm_slot(comm, mine, seq, r)) + tid);
+        s_gc[tid] = v;
+        ws.gcounts[tid] = v;
+    }
+    if (tid == 0) {
+        long long acc = 0;
+        for (int r = 0; r < comm.world; ++r) {
+            s_pref[r] = acc;
+            acc += __ldcg(reinterpret_cast<const long long *>(comm_slot(comm, mine, seq, r)) + 17);
+        }
+        s_pref[comm.world] = acc;
+    }
+    __syncthreads();
+    const long long n = s_gc[17];
+    int C = 0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) C += s_gc[c] > 0;
+    float med = 0.f;
+    if (n > 0 && ok) {
+        auto gkey = [&](long long i) -> unsigned {                           // entry i of the concatenation over the senders
+            int r = 0;
+            while (r + 1 < comm.world && i >= s_pref[r + 1]) ++r;
+            const float *e = reinterpret_cast<const float *>(comm_slot(comm, mine, seq, r) + kShardEntryOff);
+            return __float_as_uint(__ldcg(e + (i - s_pref[r])));
+        };
+        unsigned mn = kNoKey, mx = 0u;
+        if (n <= kMedCache) {
+            for (long long i = tid; i < n; i += kShardThreads) {
+                const unsigned kb = gkey(i);
+                s_keys[i] = kb;
+                mn = min(mn, kb); mx = max(mx, kb);
+            }
+            block_minmax(mn, mx, sc);
+            __syncthreads();
+            auto key = [&](long long i) -> unsigned { return s_keys[i]; };
+            med = __uint_as_float(select_lower_median<kShardThreads>(n, n, key, sc.kmin, sc.kmax, sc));
+        } else {
+            for (long long i = tid; i < n; i += kShardThreads) {
+                const unsigned kb = gkey(i);
+                mn = min(mn, kb); mx = max(mx, kb);
+            }
+            block_minmax(mn, mx, sc);
+            __syncthreads();
+            med = __uint_as_float(select_lower_median<kShardThreads>(n, n, gkey, sc.kmin, sc.kmax, sc));
+        }
+    }
+    if (tid == 0) ws.med[0] = med;
+    __syncthreads();                                                         // the key cache becomes the Welsch buffers
+    // ---- 3. Welsch stage on this rank's records ------------------------------------------------------------------------
+    float *wbuf = reinterpret_cast<float *>(s_keys) + (tid >> 5) * 512;
+    for (int i0 = 0; i0 < nrec; i0 += kShardThreads) {                       // block-uniform
+        const long long i = i0 + tid;
+        const bool valid = i < nrec;
+        int combo = 0, k = 1, j = 1;
+        float cw = 0.f;
+        if (valid) {
+            const int kj = meta[i * 2 + 1];
+            k = kj & 255; j = (kj >> 8) & 255;
+            combo = (k - 1) * 4 + (j - 1);
+            cw = combo_weight(k, j) / (float)C / (float)s_gc[combo];
+        }
+        unsigned long long v1, v2;
+        bool nan;
+        welsch_warp(ws, valid, i, med, cw, k, j, wbuf, v1, v2, nan);
+        if (nan) s_extra = 1;                                                // benign race: every writer stores 1
+        warp_combo_add(s_sum, valid, combo, v1, v2);
+    }
+    __syncthreads();
+    // ---- 4. payload B: partial sums + flags; total; loss -----------------------------------------------------------------
+    unsigned long long *slotB = reinterpret_cast<unsigned long long *>(comm_slot(comm, mine, seq + 1ull, comm.rank));
+    if (tid < 32) slotB[tid] = s_sum[tid];
+    if (tid == 32) {
+        const long long nan_cand = have ? ws.stats[6] : 0;
+        const unsigned bad = have ? (ws.bad[0] | ws.bad[1]) : 0u;
+        slotB[32] = (unsigned long long)(s_extra ? 1 : 0) | ((nan_cand > 0 || bad) ? 2ull : 0ull);
+        slotB[33] = 0ull;
+    }
+    __threadfence();
+    __syncthreads();
+    ok = comm_exchange(comm, seq + 1ull, 34 * 8) && ok;
+    if (tid < 33) {
+        unsigned long long v = 0ull;
+        for (int r = 0; r < comm.world; ++r) {
+            const unsigned long long x = __ldcg(reinterpret_cast<const unsigned long long *>(comm_slot(comm, mine, seq + 1ull, r)) + tid);
+            v = tid < 32 ? v + x : (v | x);
+        }
+        if (tid < 32) ws.sums[tid] = v;
+        else { ws.flags[0] = (int)(v & 1ull); s_extra = (v & 2ull) ? RRL_STATUS_NAN : 0; }
+    }
+    if (tid == 0) *comm_epoch(mine) = seq + 1ull;
+    __threadfence();
+    __syncthreads();
+    if (tid < 32) {
+        finalize_pair(ws, 0, out_loss, out_status, out_median, out_stats, s_extra | (ok ? 0 : RRL_STATUS_COMM_BIT));
+        if (!ok && lane == 0) out_loss[0] = __int_as_float(0x7fc00000);
+    }
+}
+
+int launch_shard_tail(const Workspace &ws, const Geometry &g, const CommView &comm, float *out_loss, int *out_status,
+                      float *out_median, long long *out_stats, cudaStream_t s) {
+    static unsigned long long attr_mask = 0ull;
+    if (ensure_dyn_smem(shard_tail_kernel, kMedCache * 4, attr_mask)) return RRL_ERR_CUDA;
+    shard_tail_kernel<<<1, kShardThreads, kMedCache * 4, s>>>(ws, g, comm, out_loss, out_status, out_median, out_stats);
+    count_launch();
     return check_launch();
 }
 

@@ -10,12 +10,86 @@ host logic).  SURVEY 8(e):
                partial sums; in backward the point gradient is all-reduced, or, with reduce_grad=False, left
                local so that the caller reduces it in pose space (line_sharded_twist_loss: 6 floats).
 """
+import ctypes as C
 from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist_
 
 from . import _native as N
+
+
+class PeerComm:
+    """The ranks' peer-memory exchange buffers (include/rrl_b200.h, rrl_comm_*): one per rank, mapped by every rank of the
+    group over CUDA IPC / NVLink.  With it the line shard's exchange step runs INSIDE its kernels (rrl_shard_tail,
+    rrl_comm_allreduce_f64): no NCCL collective, no host round trip, graph-capturable.  torch.distributed only carries
+    the 64-byte IPC handles here, once.  `PeerComm.create` returns None when peer mapping is not available (the callers
+    then fall back to the NCCL protocol)."""
+
+    def __init__(self, handle, rank, world, device, nl_capacity):
+        self.handle, self.rank, self.world, self.device, self.nl_capacity = handle, rank, world, device, nl_capacity
+
+    @staticmethod
+    def slot_bytes_for(nl_local: int) -> int:
+        return 160 + 64 * int(nl_local)
+
+    @classmethod
+    def create(cls, nl_capacity: int, device=None, group=None) -> Optional["PeerComm"]:
+        """Collective over `group` (every rank must call it).  nl_capacity = the largest line shard any rank will pass."""
+        L = N.lib()
+        world = dist_.get_world_size(group) if dist_.is_initialized() else 1
+        rank = dist_.get_rank(group) if dist_.is_initialized() else 0
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = L.rrl_comm_create(rank, world, cls.slot_bytes_for(nl_capacity), C.byref(h))
+            ok = rc == 0
+            mine = torch.zeros(64, dtype=torch.uint8)
+            if ok and world > 1:
+                buf = (C.c_ubyte * 64)()
+                ok = L.rrl_comm_ipc_handle(h, buf) == 0
+                mine = torch.tensor(list(buf), dtype=torch.uint8)
+            if world > 1:
+                # one all-gather of (ok flag + handle): every rank learns whether EVERY rank can take part
+                send = torch.cat([torch.tensor([1 if ok else 0], dtype=torch.uint8), mine]).to(device)
+                recv = torch.empty(world * 65, dtype=torch.uint8, device=device)
+                dist_.all_gather_into_tensor(recv, send, group=group)
+                recv = recv.cpu().reshape(world, 65)
+                all_ok = bool(recv[:, 0].all())
+                if all_ok:
+                    handles = recv[:, 1:].contiguous().numpy().tobytes()
+                    all_ok = L.rrl_comm_connect_ipc(h, handles) == 0
+                # ... and whether every rank managed to map every peer
+                flag = torch.tensor([1 if all_ok else 0], dtype=torch.int32, device=device)
+                dist_.all_reduce(flag, op=dist_.ReduceOp.MIN, group=group)
+                ok = bool(flag.item())
+        if not ok:
+            if h:
+                L.rrl_comm_destroy(h)
+            return None
+        return cls(h, rank, world, device, int(nl_capacity))
+
+    def allreduce_f64_(self, buf: torch.Tensor) -> torch.Tensor:
+        """in place sum over the ranks of a float64 CUDA tensor of <= 512 elements (rank order: bit-identical everywhere)"""
+        assert buf.dtype == torch.float64 and buf.is_contiguous() and buf.numel() <= 512
+        with torch.cuda.device(buf.device):
+            N.check(N.lib().rrl_comm_allreduce_f64(self.handle, buf.data_ptr(), buf.numel(),
+                                                   torch.cuda.current_stream(buf.device).cuda_stream), "rrl_comm_allreduce_f64")
+        return buf
+
+    def error(self) -> int:
+        return int(N.lib().rrl_comm_error(self.handle))
+
+    def close(self):
+        if self.handle:
+            N.lib().rrl_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -77,6 +151,23 @@ class NativeShardBackend:
 
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def fused_forward(self, comm: "PeerComm"):
+        """stage 1 + rrl_shard_tail: the whole line-sharded forward of this rank in the kernels' own exchange"""
+        if self.nl > comm.nl_capacity:
+            raise ValueError("line shard of %d lines exceeds the communicator's capacity (%d)" % (self.nl, comm.nl_capacity))
+        w = self.window
+        loss = torch.empty(1, dtype=torch.float32, device=self.dev)
+        status = torch.empty(1, dtype=torch.int32, device=self.dev)
+        med = torch.empty(1, dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            N.check(self.L.rrl_shard_stage1_ex(self.tri1.data_ptr(), self.tri2.data_ptr(), self.lines.data_ptr(), self.nf1,
+                                               self.nf2, self.nl, w[0], w[1], w[2], w[3], self.ws.data_ptr(), self.wsb,
+                                               self.flags, self._stream()), "rrl_shard_stage1_ex")
+            N.check(self.L.rrl_shard_tail(self.ws.data_ptr(), self.wsb, self.nf1, self.nf2, self.nl, comm.handle,
+                                          loss.data_ptr(), status.data_ptr(), med.data_ptr(), None, self._stream()),
+                    "rrl_shard_tail")
+        return loss, status, med
 
     def _geom(self):
         return self.ws.data_ptr(), self.wsb, self.nf1, self.nf2, self.nl
@@ -154,9 +245,13 @@ def line_shard_forward(backend, group=None):
 
 class _LineShardedLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tri1, tri2, lines_local, window, group, reduce_grad, session=None):
+    def forward(ctx, tri1, tri2, lines_local, window, group, reduce_grad, session=None, comm=None):
         backend = NativeShardBackend(tri1, tri2, lines_local, window, session)
-        loss, status, med = line_shard_forward(backend, group)
+        if comm is not None:
+            loss, status, med = backend.fused_forward(comm)
+        else:
+            with torch.cuda.device(tri1.device):
+                loss, status, med = line_shard_forward(backend, group)
         ctx.ws, ctx.geom, ctx.group, ctx.reduce_grad = backend.ws, (backend.nf1, backend.nf2, backend.nl), group, reduce_grad
         ctx.mark_non_differentiable(status, med)
         return loss, status, med
@@ -170,49 +265,55 @@ class _LineShardedLoss(torch.autograd.Function):
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g1 = torch.empty(nf1, 9, dtype=torch.float32, device=dev) if need1 else None
         g2 = torch.empty(nf2, 9, dtype=torch.float32, device=dev) if need2 else None
-        N.check(N.lib().rrl_loss_backward(ws.data_ptr(), ws.numel(), g.data_ptr(), 1, nf1, nf2, nl,
-                                          g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None,
-                                          torch.cuda.current_stream(dev).cuda_stream), "rrl_loss_backward")
+        with torch.cuda.device(dev):
+            N.check(N.lib().rrl_loss_backward(ws.data_ptr(), ws.numel(), g.data_ptr(), 1, nf1, nf2, nl,
+                                              g1.data_ptr() if need1 else None, g2.data_ptr() if need2 else None,
+                                              torch.cuda.current_stream(dev).cuda_stream), "rrl_loss_backward")
         # every rank holds the replicated clouds, so the point gradient is summed over the line shards
         if ctx.reduce_grad:
             for t in (g1, g2):
                 if t is not None:
                     dist_.all_reduce(t, op=dist_.ReduceOp.SUM, group=ctx.group)
-        return g1, g2, None, None, None, None, None
+        return g1, g2, None, None, None, None, None, None
 
 
 class _AllReduceGrad(torch.autograd.Function):
-    """identity whose gradient is summed over the ranks"""
+    """identity whose gradient is summed over the ranks (through the peer exchange when a PeerComm is given: a few floats)"""
 
     @staticmethod
-    def forward(ctx, x, group):
-        ctx.group = group
+    def forward(ctx, x, group, comm):
+        ctx.group, ctx.comm = group, comm
         return x.view_as(x)
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.comm is not None and g.numel() <= 512:
+            g64 = g.contiguous().double()
+            ctx.comm.allreduce_f64_(g64.view(-1))
+            return g64.to(g.dtype), None, None
         g = g.contiguous().clone()
         dist_.all_reduce(g, op=dist_.ReduceOp.SUM, group=ctx.group)
-        return g, None
+        return g, None, None
 
 
-def line_sharded_twist_loss(twist, raw_tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, session=None):
+def line_sharded_twist_loss(twist, raw_tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, session=None, comm=None):
     """The demo's / large-scan configuration: cloud 1 = se(3) transform of `raw_tri1` (nf1,9) by `twist` (6,), one pair,
     lines sharded.  The sparse point gradient of every rank's line shard is reduced to pose space locally (closed-form
     se(3) backward) and only the 6 twist-gradient floats cross NVLink.  Returns (loss (1,), status, median)."""
     from . import ops
-    tw = _AllReduceGrad.apply(twist.reshape(1, 6), group)
+    tw = _AllReduceGrad.apply(twist.reshape(1, 6), group, comm)
     tri1 = ops.se3_apply(tw, raw_tri1.reshape(1, -1, 3)).reshape(-1, 9)
-    return line_sharded_loss(tri1, tri2, lines_local, window, group, reduce_grad=False, session=session)
+    return line_sharded_loss(tri1, tri2, lines_local, window, group, reduce_grad=False, session=session, comm=comm)
 
 
-def line_sharded_loss(tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, reduce_grad=True, session=None):
+def line_sharded_loss(tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, reduce_grad=True, session=None, comm=None):
     """ONE pair: tri1 (nf1,9) and tri2 (nf2,9) replicated on every rank, lines_local (nl_r,6) = this rank's shard.
     Returns (loss (1,), status (1,), median (1,)) -- identical on all ranks; the point gradients are all-reduced unless
-    reduce_grad=False (then each rank keeps the gradient of its own line shard)."""
+    reduce_grad=False (then each rank keeps the gradient of its own line shard).  With `comm` (a PeerComm) the exchange
+    step of the forward runs inside the kernels over peer memory instead of through four NCCL collectives."""
     from .ops import _cuda_f32
-    if not (dist_.is_available() and dist_.is_initialized()):
-        raise RuntimeError("line_sharded_loss needs an initialised torch.distributed process group")
+    if comm is None and not (dist_.is_available() and dist_.is_initialized()):
+        raise RuntimeError("line_sharded_loss needs an initialised torch.distributed process group (or a PeerComm)")
     w = tuple(int(v) for v in window)
     return _LineShardedLoss.apply(_cuda_f32(tri1, "points1"), _cuda_f32(tri2, "points2"),
-                                  _cuda_f32(lines_local.detach(), "line"), w, group, bool(reduce_grad), session)
+                                  _cuda_f32(lines_local.detach(), "line"), w, group, bool(reduce_grad), session, comm)

@@ -7,7 +7,7 @@ code/exps_deep_learning/pre_dataloader.py:80-166), so that the op can be fed the
 
 Host-side plumbing only (numpy); nothing here is on the hot path.  `load_pair` restates Dataset_2021_8_29.__getitem__
 (centring, the R / T bookkeeping, the DCP / FMR layout switches) and is pinned by tests/golden/loader.npz, minted from the
-unmodified reference class (oracle/make_golden_r2.py; `igl` stubbed there, so `tar_box` is pinned through its first and
+unmodified reference class (by the test infrastructure, make_golden_r2.py; `igl` stubbed there, so `tar_box` is pinned through its first and
 last corner only -- the two the hooks read).
 """
 import os

@@ -50,7 +50,8 @@ enum {
     RRL_STATUS_EMPTY = 1,          /* no (k,j) combo populated: loss = 0, gradients = 0
                                       (the reference returns the tuple (None, None, None), loss.py:232) */
     RRL_STATUS_NAN = 2,            /* a candidate distance was NaN (reference: "Exit the systerm", loss.py:89-91) */
-    RRL_STATUS_NAN_RISK = 4        /* coordinates so large that |AC|^2 cancellation may exceed 2e-4 */
+    RRL_STATUS_NAN_RISK = 4,       /* coordinates so large that |AC|^2 cancellation may exceed 2e-4 */
+    RRL_STATUS_COMM = 8            /* line shard: a peer never arrived at the exchange (rrl_shard_tail timed out) */
 };
 
 int rrl_version(void);
@@ -154,6 +155,37 @@ int rrl_shard_stage2(void *workspace, size_t workspace_bytes, int nf1, int nf2, 
                      const long long *global_counts18, const float *global_median, long long *sums32, void *stream);
 int rrl_shard_stage3(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl,
                      const long long *global_sums32, float *out_loss, int *out_status, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Peer-memory exchange of the line shard ("one exchange step", here without NCCL).  One communicator per
+ * rank (= process = GPU) of a box; the ranks publish the CUDA IPC handle of their buffer, the caller carries the
+ * 64-byte handles between the processes, every rank maps its peers (NVLink peer access).  The exchange is then done
+ * inside kernels: payloads are pushed into the peers' buffers with plain stores, arrival is signalled by a sequence
+ * number, nothing involves the host, everything is CUDA-graph capturable.  Every rank of a communicator must issue the
+ * same sequence of exchanging calls (rrl_shard_tail, rrl_comm_allreduce_f64).
+ *   slot_bytes   capacity of one payload; rrl_shard_tail needs 160 + 64 * nl_local bytes
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct rrl_comm rrl_comm;
+int rrl_comm_create(int rank, int world, size_t slot_bytes, rrl_comm **out);     /* on the current device; world <= 16 */
+void rrl_comm_destroy(rrl_comm *comm);
+size_t rrl_comm_slot_bytes(const rrl_comm *comm);
+void *rrl_comm_local_base(const rrl_comm *comm);
+int rrl_comm_ipc_handle(const rrl_comm *comm, void *out_handle64);
+int rrl_comm_connect_ipc(rrl_comm *comm, const void *handles64 /* world x 64 bytes, rank-major */);
+int rrl_comm_connect_ptrs(rrl_comm *comm, void *const *bases /* world local bases of same-process peers */);
+int rrl_comm_error(const rrl_comm *comm);                                         /* 1 after a timed-out exchange; synchronises */
+/* in-place all-reduce(sum) of n <= 512 doubles, summed in rank order on every rank (bit-identical results) */
+int rrl_comm_allreduce_f64(rrl_comm *comm, double *buf, int n, void *stream);
+/*
+ * Fused tail of the line-sharded forward: after rrl_shard_stage1(_ex) on the same workspace and stream, ONE launch per
+ * rank exchanges the counts and the D entries, selects the global lower median (loss.py:223-224 over the lines of all
+ * ranks), runs the Welsch stage on the rank's records, exchanges the 32 fixed-point partial sums and writes the loss
+ * (loss.py:225-230) -- identical on every rank.  Replaces rrl_shard_counts / rrl_shard_select_* / rrl_shard_stage2/3 and
+ * the four collectives between them.  rrl_loss_backward(B = 1) then yields the gradient share of this rank's lines.
+ * out_status additionally carries bit 8 when a peer never arrived (the loss is NaN then).
+ */
+int rrl_shard_tail(void *workspace, size_t workspace_bytes, int nf1, int nf2, int nl, rrl_comm *comm,
+                   float *out_loss, int *out_status, float *out_median, long long *out_stats, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * se(3): replaces Reconstruction_point.forward / Transform (loss.py:455-463) and se3.exp3

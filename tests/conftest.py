@@ -8,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# the peer-exchange tests run several "ranks" on ONE device, each on its own stream, whose kernels wait for each other:
+# the streams must not share a hardware queue (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def pytest_configure(config):

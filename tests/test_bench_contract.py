@@ -1,6 +1,7 @@
-"""The bench.py contract that can be checked without a GPU: the reference arm (the reference's CPU path, restated in
-oracle/torch_port.py, timed on the host cores) prints ONE JSON line with the keys the driver reads, and the workload
-table carries the sizes of BASELINE.json's configs."""
+"""The bench.py contract that can be checked without a GPU: the reference arm (the unmodified reference from
+baseline/_ref when it is there -- it is fetched by __graft_entry__.build() in the build container --, else the
+eager-torch port) prints ONE JSON line with the keys the driver reads, with the SAME config dict as the GPU arm, and the
+workload table carries the sizes of BASELINE.json's configs."""
 import json
 import os
 import subprocess
@@ -34,7 +35,13 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
     assert d["steps"] == 1 and d["warmup"] == 1 and d["ms_per_step"] > 0 and d["n_gpus"] == 1
     assert "workload" in d["config"] and d["config"]["name"] == "dcp"
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_dict("dcp", 1)                        # what the GPU arm prints: same_config
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "lines" in cb["sample"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "loss.py"))
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "lines" in cb["sample"]
+    if have_ref:
+        assert cb["port_value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0

@@ -3,7 +3,7 @@ import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import rrl_b200
-from oracle import synth
+from tools import synth
 CONFIGS = {"demo": (1, 1024, 20000), "dcp": (32, 1024, 15000), "rpm": (64, 2048, 10000), "large": (1, 500000, 100000)}
 for name in (sys.argv[1:] or ["dcp"]):
     B, nf, nl = CONFIGS[name]

@@ -5,7 +5,7 @@ surface cloud, with and without k-d refinement inside windows of W sorted points
 """
 import numpy as np, sys
 sys.path.insert(0, '.')
-from oracle import synth
+from tools import synth
 def hilbert_key(P, bits=10):
     # Skilling transpose, vectorised. P: (n,3) ints in [0,2^bits)
     X = P.astype(np.uint32).T.copy()

@@ -4,7 +4,7 @@ import numpy as np
 import torch
 sys.path.insert(0, ".")
 import rrl_b200
-from oracle import synth
+from tools import synth
 B, nf, nl = 32, 1024, 15000
 pairs = [synth.make_pair(1000 + i, nf, nl) for i in range(4)]
 idx = [i % 4 for i in range(B)]

@@ -12,7 +12,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import rrl_b200
 from oracle import c_oracle as co
-from oracle import synth
+from tools import synth
 
 dev = torch.device("cuda", local)
 # ---- line shard: one pair, lines split over the ranks ----

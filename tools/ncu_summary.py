@@ -32,6 +32,30 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
 
 
+def opcode_counts(path, metric):
+    """per-opcode instance values of a per-opcode metric for every kernel of the report: [{opcode: count}]"""
+    import re
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv", "--print-metric-instances", "details", "--metrics", metric],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3 or metric not in rows[0]:
+        return []
+    col = rows[0].index(metric)
+    out = []
+    for vals in rows[2:]:
+        d = {}
+        for name, cnt in re.findall(r"([A-Z0-9_.]+): (\d+)", vals[col]):
+            d[name] = int(cnt)
+        out.append(d)
+    return out
+
+
+def fp32_flops(thread_ops):
+    """executed FP32 flops from per-opcode THREAD-instruction counts: packed FFMA2 = 2 FMAs = 4 flops per thread-instruction"""
+    w = {"FFMA2": 4, "FFMA": 2, "FMUL2": 2, "FADD2": 2, "FMUL": 1, "FADD": 1}
+    return float(sum(thread_ops.get(k, 0) * v for k, v in w.items()))
+
+
 def rep(path, out):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -57,6 +81,17 @@ def rep(path, out):
         if r is not None and w is not None:
             d["dram_bytes_per_launch"] = r + w
         kernels.append(d)
+    thr = opcode_counts(path, "sass__thread_inst_executed_true_per_opcode")
+    wrp = opcode_counts(path, "sass__inst_executed_per_opcode")
+    for i, d in enumerate(kernels):
+        if i < len(thr) and thr[i]:
+            d["fp32_flops_per_launch"] = fp32_flops(thr[i])
+            d["fp32_thread_instructions"] = {k: thr[i][k] for k in ("FFMA2", "FFMA", "FMUL2", "FMUL", "FADD") if k in thr[i]}
+            d["thread_instructions_total"] = sum(thr[i].values())
+        if i < len(wrp) and wrp[i]:
+            top = sorted(wrp[i].items(), key=lambda kv: -kv[1])[:16]
+            d["warp_instructions_top"] = OrderedDict(top)
+            d["warp_instructions_total"] = sum(wrp[i].values())
     res = kernels[0] if len(kernels) == 1 else {"kernels": kernels, "dram_bytes_per_launch": kernels[0].get("dram_bytes_per_launch")}
     res["source"] = path
     json.dump(res, open(out, "w"), indent=1)

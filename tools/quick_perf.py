@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, ".")
 import rrl_b200
-from oracle import synth
+from tools import synth
 
 L = rrl_b200._native.lib()
 out = {}

@@ -5,7 +5,7 @@ import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import rrl_b200
-from oracle import synth
+from tools import synth
 L = rrl_b200._native.lib()
 for name, (B, nf, nl, rs) in {"dcp": (32, 1024, 15000, 0.5), "dcp-wide-sphere": (32, 1024, 15000, 2.0),
                               "large-lines": (1, 20000, 100000, 0.5)}.items():

@@ -4,7 +4,7 @@ import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import rrl_b200
-from oracle import synth
+from tools import synth
 name = sys.argv[1] if len(sys.argv) > 1 else "dcp"
 B, nf, nl = {"dcp": (32, 1024, 15000), "rpm": (64, 2048, 10000), "fmr": (128, 1024, 15000)}[name]
 pairs = [synth.make_pair(1000 + i, nf, nl) for i in range(8)]

@@ -3,7 +3,7 @@ import ctypes as C, json, sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import rrl_b200
-from oracle import synth
+from tools import synth
 L = rrl_b200._native.lib()
 CONFIGS = {"demo": (1, 1024, 20000), "dcp": (32, 1024, 15000), "rpm": (64, 2048, 10000), "fmr": (128, 1024, 15000), "large": (1, 500000, 100000),
            "mid": (8, 8192, 10000), "big": (2, 65536, 20000)}
