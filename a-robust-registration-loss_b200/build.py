@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
             sys.stderr.write("== %s ==\n%s\n" % (src, out))
         if p.returncode:
             raise RuntimeError("nvcc failed on " + src)
-    subprocess.run([_nvcc()] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart"], check=True)
+    subprocess.run([_nvcc()] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"], check=True)
     return OUT
 
 

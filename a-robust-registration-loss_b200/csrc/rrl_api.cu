@@ -117,10 +117,18 @@ static Geometry make_geometry(int B, int nf1, int nf2, int nl) {
 static int stage_dense_and_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws,
                                  const Geometry &g, int k_lo, int j_lo, int k_hi, int j_hi, int flags, cudaStream_t s) {
     const int window = k_lo | (j_lo << 8) | (k_hi << 16) | (j_hi << 24);
-    int rc = launch_prep(tri1, tri2, lines, ws, g, window, (flags & RRL_REUSE_ORDER) != 0, s);
+    int rc;
+    {
+        Range r("rrl.prep (thresholds, order, bounding spheres)");
+        rc = launch_prep(tri1, tri2, lines, ws, g, window, (flags & RRL_REUSE_ORDER) != 0, s);
+    }
     if (rc) return rc;
-    rc = launch_dense(tri1, tri2, lines, ws, g, s);
+    {
+        Range r("rrl.dense (filtered point-line predicate + exact test)");
+        rc = launch_dense(tri1, tri2, lines, ws, g, s);
+    }
     if (rc) return rc;
+    Range r("rrl.build (intersection points, D)");
     return launch_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, s);
 }
 
@@ -160,8 +168,10 @@ extern "C" int rrl_loss_forward_ex(const float *tri1, const float *tri2, const f
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
     const Geometry g = make_geometry(B, nf1, nf2, nl);
     cudaStream_t s = (cudaStream_t)stream;
+    Range fwd("rrl_loss_forward");
     int rc = stage_dense_and_build(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi, flags, s);
     if (rc) return rc;
+    Range r("rrl.tail (median, Welsch, loss)");
     return launch_tail(ws, g, out_loss, out_status, out_median, out_stats, s);
 }
 
@@ -178,6 +188,7 @@ extern "C" int rrl_loss_backward(const void *workspace, size_t workspace_bytes, 
     const Workspace ws = carve(const_cast<void *>(workspace), B, nf1, nf2, nl);
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
     if (!grad_tri1 && !grad_tri2) return RRL_OK;
+    Range r("rrl_loss_backward");
     return launch_backward(ws, make_geometry(B, nf1, nf2, nl), grad_out, grad_tri1, grad_tri2, (cudaStream_t)stream);
 }
 
@@ -199,6 +210,7 @@ extern "C" int rrl_shard_stage1_ex(const float *tri1, const float *tri2, const f
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return RRL_ERR_ARG;
     const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    Range r("rrl_shard_stage1");
     return stage_dense_and_build(tri1, tri2, lines, ws, make_geometry(1, nf1, nf2, nl), k_lo, j_lo, k_hi, j_hi, flags,
                                  (cudaStream_t)stream);
 }

@@ -134,6 +134,7 @@ extern "C" int rrl_comm_error(const rrl_comm *c) {
 extern "C" int rrl_comm_allreduce_f64(rrl_comm *c, double *buf, int n, void *stream) {
     if (!c || !buf || n <= 0 || n > kMaxAllreduce || !c->connected) return RRL_ERR_ARG;
     if ((size_t)(n + 1) * 8 > c->slot_bytes) return RRL_ERR_WORKSPACE;
+    Range r("rrl_comm_allreduce_f64");
     comm_allreduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(comm_view(c), buf, n);
     count_launch();
     return check_launch();
@@ -149,6 +150,7 @@ extern "C" int rrl_shard_tail(void *workspace, size_t workspace_bytes, int nf1, 
     const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
     if ((size_t)160 + (size_t)64 * nl > c->slot_bytes) return RRL_ERR_WORKSPACE;
+    Range r("rrl_shard_tail (peer exchange, global median, Welsch, loss)");
     Geometry g;
     g.B = 1; g.nf1 = nf1; g.nf2 = nf2; g.nl = nl; g.nf1p = pad_points(nf1); g.nf2p = pad_points(nf2);
     return launch_shard_tail(ws, g, comm_view(c), out_loss, out_status, out_median, out_stats, (cudaStream_t)stream);

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -114,6 +115,15 @@ size_t sort_scratch_bytes(int nfp_max, int B);
 int node_size(const Geometry &g);       // triplets per bounding-sphere node for this geometry (8 or 16)
 
 Workspace carve(void *base, int B, int nf1, int nf2, int nl);
+
+// ---- tracing: NVTX ranges around the stages of every entry point; header-only NVTX3 costs one pointer check per
+// call unless a profiler (nsys / ncu --nvtx) injected itself
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range &) = delete;
+    Range &operator=(const Range &) = delete;
+};
 
 // ---- launch bookkeeping -------------------------------------------------------------------------------
 int sm_count();              // multiprocessors of the CURRENT device (cached per device; 148 on a B200)

@@ -317,6 +317,7 @@ extern "C" int rrl_sample_lines(const float *radius, const float *centers, const
     if (B <= 0 || n1 <= 0 || n2 <= 0 || N <= 0 || rounds <= 0) return RRL_ERR_ARG;
     if ((long long)rounds * N >= (1LL << 31) - kChunk) return RRL_ERR_ARG;
     if (workspace_bytes < rrl_sampler_workspace_bytes(B, N, rounds)) return RRL_ERR_WORKSPACE;
+    Range range("rrl_sample_lines");
     cudaStream_t s = (cudaStream_t)stream;
     SamplerArgs a;
     a.radius = radius; a.centers = centers; a.uniforms = uniforms;

@@ -276,6 +276,7 @@ extern "C" int rrl_se3_expmap_backward(const float *twist, const float *grad_g, 
 
 extern "C" int rrl_se3_apply(const float *twist, const float *points, int B, int n, float *out, void *stream) {
     if (!twist || !points || !out || B <= 0 || n <= 0) return RRL_ERR_ARG;
+    Range r("rrl_se3_apply");
     apply_kernel<true><<<point_grid(B, n), 256, 0, (cudaStream_t)stream>>>(twist, nullptr, points, n, out);
     count_launch();
     return check_launch();
@@ -284,6 +285,7 @@ extern "C" int rrl_se3_apply(const float *twist, const float *points, int B, int
 extern "C" int rrl_se3_apply_backward(const float *twist, const float *points, const float *grad_out, int B, int n,
                                       float *grad_twist, double *scratch, void *stream) {
     if (!twist || !points || !grad_out || !grad_twist || !scratch || B <= 0 || n <= 0) return RRL_ERR_ARG;
+    Range r("rrl_se3_apply_backward");
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(scratch, 0, sizeof(double) * 12 * (size_t)B, s) != cudaSuccess) return RRL_ERR_CUDA;
     reduce_pg_kernel<<<point_grid(B, n), 256, 0, s>>>(points, grad_out, n, scratch);

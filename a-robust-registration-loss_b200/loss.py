@@ -75,18 +75,24 @@ def _batch_of_slice(t):
 class _SliceBatch:
     """One batched evaluation serving the per-pair calls of a hook's Python loop."""
 
-    def __init__(self, bases, window):
+    def __init__(self, bases, slices, window):
         self.bases = bases                                    # the three base tensors (kept alive: ids stay unique)
         self.versions = tuple(b._version for b in bases)
         self.window = window
-        self.per_pair = None
+        self.offs = tuple(t.storage_offset() for t in slices)              # storage offsets of slice 0 ...
+        self.steps = tuple(t.shape[1] * t.shape[2] for t in slices)        # ... and their increment per pair
+        self.shapes = tuple(t.shape for t in slices)
+        self.parts = None                                     # per-pair losses, split ONCE: (1,) views under one autograd node
         self.info = None
         self.next = 0
 
-    def matches(self, bases, window, j):
-        return (self.per_pair is not None and j == self.next and window == self.window and
-                all(a is b for a, b in zip(self.bases, bases)) and
-                self.versions == tuple(b._version for b in bases))
+    def serves(self, slices, window):
+        """is this call the next slice of the same, unmodified tensors?  (the cheap test made on every call of the loop)"""
+        j = self.next
+        for t, b, v, o, st, sh in zip(slices, self.bases, self.versions, self.offs, self.steps, self.shapes):
+            if t._base is not b or b._version != v or t.storage_offset() != o + j * st or t.shape != sh:
+                return False
+        return window == self.window
 
 
 _slice_batch = None
@@ -95,22 +101,22 @@ _slice_batch = None
 def _loss_of_slices(points1, points2, line, window):
     """per-pair loss (1,) of a B = 1 call, served from a batched evaluation when the arguments are slices of one batch"""
     global _slice_batch, last_info
-    found = [_batch_of_slice(t) for t in (points1, points2, line)]
-    if any(f is None for f in found) or len({f[1] for f in found}) != 1 or len({f[0].shape[0] for f in found}) != 1:
-        return None
-    j = found[0][1]
-    bases = tuple(t._base for t in (points1, points2, line))
+    slices = (points1, points2, line)
     sb = _slice_batch
-    if sb is None or not sb.matches(bases, window, j):
-        if j != 0:
-            return None                                       # not the start of a loop over the batch: evaluate it alone
-        sb = _SliceBatch(bases, window)
-        sb.per_pair, sb.info = ops.intersected_line_loss(found[0][0], found[1][0], found[2][0], window, return_info=True)
+    if sb is None or not sb.serves(slices, window):
+        found = [_batch_of_slice(t) for t in slices]
+        if any(f is None for f in found) or found[0][1] != 0 or found[1][1] != 0 or found[2][1] != 0:
+            return None                                       # not the start of a loop over a batch: evaluate it alone
+        if len({f[0].shape[0] for f in found}) != 1:
+            return None
+        sb = _SliceBatch(tuple(t._base for t in slices), slices, window)
+        per_pair, sb.info = ops.intersected_line_loss(found[0][0], found[1][0], found[2][0], window, return_info=True)
+        sb.parts = per_pair.split(1)
         _slice_batch = sb
-    sb.next = j + 1
+    out = sb.parts[sb.next]
+    sb.next += 1
     last_info = sb.info
-    out = sb.per_pair[j:j + 1]
-    if sb.next >= sb.per_pair.shape[0]:
+    if sb.next >= len(sb.parts):
         _slice_batch = None                                   # loop finished: let the workspace go with the graph
     return out
 

@@ -363,26 +363,32 @@ class Timer:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
-    def run(self, step, steps, warmup, after=None):
+    def run(self, step, steps, warmup, after=None, repeats=1):
+        """`repeats` timed regions of EXACTLY `steps` steps each (barrier + synchronize on both sides, CUDA events, max over
+        ranks); returns the median region's ms per step, the last step's outputs and every region's ms per step"""
         torch = self.torch
         for i in range(warmup):
             step(i)
         if after:
             after()
-        self.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        per = []
         last = None
-        for i in range(steps):
-            last = step(i)
-        if after:
-            after()
-        e1.record()
-        self.barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
-        if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return float(t.item()) / steps, last
+        for _ in range(repeats):
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                last = step(i)
+            if after:
+                after()
+            e1.record()
+            self.barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+            if self.world > 1:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            per.append(float(t.item()) / steps)
+        self.last_repeats = per
+        return float(np.median(per)), last
 
 
 def capture_graphs(torch, rrl_b200, compute, n_sets, dev, barrier):
@@ -521,12 +527,13 @@ def run_gpu(args):
     warm = max(args.warmup, 3)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = rrl_b200.launch_count()
-    ms_per_step, last = T.run(step, args.steps, warm, after=drain)
+    ms_per_step, last = T.run(step, args.steps, warm, after=drain, repeats=args.repeats)
+    main_repeats = list(T.last_repeats)
     launches = rrl_b200.launch_count() - launches0
     if graphs:                                            # replayed, not re-issued by the host: count what each graph holds
         launches = sum(graphs[i % n_sets][2] for i in range(args.steps))
     else:
-        launches = launches * args.steps // (args.steps + warm)
+        launches = launches * args.steps // (args.steps * args.repeats + warm)
     clocks = sampler.stop() if sampler else None
     value = world * B * nl / (ms_per_step * 1e-3)
 
@@ -562,6 +569,9 @@ def run_gpu(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg,
             "run": {"launch": "one CUDA graph per input set" if graphs else "eager launches", "input_sets": n_sets,
+                    "timed_regions_ms_per_step": main_repeats,
+                    "statistic": "median of %d timed regions of exactly %d steps each (a single region of %d steps lasts a few "
+                                 "milliseconds)" % (args.repeats, args.steps, args.steps),
                     "api": "rrl_b200.intersected_line_loss (torch.autograd.Function over the C ABI), forward + backward"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "lines_sampled_on_device": sampled, "dropin": dropin, "hooks": hooks, "large": large,
@@ -672,16 +682,31 @@ def bench_hook_paths(args, torch, rrl_b200, T, dev_sets, B, nf, nl, world, n_set
     res = {}
     steps = max(10, min(args.steps, 50))
     M.BATCH_SLICES = True
-    ms_b, out_b = T.run(loop_step, steps, 3)
+    ms_b, _ = T.run(loop_step, steps, 3)
+    out_b = loop_step(0)
     M.BATCH_SLICES = False
     try:
-        ms_u, out_u = T.run(loop_step, max(3, steps // 5), 1)
+        ms_u, _ = T.run(loop_step, max(3, steps // 5), 1)
+        out_u = loop_step(0)
     finally:
         M.BATCH_SLICES = True
+    # what the caller's own Python costs: the same loop with the loss call replaced by a constant (1,) tensor -- slicing,
+    # `/ 5.0`, `+=`, the transform and their autograd nodes are the hook's, not the library's
+    const = torch.zeros(1, device=dev, requires_grad=True)
+    real = M.cal_loss_intersection_batch_whole_median_pts_lines
+    M.cal_loss_intersection_batch_whole_median_pts_lines = lambda *a, **k: const * 1.0
+    try:
+        ms_floor, _ = T.run(loop_step, steps, 3)
+    finally:
+        M.cal_loss_intersection_batch_whole_median_pts_lines = real
     dropin = {"api": "rrl_b200.loss.cal_loss_intersection_batch_whole_median_pts_lines called on B=1 slices in the reference's "
                      "own Python loop (Train_DCP.py:252-297 replayed literally, eager launches, backward to the predicted R, t)",
               "ms_per_step": ms_b, "value": world * B * nl / (ms_b * 1e-3), "unit": "pairs*lines/s",
               "vs_batched_step": ms_b / batched_ms,
+              "callers_own_python_ms_per_step": ms_floor,
+              "callers_own_python_note": "the same hook loop with the loss call stubbed by a constant tensor: the 32 x (3 slices, "
+                                         "/ 5.0, +=) eager torch ops and autograd nodes of Train_DCP.py:266-270 themselves",
+              "library_share_ms_per_step": ms_b - ms_floor,
               "without_slice_batching_ms_per_step": ms_u, "without_slice_batching_value": world * B * nl / (ms_u * 1e-3),
               "loss_equal_bits": bool(out_b[0].item() == out_u[0].item())}
     ms_h, _ = T.run(hook_step, steps, 3)
@@ -900,6 +925,7 @@ def main():
     ap.add_argument("--reuse-order", type=int, default=0, help="workload large: headline = the step with the clouds' order kept from step to step")
     ap.add_argument("--large-block", type=int, default=1, help="default workload: also measure BASELINE configs[4] (block `large` of the line)")
     ap.add_argument("--e2e-repeats", type=int, default=5)
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps each; the median is reported")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

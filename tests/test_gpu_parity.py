@@ -84,10 +84,16 @@ def test_empty_selection(rrl):
     out = _run(rrl, g["tri1"], g["tri2"], g["lines"])
     assert out["status"] & 1 and out["loss"] == 0.0
     assert not out["grad1"].any() and not out["grad2"].any()
-    rrl.loss.STRICT_EMPTY_RETURN = True
-    res = rrl.loss.cal_loss_intersection_batch_whole_median_pts_lines(
-        1, 1, 5, 5, torch.from_numpy(g["tri1"]).cuda()[None], torch.from_numpy(g["tri2"]).cuda()[None],
-        torch.from_numpy(g["lines"]).cuda()[None], "cuda")
+    args = (1, 1, 5, 5, torch.from_numpy(g["tri1"]).cuda()[None], torch.from_numpy(g["tri2"]).cuda()[None],
+            torch.from_numpy(g["lines"]).cuda()[None], "cuda")
+    # default: asynchronous, an empty pair is a zero loss with the status bit in the side channel
+    res = rrl.loss.cal_loss_intersection_batch_whole_median_pts_lines(*args)
+    assert res.shape == (1,) and res.item() == 0.0 and int(rrl.loss.last_info.status[0]) & 1
+    rrl.loss.STRICT_EMPTY_RETURN = True             # opt-in: the reference's return value (one host read per call)
+    try:
+        res = rrl.loss.cal_loss_intersection_batch_whole_median_pts_lines(*args)
+    finally:
+        rrl.loss.STRICT_EMPTY_RETURN = False
     assert res == (None, None, None)                # loss.py:232
 
 
@@ -347,22 +353,35 @@ def test_host_buffer_pipelined_submit_wait(rrl):
 
 
 def test_full_size_dcp_batch_properties(rrl):
-    """BASELINE config 2 at full size (32 x 1024 triplets x 15000 lines): the oracle checks a few pairs completely,
-    every pair through size-independent properties."""
+    """BASELINE config 2 at full size (32 x 1024 triplets x 15000 lines): the oracle checks EVERY pair completely (hit
+    lists of both clouds, median, loss), three of them with gradients; every pair also through size-independent
+    properties."""
     B, nf, nl = 32, 1024, 15000
     pairs = [synth.make_pair(2000 + i, nf, nl) for i in range(B)]
     t1 = torch.from_numpy(np.stack([p["tri1"] for p in pairs])).cuda()
     t2 = torch.from_numpy(np.stack([p["tri2"] for p in pairs])).cuda()
     ln = torch.from_numpy(np.stack([p["lines"] for p in pairs])).cuda()
+    t1.requires_grad_(True)
     loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True)
+    loss.sum().backward()
+    _g1 = t1.grad.cpu().numpy()
+    t1 = t1.detach()
+    loss = loss.detach()
     c1, h1 = info.hits(1)
-    for i in (0, 13, 31):
-        orc = co.loss(pairs[i]["tri1"], pairs[i]["tri2"], pairs[i]["lines"], want_grad=False)
-        assert np.array_equal(c1[i].cpu().numpy(), orc.counts1)
+    c2, h2 = info.hits(2)
+    c1n, h1n, c2n, h2n = (x.cpu().numpy() for x in (c1, h1, c2, h2))
+    for i in range(B):
+        orc = co.loss(pairs[i]["tri1"], pairs[i]["tri2"], pairs[i]["lines"], want_grad=i in (0, 13, 31))
+        assert np.array_equal(c1n[i], orc.counts1) and np.array_equal(c2n[i], orc.counts2)
         keep = orc.counts1 <= co.CAP
-        assert np.array_equal(h1[i].cpu().numpy()[keep], orc.hits1[keep])
+        assert np.array_equal(h1n[i][keep], orc.hits1[keep])
+        keep2 = orc.counts2 <= co.CAP
+        assert np.array_equal(h2n[i][keep2], orc.hits2[keep2])
         assert float(info.median[i]) == orc.median
         assert abs(loss[i].item() - orc.loss) <= REL_TOL * orc.loss
+        assert int(info.stats[i, 5]) == orc.band
+        if i in (0, 13, 31):
+            assert _rel(_g1[i], orc.grad1) <= REL_TOL
     # swapping the clouds of every pair transposes every D matrix: same medians, same losses (symmetry of loss.py:227-229)
     loss_sw, info_sw = rrl.intersected_line_loss(t2, t1, ln, return_info=True)
     assert torch.equal(info_sw.median, info.median)
@@ -373,6 +392,72 @@ def test_full_size_dcp_batch_properties(rrl):
         ok = (c > s + 1)
         assert np.all(h[..., s][ok] < h[..., s + 1][ok])
     assert h.max() < nf and int(info.stats[:, 6].sum()) == 0
+
+
+def _bruteforce_all(rrl, t1, t2, ln):
+    L = rrl._native.lib()
+    try:
+        L.rrl_debug_set_param(5, 1)
+        loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True)
+        out = [x.cpu().numpy() for x in info.hits(1) + info.hits(2)] + [loss.cpu().numpy(), info.median.cpu().numpy()]
+    finally:
+        L.rrl_debug_set_param(5, 0)
+    return out
+
+
+@pytest.mark.parametrize("name,B,nf,nl,kw,n_oracle", [
+    ("rpm", 64, 2048, 10000, dict(radius_scale=1.0, noise=0.01, outlier_frac=0.1, keep_frac=0.7), 6),
+    ("fmr", 128, 1024, 15000, dict(radius_scale=0.5), 6),
+])
+def test_full_size_rpm_and_fmr_batches(rrl, name, B, nf, nl, kw, n_oracle):
+    """BASELINE configs 3 and 4 at full size (64 x 2048 x 10000 with noise / outliers / partial overlap; 128 x 1024 x 15000):
+    distinct pairs, `n_oracle` of them checked completely against the C oracle (hit lists, median, loss, gradient), ALL of
+    them against the on-device brute-force kernel (every (line, triplet) tested with the reference's own arithmetic)."""
+    base = [synth.make_pair(3000 + 131 * B + i, nf, nl, **kw) for i in range(16)]
+    rng = np.random.default_rng(B)
+    t1l, t2l, lnl = [], [], []
+    for i in range(B):
+        p = base[i % 16]
+        if i < 16:
+            Rm, t = np.eye(3), np.zeros(3)
+        else:                                              # rigidly moved copies: distinct bits, same statistics
+            Rm, t = synth.random_rotation(rng, 180.0), rng.uniform(-0.5, 0.5, 3)
+        mv = lambda x: (x.reshape(-1, 3).astype(np.float64) @ Rm.T + t).astype(np.float32)
+        t1l.append(mv(p["tri1"]).reshape(-1, 9)); t2l.append(mv(p["tri2"]).reshape(-1, 9))
+        l64 = p["lines"].astype(np.float64)
+        lnl.append(np.concatenate([l64[:, :3] @ Rm.T, l64[:, 3:] @ Rm.T + t], 1).astype(np.float32))
+    tri1, tri2, lines = np.stack(t1l), np.stack(t2l), np.stack(lnl)
+    t1 = torch.from_numpy(tri1).cuda().requires_grad_(True)
+    t2 = torch.from_numpy(tri2).cuda(); ln = torch.from_numpy(lines).cuda()
+    loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True)
+    loss.sum().backward()
+    c1, h1 = (x.cpu().numpy() for x in info.hits(1))
+    c2, h2 = (x.cpu().numpy() for x in info.hits(2))
+    g1 = t1.grad.cpu().numpy()
+    for i in list(range(n_oracle - 2)) + [B // 2, B - 1]:
+        orc = co.loss(tri1[i], tri2[i], lines[i])
+        assert np.array_equal(c1[i], orc.counts1) and np.array_equal(c2[i], orc.counts2)
+        assert np.array_equal(h1[i][orc.counts1 <= co.CAP], orc.hits1[orc.counts1 <= co.CAP])
+        assert np.array_equal(h2[i][orc.counts2 <= co.CAP], orc.hits2[orc.counts2 <= co.CAP])
+        assert float(info.median[i]) == orc.median and int(info.stats[i, 5]) == orc.band
+        assert abs(loss[i].item() - orc.loss) <= REL_TOL * orc.loss
+        assert _rel(g1[i], orc.grad1) <= REL_TOL
+    b1, bh1, b2, bh2, bloss, bmed = _bruteforce_all(rrl, t1.detach(), t2, ln)
+    assert np.array_equal(c1, b1) and np.array_equal(c2, b2)
+    assert np.array_equal(h1[c1 <= co.CAP], bh1[c1 <= co.CAP]) and np.array_equal(h2[c2 <= co.CAP], bh2[c2 <= co.CAP])
+    assert np.array_equal(loss.detach().cpu().numpy(), bloss) and np.array_equal(info.median.cpu().numpy(), bmed)
+    assert int(info.stats[:, 6].sum()) == 0 and not bool((info.status != 0).any())
+
+
+def test_more_d_entries_than_the_median_cache(rrl):
+    """a pair whose selected lines hold more D entries than the tail kernel caches in shared memory (49152): the median
+    is then selected by sweeps over the records in global memory"""
+    nf, nl = 1024, 100000
+    p = synth.make_pair(4100, nf, nl)
+    out = _run(rrl, p["tri1"], p["tri2"], p["lines"])
+    orc = co.loss(p["tri1"], p["tri2"], p["lines"])
+    assert orc.n_entries > 49152                               # the premise
+    _check_against_oracle(out, orc)
 
 
 def test_large_cloud_path_vs_oracle(rrl):
