@@ -67,6 +67,9 @@ def lib():
         "rrl_rigid_apply_backward": (ci, [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]),
         "rrl_sampler_workspace_bytes": (cz, [ci, ci, ci]),
         "rrl_sample_lines": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, cull, cull, vp, vp, vp, vp, cz, vp]),
+        "rrl_sampler_num_chunks": (ci, [ci, ci]),
+        "rrl_sample_lines_shard_flags": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, cull, cull, vp, ci, ci, vp, vp, cz, vp]),
+        "rrl_sample_lines_shard_scatter": (ci, [vp, vp, ci, ci, ci, cull, cull, vp, ci, ci, vp, vp, vp, vp, vp, cz, vp]),
         "rrl_chamfer": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),
         "rrl_chamfer_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp]),
         "rrl_chamfer_backward": (ci, [vp, vp, vp, vp, ci, ci, ci, vp, vp, vp]),
@@ -105,7 +108,7 @@ EXPORTED = ["rrl_version", "rrl_error_string", "rrl_launch_count", "rrl_workspac
             "rrl_comm_create", "rrl_comm_destroy", "rrl_comm_slot_bytes", "rrl_comm_local_base", "rrl_comm_ipc_handle",
             "rrl_comm_connect_ipc", "rrl_comm_connect_ptrs", "rrl_comm_error", "rrl_comm_allreduce_f64",
             "rrl_se3_exp", "rrl_se3_exp4", "rrl_se3_expmap_backward", "rrl_se3_apply", "rrl_se3_apply_backward", "rrl_rigid_apply", "rrl_rigid_apply_backward",
-            "rrl_sampler_workspace_bytes", "rrl_sample_lines", "rrl_chamfer", "rrl_chamfer_forward", "rrl_chamfer_backward", "rrl_fps_workspace_bytes", "rrl_fps", "rrl_knn", "rrl_host_create", "rrl_host_destroy",
+            "rrl_sampler_workspace_bytes", "rrl_sample_lines", "rrl_sampler_num_chunks", "rrl_sample_lines_shard_flags", "rrl_sample_lines_shard_scatter", "rrl_chamfer", "rrl_chamfer_forward", "rrl_chamfer_backward", "rrl_fps_workspace_bytes", "rrl_fps", "rrl_knn", "rrl_host_create", "rrl_host_destroy",
             "rrl_host_pinned_tri1", "rrl_host_pinned_tri2", "rrl_host_pinned_lines", "rrl_host_subbatches", "rrl_host_loss_fwd_bwd",
             "rrl_host_slots", "rrl_host_submit", "rrl_host_wait",
             "rrl_measure_fp32_peak", "rrl_measure_dense", "rrl_measure_stages", "rrl_debug_set_dense_variant",

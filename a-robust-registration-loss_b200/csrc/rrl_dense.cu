@@ -537,8 +537,23 @@ __device__ __forceinline__ float make_super_block(const float *__restrict__ tri,
     return rad;
 }
 
+#ifndef RRL_PF_LEVEL1
+#define RRL_PF_LEVEL1 0
+#endif
+#ifndef RRL_PF_LEVEL2
+#define RRL_PF_LEVEL2 0
+#endif
+#ifndef RRL_L2_PRELOAD
+#define RRL_L2_PRELOAD 0
+#endif
+#ifndef RRL_SUPER_MINBLOCKS
+#define RRL_SUPER_MINBLOCKS 0
+#endif
+#ifndef RRL_NODE_MINBLOCKS
+#define RRL_NODE_MINBLOCKS 4                  // 64 registers: 4 CTAs per SM (139 registers = ONE CTA per SM took 196 us at 500k, 4 take 84)
+#endif
 template <int kNode>
-__global__ void __launch_bounds__(256) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g, int ball_iters,
+__global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g, int ball_iters,
                                                    int supers) {
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
@@ -968,7 +983,7 @@ struct DenseCfg {
     static constexpr int kLines = kDenseThreads * LPT;                 // lines per CTA
     static constexpr int kTile = LPT >= 4 ? 256 : 128;                 // nodes per TMA stage
     static constexpr int kStage = (kTile / 4) * 5;                     // float4 per stage: 5 per group of 4 nodes
-    static constexpr int kWq = LPT >= 4 || kSuper ? 512 : 256;         // per warp: (line, group) entries, or (line, node) when kPerNode
+    static constexpr int kWq = LPT >= 4 || (kSuper && LPT > 1) ? 512 : 256;         // per warp: (line, group) entries, or (line, node) when kPerNode
     static constexpr int kNq = 256;                                    // per warp: (line, node) entries of the 3-level pipeline
     static constexpr int kXq = 32 * kNode + 64;                        // per warp: (line, triplet); one level-2 pass appends <= 32 * kNode
     // kPerNode (small clouds): the chunk's point records are staged in shared memory -- the launch sizes the chunks to
@@ -983,7 +998,9 @@ struct DenseCfg {
     static constexpr int kOffPts = kOffXq + kNumWarps * kXq * 4;
     static constexpr int kOffPts12 = kOffPts + kPts * 16;
     static constexpr int kSmem = kOffPts12 + kPts12 * 16;
-    static constexpr int kMinBlocks = (227 * 1024) / (kSmem + 2048) >= 4 && LPT < 4 ? 4 : ((227 * 1024) / (kSmem + 2048) >= 3 && LPT < 4 ? 3 : 2);
+    static constexpr int kFitBlocks = (227 * 1024) / (kSmem + 2048);
+    // one line per thread (super-node mode only): the main loop is a small part there, the queue levels want warps
+    static constexpr int kMinBlocks = (kSuper && RRL_SUPER_MINBLOCKS > 0) ? (RRL_SUPER_MINBLOCKS < kFitBlocks ? RRL_SUPER_MINBLOCKS : kFitBlocks) : LPT == 1 ? (kFitBlocks >= 5 ? 5 : kFitBlocks) : (kFitBlocks >= 4 && LPT < 4 ? 4 : (kFitBlocks >= 3 && LPT < 4 ? 3 : 2));
     static_assert(kMinBlocks * (kSmem + 2048) <= 227 * 1024, "CTAs per SM must fit (dynamic + static + 1 KB reserved each)");
 };
 
@@ -1180,6 +1197,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                     keep = (fmaf(t1, t1, s1) > c1.w) & (fmaf(t2, t2, s2) > c1.w);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();                                  // every lane has read its entry before any slot is overwritten
                 if (keep) xq[kept + __popc(bal & ((1u << lane) - 1u))] = xent;
                 kept += __popc(bal);
                 __syncwarp();
@@ -1222,6 +1240,17 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         for (int base = 0; base < nq_cnt; base += 32) {
             if (xq_cnt + 32 * kNode > kExactQueue) run_exact();
             unsigned pm = 0, key = 0;
+#if RRL_PF_LEVEL2
+            if constexpr (!kPerNode) {
+                // the NEXT pass's triplet records (one node = (kNode + 1) float4, scattered over the cloud) towards L1 while
+                // this pass computes: a pass otherwise starts with a full L2 round trip per group of loads
+                if (base + 32 + lane < nq_cnt) {
+                    const char *nx = reinterpret_cast<const char *>(pts + (int)(nq[base + 32 + lane] & 0x3FFFFFu) * (kNode + 1));
+#pragma unroll
+                    for (int o = 0; o < (kNode + 1) * 16; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + o));
+                }
+            }
+#endif
             if (base + lane < nq_cnt) {
                 const unsigned ent = nq[base + lane];
                 const int lrel = (int)(ent >> 22), nrel = (int)(ent & 0x3FFFFFu);
@@ -1230,9 +1259,22 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
                 const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
                 const float4 *pp = pts + nrel * (kNode + 1);
+#if RRL_L2_PRELOAD
+                // large clouds read the records through L2 (every lane another node): all kNode loads are issued before the
+                // first use, so a pass waits for ONE L2 round trip instead of one per group the register budget allowed
+                float4 rec[kPerNode ? 1 : kNode];
+                if constexpr (!kPerNode) {
+#pragma unroll
+                    for (int j = 0; j < kNode; ++j) rec[j] = __ldg(pp + j);
+                }
+#endif
 #pragma unroll
                 for (int j = 0; j < kNode / 2; ++j) {
+#if RRL_L2_PRELOAD
+                    const float4 A = kPerNode ? pp[2 * j] : rec[kPerNode ? 0 : 2 * j], Bq = kPerNode ? pp[2 * j + 1] : rec[kPerNode ? 0 : 2 * j + 1];
+#else
                     const float4 A = pp[2 * j], Bq = pp[2 * j + 1];
+#endif
                     const float2 x2 = make_float2(A.x, A.y), y2 = make_float2(A.z, A.w), z2 = make_float2(Bq.x, Bq.y), w2 = make_float2(Bq.z, Bq.w);
                     const float2 t2 = __ffma2_rn(z2, u2, __ffma2_rn(y2, u1, __fmul2_rn(x2, u0)));
                     const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
@@ -1260,6 +1302,10 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         for (int base = 0; base < wq_cnt; base += 32) {
             if (nq_cnt + 128 > kNodeCap) run_nodes();
             unsigned nm = 0, key = 0;
+#if RRL_PF_LEVEL1
+            if (base + 32 + lane < wq_cnt)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(node_src + (int)(wq[base + 32 + lane] & 0xFFFFFu) * 5));
+#endif
             if (base + lane < wq_cnt) {
                 const unsigned ent = wq[base + lane];
                 const int lrel = (int)(ent >> 20);
@@ -1640,14 +1686,15 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     a.tri[0] = tri1; a.tri[1] = tri2; a.lines = lines; a.chunk_nodes = 0;
     if (g_param[5]) return launch_bruteforce(tri1, tri2, lines, ws, g, 1, s);      // measurement / cross-check only
     const int G = node_size(g);
-    const int lpt = g_param[6] == 2 || g_param[6] == 4 ? g_param[6] : 2;
+    const int lpt = g_param[6] == 2 || g_param[6] == 4 || g_param[6] == 1 ? g_param[6] : 2;
     int rc;
     if (use_supers(g)) {
-        if (G == 8) rc = lpt == 2 ? launch_dense_variant<8, false, 2, true>(a, ws, g, G, s) : launch_dense_variant<8, false, 4, true>(a, ws, g, G, s);
-        else rc = lpt == 2 ? launch_dense_variant<16, false, 2, true>(a, ws, g, G, s) : launch_dense_variant<16, false, 4, true>(a, ws, g, G, s);
-    } else if (G == 8 && g_param[4] == 0) rc = lpt == 2 ? launch_dense_variant<8, true, 2>(a, ws, g, G, s) : launch_dense_variant<8, true, 4>(a, ws, g, G, s);
-    else if (G == 8) rc = lpt == 2 ? launch_dense_variant<8, false, 2>(a, ws, g, G, s) : launch_dense_variant<8, false, 4>(a, ws, g, G, s);
-    else rc = lpt == 2 ? launch_dense_variant<16, false, 2>(a, ws, g, G, s) : launch_dense_variant<16, false, 4>(a, ws, g, G, s);
+        if (G == 8) rc = lpt != 4 ? launch_dense_variant<8, false, 2, true>(a, ws, g, G, s) : launch_dense_variant<8, false, 4, true>(a, ws, g, G, s);
+        else rc = lpt == 1 ? launch_dense_variant<16, false, 1, true>(a, ws, g, G, s)
+                           : (lpt == 2 ? launch_dense_variant<16, false, 2, true>(a, ws, g, G, s) : launch_dense_variant<16, false, 4, true>(a, ws, g, G, s));
+    } else if (G == 8 && g_param[4] == 0) rc = lpt != 4 ? launch_dense_variant<8, true, 2>(a, ws, g, G, s) : launch_dense_variant<8, true, 4>(a, ws, g, G, s);
+    else if (G == 8) rc = lpt != 4 ? launch_dense_variant<8, false, 2>(a, ws, g, G, s) : launch_dense_variant<8, false, 4>(a, ws, g, G, s);
+    else rc = lpt != 4 ? launch_dense_variant<16, false, 2>(a, ws, g, G, s) : launch_dense_variant<16, false, 4>(a, ws, g, G, s);
     if (rc) return rc;
     const int xgrid = sm_count() * 8;
     if (g_param[11] == 4) exact_kernel<4><<<xgrid, 256, 0, s>>>(a, ws, g);

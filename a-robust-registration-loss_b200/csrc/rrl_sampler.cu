@@ -65,12 +65,15 @@ __device__ void make_box(const float *lo, const float *hi, BoxTris *bt, int f) {
     bt->S[f] = S;
 }
 
-// does the line "hit" at least one of the box's 12 triangles by the reference's area test (loss.py:289-316)?  The
+// does the line "hit" at least one of the box's triangles in `mask` by the reference's area test (loss.py:289-316)?  The
 // reference counts the hits per box and keeps a line when hits1 * hits2 > 0 (loss.py:430): only whether each count is
-// positive matters, so the loop stops at the first hit.
-__device__ bool box_hit(const BoxTris *bt, const float *ln) {
+// positive matters, so the loop stops at the first hit.  Every lane walks ITS OWN list of triangles (the set bits of its
+// mask, see tri_mask): a warp runs as many iterations as its busiest lane has candidates (2-3 faces = 4-6 triangles), not 12.
+__device__ bool box_hit(const BoxTris *bt, const float *ln, unsigned mask) {
 #pragma unroll 1
-    for (int f = 0; f < 12; ++f) {
+    while (mask) {
+        const int f = __ffs(mask) - 1;
+        mask &= mask - 1u;
         const float *A = bt->A[f], *Bp = bt->Bv[f], *C = bt->C[f], *n = bt->n[f];
         const float num = (n[0] * (A[0] - ln[3]) + n[1] * (A[1] - ln[4])) + n[2] * (A[2] - ln[5]);
         const float den = ((n[0] * ln[0] + n[1] * ln[1]) + n[2] * ln[2]) + 1e-12f;
@@ -116,6 +119,7 @@ struct SamplerArgs {
     int *acc;                 // (B, kPhases + 1): accepted candidates of each phase of rounds (slot 0 stays 0)
     int B, N, rounds, nchunks;
     unsigned long long seed, offset;
+    int shard_rank, shard_world;   // candidate shard: this rank evaluates the chunks ch with ch % shard_world == shard_rank
 };
 
 __device__ __forceinline__ void candidate(const SamplerArgs &a, int b, int rd, int i, float *ln) {
@@ -161,28 +165,37 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float *__restrict__ v1,
 
 constexpr int kChunk = 256;                   // candidates per chunk = threads per block of flags_kernel / scatter_kernel
 
-// Conservative "cannot hit" test: true when the line misses the box inflated by `margin` on every side (slab test in
-// float, with the comparison slackened so that rounding can only make it answer "may hit").  For such a line the
-// intersection point with every face plane lies at least `margin` outside the face, so the sum of the three sub-triangle
-// areas exceeds the face triangle's by ~margin x edge length -- orders of magnitude above the rounding of the area sums --
-// and all 12 triangle tests of box_hit fail.  Only used for boxes that are not degenerate (see flags_kernel).
-__device__ __forceinline__ bool misses_inflated_box(const float *lo, const float *hi, float margin, const float *ln) {
-    float tn = -INFINITY, tf = INFINITY;
+// Which triangles of a box can the line hit at all?  Bit f = triangle f of kBoxFaces.  The two triangles of a face lie in
+// the face's plane; the reference intersects the line with that plane (point X) and accepts when the three sub-triangle
+// areas add up to the triangle's -- possible only for X inside the triangle.  A face whose plane the line crosses at
+// least `margin` (1 % of the box's largest extent, plus a relative allowance for the rounding of X) OUTSIDE the face's
+// rectangle fails that test for both of its triangles by a margin orders of magnitude above the rounding of the area sums
+// (excess ~ margin x edge length against areas ~ edge^2 with 1e-7 relative rounding), so only the faces the line may
+// cross -- two, three near an edge -- are tested at all.  Conservative throughout: a face is dropped only when X is
+// provably outside.  Lines (nearly) parallel to a pair of planes keep both faces; degenerate (flat) boxes keep all 12
+// triangles (see flags_kernel).  face = axis * 2 + (1 = max side); triangles per face from kBoxFaces + generate_bbox's corners.
+__device__ __forceinline__ unsigned tri_mask(const float *lo, const float *hi, float margin, const float *ln) {
+    const unsigned kFaceTris[6] = {0x030u, 0x0c0u, 0x300u, 0x00cu, 0xc00u, 0x003u};
+    unsigned m = 0u;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float l = lo[a] - margin, h = hi[a] + margin;
-        const float u = ln[a], x = ln[3 + a];
-        if (fabsf(u) < 1e-12f) {
-            if (x < l || x > h) return true;                     // parallel to the slab and outside it
-        } else {
-            const float inv = 1.0f / u;
-            const float t0 = (l - x) * inv, t1 = (h - x) * inv;
-            tn = fmaxf(tn, fminf(t0, t1));
-            tf = fminf(tf, fmaxf(t0, t1));
+    for (int k = 0; k < 3; ++k) {
+        const int i = (k + 1) % 3, j = (k + 2) % 3;
+        const float u = ln[k], x = ln[3 + k];
+        if (!(fabsf(u) >= 1e-6f)) {                              // parallel (or NaN): no statement about these two faces
+            m |= kFaceTris[2 * k] | kFaceTris[2 * k + 1];
+            continue;
+        }
+        const float inv = 1.0f / u;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const float t = ((side ? hi[k] : lo[k]) - x) * inv;
+            const float Xi = ln[3 + i] + t * ln[i], Xj = ln[3 + j] + t * ln[j];
+            const float si = margin + 1e-4f * (fabsf(Xi) + fabsf(ln[3 + i])), sj = margin + 1e-4f * (fabsf(Xj) + fabsf(ln[3 + j]));
+            const bool outside = Xi < lo[i] - si || Xi > hi[i] + si || Xj < lo[j] - sj || Xj > hi[j] + sj;
+            if (!outside) m |= kFaceTris[2 * k + side];
         }
     }
-    // slack: |t| values are O((|x0| + extent) / |u|); a relative 1e-4 dwarfs the rounding of three float operations
-    return tn > tf + 1e-4f * (fabsf(tn) + fabsf(tf)) + 1e-30f;
+    return m;
 }
 
 // One phase of rounds = the chunks [ch_begin, ch_end).  A pair whose rows were already filled by the EARLIER phases
@@ -191,31 +204,33 @@ __device__ __forceinline__ bool misses_inflated_box(const float *lo, const float
 // their flags.  The reference always evaluates all 10 rounds (loss.py:425-431) and throws the surplus away.
 __global__ void __launch_bounds__(kChunk) flags_kernel(SamplerArgs a, int phase, int ch_begin, int ch_end) {
     __shared__ BoxTris bt[2];
+    __shared__ float s_box[12];
     const int b = blockIdx.y;
     int before = 0;
     for (int j = 0; j <= phase; ++j) before += a.acc[b * (kPhases + 1) + j];
     if (before >= a.N) return;                                               // block-uniform
     if (threadIdx.x < 24) make_box(a.bbox + (b * 2 + threadIdx.x / 12) * 6, a.bbox + (b * 2 + threadIdx.x / 12) * 6 + 3, &bt[threadIdx.x / 12], threadIdx.x % 12);
+    if (threadIdx.x >= 32 && threadIdx.x < 44) s_box[threadIdx.x - 32] = a.bbox[b * 12 + threadIdx.x - 32];
     __syncthreads();
     const long long total = (long long)a.rounds * a.N;
     int mine = 0;
     for (int ch = ch_begin + blockIdx.x; ch < ch_end; ch += gridDim.x) {     // block-uniform trip count
+        if (a.shard_world > 1 && ch % a.shard_world != a.shard_rank) continue;   // another rank's chunk (count stays 0)
         const long long c = (long long)ch * kChunk + threadIdx.x;
         int f = 0;
         if (c < total) {
             float ln[6];
             candidate(a, b, (int)(c / a.N), (int)(c % a.N), ln);
-            // boxes whose smallest extent is at least 5 % of their largest get the conservative miss test first
-            // (acceptance is ~10 % on the shipped pairs: most candidates end here)
-            bool may = true;
+            // boxes whose smallest extent is at least 5 % of their largest: only the triangles of the faces the line may cross
+            unsigned mask[2];
 #pragma unroll
-            for (int q = 0; q < 2 && may; ++q) {
-                const float *lo = a.bbox + (b * 2 + q) * 6, *hi = lo + 3;
+            for (int q = 0; q < 2; ++q) {
+                const float *lo = s_box + q * 6, *hi = lo + 3;
                 const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
                 const float emax = fmaxf(ex, fmaxf(ey, ez)), emin = fminf(ex, fminf(ey, ez));
-                if (emin >= 0.05f * emax && emax > 0.f && misses_inflated_box(lo, hi, 0.01f * emax, ln)) may = false;
+                mask[q] = (emin >= 0.05f * emax && emax > 0.f) ? tri_mask(lo, hi, 0.01f * emax, ln) : 0xFFFu;
             }
-            f = may && box_hit(&bt[0], ln) && box_hit(&bt[1], ln);           // loss.py:430
+            f = mask[0] && mask[1] && box_hit(&bt[0], ln, mask[0]) && box_hit(&bt[1], ln, mask[1]);      // loss.py:430
             a.flags[(long long)b * total + c] = (unsigned char)f;
         }
         const int cnt = __syncthreads_count(f);
@@ -296,6 +311,120 @@ __global__ void __launch_bounds__(kChunk) scatter_kernel(SamplerArgs a, float *o
         out[i] = 0.f;
 }
 
+// ---- candidate shard across ranks -------------------------------------------------------------------
+// The candidates are a pure function of (seed, offset, pair, round, index) (counter-based Philox), so any rank can evaluate
+// any of them: rank r takes the chunks ch = r (mod world).  The ordered compaction of generate_lines (first N accepted in
+// (round, index) order) then needs, per chunk, how many candidates the chunks BEFORE it accepted -- on any rank: the ranks
+// sum their per-chunk counts (one all-reduce of nchunks ints, the caller's), every rank scans the summed counts itself and
+// keeps, of each of ITS chunks, the accepted candidates whose global row is below N.  The loss does not depend on the
+// order of the lines, so nobody needs anybody else's lines: a rank evaluates exactly the rows it produced, plus its share
+// of the rows that stay unfilled (all-zero lines, which the reference still evaluates, loss.py:423-432).
+//   gcnt: summed counts in, exclusive global prefix out;  lcnt: this rank's counts in, local row offsets of its chunks out;
+//   kept (reuses the flags' chunk array): rows each own chunk contributes;  out3 = {rows placed, zero rows appended, filled}
+__global__ void __launch_bounds__(1024) shard_scan_kernel(SamplerArgs a, int *gcnt, int *lcnt, int *out3) {
+    __shared__ int warp_tot[2][32];
+    __shared__ int s_carry[2];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *g = gcnt + (long long)b * a.nchunks, *l = lcnt + (long long)b * a.nchunks, *kept = a.chunk + (long long)b * a.nchunks;
+    if (threadIdx.x < 2) s_carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int base = 0; base < a.nchunks; base += 1024) {                     // block-uniform trip count
+        const int i = base + threadIdx.x;
+        const bool in = i < a.nchunks;
+        const int gv = in ? g[i] : 0;
+        int ginc = gv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, ginc, d);
+            if (lane >= d) ginc += up;
+        }
+        if (lane == 31) warp_tot[0][wid] = ginc;
+        __syncthreads();
+        int gbefore = 0, gall = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const int t = warp_tot[0][w];
+            gbefore += w < wid ? t : 0;
+            gall += t;
+        }
+        const int goff = s_carry[0] + gbefore + ginc - gv;                  // accepted candidates before chunk i, all ranks
+        const bool own = in && (a.shard_world <= 1 || i % a.shard_world == a.shard_rank);
+        const int lv = own ? l[i] : 0;
+        const int kv = own ? max(0, min(lv, a.N - goff)) : 0;               // rows of chunk i that land below N
+        int kinc = kv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, kinc, d);
+            if (lane >= d) kinc += up;
+        }
+        if (lane == 31) warp_tot[1][wid] = kinc;
+        __syncthreads();
+        int kbefore = 0, kall = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const int t = warp_tot[1][w];
+            kbefore += w < wid ? t : 0;
+            kall += t;
+        }
+        if (in) {
+            g[i] = goff;
+            l[i] = s_carry[1] + kbefore + kinc - kv;                        // local row of the chunk's first kept candidate
+            kept[i] = kv;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_carry[0] += gall; s_carry[1] += kall; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int filled = min(a.N, s_carry[0]);
+        // unfilled rows [filled, N): row r belongs to rank r % world
+        int zeros = 0;
+        if (a.N > filled) {
+            const int w = a.shard_world > 1 ? a.shard_world : 1, r = a.shard_world > 1 ? a.shard_rank : 0;
+            const int first = filled + ((r - filled % w) % w + w) % w;
+            zeros = first < a.N ? (a.N - 1 - first) / w + 1 : 0;
+        }
+        out3[b * 3] = s_carry[1]; out3[b * 3 + 1] = zeros; out3[b * 3 + 2] = filled;
+    }
+}
+
+__global__ void __launch_bounds__(kChunk) shard_scatter_kernel(SamplerArgs a, const int *__restrict__ lcnt, float *out_lines,
+                                                               const int *__restrict__ out3) {
+    __shared__ int warp_tot[kChunk / 32];
+    const int b = blockIdx.y;
+    const long long total = (long long)a.rounds * a.N;
+    const unsigned char *fl = a.flags + (long long)b * total;
+    const int *loff = lcnt + (long long)b * a.nchunks, *kept = a.chunk + (long long)b * a.nchunks;
+    float *out = out_lines + (long long)b * a.N * 6;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int ch = blockIdx.x; ch < a.nchunks; ch += gridDim.x) {             // block-uniform
+        if (a.shard_world > 1 && ch % a.shard_world != a.shard_rank) continue;
+        const int keep = kept[ch];
+        if (keep <= 0) continue;
+        const long long c = (long long)ch * kChunk + threadIdx.x;
+        const int f = c < total ? fl[c] : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < kChunk / 32; ++w) before += w < wid ? warp_tot[w] : 0;
+        const int rank_in_chunk = before + __popc(bal & ((1u << lane) - 1u));
+        if (f && rank_in_chunk < keep) {
+            float ln[6];
+            candidate(a, b, (int)(c / a.N), (int)(c % a.N), ln);
+            const long long pos = loff[ch] + rank_in_chunk;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) out[pos * 6 + q] = ln[q];
+        }
+        __syncthreads();
+    }
+    // the rank's share of the unfilled rows follows its lines; whatever lies beyond is zeroed too (the caller slices)
+    const long long placed = out3[b * 3];
+    for (long long i = placed * 6 + (long long)blockIdx.x * kChunk + threadIdx.x; i < (long long)a.N * 6; i += (long long)gridDim.x * kChunk)
+        out[i] = 0.f;
+}
+
 }  // namespace rrl
 
 using namespace rrl;
@@ -328,6 +457,7 @@ extern "C" int rrl_sample_lines(const float *radius, const float *centers, const
     w += up256((size_t)B * (size_t)rounds * (size_t)N);
     a.chunk = reinterpret_cast<int *>(w);
     a.B = B; a.N = N; a.rounds = rounds; a.seed = seed; a.offset = offset;
+    a.shard_rank = 0; a.shard_world = 1;
     a.nchunks = (int)sampler_chunks(N, rounds);
     a.acc = a.chunk + (size_t)B * a.nchunks;
     if (cudaMemsetAsync(a.chunk, 0, (size_t)B * (a.nchunks + kPhases + 1) * sizeof(int), s) != cudaSuccess) return RRL_ERR_CUDA;
@@ -350,5 +480,75 @@ extern "C" int rrl_sample_lines(const float *radius, const float *centers, const
     scan_kernel<<<B, 1024, 0, s>>>(a, out_filled);
     scatter_kernel<<<dim3(bx, B), kChunk, 0, s>>>(a, out_lines, out_filled);
     count_launch(3);
+    return check_launch();
+}
+
+// ---- candidate-sharded sampler: two calls with the caller's all-reduce of the chunk counts between them ---------------
+static SamplerArgs shard_args(const float *radius, const float *centers, const float *uniforms, int B, int N, int rounds,
+                              unsigned long long seed, unsigned long long offset, int rank, int world, void *workspace) {
+    SamplerArgs a;
+    a.radius = radius; a.centers = centers; a.uniforms = uniforms;
+    char *w = reinterpret_cast<char *>(workspace);
+    a.bbox = reinterpret_cast<float *>(w);
+    w += up256((size_t)B * 12 * sizeof(float));
+    a.flags = reinterpret_cast<unsigned char *>(w);
+    w += up256((size_t)B * (size_t)rounds * (size_t)N);
+    a.chunk = reinterpret_cast<int *>(w);
+    a.B = B; a.N = N; a.rounds = rounds; a.seed = seed; a.offset = offset;
+    a.shard_rank = rank; a.shard_world = world;
+    a.nchunks = (int)sampler_chunks(N, rounds);
+    a.acc = a.chunk + (size_t)B * a.nchunks;
+    return a;
+}
+
+extern "C" int rrl_sampler_num_chunks(int N, int rounds) {
+    if (N <= 0 || rounds <= 0 || (long long)rounds * N >= (1LL << 31) - kChunk) return 0;
+    return (int)sampler_chunks(N, rounds);
+}
+
+extern "C" int rrl_sample_lines_shard_flags(const float *radius, const float *centers, const float *verts1, const float *verts2,
+                                            int B, int n1, int n2, int N, int rounds, unsigned long long seed,
+                                            unsigned long long offset, const float *uniforms, int shard_rank, int shard_world,
+                                            int *out_chunk_counts, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!radius || !centers || !verts1 || !verts2 || !out_chunk_counts || !workspace) return RRL_ERR_ARG;
+    if (B <= 0 || n1 <= 0 || n2 <= 0 || N <= 0 || rounds <= 0 || shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return RRL_ERR_ARG;
+    if ((long long)rounds * N >= (1LL << 31) - kChunk) return RRL_ERR_ARG;
+    if (workspace_bytes < rrl_sampler_workspace_bytes(B, N, rounds)) return RRL_ERR_WORKSPACE;
+    Range range("rrl_sample_lines_shard_flags");
+    cudaStream_t s = (cudaStream_t)stream;
+    const SamplerArgs a = shard_args(radius, centers, uniforms, B, N, rounds, seed, offset, shard_rank, shard_world, workspace);
+    if (cudaMemsetAsync(a.chunk, 0, (size_t)B * (a.nchunks + kPhases + 1) * sizeof(int), s) != cudaSuccess) return RRL_ERR_CUDA;
+    bbox_kernel<<<dim3(B, 2), 256, 0, s>>>(verts1, verts2, n1, n2, a.bbox);
+    // every round is evaluated (a rank sees only its own counts, so the phases' early exit has nothing to decide on)
+    // block x walks the chunks x, x + grid, ...: with a grid that is a multiple of `world`, the blocks x = rank (mod world)
+    // own every chunk they visit and the others return at once
+    const int cap = (sm_count() * 8 + B - 1) / B;
+    int bx = (cap < 1 ? 1 : cap) * shard_world;
+    if (bx > a.nchunks) bx = (a.nchunks + shard_world - 1) / shard_world * shard_world;
+    flags_kernel<<<dim3(bx, B), kChunk, 0, s>>>(a, 0, 0, a.nchunks);
+    count_launch(2);
+    if (cudaMemcpyAsync(out_chunk_counts, a.chunk, (size_t)B * a.nchunks * sizeof(int), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        return RRL_ERR_CUDA;
+    return check_launch();
+}
+
+extern "C" int rrl_sample_lines_shard_scatter(const float *radius, const float *centers, int B, int N, int rounds,
+                                              unsigned long long seed, unsigned long long offset, const float *uniforms,
+                                              int shard_rank, int shard_world, int *chunk_counts_global, int *chunk_counts_local,
+                                              float *out_lines_local, int *out_counts3, void *workspace, size_t workspace_bytes,
+                                              void *stream) {
+    if (!radius || !centers || !chunk_counts_global || !chunk_counts_local || !out_lines_local || !out_counts3 || !workspace) return RRL_ERR_ARG;
+    if (B <= 0 || N <= 0 || rounds <= 0 || shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return RRL_ERR_ARG;
+    if ((long long)rounds * N >= (1LL << 31) - kChunk) return RRL_ERR_ARG;
+    if (workspace_bytes < rrl_sampler_workspace_bytes(B, N, rounds)) return RRL_ERR_WORKSPACE;
+    Range range("rrl_sample_lines_shard_scatter");
+    cudaStream_t s = (cudaStream_t)stream;
+    const SamplerArgs a = shard_args(radius, centers, uniforms, B, N, rounds, seed, offset, shard_rank, shard_world, workspace);
+    shard_scan_kernel<<<B, 1024, 0, s>>>(a, chunk_counts_global, chunk_counts_local, out_counts3);
+    int bx = a.nchunks;
+    const int cap = (sm_count() * 8 + B - 1) / B;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    shard_scatter_kernel<<<dim3(bx, B), kChunk, 0, s>>>(a, chunk_counts_local, out_lines_local, out_counts3);
+    count_launch(2);
     return check_launch();
 }

@@ -296,6 +296,81 @@ class _AllReduceGrad(torch.autograd.Function):
         return g, None, None
 
 
+class ShardedSampler:
+    """Candidate-sharded line sampler for ONE pair (loss.py:415-432): rank r evaluates the candidate
+    chunks r (mod world) of every round, the ranks sum their per-chunk accepted counts (ONE all-reduce of
+    rrl_sampler_num_chunks ints -- the "scan of accepted counts" of the survey), and every rank keeps the accepted
+    candidates of its own chunks that fall among the first N of the reference's ordered compaction, plus its share of the
+    unfilled (all-zero) rows.  The union of the ranks' rows is exactly the line set `ops.sample_lines` returns; the loss is
+    independent of the order of the lines, so no line is ever exchanged.  The number of local rows is data dependent: one
+    3-int device->host read per call (the loss kernels need the row count on the host)."""
+
+    def __init__(self, n_lines: int, rounds: int = 10, device=None, group=None, rank: Optional[int] = None,
+                 world: Optional[int] = None):
+        self.L = N.lib()
+        self.N, self.rounds, self.group = int(n_lines), int(rounds), group
+        if rank is None:
+            rank = dist_.get_rank(group) if dist_.is_initialized() else 0
+            world = dist_.get_world_size(group) if dist_.is_initialized() else 1
+        self.rank, self.world = int(rank), int(world)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.nchunks = int(self.L.rrl_sampler_num_chunks(self.N, self.rounds))
+        if self.nchunks <= 0:
+            raise ValueError("unsupported sampler geometry N=%d rounds=%d" % (self.N, self.rounds))
+        self.wsb = self.L.rrl_sampler_workspace_bytes(1, self.N, self.rounds)
+        self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=self.dev)
+
+    def _args(self, radius, centers, uniforms):
+        from .ops import _cuda_f32
+        radius = _cuda_f32(radius.detach().reshape(-1).to(self.dev), "r")
+        centers = _cuda_f32(centers.detach().reshape(-1, 3).to(self.dev), "centers")
+        if radius.numel() != 1 or centers.shape[0] != 1:
+            raise ValueError("the sharded sampler handles one pair (B = 1)")
+        if uniforms is not None:
+            uniforms = _cuda_f32(uniforms.to(self.dev), "uniforms")
+            if tuple(uniforms.shape) != (1, self.rounds, 4, self.N):
+                raise ValueError("uniforms must have shape (1, rounds, 4, N)")
+        return radius, centers, uniforms
+
+    def local_counts(self, radius, centers, verts1, verts2, seed=0, offset=0, uniforms=None) -> torch.Tensor:
+        """step 1: evaluate this rank's candidate chunks; returns its per-chunk accepted counts (nchunks,) int32"""
+        from .ops import _cuda_f32
+        radius, centers, uniforms = self._args(radius, centers, uniforms)
+        verts1, verts2 = _cuda_f32(verts1.detach(), "vertices1"), _cuda_f32(verts2.detach(), "vertices2")
+        counts = torch.empty(self.nchunks, dtype=torch.int32, device=self.dev)
+        self._call = (radius, centers, uniforms, int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1))
+        with torch.cuda.device(self.dev):
+            N.check(self.L.rrl_sample_lines_shard_flags(radius.data_ptr(), centers.data_ptr(), verts1.data_ptr(), verts2.data_ptr(), 1,
+                                                        verts1.shape[1], verts2.shape[1], self.N, self.rounds, self._call[3], self._call[4],
+                                                        uniforms.data_ptr() if uniforms is not None else None, self.rank, self.world,
+                                                        counts.data_ptr(), self.ws.data_ptr(), self.wsb,
+                                                        torch.cuda.current_stream(self.dev).cuda_stream), "rrl_sample_lines_shard_flags")
+        return counts
+
+    def place(self, local_counts: torch.Tensor, global_counts: torch.Tensor):
+        """step 3: given the counts summed over the ranks; returns (lines_local (rows, 6), rows filled globally)"""
+        radius, centers, uniforms, seed, offset = self._call
+        lines = torch.empty(self.N, 6, dtype=torch.float32, device=self.dev)
+        out3 = torch.empty(3, dtype=torch.int32, device=self.dev)
+        g, l = global_counts.clone(), local_counts.clone()
+        with torch.cuda.device(self.dev):
+            N.check(self.L.rrl_sample_lines_shard_scatter(radius.data_ptr(), centers.data_ptr(), 1, self.N, self.rounds, seed, offset,
+                                                          uniforms.data_ptr() if uniforms is not None else None, self.rank, self.world,
+                                                          g.data_ptr(), l.data_ptr(), lines.data_ptr(), out3.data_ptr(),
+                                                          self.ws.data_ptr(), self.wsb,
+                                                          torch.cuda.current_stream(self.dev).cuda_stream), "rrl_sample_lines_shard_scatter")
+        placed, zeros, filled = out3.tolist()                   # the one host read: the loss needs the row count
+        return lines[:placed + zeros], filled
+
+    def sample(self, radius, centers, verts1, verts2, seed=0, offset=0, uniforms=None):
+        """all three steps with the all-reduce over `group`"""
+        local = self.local_counts(radius, centers, verts1, verts2, seed, offset, uniforms)
+        total = local.clone()
+        if self.world > 1:
+            dist_.all_reduce(total, op=dist_.ReduceOp.SUM, group=self.group)
+        return self.place(local, total)
+
+
 def line_sharded_twist_loss(twist, raw_tri1, tri2, lines_local, window=(1, 1, 5, 5), group=None, session=None, comm=None):
     """The demo's / large-scan configuration: cloud 1 = se(3) transform of `raw_tri1` (nf1,9) by `twist` (6,), one pair,
     lines sharded.  The sparse point gradient of every rank's line shard is reduced to pose space locally (closed-form

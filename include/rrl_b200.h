@@ -225,6 +225,28 @@ int rrl_sample_lines(const float *radius, const float *centers, const float *ver
                      const float *uniforms, float *out_lines, int *out_filled,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* Candidate-sharded form for a line-sharded evaluation.  Candidates are a pure function of (seed,
+ * offset, pair, round, index), so rank r of `world` evaluates the chunks of 256 candidates with chunk = r (mod world):
+ *   1. rrl_sample_lines_shard_flags   -> out_chunk_counts (B, rrl_sampler_num_chunks(N, rounds)) int32: accepted candidates of
+ *                                        the rank's own chunks (0 elsewhere); all `rounds` rounds are evaluated;
+ *   2. the caller sums the counts over the ranks (one all-reduce of nchunks ints) and keeps its own copy;
+ *   3. rrl_sample_lines_shard_scatter -> out_lines_local (B, N, 6): the accepted candidates of the rank's chunks whose row in the
+ *                                        reference's ordered compaction (loss.py:365-381) is below N, followed by the rank's share
+ *                                        (row = rank mod world) of the rows that stay unfilled (all-zero lines), zeros beyond;
+ *                                        out_counts3 (B,3) int32 = {lines placed, zero rows appended, rows filled globally}.
+ * The union over the ranks of the first counts3[0] + counts3[1] local rows is exactly the set of N rows rrl_sample_lines
+ * returns (the loss does not depend on their order), so no line ever crosses NVLink.  Same workspace for both calls. */
+int rrl_sampler_num_chunks(int N, int rounds);
+int rrl_sample_lines_shard_flags(const float *radius, const float *centers, const float *verts1, const float *verts2,
+                                 int B, int n1, int n2, int N, int rounds, unsigned long long seed, unsigned long long offset,
+                                 const float *uniforms, int shard_rank, int shard_world, int *out_chunk_counts,
+                                 void *workspace, size_t workspace_bytes, void *stream);
+int rrl_sample_lines_shard_scatter(const float *radius, const float *centers, int B, int N, int rounds,
+                                   unsigned long long seed, unsigned long long offset, const float *uniforms,
+                                   int shard_rank, int shard_world, int *chunk_counts_global, int *chunk_counts_local,
+                                   float *out_lines_local, int *out_counts3, void *workspace, size_t workspace_bytes,
+                                   void *stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Monitoring metric: replaces chamfer_dist (loss.py:236-252).  x (B,M,3), y (B,N,3) -> out (1) = mean over the
  * concatenation of both directed min-squared-distances of all pairs.  scratch: B*(M+N) floats.

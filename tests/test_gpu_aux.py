@@ -63,7 +63,7 @@ def test_sampler_replays_recorded_uniforms(rrl):
     lines = lines[0].cpu().numpy(); filled = int(filled[0])
     ref_filled = int(g["ref_filled"])
     # the area test is a rounding-noise knife edge: same statistics, not the same coin flips
-    assert abs(filled - ref_filled) <= 0.15 * ref_filled + 8
+    assert abs(filled - ref_filled) <= 0.05 * ref_filled + 8
     assert np.all(lines[filled:] == 0)
     assert np.all(np.abs(np.linalg.norm(lines[:filled, :3], axis=1) - 1) < 1e-5)
     # every accepted line is one of the reference's candidates (same draws -> same chords to float tolerance),
@@ -81,7 +81,58 @@ def test_sampler_replays_recorded_uniforms(rrl):
         assert np.all(np.minimum(ta, tb).max(1) <= np.maximum(ta, tb).min(1) + 1e-4)
     # the C oracle fed the same draws accepts a statistically identical number
     _, cf = co.sample_lines(float(g["radius"]), g["center"], n, lo1, hi1, lo2, hi2, g["uniforms"])
-    assert abs(filled - cf) <= 0.15 * cf + 8
+    assert abs(filled - cf) <= 0.05 * cf + 8
+
+
+@pytest.mark.parametrize("seed,ext,rscale", [(1, (3.6, 9.6, 5.2), 0.5), (2, (2.0, 2.2, 2.1), 1.0), (3, (9.8, 7.8, 0.45), 0.7)])
+def test_sampler_statistics_over_a_million_candidates(rrl, seed, ext, rscale):
+    """10 rounds x 100 000 recorded uniforms = 10^6 candidates against the bit-exact torch restatement of the reference
+    sampler (oracle/torch_port.py, itself pinned by tests/golden/sampler.npz).  The area test `A + B + C <= S` is a
+    rounding coin flip for every true hit, so the two implementations cannot take the same decisions; what
+    must hold: the per-candidate ACCEPTANCE RATE agrees within 2 % (binomial noise at these counts is ~0.3 %), every row the
+    GPU fills is one of the candidates, the rows come in candidate order (checked over ALL rows), and nothing is accepted
+    that geometrically misses a box."""
+    from oracle import torch_port as tp
+    rng = np.random.default_rng(seed)
+    n, rounds = 100000, 10
+    v1 = (rng.uniform(-0.5, 0.5, (400, 3)) * np.asarray(ext)).astype(np.float32)
+    v2 = ((rng.uniform(-0.5, 0.5, (400, 3)) * np.asarray(ext)) @ synth_rot(rng).T + rng.uniform(-0.3, 0.3, 3)).astype(np.float32)
+    radius = float(rscale * np.linalg.norm(v2.max(0) - v2.min(0)))
+    center = v2.mean(0).astype(np.float32)
+    U = torch.rand(rounds, 4, n, generator=torch.Generator().manual_seed(seed))
+    # reference acceptance per candidate, all 10 rounds evaluated (no early stop: the RATE is what is compared)
+    t1, t2 = tp.box_triangles(torch.from_numpy(v1)), tp.box_triangles(torch.from_numpy(v2))
+    ref_acc, cands = 0, []
+    for rd in range(rounds):
+        cand = tp.lines_from_uniforms(radius, torch.from_numpy(center), *[U[rd, q] for q in range(4)])
+        ref_acc += int(((tp.triangle_hits(t1, cand) * tp.triangle_hits(t2, cand)) > 0).sum())
+        cands.append(cand.numpy())
+    # GPU: N = all candidates, so nothing is cut off and `filled` counts every accepted candidate of every round
+    big_n = rounds * n
+    Ubig = torch.zeros(1, rounds, 4, big_n)
+    Ubig[0, :, :, :n] = U                                        # candidates beyond n: u = 0 -> a degenerate chord (q1 == q2)
+    lines, filled = rrl.sample_lines(torch.tensor([radius]), torch.from_numpy(center)[None], big_n, torch.from_numpy(v1)[None].cuda(),
+                                     torch.from_numpy(v2)[None].cuda(), uniforms=Ubig.cuda(), rounds=rounds)
+    lines = lines[0].cpu().numpy(); filled = int(filled[0])
+    assert ref_acc > 20000
+    assert abs(filled - ref_acc) <= 0.02 * ref_acc, (filled, ref_acc)
+    assert np.all(lines[filled:] == 0)
+    # full-order check: walk the candidates of all rounds once; every filled row must be matched, in order
+    from scipy.spatial import cKDTree
+    flat = np.concatenate(cands).astype(np.float64)               # (rounds * n, 6) in (round, index) order
+    dist, idx = cKDTree(flat).query(lines[:filled].astype(np.float64), distance_upper_bound=1e-4)
+    assert np.all(np.isfinite(dist))                              # every filled row IS one of the candidates (same draws)
+    assert np.all(np.diff(idx) > 0)                               # strictly increasing candidate indices = the reference's order
+    d, x0 = lines[:filled, :3].astype(np.float64), lines[:filled, 3:].astype(np.float64)
+    for v in (v1, v2):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ta, tb = (v.min(0) - x0) / d, (v.max(0) - x0) / d
+        assert np.all(np.minimum(ta, tb).max(1) <= np.maximum(ta, tb).min(1) + 1e-4)
+
+
+def synth_rot(rng):
+    from oracle import synth
+    return synth.random_rotation(rng, 30.0)
 
 
 def test_sampler_philox_is_reproducible(rrl):

@@ -289,3 +289,39 @@ def test_stale_workspace_is_inert(rrl):
     assert L.rrl_loss_backward(ws.data_ptr(), wsb, go.data_ptr(), 1, nf, nf, nl, g1.data_ptr(), None, None) == 0
     torch.cuda.synchronize()
     assert _rel(g1.cpu().numpy(), co.loss(p["tri1"], p["tri2"], p["lines"]).grad1) <= REL_TOL
+
+
+@pytest.mark.parametrize("R,n,rscale", [(2, 5000, 0.5), (3, 4097, 1.0), (8, 20000, 2.5)])
+def test_candidate_sharded_sampler_reproduces_the_unsharded_line_set(rrl, R, n, rscale):
+    """R ranks each evaluate the candidate chunks r (mod R), sum their per-chunk accepted counts (here: a
+    device-side addition in place of the all-reduce) and keep their own rows.  The union of the ranks' rows must be EXACTLY
+    the N rows of the unsharded sampler (same Philox stream): same accepted lines bit for bit, same number of all-zero
+    rows -- for a geometry that fills all rows early, one that fills them late, and one that leaves rows unfilled."""
+    p = synth.make_pair(690 + R, 800, 64)
+    v1 = torch.from_numpy(p["tri1"][:, :3]).cuda()[None].contiguous()
+    v2 = torch.from_numpy(p["tri2"][:, :3]).cuda()[None].contiguous()
+    lo2, hi2 = v2[0].min(0)[0], v2[0].max(0)[0]
+    radius = ((hi2 - lo2).norm() * rscale).reshape(1)
+    center = v2[0].mean(0)[None]
+    ref, ref_filled = rrl.sample_lines(radius, center, n, v1, v2, seed=21, offset=5)
+    ref = ref[0].cpu().numpy(); ref_filled = int(ref_filled[0])
+    ranks = [rrl.dist.ShardedSampler(n, rank=r, world=R) for r in range(R)]
+    local = [s.local_counts(radius, center, v1, v2, seed=21, offset=5) for s in ranks]
+    total = torch.stack(local).sum(0).to(torch.int32)
+    rows, filled = [], set()
+    for s, lc in zip(ranks, local):
+        mine, f = s.place(lc, total)
+        rows.append(mine.cpu().numpy()); filled.add(f)
+    assert filled == {ref_filled}
+    got = np.concatenate(rows)
+    assert got.shape == (n, 6)
+    key = lambda a: sorted(map(bytes, np.ascontiguousarray(a)))
+    assert key(got) == key(ref)                                  # the same multiset of rows, bit for bit
+    assert int((~got.any(1)).sum()) == n - ref_filled
+    if rscale > 2:
+        assert ref_filled < n                                    # the premise of the third case: rows stay unfilled
+    # and the loss of the sharded line set equals the loss of the reference set (order independence, fixed-point sums)
+    t1 = torch.from_numpy(p["tri1"]).cuda()[None]; t2 = torch.from_numpy(p["tri2"]).cuda()[None]
+    a = rrl.intersected_line_loss(t1, t2, torch.from_numpy(ref).cuda()[None])
+    b = rrl.intersected_line_loss(t1, t2, torch.from_numpy(got).cuda()[None])
+    assert torch.equal(a, b)
