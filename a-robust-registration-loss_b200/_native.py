@@ -40,6 +40,8 @@ def lib():
         "rrl_shard_stage1_ex": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, cz, ci, vp]),
         "rrl_loss_backward": (ci, [vp, cz, vp, ci, ci, ci, ci, vp, vp, vp]),
         "rrl_loss_export_hits": (ci, [vp, cz, ci, ci, ci, ci, ci, vp, vp, vp]),
+        "rrl_loss_backward_twist": (ci, [vp, cz, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]),
+        "rrl_se3_chain": (ci, [vp, vp, ci, vp, vp]),
         "rrl_shard_stage1": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, cz, vp]),
         "rrl_shard_counts": (ci, [vp, cz, ci, ci, ci, vp, vp]),
         "rrl_shard_pack_entries": (ci, [vp, cz, ci, ci, ci, vp, cl, vp]),
@@ -102,7 +104,7 @@ def lib():
 
 EXPORTED = ["rrl_version", "rrl_error_string", "rrl_launch_count", "rrl_workspace_bytes", "rrl_loss_forward",
             "rrl_loss_forward_ex", "rrl_shard_stage1_ex",
-            "rrl_loss_backward", "rrl_loss_export_hits", "rrl_shard_stage1", "rrl_shard_counts",
+            "rrl_loss_backward", "rrl_loss_backward_twist", "rrl_se3_chain", "rrl_loss_export_hits", "rrl_shard_stage1", "rrl_shard_counts",
             "rrl_shard_pack_entries", "rrl_select_lower_median", "rrl_shard_select_hist", "rrl_shard_select_pick",
             "rrl_shard_stage2", "rrl_shard_stage3", "rrl_shard_tail",
             "rrl_comm_create", "rrl_comm_destroy", "rrl_comm_slot_bytes", "rrl_comm_local_base", "rrl_comm_ipc_handle",

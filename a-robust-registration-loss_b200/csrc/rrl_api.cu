@@ -192,6 +192,21 @@ extern "C" int rrl_loss_backward(const void *workspace, size_t workspace_bytes, 
     return launch_backward(ws, make_geometry(B, nf1, nf2, nl), grad_out, grad_tri1, grad_tri2, (cudaStream_t)stream);
 }
 
+extern "C" int rrl_se3_chain(const float *twist, const double *acc, int B, float *grad_twist, void *stream);
+
+extern "C" int rrl_loss_backward_twist(const void *workspace, size_t workspace_bytes, const float *grad_out, int B, int nf1,
+                                       int nf2, int nl, const float *twist, const float *raw_tri1, double *acc12,
+                                       float *grad_twist, void *stream) {
+    if (!workspace || !grad_out || !raw_tri1 || !acc12 || !geometry_ok(B, nf1, nf2, nl)) return RRL_ERR_ARG;
+    if (grad_twist && !twist) return RRL_ERR_ARG;
+    const Workspace ws = carve(const_cast<void *>(workspace), B, nf1, nf2, nl);
+    if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
+    Range r("rrl_loss_backward_twist");
+    const int rc = launch_backward_pose(ws, make_geometry(B, nf1, nf2, nl), grad_out, raw_tri1, acc12, (cudaStream_t)stream);
+    if (rc || !grad_twist) return rc;
+    return rrl_se3_chain(twist, acc12, B, grad_twist, stream);
+}
+
 extern "C" int rrl_loss_export_hits(const void *workspace, size_t workspace_bytes, int B, int nf1, int nf2, int nl,
                                     int cloud, int *out_counts, int *out_hits, void *stream) {
     if (!workspace || !out_counts || !out_hits || !geometry_ok(B, nf1, nf2, nl) || (cloud != 1 && cloud != 2)) return RRL_ERR_ARG;

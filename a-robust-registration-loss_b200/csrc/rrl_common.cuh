@@ -158,6 +158,7 @@ int launch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int
 int launch_tail(const Workspace &ws, const Geometry &g, float *out_loss, int *out_status, float *out_median,
                            long long *out_stats, cudaStream_t s);
 int launch_backward(const Workspace &ws, const Geometry &g, const float *grad_out, float *g1, float *g2, cudaStream_t s);
+int launch_backward_pose(const Workspace &ws, const Geometry &g, const float *grad_out, const float *raw, double *acc, cudaStream_t s);
 int launch_export_hits(const Workspace &ws, const Geometry &g, int cloud, int *out_counts, int *out_hits, cudaStream_t s);
 int launch_pack_entries(const Workspace &ws, const Geometry &g, float *out, long long cap, cudaStream_t s);
 int launch_select_median(const float *vals, long long n, float *out, cudaStream_t s);
@@ -252,6 +253,15 @@ __device__ __forceinline__ float point_line_x_exact(float px, float py, float pz
 }
 
 __device__ __forceinline__ float ulp_up(float x) { return __uint_as_float(__float_as_uint(x) + 1u) - x; }
+
+// The north star's separately reported bucket: how many of a triplet's three tests lie within 1 ulp of the threshold AND can
+// decide the label -- a distance in the band matters only when both other points pass or sit in the band themselves.  (Every
+// such triplet passes all the conservative filters, so it always reaches the exact test; the oracle counts the same set.)
+__device__ __forceinline__ int decisive_band(float d0, float d1, float d2, float thr, float ulp) {
+    const bool b0 = fabsf(d0 - thr) <= ulp, b1 = fabsf(d1 - thr) <= ulp, b2 = fabsf(d2 - thr) <= ulp;
+    const bool o0 = (d0 < thr) | b0, o1 = (d1 < thr) | b1, o2 = (d2 < thr) | b2;
+    return (int)(b0 & o1 & o2) + (int)(b1 & o0 & o2) + (int)(b2 & o0 & o1);
+}
 
 // warp-aggregated atomicMax of non-negative floats (which order like their bit patterns)
 __device__ __forceinline__ void warp_atomic_max_bits(unsigned int *addr, float v) {

@@ -960,12 +960,12 @@ __device__ __forceinline__ void exact_test_and_record(const float *__restrict__ 
     const float ulp = ulp_up(thr);
     const float d0 = __fsqrt_rn(point_line_x_exact(__ldg(t + 0), __ldg(t + 1), __ldg(t + 2), ln));
     nan += (d0 != d0);
-    band += (fabsf(d0 - thr) <= ulp);
-    if (!(d0 < thr)) return;
+    if (!(d0 < thr) && !(fabsf(d0 - thr) <= ulp)) return;          // point 0 fails outside the band: nothing left to decide
     const float d1 = __fsqrt_rn(point_line_x_exact(__ldg(t + 3), __ldg(t + 4), __ldg(t + 5), ln));
     const float d2 = __fsqrt_rn(point_line_x_exact(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8), ln));
     nan += (d1 != d1) + (d2 != d2);
-    band += (fabsf(d1 - thr) <= ulp) + (fabsf(d2 - thr) <= ulp);
+    band += decisive_band(d0, d1, d2, thr, ulp);
+    if (!(d0 < thr)) return;
     if ((d1 < thr) & (d2 < thr)) {
         const int slot = atomicAdd(cnt_line, 1);
         if (slot < kCap) hits_line[slot] = f;
@@ -1582,10 +1582,11 @@ __global__ void __launch_bounds__(256) exact_kernel(DenseArgs a, Workspace ws, G
             const float d0 = __fsqrt_rn(point_line_x_exact(t[u][0], t[u][1], t[u][2], ln[u]));
             const float d1 = __fsqrt_rn(point_line_x_exact(t[u][3], t[u][4], t[u][5], ln[u]));
             const float d2 = __fsqrt_rn(point_line_x_exact(t[u][6], t[u][7], t[u][8], ln[u]));
-            // band / NaN accounting as in exact_test_and_record: points 1 and 2 only count when point 0 passes
+            // NaN accounting as in exact_test_and_record (points 1 and 2 only count when point 0 passes or sits in the band)
             const bool p0 = d0 < thr[u];
-            const int nan = (d0 != d0) + (p0 ? (d1 != d1) + (d2 != d2) : 0);
-            const int band = (fabsf(d0 - thr[u]) <= ulp) + (p0 ? (fabsf(d1 - thr[u]) <= ulp) + (fabsf(d2 - thr[u]) <= ulp) : 0);
+            const bool look = p0 || fabsf(d0 - thr[u]) <= ulp;
+            const int nan = (d0 != d0) + (look ? (d1 != d1) + (d2 != d2) : 0);
+            const int band = decisive_band(d0, d1, d2, thr[u], ulp);
             if (p0 & (d1 < thr[u]) & (d2 < thr[u])) {
                 const int slot = atomicAdd(ws.cnt[cloud] + gl, 1);
                 if (slot < kCap) ws.hits[cloud][gl * kCap + slot] = f;
@@ -1621,12 +1622,12 @@ __global__ void __launch_bounds__(128) bruteforce_kernel(DenseArgs a, Workspace 
         const float ulp = ulp_up(thr);
         const float d0 = __fsqrt_rn(point_line_x_exact(__ldg(t + 0), __ldg(t + 1), __ldg(t + 2), ln));
         nan += (d0 != d0);
-        band += (fabsf(d0 - thr) <= ulp);
-        if (!(d0 < thr)) continue;
+        if (!(d0 < thr) && !(fabsf(d0 - thr) <= ulp)) continue;
         const float d1 = __fsqrt_rn(point_line_x_exact(__ldg(t + 3), __ldg(t + 4), __ldg(t + 5), ln));
         const float d2 = __fsqrt_rn(point_line_x_exact(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8), ln));
         nan += (d1 != d1) + (d2 != d2);
-        band += (fabsf(d1 - thr) <= ulp) + (fabsf(d2 - thr) <= ulp);
+        band += decisive_band(d0, d1, d2, thr, ulp);
+        if (!(d0 < thr)) continue;
         if ((d1 < thr) & (d2 < thr)) {
             if (count < kCap) hits_line[count] = f;
             ++count;

@@ -294,6 +294,13 @@ extern "C" int rrl_se3_apply_backward(const float *twist, const float *points, c
     return check_launch();
 }
 
+extern "C" int rrl_se3_chain(const float *twist, const double *acc, int B, float *grad_twist, void *stream) {
+    if (!twist || !acc || !grad_twist || B <= 0) return RRL_ERR_ARG;
+    se3_chain_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(twist, acc, B, grad_twist);
+    count_launch();
+    return check_launch();
+}
+
 extern "C" int rrl_rigid_apply(const float *R, const float *t, const float *points, int B, int n, float *out, void *stream) {
     if (!R || !t || !points || !out || B <= 0 || n <= 0) return RRL_ERR_ARG;
     apply_kernel<false><<<point_grid(B, n), 256, 0, (cudaStream_t)stream>>>(R, t, points, n, out);

@@ -1104,6 +1104,68 @@ __global__ void __launch_bounds__(128) backward_kernel(Workspace ws, Geometry g,
     }
 }
 
+// Backward straight to pose space (north star (4): "scatters dLoss/dpoint and reduces it to the 6-DoF twist gradient"): when
+// cloud 1 is a rigid transform of `raw` (B, nf1, 9), the sparse point gradient of every record is contracted with the RAW
+// points on the spot -- acc[b][0..8] += p_raw (x) g, acc[b][9..11] += g, in double -- instead of being scattered into a
+// dense (B, nf1, 9) tensor that a second kernel then reads back in full (at 500k triplets: 18 MB zeroed, 18 MB + 18 MB
+// re-read, for ~3000 records that touch ~10^4 triplets).  rrl_se3_chain turns acc into the twist gradient.
+__global__ void __launch_bounds__(128) backward_pose_kernel(Workspace ws, Geometry g, const float *__restrict__ grad_out,
+                                                            const float *__restrict__ raw, double *__restrict__ acc) {
+    const int b = blockIdx.y;
+    double a[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) a[q] = 0.0;
+    const bool ok = hdr_ok(ws, g) && ws.hdr[6] == 1;
+    const long long nrec = ok ? ws.nrec[b] : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = (long long)b * g.nl + i;
+        const int k = ws.recMeta[r * 2 + 1] & 255;
+        const float go = grad_out[b] * (1.0f / 3.0f);
+        const float *G = ws.recG + r * 24, *Wt = ws.recW + r * 24;
+        const int *idx = ws.recIdx + r * 8;
+        const float *R0 = raw + (long long)b * g.nf1 * 9;
+        for (int h = 0; h < k; ++h) {
+            const float *t = R0 + (long long)idx[h] * 9;
+            const float gx = G[h * 3] * go, gy = G[h * 3 + 1] * go, gz = G[h * 3 + 2] * go;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const float w = Wt[h * 3 + p];
+                const double gv[3] = {(double)(w * gx), (double)(w * gy), (double)(w * gz)};      // the float products the scatter adds
+                const double pv[3] = {(double)__ldg(t + 3 * p), (double)__ldg(t + 3 * p + 1), (double)__ldg(t + 3 * p + 2)};
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) a[3 * m + q] += pv[m] * gv[q];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) a[9 + q] += gv[q];
+            }
+        }
+    }
+    __shared__ double sm[4][12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+        double v = a[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const double v = (sm[0][threadIdx.x] + sm[1][threadIdx.x]) + (sm[2][threadIdx.x] + sm[3][threadIdx.x]);
+        if (v != 0.0) atomicAdd(acc + b * 12 + threadIdx.x, v);
+    }
+}
+
+int launch_backward_pose(const Workspace &ws, const Geometry &g, const float *grad_out, const float *raw, double *acc, cudaStream_t s) {
+    if (cudaMemsetAsync(acc, 0, sizeof(double) * 12 * (size_t)g.B, s) != cudaSuccess) return RRL_ERR_CUDA;
+    // records per pair are a small fraction of the lines; the grid covers the capacity and blocks beyond nrec fall through
+    int bx = (g.nl + 127) / 128;
+    const int cap = (sm_count() * 16 + g.B - 1) / g.B;
+    if (bx > cap) bx = cap;
+    backward_pose_kernel<<<dim3(bx, g.B), 128, 0, s>>>(ws, g, grad_out, raw, acc);
+    count_launch();
+    return check_launch();
+}
+
 int launch_backward(const Workspace &ws, const Geometry &g, const float *grad_out, float *g1, float *g2, cudaStream_t s) {
     if (g1 && cudaMemsetAsync(g1, 0, sizeof(float) * 9 * (size_t)g.B * g.nf1, s) != cudaSuccess) return RRL_ERR_CUDA;
     if (g2 && cudaMemsetAsync(g2, 0, sizeof(float) * 9 * (size_t)g.B * g.nf2, s) != cudaSuccess) return RRL_ERR_CUDA;

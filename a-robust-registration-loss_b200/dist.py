@@ -376,6 +376,12 @@ def line_sharded_twist_loss(twist, raw_tri1, tri2, lines_local, window=(1, 1, 5,
     lines sharded.  The sparse point gradient of every rank's line shard is reduced to pose space locally (closed-form
     se(3) backward) and only the 6 twist-gradient floats cross NVLink.  Returns (loss (1,), status, median)."""
     from . import ops
+    if comm is not None:
+        # everything inside the kernels: exp + transform + dense + exchange + loss forward; pose-space contraction + 12-double
+        # peer all-reduce + exp3 derivative backward
+        loss, info, _ = ops.twist_loss(twist.reshape(1, 6), raw_tri1.reshape(1, -1, 9), tri2.reshape(1, -1, 9),
+                                       lines_local.reshape(1, -1, 6), window, return_info=True, session=session, comm=comm)
+        return loss, info.status, info.median
     tw = _AllReduceGrad.apply(twist.reshape(1, 6), group, comm)
     tri1 = ops.se3_apply(tw, raw_tri1.reshape(1, -1, 3)).reshape(-1, 9)
     return line_sharded_loss(tri1, tri2, lines_local, window, group, reduce_grad=False, session=session, comm=comm)

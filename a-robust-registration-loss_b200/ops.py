@@ -138,6 +138,96 @@ class _IntersectedLineLoss(torch.autograd.Function):
         return g1, g2, None, None, None, None
 
 
+class _TwistLoss(torch.autograd.Function):
+    """twist (B,6) -> exp3 -> raw_tri1 @ R + T -> loss (B,), with the backward contracted to pose space inside the kernels
+    (rrl_loss_backward_twist): no dense point gradient is ever written.  `shard` = (PeerComm, NativeShardBackend factory)
+    is used by dist.line_sharded_twist_loss."""
+
+    @staticmethod
+    def forward(ctx, twist, raw_tri1, tri2, lines, window, holder, session, comm):
+        B, nf1, _ = raw_tri1.shape
+        nf2, nl = tri2.shape[1], lines.shape[1]
+        dev = raw_tri1.device
+        L = N.lib()
+        tri1 = torch.empty_like(raw_tri1)
+        ws_bytes = L.rrl_workspace_bytes(B, nf1, nf2, nl)
+        if ws_bytes == 0:
+            raise ValueError("unsupported geometry B=%d nf1=%d nf2=%d nl=%d" % (B, nf1, nf2, nl))
+        if session is not None:
+            ws, flags = session.acquire((B, nf1, nf2, nl), dev, ws_bytes)
+        else:
+            ws, flags = torch.empty(ws_bytes, dtype=torch.uint8, device=dev), 0
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        median = torch.empty(B, dtype=torch.float32, device=dev)
+        stats = torch.empty(B, N.NSTAT, dtype=torch.int64, device=dev)
+        st = _stream(raw_tri1)
+        with _on(raw_tri1):
+            N.check(L.rrl_se3_apply(twist.data_ptr(), raw_tri1.data_ptr(), B, nf1 * 3, tri1.data_ptr(), st), "rrl_se3_apply")
+            if comm is None:
+                N.check(L.rrl_loss_forward_ex(tri1.data_ptr(), tri2.data_ptr(), lines.data_ptr(), B, nf1, nf2, nl,
+                                              window[0], window[1], window[2], window[3], ws.data_ptr(), ws_bytes,
+                                              loss.data_ptr(), status.data_ptr(), median.data_ptr(), stats.data_ptr(), flags, st),
+                        "rrl_loss_forward_ex")
+            else:                                           # one pair, this rank's line shard, exchange inside the kernels
+                N.check(L.rrl_shard_stage1_ex(tri1.data_ptr(), tri2.data_ptr(), lines.data_ptr(), nf1, nf2, nl,
+                                              window[0], window[1], window[2], window[3], ws.data_ptr(), ws_bytes, flags, st),
+                        "rrl_shard_stage1_ex")
+                N.check(L.rrl_shard_tail(ws.data_ptr(), ws_bytes, nf1, nf2, nl, comm.handle, loss.data_ptr(), status.data_ptr(),
+                                         median.data_ptr(), stats.data_ptr(), st), "rrl_shard_tail")
+        ctx.save_for_backward(twist, raw_tri1)
+        ctx.ws, ctx.geom, ctx.comm = ws, (B, nf1, nf2, nl), comm
+        ctx.mark_non_differentiable(status, median, stats)
+        if holder is not None:
+            holder.append(LossInfo(status, median, stats, ws, ctx.geom))
+            holder.append(tri1)
+        return loss, status, median, stats
+
+    @staticmethod
+    def backward(ctx, grad_loss, *_unused):
+        twist, raw = ctx.saved_tensors
+        B, nf1, nf2, nl = ctx.geom
+        ws = ctx.ws
+        g = grad_loss.contiguous().float()
+        acc = torch.empty(B, 12, dtype=torch.float64, device=ws.device)
+        gt = torch.empty(B, 6, dtype=torch.float32, device=ws.device)
+        L = N.lib()
+        with _on(ws):
+            if ctx.comm is None:
+                N.check(L.rrl_loss_backward_twist(ws.data_ptr(), ws.numel(), g.data_ptr(), B, nf1, nf2, nl, twist.data_ptr(),
+                                                  raw.data_ptr(), acc.data_ptr(), gt.data_ptr(), _stream(ws)), "rrl_loss_backward_twist")
+            else:                                           # the 12 pose-space sums of every rank's line shard, then the chain
+                N.check(L.rrl_loss_backward_twist(ws.data_ptr(), ws.numel(), g.data_ptr(), B, nf1, nf2, nl, None,
+                                                  raw.data_ptr(), acc.data_ptr(), None, _stream(ws)), "rrl_loss_backward_twist")
+                ctx.comm.allreduce_f64_(acc.view(-1))
+                N.check(L.rrl_se3_chain(twist.data_ptr(), acc.data_ptr(), B, gt.data_ptr(), _stream(ws)), "rrl_se3_chain")
+        return gt, None, None, None, None, None, None, None
+
+
+def twist_loss(twist: torch.Tensor, raw_tri1: torch.Tensor, tri2: torch.Tensor, lines: torch.Tensor, window=(1, 1, 5, 5),
+               return_info: bool = False, session: Optional["LossSession"] = None, comm=None):
+    """The registration step in one op (test_demo_optimized_Lie_Algebra.py:57-66): cloud 1 = exp(twist) applied to
+    `raw_tri1` (B,nf1,9) (Reconstruction_point.forward, loss.py:455-463), per-pair losses (B,) against `tri2`, differentiable
+    w.r.t. the twist only; forward = fused exp + transform + loss, backward = pose-space contraction + closed-form exp3
+    derivative.  With return_info also returns (LossInfo, transformed tri1)."""
+    for name, t, last in (("points1", raw_tri1, 9), ("points2", tri2, 9), ("line", lines, 6)):
+        if t.dim() != 3 or t.shape[-1] != last:
+            raise ValueError("%s must have shape (B, n, %d), got %s" % (name, last, tuple(t.shape)))
+    B = raw_tri1.shape[0]
+    if twist.shape != (B, 6) or tri2.shape[0] != B or lines.shape[0] != B:
+        raise ValueError("expected twist (B,6) and matching batch sizes")
+    w = tuple(int(v) for v in window)
+    if not (1 <= w[0] < w[2] <= 5 and 1 <= w[1] < w[3] <= 5):
+        raise ValueError("hit-count window must satisfy 1 <= lo < hi <= 5, got %s" % (w,))
+    twist = _cuda_f32(twist, "twist")
+    raw_tri1, tri2 = _cuda_f32(raw_tri1.detach(), "points1"), _cuda_f32(tri2.detach(), "points2")
+    lines = _cuda_f32(lines.detach(), "line")
+    _same_device(twist, raw_tri1, tri2, lines)
+    holder = [] if return_info else None
+    loss, _, _, _ = _TwistLoss.apply(twist, raw_tri1, tri2, lines, w, holder, session, comm)
+    return (loss, holder[0], holder[1]) if return_info else loss
+
+
 def intersected_line_loss(tri1: torch.Tensor, tri2: torch.Tensor, lines: torch.Tensor,
                           window=(1, 1, 5, 5), return_info: bool = False, session: Optional[LossSession] = None):
     """Batched native API: tri1 (B,nf1,9), tri2 (B,nf2,9), lines (B,nl,6) -> per-pair losses (B,).

@@ -473,6 +473,8 @@ def run_gpu(args):
     twist_mode = args.workload in ("demo", "fmr")
     twist0 = torch.tensor([0.01, -0.02, 0.015, 0.03, -0.01, 0.02], device=dev).repeat(B, 1)
     rows = [s[0].reshape(B, -1, 3) for s in dev_sets] if twist_mode else None
+    # --reuse-order 1 (demo): the clouds' spatial order is kept from step to step (LossSession), as in a registration loop
+    demo_session = rrl_b200.LossSession() if (args.workload == "demo" and args.reuse_order) else None
 
     def compute(i):
         """the device work of one step on input set i: forward + backward"""
@@ -485,8 +487,7 @@ def run_gpu(args):
             return total.detach(), tw.grad
         if args.workload == "demo":                          # the se(3) optimiser's step (test_demo...py:57-66)
             tw = twist0.clone().requires_grad_(True)
-            tri1 = rrl_b200.se3_apply(tw, rows[i % n_sets]).reshape(B, -1, 9)
-            total = rrl_b200.intersected_line_loss(tri1, t2, ln).sum()
+            total = rrl_b200.twist_loss(tw, t1, t2, ln, session=demo_session).sum()
             total.backward()
             return total.detach(), tw.grad
         t1 = t1.detach().requires_grad_(True)
@@ -572,7 +573,9 @@ def run_gpu(args):
                     "timed_regions_ms_per_step": main_repeats,
                     "statistic": "median of %d timed regions of exactly %d steps each (a single region of %d steps lasts a few "
                                  "milliseconds)" % (args.repeats, args.steps, args.steps),
-                    "api": "rrl_b200.intersected_line_loss (torch.autograd.Function over the C ABI), forward + backward"},
+                    "api": {"demo": "rrl_b200.twist_loss (exp + transform + loss forward, pose-space backward)",
+                            "fmr": "rrl_b200.hooks.fmr_twist_loss (Exp -> fused rigid transform -> loss; ExpMap gradient)"}.get(
+                                args.workload, "rrl_b200.intersected_line_loss (torch.autograd.Function over the C ABI), forward + backward")},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "lines_sampled_on_device": sampled, "dropin": dropin, "hooks": hooks, "large": large,
             "loss_checksum": float(last[0].item())}
@@ -850,8 +853,7 @@ def bench_large(args, torch, dist, rrl_b200, T, rank, local_rank, world, dev, he
                 if world > 1:
                     loss, _, _ = rrl_b200.dist.line_sharded_twist_loss(tw, t1, t2, ln, session=sess, comm=comm)
                 else:
-                    tri1 = rrl_b200.se3_apply(tw.reshape(1, 6), t1.reshape(1, -1, 3)).reshape(1, -1, 9)
-                    loss = rrl_b200.intersected_line_loss(tri1, t2[None], ln[None], session=sess)
+                    loss = rrl_b200.twist_loss(tw.reshape(1, 6), t1[None], t2[None], ln[None], session=sess)
                 total = loss.sum()
                 total.backward()
                 return total.detach(), tw.grad
@@ -922,7 +924,7 @@ def main():
     ap.add_argument("--large-scaling", default="strong", choices=["strong", "weak"],
                     help="workload large at N > 1: strong = the 100k lines of the pair are split over the ranks (BASELINE "
                          "configs[4]); weak = every rank keeps 100k lines of a pair with N x 100k lines")
-    ap.add_argument("--reuse-order", type=int, default=0, help="workload large: headline = the step with the clouds' order kept from step to step")
+    ap.add_argument("--reuse-order", type=int, default=0, help="workloads large / demo: the step with the clouds' order kept from step to step (LossSession)")
     ap.add_argument("--large-block", type=int, default=1, help="default workload: also measure BASELINE configs[4] (block `large` of the line)")
     ap.add_argument("--e2e-repeats", type=int, default=5)
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps each; the median is reported")

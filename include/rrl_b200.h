@@ -76,7 +76,8 @@ size_t rrl_workspace_bytes(int B, int nf1, int nf2, int nl);
  *   out_median [B]          lower median of the pair's D entries (loss.py:223-224); may be NULL
  *   out_stats  [B*RRL_NSTAT] int64: {0: #selected lines, 1: #D entries, 2: #non-empty combos C,
  *                            3: #queued (line, node-group) candidates cloud 1, 4: same for cloud 2,
- *                            5: #tests within 1 ulp of the threshold (the north star's separately reported band),
+ *                            5: #tests within 1 ulp of the threshold that can decide a label, i.e. whose two sibling points pass
+ *                               or sit in the band themselves (the north star's separately reported band),
  *                            6: #NaN distances among candidates, 7: reserved}; may be NULL
  */
 int rrl_loss_forward(const float *tri1, const float *tri2, const float *lines,
@@ -202,6 +203,15 @@ int rrl_se3_apply(const float *twist, const float *points, int B, int n, float *
 /* grad_out (B,n,3) = d loss / d out  ->  grad_twist (B,6).  scratch: B*12 doubles. */
 int rrl_se3_apply_backward(const float *twist, const float *points, const float *grad_out, int B, int n,
                            float *grad_twist, double *scratch, void *stream);
+/* Backward straight to pose space for a cloud 1 that is exp(twist) applied to `raw_tri1` (B,nf1,9) (the demo's
+ * Reconstruction_point -> loss -> backward chain, test_demo_optimized_Lie_Algebra.py:57-66): contracts the sparse point
+ * gradient of the forward held in `workspace` with the raw points, acc12 (B,12) double = {sum p (x) g (9), sum g (3)}
+ * (zeroed here), without materialising a dense (B,nf1,9) gradient; with grad_twist != NULL the closed-form derivative of
+ * exp3 is applied right away, else the caller reduces acc12 over its line shards first and calls rrl_se3_chain. */
+int rrl_loss_backward_twist(const void *workspace, size_t workspace_bytes, const float *grad_out,
+                            int B, int nf1, int nf2, int nl, const float *twist, const float *raw_tri1,
+                            double *acc12, float *grad_twist, void *stream);
+int rrl_se3_chain(const float *twist, const double *acc12, int B, float *grad_twist, void *stream);
 /* rigid transform with explicit (R,t) for the DCP / RPM-Net / FMR hooks (utils.py:32-37,
  * rpm/common/math_torch/se3.py:55-82, fmr/se_math/se3.py:110-124): out = points @ R^T + t (column convention
  * R p + t).  Backward: grad_R (B,3,3), grad_t (B,3), and optionally grad_points. */

@@ -87,7 +87,7 @@ static inline float ulp_of(float x) { return nextafterf(x, INFINITY) - x; }
  * Dense phase for one cloud.  counts[nl]: number of hit triplets per line (uncapped);
  * hits[nl*RRL_CAP]: the first RRL_CAP hit triplet indices in ascending order (-1 padded);
  * hit_d[nl*RRL_CAP*3]: their three distances.  stats[0] += #NaN distances (the reference
- * exits on any, loss.py:89-91), stats[1] += #tests with |d-thr| <= 1 ulp(thr).
+ * exits on any, loss.py:89-91), stats[1] += #tests with |d-thr| <= 1 ulp(thr) that can decide the label (see below).
  */
 void rrl_oracle_dense(const float *tri, int nf, const float *lines, int64_t nl,
                       int32_t *counts, int32_t *hits, float *hit_d, int64_t *stats) {
@@ -110,7 +110,14 @@ void rrl_oracle_dense(const float *tri, int nf, const float *lines, int64_t nl,
             float th = thr[f];
             nan_total += (d0 != d0) + (d1 != d1) + (d2 != d2);
             float u = ulp_of(th);
-            band_total += (fabsf(d0 - th) <= u) + (fabsf(d1 - th) <= u) + (fabsf(d2 - th) <= u);
+            /* DECISIVE band tests only: a distance within 1 ulp of the threshold can change the label only when both other
+             * points of the triplet pass or sit in the band themselves (point 0 failing by a mile makes the rounding of
+             * points 1 and 2 irrelevant) */
+            {
+                int b0 = fabsf(d0 - th) <= u, b1 = fabsf(d1 - th) <= u, b2 = fabsf(d2 - th) <= u;
+                int o0 = (d0 < th) | b0, o1 = (d1 < th) | b1, o2 = (d2 < th) | b2;
+                band_total += (b0 & o1 & o2) + (b1 & o0 & o2) + (b2 & o0 & o1);
+            }
             if ((d0 < th) & (d1 < th) & (d2 < th)) {
                 if (c < RRL_CAP) {
                     hits[l * RRL_CAP + c] = f;

@@ -75,7 +75,7 @@ class DenseResult:
     hit_tris: torch.Tensor                  # (H,) int64 triplet index, ascending inside a line
     hit_d: torch.Tensor                     # (H, 3) float32 distances of the hit triplet
     nan_seen: bool = False
-    band: int = 0                           # tests with |d - thr| <= 1 ulp(thr)
+    band: int = 0                           # tests with |d - thr| <= 1 ulp(thr) that can decide the label
 
 
 def dense_phase(tri: torch.Tensor, lines: torch.Tensor, chunk: int = 1024,
@@ -95,7 +95,10 @@ def dense_phase(tri: torch.Tensor, lines: torch.Tensor, chunk: int = 1024,
         label = (d < thr).sum(-1) == 3
         if count_band:
             ulp = torch.nextafter(thr, thr + 1) - thr
-            band += int(((d - thr).abs() <= ulp).sum())
+            inb = (d - thr).abs() <= ulp                     # within 1 ulp of the threshold ...
+            okb = (d < thr) | inb
+            others = torch.stack([okb[..., 1] & okb[..., 2], okb[..., 0] & okb[..., 2], okb[..., 0] & okb[..., 1]], -1)
+            band += int((inb & others).sum())                # ... and able to decide the label (the other two pass or are in the band)
         counts[s:s + chunk] = label.sum(-1)
         nz = label.nonzero()
         hl.append(nz[:, 0] + s)

@@ -184,6 +184,40 @@ def test_rpm_and_fmr_hooks(rrl):
     assert per.shape == (B,) and tw.grad.shape == (B, 6) and bool(tw.grad.abs().sum() > 0)
 
 
+@pytest.mark.parametrize("B,nf,nl", [(1, 1024, 4000), (3, 700, 1500), (1, 20000, 1200)])
+def test_twist_loss_backward_in_pose_space(rrl, B, nf, nl):
+    """rrl_b200.twist_loss (exp + transform + loss forward, pose-space contraction backward: no dense point gradient) against
+    the two-op chain se3_apply -> intersected_line_loss and against the oracle's point gradient pushed through exp3"""
+    pairs = [synth.make_pair(780 + i, nf, nl) for i in range(B)]
+    raw = torch.from_numpy(np.stack([p["tri1"] for p in pairs])).cuda()
+    t2 = torch.from_numpy(np.stack([p["tri2"] for p in pairs])).cuda()
+    ln = torch.from_numpy(np.stack([p["lines"] for p in pairs])).cuda()
+    rng = np.random.default_rng(B)
+    tw0 = torch.from_numpy(rng.normal(scale=0.02, size=(B, 6)).astype(np.float32)).cuda()
+    up = torch.arange(1, B + 1, device="cuda", dtype=torch.float32)
+    a = tw0.clone().requires_grad_(True)
+    la, info, moved = rrl.twist_loss(a, raw, t2, ln, return_info=True)
+    (la * up).sum().backward()
+    b = tw0.clone().requires_grad_(True)
+    tri1 = rrl.se3_apply(b, raw.reshape(B, -1, 3)).reshape(B, -1, 9)
+    lb = rrl.intersected_line_loss(tri1, t2, ln)
+    (lb * up).sum().backward()
+    assert torch.equal(la, lb) and torch.equal(moved, tri1.detach())
+    assert _rel(a.grad.cpu().numpy(), b.grad.cpu().numpy()) <= 1e-6
+    for i, p in enumerate(pairs):
+        o = co.loss(moved[i].cpu().numpy(), p["tri2"], p["lines"])
+        gt = co.se3_backward(tw0[i].cpu().numpy(), p["tri1"].reshape(-1, 3), (i + 1) * o.grad1.reshape(-1, 3))
+        assert abs(la[i].item() - o.loss) <= REL_TOL * o.loss and _rel(a.grad[i].cpu().numpy(), gt) <= REL_TOL
+        assert float(info.median[i]) == o.median
+    # a session keeps the clouds' order from call to call; results do not change
+    sess = rrl.LossSession()
+    for _ in range(2):
+        c = tw0.clone().requires_grad_(True)
+        lc = rrl.twist_loss(c, raw, t2, ln, session=sess)
+        (lc * up).sum().backward()
+        assert torch.equal(lc, la) and _rel(c.grad.cpu().numpy(), a.grad.cpu().numpy()) <= 1e-6
+
+
 def test_expmap_against_the_reference(rrl):
     """fmr/se_math/se3.py Exp forward and ExpMap.backward (tests/golden/expmap.npz, minted from the reference)"""
     g = golden("expmap")
