@@ -12,6 +12,7 @@ HIT_CAP = 5
 NSTAT = 8
 STATUS_EMPTY, STATUS_NAN, STATUS_NAN_RISK, STATUS_COMM = 1, 2, 4, 8
 REUSE_ORDER = 1                  # RRL_REUSE_ORDER flag of rrl_loss_forward_ex / rrl_shard_stage1_ex
+REUSE_TARGET = 2                 # RRL_REUSE_TARGET: cloud 2 unchanged since the previous forward in the workspace
 
 _lib = None
 

@@ -51,6 +51,7 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     const size_t sB = (size_t)B, lines = (size_t)B * nl;
     const int nf1p = pad_points(nf1), nf2p = pad_points(nf2);
     w.hdr = reinterpret_cast<int *>(take(8 * sizeof(int)));
+    w.keep = reinterpret_cast<unsigned int *>(take(sB * 8 * sizeof(unsigned int)));
     // ---- per-pair block, contiguous and zeroed by one memset in launch_prep (order matters) ----
     char *pair = take(16 + sB * (5 * 2 * 4 + 4 + 16 * 4 + 4 + 4 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
     w.xcursor = reinterpret_cast<unsigned long long *>(pair);         pair += 16;
@@ -120,7 +121,7 @@ static int stage_dense_and_build(const float *tri1, const float *tri2, const flo
     int rc;
     {
         Range r("rrl.prep (thresholds, order, bounding spheres)");
-        rc = launch_prep(tri1, tri2, lines, ws, g, window, (flags & RRL_REUSE_ORDER) != 0, s);
+        rc = launch_prep(tri1, tri2, lines, ws, g, window, flags, s);
     }
     if (rc) return rc;
     {
@@ -162,7 +163,7 @@ extern "C" int rrl_loss_forward_ex(const float *tri1, const float *tri2, const f
                                    void *stream) {
     if (!tri1 || !tri2 || !lines || !workspace || !out_loss) return RRL_ERR_ARG;
     if (!geometry_ok(B, nf1, nf2, nl) || !window_ok(k_lo, j_lo, k_hi, j_hi)) return RRL_ERR_ARG;
-    if (flags & ~RRL_REUSE_ORDER) return RRL_ERR_ARG;
+    if (flags & ~(RRL_REUSE_ORDER | RRL_REUSE_TARGET)) return RRL_ERR_ARG;
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return RRL_ERR_ARG;
     const Workspace ws = carve(workspace, B, nf1, nf2, nl);
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;
@@ -221,7 +222,7 @@ extern "C" int rrl_shard_stage1_ex(const float *tri1, const float *tri2, const f
                                    void *stream) {
     if (!tri1 || !tri2 || !lines || !workspace) return RRL_ERR_ARG;
     if (!geometry_ok(1, nf1, nf2, nl) || !window_ok(k_lo, j_lo, k_hi, j_hi)) return RRL_ERR_ARG;
-    if (flags & ~RRL_REUSE_ORDER) return RRL_ERR_ARG;
+    if (flags & ~(RRL_REUSE_ORDER | RRL_REUSE_TARGET)) return RRL_ERR_ARG;
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return RRL_ERR_ARG;
     const Workspace ws = carve(workspace, 1, nf1, nf2, nl);
     if (workspace_bytes < ws.bytes) return RRL_ERR_WORKSPACE;

@@ -48,7 +48,9 @@ struct Geometry {
 
 // One forward's scratch, carved out of the caller's workspace.  All pointers are device pointers.
 struct Workspace {
-    int *hdr;                // [8]: {magic, B, nf1, nf2, nl, window, Welsch stage done, 0}; checked by hdr_ok() on the device
+    int *hdr;                // [8]: {magic, B, nf1, nf2, nl, window, Welsch stage done, order token}; checked by hdr_ok() on the device
+    unsigned int *keep;      // (B,8): what RRL_REUSE_TARGET needs of cloud 2 from the previous forward (never zeroed by prep; written
+                             //        by the last kernel of a forward): {pmax, rmax, smax, bad, xmax its node records were built for}
     // launch-wide + per pair (one contiguous block, zeroed by a single memset)
     unsigned long long *xcursor; // [2]: {entries reserved in xcand, reserved}
     unsigned int *pmax;      // (B,2): bits of max |p|^2 over all 3 points of all triplets of the cloud
@@ -145,7 +147,7 @@ void stage_mark(int stage, cudaStream_t s);   // measurement hook: records an ev
 
 // ---- stage launchers (rrl_dense.cu, rrl_sparse.cu) ------------------------------------------------------
 int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
-                int window, int reuse_order, cudaStream_t s);
+                int window, int reuse_flags, cudaStream_t s);      // reuse_flags: RRL_REUSE_ORDER | RRL_REUSE_TARGET
 int launch_bruteforce(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                       int force, cudaStream_t s);
 int launch_dense(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g, cudaStream_t s);

@@ -49,8 +49,12 @@ __device__ __forceinline__ float finite_extent(const float *v, int &bad) {
 // prep: thresholds, line constants, extents
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
-                                                   const float *__restrict__ lines, Workspace ws, Geometry g, int window) {
+                                                   const float *__restrict__ lines, Workspace ws, Geometry g, int window,
+                                                   int reuse_target) {
     const int b = blockIdx.y;
+    // RRL_REUSE_TARGET: cloud 2's thresholds and extent survive from the previous forward of this geometry (hdr[7] is written by
+    // that forward's last kernel, by nobody in this launch: every CTA takes the same decision)
+    const bool keep2 = reuse_target && ws.hdr[7] == order_token(g);
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0 && t0 == 0) {
@@ -65,6 +69,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
         const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
         float *thr = ws.thr[cloud] + (long long)b * nf;
         float pm = 0.f;                                                           // running maximum: ONE atomic per warp
+        if (cloud == 1 && keep2) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                ws.pmax[b * 2 + 1] = ws.keep[b * 8 + 0];
+                ws.bad[b * 2 + 1] = ws.keep[b * 8 + 3];
+            }
+            block_max[cloud] = 0.f;
+            continue;
+        }
         for (int base = blockIdx.x * blockDim.x; base < nf; base += stride) {      // warp-uniform trip count
             const int f = base + threadIdx.x;
             if (f < nf) {
@@ -554,14 +566,30 @@ __device__ __forceinline__ float make_super_block(const float *__restrict__ tri,
 #endif
 template <int kNode>
 __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g, int ball_iters,
-                                                   int supers) {
+                                                   int supers, int reuse_target) {
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
     const int nnodes = nfp / kNode;
     const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
     const float *thr = ws.thr[cloud] + (long long)b * nf;
     const int *perm = ws.perm[cloud] + (long long)b * nfp;
-    const float E = node_slack(ws.pmax[b * 2 + cloud], ws.xmax[b * 2]);
+    unsigned xmax_bits = ws.xmax[b * 2];                  // final: prep_kernel has completed
+    if (cloud == 1 && reuse_target) {
+        // the target's records are valid for every line extent up to the one they were built for (the slack E grows with it):
+        // keep[4] is only rewritten by the LAST kernel of a forward, so all CTAs of cloud 2 decide alike
+        if (ws.hdr[7] == order_token(g) && xmax_bits <= ws.keep[b * 8 + 4]) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                atomicMax(ws.rmax + b * 2 + 1, ws.keep[b * 8 + 1]);
+                atomicMax(ws.smax + b * 2 + 1, ws.keep[b * 8 + 2]);
+                ws.xmax[b * 2 + 1] = ws.keep[b * 8 + 4];          // the records stay valid for the extent they were built for
+            }
+            return;
+        }
+        // (re)build for a 1.1x larger extent, so that the next steps' lines (resampled every step) rarely force another rebuild
+        xmax_bits = __float_as_uint(__fmul_ru(__uint_as_float(xmax_bits), 1.21f));
+        if (blockIdx.x == 0 && threadIdx.x == 0) ws.xmax[b * 2 + 1] = xmax_bits;      // -> keep[4] at the end of this forward
+    }
+    const float E = node_slack(ws.pmax[b * 2 + cloud], xmax_bits);
     // one thread per sorted position; nfp is a multiple of kPointPad = 256 = blockDim.x, so every warp is full
     float rad = 0.f, srad = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nfp; i += (long long)gridDim.x * blockDim.x) {
@@ -821,7 +849,8 @@ static int g_dense_variant = 1;        // 1 = Morton-sorted nodes (default), 0 =
 void set_dense_variant(int v) { g_dense_variant = v; }
 
 int launch_prep(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
-                int window, int reuse_order, cudaStream_t s) {
+                int window, int reuse_flags, cudaStream_t s) {
+    const int reuse_order = (reuse_flags & (RRL_REUSE_ORDER | RRL_REUSE_TARGET)) ? 1 : 0;
     const int sorted = g_dense_variant ? 1 : 0;
     const int nfp_max = g.nf1p > g.nf2p ? g.nf1p : g.nf2p;
     const int G = node_size(g);
@@ -849,7 +878,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     const int cap = (sm_count() * 8 + g.B - 1) / g.B;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    prep_kernel<<<dim3(bx, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, window);
+    const int reuse_target = (reuse_flags & RRL_REUSE_TARGET) ? 1 : 0;
+    prep_kernel<<<dim3(bx, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, window, reuse_target);
     count_launch();
     stage_mark(1, s);
     if (reuse_order) {
@@ -909,8 +939,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     stage_mark(2, s);
     int nbx = nfp_max / 256;
     if (nbx > 4096) nbx = 4096;
-    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g));
-    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g));
+    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g), reuse_target);
+    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g), reuse_target);
     count_launch();
     stage_mark(3, s);
     return check_launch();

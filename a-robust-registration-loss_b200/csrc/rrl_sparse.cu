@@ -599,6 +599,18 @@ __device__ __forceinline__ void finalize_pair(const Workspace &ws, int b, float 
     // reference's dense tensor, which is what makes it exit (loss.py:89-91).  Here such triplets and lines never hit
     // (comparisons with NaN are false) and may never reach the exact test, so the inputs themselves raise the flag.
     if (__ldcg(ws.bad + b * 2) | __ldcg(ws.bad + b * 2 + 1)) status |= RRL_STATUS_NAN;
+    // what RRL_REUSE_TARGET needs of cloud 2 in the next forward (the per-pair block is zeroed by its prep stage)
+    if (lane == 0) {
+        unsigned int *kp = ws.keep + b * 8;
+        kp[0] = pm1;
+        kp[1] = __ldcg(ws.rmax + b * 2 + 1);
+        kp[2] = __ldcg(ws.smax + b * 2 + 1);
+        kp[3] = __ldcg(ws.bad + b * 2 + 1);
+        // the line extent cloud 2's records are valid for: xmax[1] when the node stage ran under RRL_REUSE_TARGET (it carries the
+        // kept or the freshly inflated value), else the extent of this forward's own lines
+        const unsigned built = __ldcg(ws.xmax + b * 2 + 1);
+        kp[4] = built ? built : __ldcg(ws.xmax + b * 2);
+    }
     const long long outstat = lane == 0 ? nrec : lane == 1 ? nD : lane == 2 ? (long long)C : mystat;
     if (lane < 3) st[lane] = outstat;
     if (out_stats && lane < RRL_NSTAT) out_stats[(long long)b * RRL_NSTAT + lane] = outstat;

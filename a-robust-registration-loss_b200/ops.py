@@ -75,8 +75,11 @@ class LossSession:
     one.  The backward of a call must run before the next forward on the same session (they share the workspace).
     `reset()` forces a fresh sort (e.g. when the clouds were replaced by different ones)."""
 
-    def __init__(self):
+    def __init__(self, static_target: bool = False):
+        """static_target: cloud 2 (the registration target) is the SAME tensor contents in every call of this session --
+        its thresholds / records / bounding spheres are then kept too (RRL_REUSE_TARGET; clouds above 4096 triplets)."""
         self._ws, self._key, self._ready = None, None, False
+        self._flags = N.REUSE_ORDER | (N.REUSE_TARGET if static_target else 0)
 
     def reset(self):
         self._ready = False
@@ -86,7 +89,7 @@ class LossSession:
         if self._ws is None or self._key != key:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             self._key, self._ready = key, False
-        flags = N.REUSE_ORDER if self._ready else 0
+        flags = self._flags if self._ready else 0
         self._ready = True                      # the forward about to be queued leaves a complete order behind
         return self._ws, flags
 

@@ -95,6 +95,12 @@ int rrl_loss_forward(const float *tri1, const float *tri2, const float *lines,
  * test_demo_optimized_Lie_Algebra.py:46-66) or the iterations of RPM-Net / FMR on one batch.
  */
 #define RRL_REUSE_ORDER 1
+/* RRL_REUSE_TARGET (implies RRL_REUSE_ORDER; clouds above 4096 triplets, ignored below): additionally, cloud 2 -- the
+ * registration TARGET -- is bit-identical to the previous forward's in this workspace (the caller's contract: the target of a
+ * registration loop never changes, test_demo_optimized_Lie_Algebra.py:46-66).  Its thresholds, triplet records and
+ * bounding-sphere levels are then kept instead of rebuilt -- unless the new lines reach farther out than the slack those
+ * records were built for, which is checked on the device (they are rebuilt in that case, for 1.1x the new extent). */
+#define RRL_REUSE_TARGET 2
 int rrl_loss_forward_ex(const float *tri1, const float *tri2, const float *lines,
                         int B, int nf1, int nf2, int nl,
                         int k_lo, int j_lo, int k_hi, int j_hi,

@@ -452,7 +452,7 @@ def test_full_size_rpm_and_fmr_batches(rrl, name, B, nf, nl, kw, n_oracle):
 def test_more_d_entries_than_the_median_cache(rrl):
     """a pair whose selected lines hold more D entries than the tail kernel caches in shared memory (49152): the median
     is then selected by sweeps over the records in global memory"""
-    nf, nl = 1024, 100000
+    nf, nl = 1024, 160000
     p = synth.make_pair(4100, nf, nl)
     out = _run(rrl, p["tri1"], p["tri2"], p["lines"])
     orc = co.loss(p["tri1"], p["tri2"], p["lines"])
@@ -542,6 +542,40 @@ def test_reused_order_gives_identical_results(rrl, nf, nl):
         assert np.array_equal(h1[orc.counts1 <= co.CAP], orc.hits1[orc.counts1 <= co.CAP])
         assert float(info.median[0]) == orc.median
         assert abs(loss.item() - orc.loss) <= REL_TOL * orc.loss
+        assert _rel(t1.grad[0].cpu().numpy(), orc.grad1) <= REL_TOL
+
+
+def test_static_target_session_keeps_the_targets_records(rrl):
+    """RRL_REUSE_TARGET (LossSession(static_target=True)): the target's thresholds, records and bounding spheres survive from
+    call to call while the source moves and the lines change.  Every call is compared completely with the oracle: same
+    lines again; a rigidly moved source; lines that reach farther out than anything before (the device-side extent check
+    must rebuild the target's spheres with a larger slack); the first lines again (reuse of the rebuilt records); lines
+    pulled towards the origin."""
+    nf, nl = 20000, 1500
+    p = synth.make_pair(181, nf, nl, nf2=17000)
+    rng = np.random.default_rng(8)
+    Rm = synth.random_rotation(rng, 4.0)
+    moved = (p["tri1"].reshape(-1, 3).astype(np.float64) @ Rm.T + 0.015).astype(np.float32).reshape(-1, 9)
+    far = p["lines"].copy()
+    far[:, 3:] = far[:, 3:] + far[:, :3] * 3.0 * rng.uniform(0.5, 1.0, size=(nl, 1)).astype(np.float32)   # slide x0 along the line: same lines,
+    near = p["lines"].copy()                                                                                  # larger |x0| (same hits)
+    d = near[:, :3].astype(np.float64); x0 = near[:, 3:].astype(np.float64)
+    near[:, 3:] = (x0 - (x0 * d).sum(1, keepdims=True) * d).astype(np.float32)                              # foot point: smallest |x0|
+    sess = rrl.LossSession(static_target=True)
+    t2 = torch.from_numpy(p["tri2"]).cuda()[None]
+    for tri1, lines in ((p["tri1"], p["lines"]), (p["tri1"], p["lines"]), (moved, p["lines"]), (moved, far), (p["tri1"], p["lines"]),
+                        (moved, near)):
+        t1 = torch.from_numpy(tri1).cuda()[None].requires_grad_(True)
+        ln = torch.from_numpy(lines).cuda()[None]
+        loss, info = rrl.intersected_line_loss(t1, t2, ln, return_info=True, session=sess)
+        loss.sum().backward()
+        c1, h1 = (x[0].cpu().numpy() for x in info.hits(1))
+        c2, h2 = (x[0].cpu().numpy() for x in info.hits(2))
+        orc = co.loss(tri1, p["tri2"], lines)
+        assert np.array_equal(c1, orc.counts1) and np.array_equal(c2, orc.counts2)
+        assert np.array_equal(h1[orc.counts1 <= co.CAP], orc.hits1[orc.counts1 <= co.CAP])
+        assert np.array_equal(h2[orc.counts2 <= co.CAP], orc.hits2[orc.counts2 <= co.CAP])
+        assert float(info.median[0]) == orc.median and abs(loss.item() - orc.loss) <= REL_TOL * orc.loss
         assert _rel(t1.grad[0].cpu().numpy(), orc.grad1) <= REL_TOL
 
 
