@@ -109,7 +109,9 @@ __device__ __forceinline__ void make_line(float r, const float *center, float a1
     ln[3] = q1[0] + center[0]; ln[4] = q1[1] + center[1]; ln[5] = q1[2] + center[2];
 }
 
-constexpr int kPhases = 4;                    // the rounds are evaluated in phases [0,1) [1,2) [2,4) [4,rounds)
+constexpr int kPhases = 6;                    // the rounds are evaluated in phases [0,1) [1,2) [2,3) [3,4) [4,6) [6,rounds): a phase is one
+                                              // launch (~3 us); at 42 % acceptance per round the rows fill up during round 2, at 30 % during
+                                              // round 3 -- with [2,4) as one phase both cases evaluated four rounds
 
 struct SamplerArgs {
     const float *radius, *centers, *uniforms;
@@ -464,7 +466,9 @@ extern "C" int rrl_sample_lines(const float *radius, const float *centers, const
     bbox_kernel<<<dim3(B, 2), 256, 0, s>>>(verts1, verts2, n1, n2, a.bbox);
     const int cap = (sm_count() * 8 + B - 1) / B;
     // a chunk belongs to the phase of rounds that holds its first candidate
-    const int edge[kPhases + 1] = {0, 1 < rounds ? 1 : rounds, 2 < rounds ? 2 : rounds, 4 < rounds ? 4 : rounds, rounds};
+    const int raw_edge[kPhases + 1] = {0, 1, 2, 3, 4, 6, rounds};
+    int edge[kPhases + 1];
+    for (int q = 0; q <= kPhases; ++q) edge[q] = raw_edge[q] < rounds ? raw_edge[q] : rounds;
     int bx_all = 1;
     for (int ph = 0; ph < kPhases; ++ph) {
         const int ch_begin = (int)(((long long)edge[ph] * N + kChunk - 1) / kChunk);

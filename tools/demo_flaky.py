@@ -14,5 +14,12 @@ for r in range(runs):
     data = demo.load_case(args, "cuda")
     model, hist = demo.test_one_case(data, n_epoch=epochs, n_sample_line=8000, device="cuda", log=None)
     cf = [h[0] for h in hist]
+    R, T = model.Transform()
+    Rn = R[0].cpu().numpy().astype(np.float64)
+    ang = np.deg2rad(12.0)
+    Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    # row-vector convention: p' = p @ R, the target is base @ Rz.T  =>  R should approach Rz.T
+    err = np.rad2deg(np.arccos(np.clip((np.trace(Rn @ Rz) - 1) / 2, -1, 1)))
+    print("rot err deg %.3f  median last15 %.5f  median first3 %.5f" % (err, np.median(cf[-15:]), np.mean(cf[:3])))
     print(r, len(hist), "chamfer first3 %.5f last3 %.5f min %.5f | at 20/40/60/80/100: %s" % (
         np.mean(cf[:3]), np.mean(cf[-3:]), min(cf), " ".join("%.5f" % cf[i] for i in range(19, len(cf), 20))), flush=True)

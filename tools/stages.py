@@ -6,7 +6,7 @@ import rrl_b200
 from tools import synth
 L = rrl_b200._native.lib()
 CONFIGS = {"demo": (1, 1024, 20000), "dcp": (32, 1024, 15000), "rpm": (64, 2048, 10000), "fmr": (128, 1024, 15000), "large": (1, 500000, 100000),
-           "mid": (8, 8192, 10000), "big": (2, 65536, 20000)}
+           "mid": (8, 8192, 10000), "big": (2, 65536, 20000), "large8": (1, 500000, 12500), "large2": (1, 500000, 50000)}
 NAMES = ["prep", "sort", "node", "dense", "select", "build", "median", "welsch", "backward", "total"]
 args = [a for a in sys.argv[1:] if "=" not in a]
 for kv in [a for a in sys.argv[1:] if "=" in a]:          # e.g. 6=4 -> rrl_debug_set_param(6, 4)
