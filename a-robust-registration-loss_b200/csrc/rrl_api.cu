@@ -53,12 +53,13 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.hdr = reinterpret_cast<int *>(take(8 * sizeof(int)));
     w.keep = reinterpret_cast<unsigned int *>(take(sB * 8 * sizeof(unsigned int)));
     // ---- per-pair block, contiguous and zeroed by one memset in launch_prep (order matters) ----
-    char *pair = take(16 + sB * (5 * 2 * 4 + 4 + 16 * 4 + 4 + 4 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
+    char *pair = take(16 + sB * (6 * 2 * 4 + 4 + 16 * 4 + 4 + 4 * 4 + 32 * 8 + RRL_NSTAT * 8 + 18 * 8));
     w.xcursor = reinterpret_cast<unsigned long long *>(pair);         pair += 16;
     w.pmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.xmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.rmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.smax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
+    w.tmax = reinterpret_cast<unsigned int *>(pair);                  pair += sB * 2 * 4;
     w.bad = reinterpret_cast<unsigned int *>(pair);                   pair += sB * 2 * 4;
     w.nrec = reinterpret_cast<int *>(pair);                           pair += sB * 4;
     w.n_kj = reinterpret_cast<int *>(pair);                           pair += sB * 16 * 4;

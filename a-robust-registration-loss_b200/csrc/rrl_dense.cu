@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
         ws.hdr[0] = kMagic; ws.hdr[1] = g.B; ws.hdr[2] = g.nf1; ws.hdr[3] = g.nf2; ws.hdr[4] = g.nl; ws.hdr[5] = window;
         ws.hdr[6] = 0;
     }
-    float block_max[3];
+    float block_max[3], block_thr[2];
     int badv = 0;
 #pragma unroll
     for (int cloud = 0; cloud < 2; ++cloud) {
@@ -69,12 +69,15 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
         const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
         float *thr = ws.thr[cloud] + (long long)b * nf;
         float pm = 0.f;                                                           // running maximum: ONE atomic per warp
+        float tm = 0.f;
         if (cloud == 1 && keep2) {
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 ws.pmax[b * 2 + 1] = ws.keep[b * 8 + 0];
                 ws.bad[b * 2 + 1] = ws.keep[b * 8 + 3];
+                ws.tmax[b * 2 + 1] = ws.keep[b * 8 + 5];
             }
             block_max[cloud] = 0.f;
+            block_thr[cloud] = 0.f;
             continue;
         }
         for (int base = blockIdx.x * blockDim.x; base < nf; base += stride) {      // warp-uniform trip count
@@ -83,11 +86,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
                 float v[9];
 #pragma unroll
                 for (int q = 0; q < 9; ++q) v[q] = __ldg(tri + (long long)f * 9 + q);
-                thr[f] = triplet_thr_exact(v);
+                const float th = triplet_thr_exact(v);
+                thr[f] = th;
+                if (th < INFINITY) tm = fmaxf(tm, th);            // a NaN / infinite threshold never hits and stays out
                 pm = fmaxf(pm, finite_extent(v, badv));
             }
         }
         block_max[cloud] = pm;
+        block_thr[cloud] = tm;
         if (__any_sync(0xffffffffu, badv) && (threadIdx.x & 31) == 0) atomicOr(ws.bad + b * 2 + cloud, 1u);
         badv = 0;
     }
@@ -116,17 +122,18 @@ __global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ tri
     block_max[2] = xmw;
     if (__any_sync(0xffffffffu, badv) && (threadIdx.x & 31) == 0) atomicOr(ws.bad + b * 2, 1u);
     // one atomic per CTA and array: thousands of same-address atomics would serialise in L2
-    __shared__ unsigned s_max[3];
-    if (threadIdx.x < 3) s_max[threadIdx.x] = 0u;
+    __shared__ unsigned s_max[5];
+    if (threadIdx.x < 5) s_max[threadIdx.x] = 0u;
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(block_max[q]));
+    for (int q = 0; q < 5; ++q) {
+        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(q < 3 ? block_max[q] : block_thr[q - 3]));
         if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max[q], m);
     }
     __syncthreads();
-    if (threadIdx.x < 3 && s_max[threadIdx.x])
-        atomicMax(threadIdx.x < 2 ? ws.pmax + b * 2 + threadIdx.x : ws.xmax + b * 2, s_max[threadIdx.x]);
+    if (threadIdx.x < 5 && s_max[threadIdx.x])
+        atomicMax(threadIdx.x < 2 ? ws.pmax + b * 2 + threadIdx.x : (threadIdx.x == 2 ? ws.xmax + b * 2 : ws.tmax + b * 2 + threadIdx.x - 3),
+                  s_max[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -363,8 +370,12 @@ __device__ __forceinline__ float4 sphere_record_up(float R, float qx, float qy, 
 // the lane group (x + y == y + x exactly, so every lane of a group holds the same bits); lane s == 0 writes the node
 // record.  Must be called by converged warps (whole groups, full mask).  Returns the node radius in lane s == 0.
 template <int kNode>
+// pt_stride / grp_stride: float4 per node of the triplet records and per group of 4 node records: kNode + 1 and 5 (one pad: odd
+// strides, conflict-free when the records are read from shared memory, and -- measured -- also the better layout for the
+// scattered per-lane gathers from L2 of the large-cloud modes).
 __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, float th, int f, long long i, float E_up,
-                                                float4 *pt_base, float4 *pt12, float4 *node4, int ball_iters) {
+                                                float4 *pt_base, float4 *pt12, float4 *node4, int ball_iters, int pt_stride,
+                                                int grp_stride) {
     const long long n = i / kNode;
     const int s = (int)(i % kNode);
     double px = 0, py = 0, pz = 0, cut = 0;
@@ -432,31 +443,34 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     pt12[i * 2 + 1] = pr2;
     {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB};
         // a node occupies kNode + 1 float4 (odd stride: lanes reading different nodes hit different banks)
-        float *dp = reinterpret_cast<float *>(pt_base + n * (kNode + 1) + (s & ~1)) + (s & 1);
+        float *dp = reinterpret_cast<float *>(pt_base + n * pt_stride + (s & ~1)) + (s & 1);
         dp[0] = pr.x; dp[2] = pr.y; dp[4] = pr.z; dp[6] = pr.w;
     }
     float rad = 0.f;
     if (s == 0) {
         float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);           // empty node: never a candidate
         if (cntv > 0) rec = sphere_record_up(R, qx, qy, qz, rad);
-        pt_base[n * (kNode + 1) + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);                  // pad slot
-        // node records: a group of 4 nodes = two interleaved pairs + one pad = 5 float4 (odd stride again)
-        float4 *grp = node4 + (n >> 2) * 5;
+        if (pt_stride > kNode) pt_base[n * pt_stride + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);                  // pad slot
+        // node records: a group of 4 nodes = two interleaved pairs (+ one pad = 5 float4: odd stride again)
+        float4 *grp = node4 + (n >> 2) * grp_stride;
         float *dst = reinterpret_cast<float *>(grp + ((n >> 1) & 1) * 2) + (n & 1);
         dst[0] = rec.x; dst[2] = rec.y; dst[4] = rec.z; dst[6] = rec.w;
-        if ((n & 3) == 0) grp[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((n & 3) == 0 && grp_stride > 4) grp[4] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     return rad;
 }
 
 __device__ __forceinline__ int pad_supers_dev(int nfp) { return ((nfp / kSuperPts + kNodePad - 1) / kNodePad) * kNodePad; }
 
-// slack of the node radius for the rounding of the reference-order test: E = kGuardRef eps (P + Xmax)^2
-__device__ __forceinline__ float node_slack(unsigned pmax_bits, unsigned xmax_bits) {   // rounded up throughout
+// slack of the node radius for the rounding of the reference-order test (rrl_common.cuh): E = kMargin eps (kRefPX (P + Xmax)^2 +
+// kRefT thr_max^2)
+__device__ __forceinline__ float node_slack(unsigned pmax_bits, unsigned xmax_bits, unsigned tmax_bits) {   // rounded up throughout
     const float P = __fmul_ru(__fsqrt_ru(__uint_as_float(pmax_bits)), 1.000001f);
     const float Xm = __fmul_ru(__fsqrt_ru(__uint_as_float(xmax_bits)), 1.000001f);
     const float PX = __fadd_ru(P, Xm);
-    return __fadd_ru(__fmul_ru(__fmul_ru(kGuardRef * kEps24, PX), PX), 1e-12f);
+    const float T = __uint_as_float(tmax_bits);
+    const float sum = __fadd_ru(__fmul_ru(__fmul_ru(kRefPX, PX), PX), __fmul_ru(__fmul_ru(kRefT, T), T));
+    return __fadd_ru(__fmul_ru(kMargin * kEps24, sum), 1e-12f);
 }
 
 // Super node = bounding sphere of the kSuperPts = 256 sorted triplets one node_kernel CTA handles per trip (16 nodes of
@@ -589,15 +603,21 @@ __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const flo
         xmax_bits = __float_as_uint(__fmul_ru(__uint_as_float(xmax_bits), 1.21f));
         if (blockIdx.x == 0 && threadIdx.x == 0) ws.xmax[b * 2 + 1] = xmax_bits;      // -> keep[4] at the end of this forward
     }
-    const float E = node_slack(ws.pmax[b * 2 + cloud], xmax_bits);
+    const float E = node_slack(ws.pmax[b * 2 + cloud], xmax_bits, ws.tmax[b * 2 + cloud]);
     // one thread per sorted position; nfp is a multiple of kPointPad = 256 = blockDim.x, so every warp is full
     float rad = 0.f, srad = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nfp; i += (long long)gridDim.x * blockDim.x) {
         int f = perm[i];
         if ((unsigned)f >= (unsigned)nf) f = -1;      // padding; also keeps a violated RRL_REUSE_ORDER contract memory-safe
         const float th = f >= 0 ? thr[f] : 0.f;
-        rad = fmaxf(rad, make_node_coop<kNode>(tri, th, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
-                                               ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters));
+        // (sector-aligned strides -- kNode and 4 -- were measured for the super-node mode, whose records are only ever gathered
+        // from L2: 25 % SLOWER, 1354 against 1083 us on the large pair.  With every node at the same offset modulo 256 bytes the
+        // lanes of a gather collide in the same L1 sets / L2 slices; the odd strides spread them.)
+        const int pt_stride = kNode + 1, grp_stride = 5;
+        (void)supers;
+        rad = fmaxf(rad, make_node_coop<kNode>(tri, th, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * pt_stride,
+                                               ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * grp_stride,
+                                               ball_iters, pt_stride, grp_stride));
         if (supers)
             srad = fmaxf(srad, make_super_block(tri, th, f, i, E, ws.super4[cloud] + (long long)b * (pad_supers_dev(nfp) / 4) * 5,
                                                 nfp / kSuperPts, pad_supers_dev(nfp), ball_iters));
@@ -639,7 +659,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
                                                           const float *__restrict__ lines, Workspace ws, Geometry g, int window,
                                                           int sorted, int line_blocks, int ball_iters, int refine, int reuse) {
     extern __shared__ unsigned long long skeys[];
-    __shared__ unsigned s_red[3];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius
+    __shared__ unsigned s_red[4];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius, max threshold
     const int b = blockIdx.x, tid = threadIdx.x;
     // RRL_REUSE_ORDER is honoured only when an earlier forward of this very geometry completed in this workspace (hdr[7]
     // is written by that forward's LAST kernel and by nobody in this launch, so every CTA reads the same value); on a
@@ -660,7 +680,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
     const float *tri = (cloud ? tri2 : tri1) + (long long)b * nf * 9;
     float *thr = ws.thr[cloud] + (long long)b * nf;
-    if (tid < 3) s_red[tid] = 0u;
+    if (tid < 4) s_red[tid] = 0u;
     if (cloud == 0) {
         if (b == 0 && tid == 0) {
             ws.hdr[0] = kMagic; ws.hdr[1] = g.B; ws.hdr[2] = g.nf1; ws.hdr[3] = g.nf2; ws.hdr[4] = g.nl; ws.hdr[5] = window;
@@ -676,13 +696,15 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     }
     __syncthreads();
     // thresholds, extent of the cloud, extent of the pair's lines
-    float pm = 0.f, xm = 0.f;
+    float pm = 0.f, xm = 0.f, tm = 0.f;
     int badv = 0;
     for (int f = tid; f < nf; f += 1024) {
         float v[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) v[q] = __ldg(tri + (long long)f * 9 + q);
-        thr[f] = triplet_thr_exact(v);
+        const float th = triplet_thr_exact(v);
+        thr[f] = th;
+        if (th < INFINITY) tm = fmaxf(tm, th);
         pm = fmaxf(pm, finite_extent(v, badv));
     }
 #pragma unroll 4
@@ -697,11 +719,13 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     }
     {
         const unsigned a = __reduce_max_sync(0xffffffffu, __float_as_uint(pm)), c = __reduce_max_sync(0xffffffffu, __float_as_uint(xm));
-        if ((tid & 31) == 0) { atomicMax(&s_red[0], a); atomicMax(&s_red[1], c); }
+        const unsigned t = __reduce_max_sync(0xffffffffu, __float_as_uint(tm));
+        if ((tid & 31) == 0) { atomicMax(&s_red[0], a); atomicMax(&s_red[1], c); atomicMax(&s_red[3], t); }
     }
     const int bad_any = __syncthreads_or(badv);          // (also the barrier the reductions above need)
     if (tid == 0) {
         ws.pmax[b * 2 + cloud] = s_red[0];
+        ws.tmax[b * 2 + cloud] = s_red[3];
         if (cloud == 0) ws.xmax[b * 2] = s_red[1];
         ws.bad[b * 2 + cloud] = bad_any ? 1u : 0u;       // this cloud's points, or any line of the pair (both CTAs scan them)
     }
@@ -779,7 +803,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
             }
     }
     const int nnodes = nfp / kNode;
-    const float Eslack = node_slack(s_red[0], s_red[1]);
+    const float Eslack = node_slack(s_red[0], s_red[1], s_red[3]);
     __syncthreads();                                     // thr (global) is re-read below by other threads; sort buffers are dead
     // sorted indices -> shared memory, k-d refinement of every window of 64 (one warp each), then the records
     int *sidx = reinterpret_cast<int *>(skeys);
@@ -811,7 +835,8 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
             const int f = sidx[i];
             perm[i] = f;
             rad = fmaxf(rad, make_node_coop<kNode>(tri, f >= 0 ? thr[f] : 0.f, f, i, Eslack, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
-                                                   ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters));
+                                                   ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters,
+                                                   kNode + 1, 5));
         }
     }
     {
@@ -949,6 +974,13 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
 // ------------------------------------------------------------------------------------------------------
 // dense
 // ------------------------------------------------------------------------------------------------------
+#ifdef RRL_COUNTERS
+// measurement builds: how many entries every queue level consumed (rrl_debug_read_counters)
+__device__ unsigned long long g_counters[8];
+#define RRL_COUNT(i, n) do { if (lane == 0) atomicAdd(&g_counters[i], (unsigned long long)(n)); } while (0)
+#else
+#define RRL_COUNT(i, n) do { } while (0)
+#endif
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
@@ -1084,7 +1116,8 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     using Cfg = DenseCfg<kNode, kPerNode, LPT, kSuper>;
     constexpr int kLinesPerThread = LPT, kLinesPerCta = Cfg::kLines, kTileNodes = Cfg::kTile, kStageF4 = Cfg::kStage;
     constexpr int kWarpQueue = Cfg::kWq, kNodeQueue = Cfg::kNq, kExactQueue = Cfg::kXq;
-    constexpr int kSmemPtsF4 = Cfg::kPts, kSmemPts12F4 = Cfg::kPts12;
+    constexpr int kPtStride = kNode + 1;                          // float4 per node of the triplet records (see make_node_coop)
+    constexpr int kGrpStride = 5;                                 // float4 per group of 4 node records
     extern __shared__ __align__(128) unsigned char dsm[];
     float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kStageF4]
     float4 *spts = reinterpret_cast<float4 *>(dsm + Cfg::kOffPts);                         // [kSmemPtsF4]
@@ -1131,7 +1164,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         tma_bulk_load(stage + (t & 1) * kStageF4, src + (long long)t * kStageF4, bytes, &mbar[t & 1]);
     };
     // the chunk's triplet records (level 2) go to shared memory when they fit, else they are read through L2
-    const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + node_begin) * (kNode + 1);   // chunk start
+    const float4 *pt4_c = ws.pt4[cloud] + ((long long)b * nnodes + node_begin) * kPtStride;   // chunk start
     constexpr bool pts_in_smem = kPerNode, pts12_in_smem = kPerNode;
     const float4 *pts = spts;
     if constexpr (!kPerNode) pts = pt4_c;
@@ -1158,6 +1191,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     // ---- per-thread lines -> filter thresholds ------------------------------------------------------------
     const float P = sqrtf(__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001f;
     const float Rmax = __uint_as_float(ws.rmax[b * 2 + cloud]);
+    const float Tmax = __uint_as_float(ws.tmax[b * 2 + cloud]);
     const float Smax = kSuper ? __uint_as_float(ws.smax[b * 2 + cloud]) : 0.f;
     const float4 *lineC = ws.lineC + (long long)b * g.nl * 2;
     float ux[kLinesPerThread], uy[kLinesPerThread], uz[kLinesPerThread];
@@ -1165,7 +1199,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     // threshold of the triplet-level predicate and of the node-level predicate for a line
     auto thresholds = [&](const float4 &c0, const float4 &c1, float &tl_point, float &tl_node, float &tl_super) {
         const float PX = P + c0.w;
-        const float guard = kGuardFast * kEps24 * PX * PX + 1e-12f;
+        const float guard = kMargin * kEps24 * (kFastPX * PX * PX + kFastT * Tmax * Tmax) * 1.000001f + 1e-12f;
         tl_point = c1.w - guard - fabsf(c1.w) * 1.2e-7f;                    // rounded down: admits more
         // |u| > 1 makes F slightly indefinite; e bounds the deficit, 0 for |u| <= 1 (incl. all-zero lines)
         const float s2 = (c0.x * c0.x + c0.y * c0.y + c0.z * c0.z) * 1.0000004f;
@@ -1201,13 +1235,14 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)node_begin * kNode;   // from the chunk start
     // node records for level 1: re-read through L1/L2 (a pointer that is sometimes the resident stage would make
     // every access a generic load)
-    const float4 *node_src = ws.node4[cloud] + (long long)b * (nnodes / 4) * 5 + (long long)(node_begin / 4) * 5;   // from the chunk start
+    const float4 *node_src = ws.node4[cloud] + (long long)b * (nnodes / 4) * kGrpStride + (long long)(node_begin / 4) * kGrpStride;   // from the chunk start
     int wq_cnt = 0, nq_cnt = 0, xq_cnt = 0;                      // warp-uniform fill levels
 
     // level 3 hand-off: (line, triplet) entries that passed both filters go to the launch-wide queue of the exact
     // kernel (one reservation per flush).  When the queue is full the warp runs the exact test itself.
     auto run_exact = [&]() {
         __syncwarp();
+        RRL_COUNT(2, xq_cnt);                                  // (line, triplet) entries that passed the point-0 predicate
         // refine: the same conservative FMA predicate on points 1 and 2 (one entry per lane, compacted in place):
         // about one in eight entries that passed on point 0 survives
         {
@@ -1234,6 +1269,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
             }
             xq_cnt = kept;
         }
+        RRL_COUNT(3, xq_cnt);                                  // ... and the refine on points 1 and 2: handed to the exact kernel
         if (xq_cnt > 0) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(ws.xcursor, (unsigned long long)xq_cnt);
@@ -1267,6 +1303,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     // level 2: triplet predicate on the triplets of (line, node) entries, packed two triplets per FFMA2
     auto run_nodes = [&]() {
         __syncwarp();
+        RRL_COUNT(1, nq_cnt);                                  // (line, node) entries = triplet-record fetches of (kNode + 1) float4
         for (int base = 0; base < nq_cnt; base += 32) {
             if (xq_cnt + 32 * kNode > kExactQueue) run_exact();
             unsigned pm = 0, key = 0;
@@ -1275,9 +1312,9 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 // the NEXT pass's triplet records (one node = (kNode + 1) float4, scattered over the cloud) towards L1 while
                 // this pass computes: a pass otherwise starts with a full L2 round trip per group of loads
                 if (base + 32 + lane < nq_cnt) {
-                    const char *nx = reinterpret_cast<const char *>(pts + (int)(nq[base + 32 + lane] & 0x3FFFFFu) * (kNode + 1));
+                    const char *nx = reinterpret_cast<const char *>(pts + (int)(nq[base + 32 + lane] & 0x3FFFFFu) * kPtStride);
 #pragma unroll
-                    for (int o = 0; o < (kNode + 1) * 16; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + o));
+                    for (int o = 0; o < kPtStride * 16; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + o));
                 }
             }
 #endif
@@ -1288,7 +1325,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 const float tl_point = c1.w;
                 const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
                 const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
-                const float4 *pp = pts + nrel * (kNode + 1);
+                const float4 *pp = pts + nrel * kPtStride;
 #if RRL_L2_PRELOAD
                 // large clouds read the records through L2 (every lane another node): all kNode loads are issued before the
                 // first use, so a pass waits for ONE L2 round trip instead of one per group the register budget allowed
@@ -1329,12 +1366,13 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     // level 1: node predicate on the 4 nodes of (line, group) entries
     auto run_groups = [&]() {
         __syncwarp();
+        RRL_COUNT(0, wq_cnt);                                  // (line, group of 4 nodes) entries = node-record fetches of 4 float4
         for (int base = 0; base < wq_cnt; base += 32) {
             if (nq_cnt + 128 > kNodeCap) run_nodes();
             unsigned nm = 0, key = 0;
 #if RRL_PF_LEVEL1
             if (base + 32 + lane < wq_cnt)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(node_src + (int)(wq[base + 32 + lane] & 0xFFFFFu) * 5));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(node_src + (int)(wq[base + 32 + lane] & 0xFFFFFu) * kGrpStride));
 #endif
             if (base + lane < wq_cnt) {
                 const unsigned ent = wq[base + lane];
@@ -1343,7 +1381,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 const int q0 = grp * 4;
                 const float4 c0 = slineU[lrel], c1 = slineM[lrel];
                 const float tl_node = c0.w;
-                const float4 *nr4 = node_src + grp * 5;                // 4 nodes = 2 interleaved pairs (+ 1 pad float4)
+                const float4 *nr4 = node_src + grp * kGrpStride;       // 4 nodes = 2 interleaved pairs (+ 1 pad float4)
                 const float4 A0 = nr4[0], A1 = nr4[1], B0 = nr4[2], B1 = nr4[3];
                 const float nx[4] = {A0.x, A0.y, B0.x, B0.y}, ny[4] = {A0.z, A0.w, B0.z, B0.w};
                 const float nz[4] = {A1.x, A1.y, B1.x, B1.y}, nw[4] = {A1.z, A1.w, B1.z, B1.w};
@@ -1737,3 +1775,14 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
 }
 
 }  // namespace rrl
+
+#ifdef RRL_COUNTERS
+extern "C" int rrl_debug_read_counters(unsigned long long *out8, int reset) {
+    if (cudaMemcpyFromSymbol(out8, rrl::g_counters, sizeof(unsigned long long) * 8) != cudaSuccess) return -3;
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(rrl::g_counters, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

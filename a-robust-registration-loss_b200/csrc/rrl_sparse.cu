@@ -606,6 +606,7 @@ __device__ __forceinline__ void finalize_pair(const Workspace &ws, int b, float 
         kp[1] = __ldcg(ws.rmax + b * 2 + 1);
         kp[2] = __ldcg(ws.smax + b * 2 + 1);
         kp[3] = __ldcg(ws.bad + b * 2 + 1);
+        kp[5] = __ldcg(ws.tmax + b * 2 + 1);
         // the line extent cloud 2's records are valid for: xmax[1] when the node stage ran under RRL_REUSE_TARGET (it carries the
         // kept or the freshly inflated value), else the extent of this forward's own lines
         const unsigned built = __ldcg(ws.xmax + b * 2 + 1);

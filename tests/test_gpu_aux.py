@@ -258,13 +258,19 @@ def test_demo_flow_with_the_reference_names(rrl):
     assert data["vertics1_faces_tensor"].shape == (1, 3 * 1500, 3)
     model, hist = demo.test_one_case(data, n_epoch=60, n_sample_line=8000, device="cuda", log=None)
     assert len(hist) >= 50
-    # Adam at the demo's learning rate keeps oscillating around the optimum and every epoch draws fresh lines, so the
-    # Chamfer distance of single late epochs wanders (measured over repeated runs at epoch 60: 0.000 .. 0.001 from a
-    # start of 0.0022): the alignment must be REACHED (best epoch below a tenth of the start) and must not be lost again
-    # (median of the last 15 epochs below the start)
+    # Adam at the demo's learning rate keeps oscillating around the optimum and every epoch draws fresh lines, so single late
+    # epochs wander.  Spread over repeated runs of exactly this case (tools/demo_flaky.py, 6 runs on a B200): rotation error
+    # of the final transform 0.16 .. 1.64 degrees (start: 12), median Chamfer of the last 15 epochs 0.013 .. 0.28 of the
+    # start, best epoch below 0.005 of the start.  The bounds leave a factor ~2 over the worst run seen.
     cf = [h[0] for h in hist]
     first = np.mean(cf[:3])
-    assert min(cf) < 0.1 * first, (first, min(cf))
-    assert np.median(cf[-15:]) < first, (first, np.median(cf[-15:]))
+    assert min(cf) < 0.02 * first, (first, min(cf))
+    assert np.median(cf[-15:]) < 0.5 * first, (first, np.median(cf[-15:]))
+    Rn = model.Transform()[0][0].cpu().numpy().astype(np.float64)
+    ang = np.deg2rad(12.0)
+    Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    # row-vector convention (loss.py:460-461): p' = p @ R and the target is base @ Rz.T, so R must approach Rz.T
+    rot_err = np.rad2deg(np.arccos(np.clip((np.trace(Rn @ Rz) - 1) / 2, -1, 1)))
+    assert rot_err < 3.5, rot_err
     R, T = model.Transform()
     assert R.shape == (1, 3, 3) and T.shape == (1, 3) and "parameters_" in model.state_dict()
