@@ -243,8 +243,8 @@ def test_fps_rejects_bad_arguments(rrl):
 
 def test_demo_flow_with_the_reference_names(rrl):
     """examples/demo_lie_algebra.py = test_demo_optimized_Lie_Algebra.py with `loss` shadowed by the B200 module:
-    Sample_neighs -> Reconstruction_point -> per epoch sampler + loss + Adam + chamfer.  A 12-degree misalignment of a
-    synthetic ellipsoid must shrink."""
+    Sample_neighs -> Reconstruction_point -> per epoch sampler + loss + Adam + chamfer.  A 25-degree misalignment of a
+    synthetic ellipsoid must be recovered."""
     import argparse
     import importlib.util
     import os
@@ -253,24 +253,27 @@ def test_demo_flow_with_the_reference_names(rrl):
     demo = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(demo)
     torch.manual_seed(5); np.random.seed(5); rrl.loss.manual_seed(5)
-    args = argparse.Namespace(synthetic=1500, seed=5, angle=12.0, data_path="", label1="0")
+    args = argparse.Namespace(synthetic=1500, seed=5, angle=25.0, data_path="", label1="0")
     data = demo.load_case(args, "cuda")
     assert data["vertics1_faces_tensor"].shape == (1, 3 * 1500, 3)
-    model, hist = demo.test_one_case(data, n_epoch=60, n_sample_line=8000, device="cuda", log=None)
-    assert len(hist) >= 50
-    # Adam at the demo's learning rate keeps oscillating around the optimum and every epoch draws fresh lines, so single late
-    # epochs wander.  Spread over repeated runs of exactly this case (tools/demo_flaky.py, 6 runs on a B200): rotation error
-    # of the final transform 0.16 .. 1.64 degrees (start: 12), median Chamfer of the last 15 epochs 0.013 .. 0.28 of the
-    # start, best epoch below 0.005 of the start.  The bounds leave a factor ~2 over the worst run seen.
+    model, hist = demo.test_one_case(data, n_epoch=80, n_sample_line=20000, device="cuda", log=None)     # the demo's own line count
+    assert len(hist) >= 70
+    # Adam at the demo's learning rate takes normalised steps of ~0.6 degrees per epoch even at the optimum, every epoch draws
+    # fresh lines, and the scatter of the point gradient uses float atomics, so repeated runs follow different trajectories and
+    # single late epochs wander.  Spread over 8 repeated runs of exactly this case on a B200 (tools/demo_flaky.py 8 80 20000 25,
+    # profiles/r02_demo_spread.log): rotation error of the final transform 0.2 .. 3.4 degrees (start: 25), median Chamfer of the
+    # last 15 epochs 0.002 .. 0.25 of the start, best epoch below 0.01 of the start.  (At 12 degrees and 8000 lines -- round 1's
+    # case -- the same wander is as large as the initial misalignment: final errors up to 4.9 degrees, late medians up to 1.4x the
+    # start, which is why that version could only assert "not worse than the start".)
     cf = [h[0] for h in hist]
     first = np.mean(cf[:3])
     assert min(cf) < 0.02 * first, (first, min(cf))
     assert np.median(cf[-15:]) < 0.5 * first, (first, np.median(cf[-15:]))
     Rn = model.Transform()[0][0].cpu().numpy().astype(np.float64)
-    ang = np.deg2rad(12.0)
+    ang = np.deg2rad(25.0)
     Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
     # row-vector convention (loss.py:460-461): p' = p @ R and the target is base @ Rz.T, so R must approach Rz.T
     rot_err = np.rad2deg(np.arccos(np.clip((np.trace(Rn @ Rz) - 1) / 2, -1, 1)))
-    assert rot_err < 3.5, rot_err
+    assert rot_err < 7.0, rot_err
     R, T = model.Transform()
     assert R.shape == (1, 3, 3) and T.shape == (1, 3) and "parameters_" in model.state_dict()
