@@ -27,6 +27,7 @@
 //
 // Both filters are superset tests ("filtered predicate"); the decision itself is always taken by the
 // literal arithmetic of loss.py:84-110, so the selected indices are bit-exact against the oracle.
+#include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "rrl_common.cuh"
@@ -365,6 +366,25 @@ __device__ __forceinline__ float4 sphere_record_up(float R, float qx, float qy, 
     return make_float4(qx, qy, qz, w);
 }
 
+// ---- compressed triplet records of the large-cloud modes (level 2 gathers them from L2, every lane another node) ----------
+// A node's point-0 records as 16 + 8 kNode bytes instead of 16 (kNode + 1): header {qb.xyz, scale}, then per PAIR of triplets
+// one uint4 {xA | xB << 16, yA | yB << 16, zA | zB << 16, half2(cutA, cutB)} with 16-bit offsets u.  The dense kernel
+// reconstructs  p~ = fma(float(2^23 + u), scale, qb)  -- float(2^23 + u) is the bit pattern 0x4B000000 | u, one PRMT -- and
+// evaluates the SAME packed-FMA predicate on (p~, cut~).  Superset argument: the node kernel runs the identical
+// FMA, MEASURES e >= |p~ - p| (directed rounding), and stores cut~ >= cut + 2 e sqrt(cut + E) + e^2 rounded up to half:
+// "p passes the reference test" => d(p)^2 < cut + E => d(p~)^2 <= (d(p) + e)^2 < cut~ + E.  Nothing is assumed about the
+// quantiser: a clamped or badly rounded offset only makes e, and with it cut~, larger.  The dense kernel bounds e by
+// pc_err_bound() for the |u| > 1 slack; a record that would exceed it gets cut~ = +inf (always a candidate).
+constexpr float kPcBias = 8388608.0f + 32768.0f;        // float(2^23 + u) - kPcBias = signed offset in steps
+constexpr float kPcSteps = 32000.0f;                    // largest offset in steps (headroom below 32767 for the rounding of qb)
+__device__ __forceinline__ float pc_err_bound(float R, float P) {      // >= |p~ - p| for every member of a node of radius <= R
+    // sqrt(3) (half a step of R / kPcSteps + one rounding of a value of magnitude <= P + R), generously rounded up
+    return 1.7321f * (R * (0.5f / kPcSteps) * 1.01f + 6.0e-8f * 1.01f * (P + R)) + 1e-37f;
+}
+__device__ __forceinline__ float pc_reconstruct(unsigned u16, float scale, float qb) {
+    return fmaf(__uint_as_float(0x4B000000u | u16), scale, qb);
+}
+
 // One bounding-sphere node, built by kNode CONSECUTIVE LANES: the lane of sorted position i = n * kNode + s loads triplet f
 // (or -1 = padding) and writes its point records; centroid, member count and radius are butterfly all-reductions inside
 // the lane group (x + y == y + x exactly, so every lane of a group holds the same bits); lane s == 0 writes the node
@@ -373,9 +393,11 @@ template <int kNode>
 // pt_stride / grp_stride: float4 per node of the triplet records and per group of 4 node records: kNode + 1 and 5 (one pad: odd
 // strides, conflict-free when the records are read from shared memory, and -- measured -- also the better layout for the
 // scattered per-lane gathers from L2 of the large-cloud modes).
+// pc != nullptr: the point-0 records are written in the compressed form above (uint4 units, stride 1 + kNode / 2) instead of
+// pt_base; P_up >= the cloud's extent (for the error bound a record must meet).
 __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, float th, int f, long long i, float E_up,
                                                 float4 *pt_base, float4 *pt12, float4 *node4, int ball_iters, int pt_stride,
-                                                int grp_stride) {
+                                                int grp_stride, uint4 *pc = nullptr, float P_up = 0.f) {
     const long long n = i / kNode;
     const int s = (int)(i % kNode);
     double px = 0, py = 0, pz = 0, cut = 0;
@@ -441,7 +463,44 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     for (int d = 1; d < kNode; d <<= 1) R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, d));
     pt12[i * 2] = pr1;
     pt12[i * 2 + 1] = pr2;
-    {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB};
+    if (pc) {
+        // scale: the largest offset component of the node's members / kPcSteps
+        float am = f >= 0 ? fmaxf(fmaxf(fabsf((float)px - qx), fabsf((float)py - qy)), fabsf((float)pz - qz)) : 0.f;
+#pragma unroll
+        for (int d = 1; d < kNode; d <<= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, d));
+        float scale = am * (1.0f / kPcSteps);
+        if (!(scale > 1e-30f)) scale = 1e-30f;
+        const float qbx = fmaf(-kPcBias, scale, qx), qby = fmaf(-kPcBias, scale, qy), qbz = fmaf(-kPcBias, scale, qz);
+        unsigned ux = 32768u, uy = 32768u, uz = 32768u;
+        __half cuth = __float2half_ru(-INFINITY);                    // padding / non-finite triplet: never a candidate
+        if (f >= 0) {
+            const double inv = 1.0 / (double)scale;                    // (one double division per lane instead of three)
+            auto quant = [&](double pv, float qb) -> unsigned {        // nearest representable offset (double: p - qb is ~2^23 steps)
+                double u = rint((pv - (double)qb) * inv) - 8388608.0;
+                u = u < 0.0 ? 0.0 : (u > 65535.0 ? 65535.0 : u);
+                return (unsigned)u;
+            };
+            ux = quant(px, qbx); uy = quant(py, qby); uz = quant(pz, qbz);
+            const float rx = pc_reconstruct(ux, scale, qbx), ry = pc_reconstruct(uy, scale, qby), rz = pc_reconstruct(uz, scale, qbz);
+            const float fx = (float)px, fy = (float)py, fz = (float)pz;
+            const float dx = fmaxf(fabsf(__fsub_ru(rx, fx)), fabsf(__fsub_rd(rx, fx)));
+            const float dy = fmaxf(fabsf(__fsub_ru(ry, fy)), fabsf(__fsub_rd(ry, fy)));
+            const float dz = fmaxf(fabsf(__fsub_ru(rz, fz)), fabsf(__fsub_rd(rz, fz)));
+            const float e = __fadd_ru(__fsqrt_ru(__fmaf_ru(dz, dz, __fmaf_ru(dy, dy, __fmul_ru(dx, dx)))), 1e-37f);
+            const float cut_up = __fadd_ru(__fmul_ru(th, th), -kAddEps);
+            const float a = __fsqrt_ru(fmaxf(__fadd_ru(cut_up, E_up), 0.f));
+            float cut_c = __fadd_ru(cut_up, __fmaf_ru(__fmul_ru(2.0f, e), a, __fmul_ru(e, e)));
+            if (!(e <= pc_err_bound(R, P_up))) cut_c = INFINITY;     // (cannot happen by the bound's derivation; kept exact anyway)
+            cuth = __float2half_ru(cut_c);
+        }
+        // the pair (s, s ^ 1) shares a uint4: the even lane gathers its neighbour's words and writes all 16 bytes
+        const unsigned short ch = __half_as_ushort(cuth);
+        const unsigned ox = __shfl_xor_sync(0xffffffffu, ux, 1), oy = __shfl_xor_sync(0xffffffffu, uy, 1), oz = __shfl_xor_sync(0xffffffffu, uz, 1);
+        const unsigned oc = __shfl_xor_sync(0xffffffffu, (unsigned)ch, 1);
+        uint4 *blk = pc + n * (1 + kNode / 2);
+        if ((s & 1) == 0) blk[1 + (s >> 1)] = make_uint4(ux | (ox << 16), uy | (oy << 16), uz | (oz << 16), (unsigned)ch | (oc << 16));
+        if (s == 0) blk[0] = make_uint4(__float_as_uint(qbx), __float_as_uint(qby), __float_as_uint(qbz), __float_as_uint(scale));
+    } else {   // pair-interleaved like the node records: triplets (2i, 2i+1) -> {xA,xB,yA,yB}{zA,zB,wA,wB};
         // a node occupies kNode + 1 float4 (odd stride: lanes reading different nodes hit different banks)
         float *dp = reinterpret_cast<float *>(pt_base + n * pt_stride + (s & ~1)) + (s & 1);
         dp[0] = pr.x; dp[2] = pr.y; dp[4] = pr.z; dp[6] = pr.w;
@@ -450,7 +509,7 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
     if (s == 0) {
         float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);           // empty node: never a candidate
         if (cntv > 0) rec = sphere_record_up(R, qx, qy, qz, rad);
-        if (pt_stride > kNode) pt_base[n * pt_stride + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);                  // pad slot
+        if (!pc && pt_stride > kNode) pt_base[n * pt_stride + kNode] = make_float4(0.f, 0.f, 0.f, 0.f);           // pad slot
         // node records: a group of 4 nodes = two interleaved pairs (+ one pad = 5 float4: odd stride again)
         float4 *grp = node4 + (n >> 2) * grp_stride;
         float *dst = reinterpret_cast<float *>(grp + ((n >> 1) & 1) * 2) + (n & 1);
@@ -569,6 +628,11 @@ __device__ __forceinline__ float make_super_block(const float *__restrict__ tri,
 #ifndef RRL_PF_LEVEL2
 #define RRL_PF_LEVEL2 0
 #endif
+// measurement only (WRONG results): level 2 reads and tests only the first half of a node's triplets when the records come
+// through L2 -- how much of the large-cloud kernel is the bytes of these gathers?
+#ifndef RRL_EXP_HALF_L2
+#define RRL_EXP_HALF_L2 0
+#endif
 #ifndef RRL_L2_PRELOAD
 #define RRL_L2_PRELOAD 0
 #endif
@@ -580,7 +644,7 @@ __device__ __forceinline__ float make_super_block(const float *__restrict__ tri,
 #endif
 template <int kNode>
 __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g, int ball_iters,
-                                                   int supers, int reuse_target) {
+                                                   int supers, int reuse_target, int compressed) {
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int nf = cloud ? g.nf2 : g.nf1, nfp = cloud ? g.nf2p : g.nf1p;
     const int nnodes = nfp / kNode;
@@ -604,6 +668,9 @@ __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const flo
         if (blockIdx.x == 0 && threadIdx.x == 0) ws.xmax[b * 2 + 1] = xmax_bits;      // -> keep[4] at the end of this forward
     }
     const float E = node_slack(ws.pmax[b * 2 + cloud], xmax_bits, ws.tmax[b * 2 + cloud]);
+    const float P_up = __fmul_ru(__fsqrt_ru(__uint_as_float(ws.pmax[b * 2 + cloud])), 1.000001f);
+    // compressed point-0 records live in the pt4 buffer (16 + 8 kNode <= 16 (kNode + 1) bytes per node)
+    uint4 *pc = compressed ? reinterpret_cast<uint4 *>(ws.pt4[cloud]) + (long long)b * nnodes * (1 + kNode / 2) : nullptr;
     // one thread per sorted position; nfp is a multiple of kPointPad = 256 = blockDim.x, so every warp is full
     float rad = 0.f, srad = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nfp; i += (long long)gridDim.x * blockDim.x) {
@@ -617,7 +684,7 @@ __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const flo
         (void)supers;
         rad = fmaxf(rad, make_node_coop<kNode>(tri, th, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * pt_stride,
                                                ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * grp_stride,
-                                               ball_iters, pt_stride, grp_stride));
+                                               ball_iters, pt_stride, grp_stride, pc, P_up));
         if (supers)
             srad = fmaxf(srad, make_super_block(tri, th, f, i, E, ws.super4[cloud] + (long long)b * (pad_supers_dev(nfp) / 4) * 5,
                                                 nfp / kSuperPts, pad_supers_dev(nfp), ball_iters));
@@ -637,6 +704,20 @@ __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const flo
 
 // ------------------------------------------------------------------------------------------------------
 // small clouds (<= kSortSmall padded triplets): memset + prep + sort + nodes in ONE launch
+#ifdef RRL_MARKS
+// phase timestamps of the cloud-0 CTA of pair 0 (measurement builds only; rrl_debug_read_marks_prep)
+__device__ unsigned long long g_marks_prep[32];
+__device__ __forceinline__ void pmark(int i) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_marks_prep[i] = t;
+    }
+}
+#else
+__device__ __forceinline__ void pmark(int) {}
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // grid (B, 2 + line blocks).  blockIdx.y < 2: one CTA per (pair, cloud) runs the whole chain -- thresholds and the
 // cloud's extent, the pair's line extent (each cloud CTA scans the pair's lines itself rather than wait for another
@@ -657,10 +738,11 @@ __device__ __forceinline__ void line_constants(const float *__restrict__ ln, flo
 template <int kNode>
 __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
                                                           const float *__restrict__ lines, Workspace ws, Geometry g, int window,
-                                                          int sorted, int line_blocks, int ball_iters, int refine, int reuse) {
+                                                          int sorted, int line_blocks, int ball_iters, int refine, int reuse, int compressed) {
     extern __shared__ unsigned long long skeys[];
     __shared__ unsigned s_red[4];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius, max threshold
     const int b = blockIdx.x, tid = threadIdx.x;
+    pmark(0);
     // RRL_REUSE_ORDER is honoured only when an earlier forward of this very geometry completed in this workspace (hdr[7]
     // is written by that forward's LAST kernel and by nobody in this launch, so every CTA reads the same value); on a
     // fresh or differently shaped workspace the cloud is simply sorted
@@ -695,6 +777,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         if (tid == 0) { ws.nrec[b] = 0; ws.med[b] = 0.f; ws.xmax[b * 2 + 1] = 0u; }
     }
     __syncthreads();
+    pmark(1);
     // thresholds, extent of the cloud, extent of the pair's lines
     float pm = 0.f, xm = 0.f, tm = 0.f;
     int badv = 0;
@@ -707,6 +790,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         if (th < INFINITY) tm = fmaxf(tm, th);
         pm = fmaxf(pm, finite_extent(v, badv));
     }
+    pmark(2);
 #pragma unroll 4
     for (int l = tid; l < g.nl; l += 1024) {
         const float *ln = lb + (long long)l * 6;
@@ -723,6 +807,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         if ((tid & 31) == 0) { atomicMax(&s_red[0], a); atomicMax(&s_red[1], c); atomicMax(&s_red[3], t); }
     }
     const int bad_any = __syncthreads_or(badv);          // (also the barrier the reductions above need)
+    pmark(3);
     if (tid == 0) {
         ws.pmax[b * 2 + cloud] = s_red[0];
         ws.tmax[b * 2 + cloud] = s_red[3];
@@ -804,6 +889,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     }
     const int nnodes = nfp / kNode;
     const float Eslack = node_slack(s_red[0], s_red[1], s_red[3]);
+    pmark(4);
     __syncthreads();                                     // thr (global) is re-read below by other threads; sort buffers are dead
     // sorted indices -> shared memory, k-d refinement of every window of 64 (one warp each), then the records
     int *sidx = reinterpret_cast<int *>(skeys);
@@ -816,6 +902,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         }
     }
     __syncthreads();
+    pmark(5);
     if (sorted && refine && !reuse) {
         __shared__ float4 s_kd[32][64];
         const int lane = tid & 31, wid = tid >> 5;
@@ -827,7 +914,10 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         }
     }
     __syncthreads();
+    pmark(6);
     float rad = 0.f;
+    uint4 *pc = compressed ? reinterpret_cast<uint4 *>(ws.pt4[cloud]) + (long long)b * nnodes * (1 + kNode / 2) : nullptr;
+    const float P_up = __fmul_ru(__fsqrt_ru(__uint_as_float(s_red[0])), 1.000001f);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int i = e * 1024 + tid;
@@ -836,7 +926,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
             perm[i] = f;
             rad = fmaxf(rad, make_node_coop<kNode>(tri, f >= 0 ? thr[f] : 0.f, f, i, Eslack, ws.pt4[cloud] + (long long)b * nnodes * (kNode + 1),
                                                    ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * 5, ball_iters,
-                                                   kNode + 1, 5));
+                                                   kNode + 1, 5, pc, P_up));
         }
     }
     {
@@ -845,6 +935,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     }
     __syncthreads();
     if (tid == 0) ws.rmax[b * 2 + cloud] = s_red[2];
+    pmark(7);
 }
 
 size_t sort_scratch_bytes(int nfp_max, int B) {
@@ -870,6 +961,12 @@ int use_supers(const Geometry &g) {
     return g_param[7] == 0 && node_size(g) == 16 && (g.nf1p > g.nf2p ? g.nf1p : g.nf2p) > kSortSmall;
 }
 
+// compressed triplet records (make_node_coop) wherever level 2 gathers them from L2 instead of a shared-memory copy
+#ifndef RRL_PC8
+#define RRL_PC8 1
+#endif
+int use_compressed(const Geometry &g) { return RRL_PC8 && (node_size(g) == 16 || g_param[4] != 0); }
+
 static int g_dense_variant = 1;        // 1 = Morton-sorted nodes (default), 0 = nodes in input order (A/B measurement)
 void set_dense_variant(int v) { g_dense_variant = v; }
 
@@ -887,8 +984,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
         static unsigned long long attr_mask8 = 0ull, attr_mask16 = 0ull;
         if (ensure_dyn_smem(small_prep_kernel<8>, 65536, attr_mask8) || ensure_dyn_smem(small_prep_kernel<16>, 65536, attr_mask16))
             return RRL_ERR_CUDA;
-        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order);
-        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order);
+        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order, use_compressed(g));
+        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order, use_compressed(g));
         count_launch();
         stage_mark(1, s);
         stage_mark(2, s);
@@ -964,8 +1061,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     stage_mark(2, s);
     int nbx = nfp_max / 256;
     if (nbx > 4096) nbx = 4096;
-    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g), reuse_target);
-    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g), reuse_target);
+    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g), reuse_target, use_compressed(g));
+    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g), reuse_target, use_compressed(g));
     count_launch();
     stage_mark(3, s);
     return check_launch();
@@ -1072,6 +1169,22 @@ struct DenseCfg {
 #define RRL_SCAN_SHFL 0
 #endif
 
+// q[0..] = key + (position of every set bit of `mask`, ascending).  The mask is bit-reversed once, so that an entry costs
+// one FLO (bfind: the highest set bit of the reversed mask = the lowest of the mask), the subtraction from key + 31, the
+// store, the pointer step and two instructions to clear the bit -- the __ffs / x & (x - 1) form spent a BREV and an address
+// computation more per entry, and these loops are 15 % of the instructions of the small-cloud kernel.
+__device__ __forceinline__ void push_bits(unsigned *q, unsigned mask, unsigned key) {
+    unsigned r = __brev(mask);
+    const unsigned key31 = key + 31u;
+    --q;
+    while (r) {
+        unsigned hb;
+        asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(r));
+        *++q = key31 - hb;
+        r &= ~(1u << hb);
+    }
+}
+
 template <int kBits>
 __device__ __forceinline__ int warp_excl_scan(int c, int lane, int &total) {
 #if RRL_SCAN_SHFL
@@ -1168,6 +1281,10 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     constexpr bool pts_in_smem = kPerNode, pts12_in_smem = kPerNode;
     const float4 *pts = spts;
     if constexpr (!kPerNode) pts = pt4_c;
+    // compressed records (make_node_coop) of the modes that gather them from L2
+    constexpr bool kCompressed = !kPerNode && RRL_PC8;
+    constexpr int kPcStride = 1 + kNode / 2;                      // uint4 per node
+    const uint4 *pcs = reinterpret_cast<const uint4 *>(ws.pt4[cloud]) + ((long long)b * nnodes + node_begin) * kPcStride;
     // point-1/2 records of the chunk (refine pass before the hand-off to the exact kernel)
     const float4 *pt12_c = ws.pt12[cloud] + ((long long)b * nfp + (long long)node_begin * kNode) * 2;
     const float4 *pts12 = spts12;
@@ -1189,21 +1306,41 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         }
     }
     // ---- per-thread lines -> filter thresholds ------------------------------------------------------------
-    const float P = sqrtf(__uint_as_float(ws.pmax[b * 2 + cloud])) * 1.000001f;
-    const float Rmax = __uint_as_float(ws.rmax[b * 2 + cloud]);
-    const float Tmax = __uint_as_float(ws.tmax[b * 2 + cloud]);
-    const float Smax = kSuper ? __uint_as_float(ws.smax[b * 2 + cloud]) : 0.f;
+    // every global load of the set-up is issued before the first use (the cloud's extents AND the thread's line records): a
+    // CTA lives for ~13 us on the DCP batch, and four dependent L2 round trips at its start were 6 % of the kernel's stall
+    // samples.  Padding lines read record 0 (always there) and are masked below.
     const float4 *lineC = ws.lineC + (long long)b * g.nl * 2;
+    float4 lc0[kLinesPerThread], lc1[kLinesPerThread];
+#pragma unroll
+    for (int i = 0; i < kLinesPerThread; ++i) {
+        const int l = line_base + tid + i * kDenseThreads;
+        const long long lr = l < g.nl ? l : 0;
+        lc0[i] = __ldg(lineC + lr * 2);
+        lc1[i] = __ldg(lineC + lr * 2 + 1);
+    }
+    const unsigned pmax_bits = ws.pmax[b * 2 + cloud], rmax_bits = ws.rmax[b * 2 + cloud], tmax_bits = ws.tmax[b * 2 + cloud];
+    const unsigned smax_bits = kSuper ? ws.smax[b * 2 + cloud] : 0u;
+    const float P = sqrtf(__uint_as_float(pmax_bits)) * 1.000001f;
+    const float Rmax = __uint_as_float(rmax_bits);
+    const float Tmax = __uint_as_float(tmax_bits);
+    const float Smax = __uint_as_float(smax_bits);
     float ux[kLinesPerThread], uy[kLinesPerThread], uz[kLinesPerThread];
     float mx[kLinesPerThread], my[kLinesPerThread], mz[kLinesPerThread], tl[kLinesPerThread];
     // threshold of the triplet-level predicate and of the node-level predicate for a line
     auto thresholds = [&](const float4 &c0, const float4 &c1, float &tl_point, float &tl_node, float &tl_super) {
         const float PX = P + c0.w;
-        const float guard = kMargin * kEps24 * (kFastPX * PX * PX + kFastT * Tmax * Tmax) * 1.000001f + 1e-12f;
+        // compressed records: w~ is formed in the kernel with three roundings of magnitude <= P^2 + T instead of one
+        constexpr float kPXc = kCompressed ? kFastPX + 2.0f : kFastPX, kTc = kCompressed ? kFastT + 2.0f : kFastT;
+        const float guard = kMargin * kEps24 * (kPXc * PX * PX + kTc * Tmax * Tmax) * 1.000001f + 1e-12f;
         tl_point = c1.w - guard - fabsf(c1.w) * 1.2e-7f;                    // rounded down: admits more
         // |u| > 1 makes F slightly indefinite; e bounds the deficit, 0 for |u| <= 1 (incl. all-zero lines)
         const float s2 = (c0.x * c0.x + c0.y * c0.y + c0.z * c0.z) * 1.0000004f;
         const float e = s2 > 1.0f ? (s2 - 1.0f) * PX * PX : 0.f;
+        if (kCompressed && e > 0.f) {
+            // F(p~) - F(p) for |p~ - p| <= eb: 2 eb sqrt(F + e) + (1 + eta) eb^2; cut~ covers 2 eb sqrt(cut + E) + eb^2
+            const float eb = pc_err_bound(Rmax, P);
+            tl_point -= (2.0f * eb * sqrtf(e) + (s2 - 1.0f) * eb * eb) * 1.00001f;
+        }
         const float slack = (2.0f * Rmax * sqrtf(e) + 2.0f * e) * 1.00001f;
         tl_node = tl_point - slack - fabsf(tl_point) * 1.2e-7f;
         const float sslack = (2.0f * Smax * sqrtf(e) + 2.0f * e) * 1.00001f;
@@ -1215,7 +1352,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         ux[i] = uy[i] = uz[i] = mx[i] = my[i] = mz[i] = 0.f;
         tl[i] = INFINITY;                                         // Q > +inf never holds: padding lines are inert
         if (l < g.nl) {
-            const float4 c0 = __ldg(lineC + (long long)l * 2), c1 = __ldg(lineC + (long long)l * 2 + 1);
+            const float4 c0 = lc0[i], c1 = lc1[i];
             ux[i] = c0.x; uy[i] = c0.y; uz[i] = c0.z;
             mx[i] = c1.x; my[i] = c1.y; mz[i] = c1.z;
             float tp, tn, ts;
@@ -1228,8 +1365,9 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     }
     __syncthreads();
 
-    if (pts_in_smem) mbar_wait(&mbar[2], 0);
-    if (pts12_in_smem) mbar_wait(&mbar[3], 0);
+    // the bulk copies of the chunk's point records are awaited where a warp first needs them (level 2 / the refine pass),
+    // not here: the main loop only reads the node records of the stage buffers
+    bool pts_ready = !pts_in_smem, pts12_ready = !pts12_in_smem;         // warp-uniform
 
     int ncand = 0;
     const int *perm_c = ws.perm[cloud] + (long long)b * nfp + (long long)node_begin * kNode;   // from the chunk start
@@ -1242,6 +1380,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     // kernel (one reservation per flush).  When the queue is full the warp runs the exact test itself.
     auto run_exact = [&]() {
         __syncwarp();
+        if (!pts12_ready) { mbar_wait(&mbar[3], 0); pts12_ready = true; }
         RRL_COUNT(2, xq_cnt);                                  // (line, triplet) entries that passed the point-0 predicate
         // refine: the same conservative FMA predicate on points 1 and 2 (one entry per lane, compacted in place):
         // about one in eight entries that passed on point 0 survives
@@ -1271,14 +1410,18 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         }
         RRL_COUNT(3, xq_cnt);                                  // ... and the refine on points 1 and 2: handed to the exact kernel
         if (xq_cnt > 0) {
+            // the first 32 entries' triplet indices are fetched BEFORE the reservation: two round trips to L2 in flight
+            // together instead of one after the other (most flushes hold fewer than 32 entries)
+            const unsigned xent0 = lane < xq_cnt ? xq[lane] : 0u;
+            const int f0 = lane < xq_cnt ? __ldg(perm_c + (int)(xent0 & 0x3FFFFFu)) : 0;
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(ws.xcursor, (unsigned long long)xq_cnt);
             base = __shfl_sync(0xffffffffu, base, 0);
             const bool fits = (long long)(base + (unsigned long long)xq_cnt) <= ws.xcap;
             for (int i = lane; i < xq_cnt; i += 32) {
-                const unsigned xent = xq[i];
+                const unsigned xent = i == lane ? xent0 : xq[i];
                 const int l = line_base + (int)(xent >> 22);
-                const int f = __ldg(perm_c + (int)(xent & 0x3FFFFFu));
+                const int f = i == lane ? f0 : __ldg(perm_c + (int)(xent & 0x3FFFFFu));
                 const long long gl = (long long)b * g.nl + l;
                 if (fits) {
                     ws.xcand[base + i] = make_uint2((unsigned)gl, (unsigned)f | ((unsigned)cloud << 31));
@@ -1301,23 +1444,19 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
         xq_cnt = 0;
     };
     // level 2: triplet predicate on the triplets of (line, node) entries, packed two triplets per FFMA2
-    auto run_nodes = [&]() {
+    // Code size matters here: the levels are lambdas inlined at every call site, and with one site per overflow check the
+    // kernel held six copies of level 2 and seven of level 3 (140 KB of SASS; "no instruction" was the top stall reason of the
+    // large-cloud kernel).  Every level therefore calls the next one from ONE site -- the overflow check and the final flush
+    // (flush = true: drain the levels below as well) share it -- and the main loop pushes from one site per mode.
+    auto run_nodes = [&](bool flush) {
         __syncwarp();
+        if (!pts_ready) { mbar_wait(&mbar[2], 0); pts_ready = true; }
         RRL_COUNT(1, nq_cnt);                                  // (line, node) entries = triplet-record fetches of (kNode + 1) float4
-        for (int base = 0; base < nq_cnt; base += 32) {
-            if (xq_cnt + 32 * kNode > kExactQueue) run_exact();
+        for (int base = 0;; base += 32) {
+            const bool more = base < nq_cnt;
+            if (more ? (xq_cnt + 32 * kNode > kExactQueue) : flush) run_exact();
+            if (!more) break;
             unsigned pm = 0, key = 0;
-#if RRL_PF_LEVEL2
-            if constexpr (!kPerNode) {
-                // the NEXT pass's triplet records (one node = (kNode + 1) float4, scattered over the cloud) towards L1 while
-                // this pass computes: a pass otherwise starts with a full L2 round trip per group of loads
-                if (base + 32 + lane < nq_cnt) {
-                    const char *nx = reinterpret_cast<const char *>(pts + (int)(nq[base + 32 + lane] & 0x3FFFFFu) * kPtStride);
-#pragma unroll
-                    for (int o = 0; o < kPtStride * 16; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + o));
-                }
-            }
-#endif
             if (base + lane < nq_cnt) {
                 const unsigned ent = nq[base + lane];
                 const int lrel = (int)(ent >> 22), nrel = (int)(ent & 0x3FFFFFu);
@@ -1325,50 +1464,66 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 const float tl_point = c1.w;
                 const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
                 const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
-                const float4 *pp = pts + nrel * kPtStride;
-#if RRL_L2_PRELOAD
-                // large clouds read the records through L2 (every lane another node): all kNode loads are issued before the
-                // first use, so a pass waits for ONE L2 round trip instead of one per group the register budget allowed
-                float4 rec[kPerNode ? 1 : kNode];
-                if constexpr (!kPerNode) {
+                if constexpr (kCompressed) {
+                    // every lane another node, straight from L2: 16 + 8 kNode bytes per node.  All loads are issued before the
+                    // first use (one round trip per pass); the offsets become floats with one PRMT each (0x4B000000 | u)
+                    const uint4 *pp = pcs + nrel * kPcStride;
+                    const uint4 hd = __ldg(pp);
+                    uint4 rec[kNode / 2];
 #pragma unroll
-                    for (int j = 0; j < kNode; ++j) rec[j] = __ldg(pp + j);
-                }
-#endif
+                    for (int j = 0; j < kNode / 2; ++j) rec[j] = __ldg(pp + 1 + j);
+                    const float sc = __uint_as_float(hd.w);
+                    const float2 sc2 = make_float2(sc, sc);
+                    const float2 bx = make_float2(__uint_as_float(hd.x), __uint_as_float(hd.x)), by = make_float2(__uint_as_float(hd.y), __uint_as_float(hd.y));
+                    const float2 bz = make_float2(__uint_as_float(hd.z), __uint_as_float(hd.z));
 #pragma unroll
-                for (int j = 0; j < kNode / 2; ++j) {
-#if RRL_L2_PRELOAD
-                    const float4 A = kPerNode ? pp[2 * j] : rec[kPerNode ? 0 : 2 * j], Bq = kPerNode ? pp[2 * j + 1] : rec[kPerNode ? 0 : 2 * j + 1];
-#else
-                    const float4 A = pp[2 * j], Bq = pp[2 * j + 1];
-#endif
-                    const float2 x2 = make_float2(A.x, A.y), y2 = make_float2(A.z, A.w), z2 = make_float2(Bq.x, Bq.y), w2 = make_float2(Bq.z, Bq.w);
-                    const float2 t2 = __ffma2_rn(z2, u2, __ffma2_rn(y2, u1, __fmul2_rn(x2, u0)));
-                    const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
-                    const float2 q2 = __ffma2_rn(t2, t2, s2);
-                    pm |= (q2.x > tl_point) ? (1u << (2 * j)) : 0u;
-                    pm |= (q2.y > tl_point) ? (2u << (2 * j)) : 0u;
+                    for (int j = 0; j < kNode / 2; ++j) {
+                        const uint4 r = rec[j];
+                        const float2 xu = make_float2(__uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7432)));
+                        const float2 yu = make_float2(__uint_as_float(__byte_perm(r.y, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(r.y, 0x4B000000u, 0x7432)));
+                        const float2 zu = make_float2(__uint_as_float(__byte_perm(r.z, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(r.z, 0x4B000000u, 0x7432)));
+                        const float2 x2 = __ffma2_rn(xu, sc2, bx), y2 = __ffma2_rn(yu, sc2, by), z2 = __ffma2_rn(zu, sc2, bz);
+                        const float2 cut2 = __half22float2(*reinterpret_cast<const __half2 *>(&r.w));
+                        // w~ = cut~ - |p~|^2 (three more roundings than the stored w of the uncompressed record: kFastPXc / kFastTc)
+                        const float2 nx2 = make_float2(-x2.x, -x2.y), ny2 = make_float2(-y2.x, -y2.y), nz2 = make_float2(-z2.x, -z2.y);
+                        const float2 w2 = __ffma2_rn(nz2, z2, __ffma2_rn(ny2, y2, __ffma2_rn(nx2, x2, cut2)));
+                        const float2 t2 = __ffma2_rn(z2, u2, __ffma2_rn(y2, u1, __fmul2_rn(x2, u0)));
+                        const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
+                        const float2 q2 = __ffma2_rn(t2, t2, s2);
+                        pm |= (q2.x > tl_point) ? (1u << (2 * j)) : 0u;
+                        pm |= (q2.y > tl_point) ? (2u << (2 * j)) : 0u;
+                    }
+                } else {
+                    const float4 *pp = pts + nrel * kPtStride;
+#pragma unroll
+                    for (int j = 0; j < kNode / 2; ++j) {
+                        const float4 A = pp[2 * j], Bq = pp[2 * j + 1];
+                        const float2 x2 = make_float2(A.x, A.y), y2 = make_float2(A.z, A.w), z2 = make_float2(Bq.x, Bq.y), w2 = make_float2(Bq.z, Bq.w);
+                        const float2 t2 = __ffma2_rn(z2, u2, __ffma2_rn(y2, u1, __fmul2_rn(x2, u0)));
+                        const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
+                        const float2 q2 = __ffma2_rn(t2, t2, s2);
+                        pm |= (q2.x > tl_point) ? (1u << (2 * j)) : 0u;
+                        pm |= (q2.y > tl_point) ? (2u << (2 * j)) : 0u;
+                    }
                 }
                 key = ((unsigned)lrel << 22) | (unsigned)(nrel * kNode);
             }
             int total;
-            int pos = xq_cnt + warp_excl_scan<(kNode == 8 ? 4 : 5)>(__popc(pm), lane, total);
-            while (pm) {
-                const int s = __ffs(pm) - 1;
-                pm &= pm - 1;
-                xq[pos++] = key + (unsigned)s;
-            }
+            const int pos = xq_cnt + warp_excl_scan<(kNode == 8 ? 4 : 5)>(__popc(pm), lane, total);
+            push_bits(xq + pos, pm, key);
             xq_cnt += total;
             __syncwarp();
         }
         nq_cnt = 0;
     };
     // level 1: node predicate on the 4 nodes of (line, group) entries
-    auto run_groups = [&]() {
+    auto run_groups = [&](bool flush) {
         __syncwarp();
         RRL_COUNT(0, wq_cnt);                                  // (line, group of 4 nodes) entries = node-record fetches of 4 float4
-        for (int base = 0; base < wq_cnt; base += 32) {
-            if (nq_cnt + 128 > kNodeCap) run_nodes();
+        for (int base = 0;; base += 32) {
+            const bool more = base < wq_cnt;
+            if (more ? (nq_cnt + 128 > kNodeCap) : flush) run_nodes(flush && !more);
+            if (!more) break;
             unsigned nm = 0, key = 0;
 #if RRL_PF_LEVEL1
             if (base + 32 + lane < wq_cnt)
@@ -1394,12 +1549,8 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 key = ((unsigned)lrel << 22) | (unsigned)q0;
             }
             int total;
-            int pos = nq_cnt + warp_excl_scan<3>(__popc(nm), lane, total);
-            while (nm) {
-                const int q = __ffs(nm) - 1;
-                nm &= nm - 1;
-                nq[pos++] = key + (unsigned)q;
-            }
+            const int pos = nq_cnt + warp_excl_scan<3>(__popc(nm), lane, total);
+            push_bits(nq + pos, nm, key);
             nq_cnt += total;
             __syncwarp();
         }
@@ -1458,39 +1609,34 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                     constexpr int kGroupsPer = kSuperNodes / 4;
                     constexpr int kPart = kWarpQueue / (32 * kGroupsPer);      // bits per part: 32 lanes x kPart x kGroupsPer entries fit
                     static_assert(kPart >= 1 && (kPart & (kPart - 1)) == 0, "part size");
-#pragma unroll
-                    for (int i = 0; i < kLinesPerThread; ++i) {
+#pragma unroll 1
+                    for (int i = 0; i < kLinesPerThread; ++i) {                       // rolled: ONE push site (see run_nodes)
                         const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
-                        const unsigned mi = m[i];
+                        unsigned mi = m[0];
+#pragma unroll
+                        for (int k = 1; k < kLinesPerThread; ++k) mi = i == k ? m[k] : mi;
                         if (!__any_sync(0xffffffffu, mi != 0u)) continue;
                         ncand += __popc(mi);
                         // fired bits are sparse (a line comes near a handful of super nodes): one scan over the whole
-                        // word; the part loop only when a window fills more than a queue
+                        // word; parts of kPart bits only when a window fills more than a queue
                         int total;
                         const int off = warp_excl_scan<6>(__popc(mi), lane, total);
-                        if (total * kGroupsPer <= kWarpQueue) {
-                            if (wq_cnt + total * kGroupsPer > kWarpQueue) run_groups();
-                            int pos = wq_cnt + off * kGroupsPer;
-                            unsigned mh = mi;
-                            while (mh) {
-                                const unsigned rec = node0 + (unsigned)(__ffs(mh) - 1);              // super node, chunk relative
-                                mh &= mh - 1;
-#pragma unroll
-                                for (int q = 0; q < kGroupsPer; ++q) wq[pos++] = (lrel << 20) | (rec * kGroupsPer + (unsigned)q);
-                            }
-                            wq_cnt += total * kGroupsPer;
-                            continue;
-                        }
+                        const bool whole = total * kGroupsPer <= kWarpQueue;
+                        const int step = whole ? 32 : kPart;
 #pragma unroll 1
-                        for (int part = 0; part < 32; part += kPart) {
-                            unsigned mh = (mi >> part) & ((1u << kPart) - 1u);
-                            if (!__any_sync(0xffffffffu, mh != 0u)) continue;
-                            int tot2;
-                            const int off2 = warp_excl_scan<3>(__popc(mh), lane, tot2);
-                            if (wq_cnt + tot2 * kGroupsPer > kWarpQueue) run_groups();
+                        for (int part = 0; part < 32; part += step) {
+                            unsigned mh = mi;
+                            int tot2 = total, off2 = off;
+                            if (!whole) {
+                                mh = (mi >> part) & ((1u << kPart) - 1u);
+                                if (!__any_sync(0xffffffffu, mh != 0u)) continue;
+                                off2 = warp_excl_scan<3>(__popc(mh), lane, tot2);
+                            }
+                            if (wq_cnt + tot2 * kGroupsPer > kWarpQueue) run_groups(false);
                             int pos = wq_cnt + off2 * kGroupsPer;
+                            const unsigned rec0 = node0 + (unsigned)(whole ? 0 : part);
                             while (mh) {
-                                const unsigned rec = node0 + (unsigned)(__ffs(mh) - 1 + part);      // super node, chunk relative
+                                const unsigned rec = rec0 + (unsigned)(__ffs(mh) - 1);              // super node, chunk relative
                                 mh &= mh - 1;
 #pragma unroll
                                 for (int q = 0; q < kGroupsPer; ++q) wq[pos++] = (lrel << 20) | (rec * kGroupsPer + (unsigned)q);
@@ -1499,40 +1645,31 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                         }
                     }
                 } else {
-#pragma unroll
-                for (int i = 0; i < kLinesPerThread; ++i) {
+#pragma unroll 1
+                for (int i = 0; i < kLinesPerThread; ++i) {                           // rolled: ONE push site (see run_nodes)
                     const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
-                    const int c = __popc(m[i]);                                    // <= 32
+                    unsigned mi = m[0];
+#pragma unroll
+                    for (int k = 1; k < kLinesPerThread; ++k) mi = i == k ? m[k] : mi;
+                    const int c = __popc(mi);                                      // <= 32
                     if (!__any_sync(0xffffffffu, c != 0)) continue;
                     ncand += c;
                     int total;
                     const int off = warp_excl_scan<6>(c, lane, total);
-                    if (total <= kNodeCap) {
-                        if (nq_cnt + total > kNodeCap) run_nodes();
-                        int pos = nq_cnt + off;
-                        unsigned mm = m[i];
-                        while (mm) {
-                            const int bp = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            nq[pos++] = (lrel << 22) | (node0 + (unsigned)bp);
-                        }
-                        nq_cnt += total;
-                    } else {                                       // rare: more than a queue-full from one window
-                        constexpr int kPart = kNodeCap / 32;       // bits per part: 32 lanes x kPart entries always fit
+                    constexpr int kPart = kNodeCap / 32;           // bits per part: 32 lanes x kPart entries always fit
+                    const bool whole = total <= kNodeCap;          // (rarely not: more than a queue-full from one window)
+                    const int step = whole ? 32 : kPart;
 #pragma unroll 1
-                        for (int part = 0; part < 32; part += kPart) {
-                            unsigned mh = (m[i] >> part) & ((1u << kPart) - 1u);
-                            int tot2;
-                            const int off2 = warp_excl_scan<5>(__popc(mh), lane, tot2);
-                            if (nq_cnt + tot2 > kNodeCap) run_nodes();
-                            int pos = nq_cnt + off2;
-                            while (mh) {
-                                const int bp = __ffs(mh) - 1 + part;
-                                mh &= mh - 1;
-                                nq[pos++] = (lrel << 22) | (node0 + (unsigned)bp);
-                            }
-                            nq_cnt += tot2;
+                    for (int part = 0; part < 32; part += step) {
+                        unsigned mh = mi;
+                        int tot2 = total, off2 = off;
+                        if (!whole) {
+                            mh = (mi >> part) & ((1u << kPart) - 1u);
+                            off2 = warp_excl_scan<5>(__popc(mh), lane, tot2);
                         }
+                        if (nq_cnt + tot2 > kNodeCap) run_nodes(false);
+                        push_bits(nq + nq_cnt + off2, mh, ((lrel << 22) | node0) + (unsigned)(whole ? 0 : part));     // node0 is a multiple of 32
+                        nq_cnt += tot2;
                     }
                 }
                 }   // !kSuper
@@ -1565,26 +1702,23 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                     }
                 }
                 // ordered push of the fired (line, group) pairs, in parts that always fit the queue
-#pragma unroll
-                for (int i = 0; i < kLinesPerThread; ++i) {
+#pragma unroll 1
+                for (int i = 0; i < kLinesPerThread; ++i) {                           // rolled: ONE push site (see run_nodes)
                     const unsigned lrel = (unsigned)(tid + i * kDenseThreads);
-                    const unsigned mi = m[i];
+                    unsigned mi = m[0];
+#pragma unroll
+                    for (int k = 1; k < kLinesPerThread; ++k) mi = i == k ? m[k] : mi;
                     if (!__any_sync(0xffffffffu, mi != 0u)) continue;
                     ncand += __popc(mi);
                     constexpr int kPart = kWarpQueue / 32;         // 16 or 8 groups per part: 32 lanes x kPart entries <= kWarpQueue
-#pragma unroll
+#pragma unroll 1
                     for (int part = 0; part < 32; part += kPart) {
                         unsigned mh = (mi >> part) & ((1u << kPart) - 1u);
                         if (!__any_sync(0xffffffffu, mh != 0u)) continue;
                         int total;
                         const int off = warp_excl_scan<5>(__popc(mh), lane, total);
-                        if (wq_cnt + total > kWarpQueue) run_groups();
-                        int pos = wq_cnt + off;
-                        while (mh) {
-                            const int gi = __ffs(mh) - 1 + part;
-                            mh &= mh - 1;
-                            wq[pos++] = (lrel << 20) | (unsigned)(group0 + w0 + gi);
-                        }
+                        if (wq_cnt + total > kWarpQueue) run_groups(false);
+                        push_bits(wq + wq_cnt + off, mh, (lrel << 20) + (unsigned)(group0 + w0 + part));
                         wq_cnt += total;
                     }
                 }
@@ -1603,9 +1737,8 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
             }
         }
     }
-    if constexpr (!kPerNode) run_groups();
-    run_nodes();
-    run_exact();
+    if constexpr (!kPerNode) run_groups(true);
+    else run_nodes(true);
 
     // ---- diagnostics ---------------------------------------------------------------------------------
     ncand = __reduce_add_sync(0xffffffffu, ncand);
@@ -1776,6 +1909,11 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
 
 }  // namespace rrl
 
+#ifdef RRL_MARKS
+extern "C" int rrl_debug_read_marks_prep(unsigned long long *out32) {
+    return cudaMemcpyFromSymbol(out32, rrl::g_marks_prep, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -3;
+}
+#endif
 #ifdef RRL_COUNTERS
 extern "C" int rrl_debug_read_counters(unsigned long long *out8, int reset) {
     if (cudaMemcpyFromSymbol(out8, rrl::g_counters, sizeof(unsigned long long) * 8) != cudaSuccess) return -3;

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
     __shared__ float s_q[256 * 24];            // intersection points of the block's records: q1[4][3], q2[4][3]
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int l = blockIdx.x * blockDim.x + tid;
+    mark(8);
     if (tid < 16) s_hist[tid] = 0;
     int k = 0, j = 0;
     bool sel = false;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
         before += w < wid ? s_warp[w] : 0;
         total += s_warp[w];
     }
+    mark(9);
     if (total == 0) return;
     if (sel) {
         const int pos = before + __popc(bal & ((1u << lane) - 1u));
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
     }
     if (tid == 0) s_base = atomicAdd(ws.nrec + b, total);
     __syncthreads();
+    mark(10);
     if (tid < 16 && s_hist[tid]) atomicAdd(ws.n_kj + b * 16 + tid, s_hist[tid]);
     const long long r0 = (long long)b * g.nl + s_base;
     for (int t = tid; t < total * 8; t += 256) {
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
         }
     }
     __syncthreads();
+    mark(11);
     for (int t = tid; t < total * 16; t += 256) {
         const int rec = t >> 4, a = (t >> 2) & 3, c = t & 3;
         const int kj = s_kj[rec];
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
         ws.recD[r0 * 16 + t] = d;
     }
     if (tid < total) reinterpret_cast<int2 *>(ws.recMeta)[r0 + tid] = make_int2(s_line[tid], s_kj[tid]);
+    mark(12);
 }
 
 int launch_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
@@ -1075,18 +1080,62 @@ int launch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int
 // ------------------------------------------------------------------------------------------------------
 // backward: scatter (w/3) G grad_out
 // ------------------------------------------------------------------------------------------------------
+#ifndef RRL_BWD_HOIST
+#define RRL_BWD_HOIST 1
+#endif
 __global__ void __launch_bounds__(128) backward_kernel(Workspace ws, Geometry g, const float *__restrict__ grad_out,
                                                        float *__restrict__ g1, float *__restrict__ g2) {
     const int b = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    mark(16);
     if (!hdr_ok(ws, g) || ws.hdr[6] != 1) return;           // no completed forward of this geometry here: gradients stay zero
     if (i >= ws.nrec[b]) return;
     const long long r = (long long)b * g.nl + i;
+#if RRL_BWD_HOIST
+    // every load of the record is issued before the first use (the record is whole whatever k and j are: unused slots hold
+    // index -1 and zero weights), so the thread waits for ONE round trip to L2 instead of one per hit
+    const int4 *I4 = reinterpret_cast<const int4 *>(ws.recIdx + r * 8);
+    const float4 *G4 = reinterpret_cast<const float4 *>(ws.recG + r * 24), *W4 = reinterpret_cast<const float4 *>(ws.recW + r * 24);
+    const int meta = ws.recMeta[r * 2 + 1];
+    const float go = grad_out[b] * (1.0f / 3.0f);
+    const int4 ia = I4[0], ib = I4[1];
+    float G[24], Wt[24];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const float4 v = G4[q], w = W4[q];
+        G[4 * q] = v.x; G[4 * q + 1] = v.y; G[4 * q + 2] = v.z; G[4 * q + 3] = v.w;
+        Wt[4 * q] = w.x; Wt[4 * q + 1] = w.y; Wt[4 * q + 2] = w.z; Wt[4 * q + 3] = w.w;
+    }
+    const int idx[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+    const int k = meta & 255, j = (meta >> 8) & 255;
+    mark(17);
+#pragma unroll
+    for (int cloud = 0; cloud < 2; ++cloud) {
+        float *O0 = cloud ? g2 : g1;
+        if (!O0) continue;
+        float *O = O0 + (long long)b * (cloud ? g.nf2 : g.nf1) * 9;
+        const int n = cloud ? j : k;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            if (a >= n) break;
+            const long long f = idx[cloud * 4 + a];
+            const float gx = G[cloud * 12 + a * 3] * go, gy = G[cloud * 12 + a * 3 + 1] * go, gz = G[cloud * 12 + a * 3 + 2] * go;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const float w = Wt[cloud * 12 + a * 3 + p];
+                atomicAdd(O + f * 9 + p * 3, w * gx);
+                atomicAdd(O + f * 9 + p * 3 + 1, w * gy);
+                atomicAdd(O + f * 9 + p * 3 + 2, w * gz);
+            }
+        }
+    }
+#else
     const int meta = ws.recMeta[r * 2 + 1];
     const int k = meta & 255, j = (meta >> 8) & 255;
     const float go = grad_out[b] * (1.0f / 3.0f);
     const float *G = ws.recG + r * 24, *Wt = ws.recW + r * 24;
     const int *idx = ws.recIdx + r * 8;
+    mark(17);
     if (g1) {
         float *O = g1 + (long long)b * g.nf1 * 9;
         for (int a = 0; a < k; ++a) {
@@ -1115,6 +1164,8 @@ __global__ void __launch_bounds__(128) backward_kernel(Workspace ws, Geometry g,
             }
         }
     }
+#endif
+    mark(18);
 }
 
 // Backward straight to pose space (north star (4): "scatters dLoss/dpoint and reduces it to the 6-DoF twist gradient"): when

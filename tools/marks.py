@@ -15,11 +15,21 @@ for name in (sys.argv[1:] or ["dcp"]):
     pairs = [synth.make_pair(1000 + i, nf, nl) for i in range(min(B, 4))]
     idx = [i % len(pairs) for i in range(B)]
     t1, t2, ln = (torch.from_numpy(np.stack([pairs[i][k] for i in idx])).cuda() for k in ("tri1", "tri2", "lines"))
+    t1.requires_grad_(True)
     for _ in range(3):
         loss = rrl_b200.intersected_line_loss(t1, t2, ln)
+        loss.sum().backward()
     torch.cuda.synchronize()
     m = (C.c_ulonglong * 32)()
     L.rrl_debug_read_marks.argtypes = [C.POINTER(C.c_ulonglong)]
     assert L.rrl_debug_read_marks(m) == 0
     v = [int(x) for x in m]
-    print(name, "marks (us since mark 0):", [round((x - v[0]) / 1e3, 2) if x else None for x in v[:12]], flush=True)
+    print(name, "tail marks (us since mark 0):", [round((x - v[0]) / 1e3, 2) if x else None for x in v[:8]], flush=True)
+    print(name, "build marks (us since mark 8):", [round((x - v[8]) / 1e3, 2) if x else None for x in v[8:14]], flush=True)
+    print(name, "backward marks (us since mark 16):", [round((x - v[16]) / 1e3, 2) if x else None for x in v[16:20]], flush=True)
+    if hasattr(L, "rrl_debug_read_marks_prep"):
+        L.rrl_debug_read_marks_prep.argtypes = [C.POINTER(C.c_ulonglong)]
+        assert L.rrl_debug_read_marks_prep(m) == 0
+        v = [int(x) for x in m]
+        print(name, "prep marks (us since mark 0; 1 zeroing, 2 thresholds, 3 line extent, 4 sort, 5 indices, 6 k-d refine, 7 node records):",
+              [round((x - v[0]) / 1e3, 2) if x else None for x in v[:8]], flush=True)

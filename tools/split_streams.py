@@ -27,9 +27,14 @@ def work(parts, streams):
     return outs
 
 
-for S in (1, 2, 4):
+_pr = torch.cuda.Stream.priority_range()
+lo_pri, hi_pri = max(_pr), min(_pr)              # numerically lower = scheduled first
+print("stream priority range", lo_pri, hi_pri, flush=True)
+for S, prio in ((1, False), (2, False), (4, False), (2, True), (4, True), (6, True), (8, True)):
     parts = [(B * k // S, B * (k + 1) // S) for k in range(S)]
-    streams = [torch.cuda.Stream() for _ in range(S)]
+    # with priorities: sub-batch 0 highest, so that the small kernels of an earlier sub-batch are scheduled ahead of the dense
+    # CTAs of a later one whenever a slot frees
+    streams = [torch.cuda.Stream(priority=min(lo_pri, hi_pri + k) if prio else 0) for k in range(S)]
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -49,4 +54,4 @@ for S in (1, 2, 4):
         g.replay()
     e1.record()
     torch.cuda.synchronize()
-    print(name, "sub-batches", S, "ms/step %.4f" % (e0.elapsed_time(e1) / 100), "loss sum %.6f" % float(sum(o[0].sum() for o in outs)), flush=True)
+    print(name, "sub-batches", S, "priorities" if prio else "no priorities", "ms/step %.4f" % (e0.elapsed_time(e1) / 100), "loss sum %.6f" % float(sum(o[0].sum() for o in outs)), flush=True)
