@@ -522,7 +522,7 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
         float4 *grp = node4 + (n >> 2) * grp_stride;
         float *dst = reinterpret_cast<float *>(grp + ((n >> 1) & 1) * 2) + (n & 1);
         dst[0] = rec.x; dst[2] = rec.y; dst[4] = rec.z; dst[6] = rec.w;
-        if ((n & 3) == 0 && grp_stride > 4) grp[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grp_stride > 4) reinterpret_cast<float *>(grp + 4)[n & 3] = rad;      // the node's radius (level 1 forms its |u| > 1 slack from it)
     }
     return rad;
 }
@@ -1252,7 +1252,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     float4 *stage = reinterpret_cast<float4 *>(dsm);                                       // [2][kStageF4]
     float4 *spts = reinterpret_cast<float4 *>(dsm + Cfg::kOffPts);                         // [kSmemPtsF4]
     float4 *spts12 = reinterpret_cast<float4 *>(dsm + Cfg::kOffPts12);                     // [kSmemPts12F4]
-    float4 *slineU = reinterpret_cast<float4 *>(dsm + Cfg::kOffLine);                      // [kLinesPerCta] {u, tl_node}
+    float4 *slineU = reinterpret_cast<float4 *>(dsm + Cfg::kOffLine);                      // [kLinesPerCta] {u, k_line = 2 sqrt(e)}
     float4 *slineM = slineU + kLinesPerCta;                                                // [kLinesPerCta] {M, tl_point}
     __shared__ __align__(8) unsigned long long mbar[4];
     __shared__ int tile_done[2];
@@ -1344,20 +1344,26 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     float ux[kLinesPerThread], uy[kLinesPerThread], uz[kLinesPerThread];
     float mx[kLinesPerThread], my[kLinesPerThread], mz[kLinesPerThread], tl[kLinesPerThread];
     // threshold of the triplet-level predicate and of the node-level predicate for a line
-    auto thresholds = [&](const float4 &c0, const float4 &c1, float &tl_point, float &tl_node, float &tl_super) {
+    // k_line = 2 sqrt(e): the level-1 predicate forms a node's slack from the node's OWN radius, tl_point - (k R_n + k^2 / 2)
+    auto thresholds = [&](const float4 &c0, const float4 &c1, float &tl_point, float &tl_node, float &tl_super, float &k_line) {
         const float PX = P + c0.w;
         // compressed records: w~ is formed in the kernel with three roundings of magnitude <= P^2 + T instead of one
         constexpr float kPXc = kCompressed ? kFastPX + 2.0f : kFastPX, kTc = kCompressed ? kFastT + 2.0f : kFastT;
         const float guard = kMargin * kEps24 * (kPXc * PX * PX + kTc * Tmax * Tmax) * 1.000001f + 1e-12f;
         tl_point = c1.w - guard - fabsf(c1.w) * 1.2e-7f;                    // rounded down: admits more
-        // |u| > 1 makes F slightly indefinite; e bounds the deficit, 0 for |u| <= 1 (incl. all-zero lines)
-        const float s2 = (c0.x * c0.x + c0.y * c0.y + c0.z * c0.z) * 1.0000004f;
-        const float e = s2 > 1.0f ? (s2 - 1.0f) * PX * PX : 0.f;
+        // |u| > 1 makes F slightly indefinite; e = eta (P + |x0|)^2 bounds the deficit, 0 for |u| <= 1 (incl. all-zero
+        // lines).  eta = |u|^2 - 1 is formed in double from the float components the exact test uses: a float sum needs a safety
+        // factor that makes EVERY normalised line pay the slack (|u|^2 = 1 +- 1e-7), and on large clouds -- sqrt(e) ~ 5e-3 against
+        // hit cylinders of radius 4e-3 -- that slack, times the cloud's LARGEST node radius, tripled the (line, node) candidates.
+        const double s2d = (double)c0.x * (double)c0.x + (double)c0.y * (double)c0.y + (double)c0.z * (double)c0.z;
+        const float eta = s2d > 1.0 ? (float)(s2d - 1.0) * 1.000001f + 1e-30f : 0.f;
+        const float e = eta * PX * PX * 1.000001f;
         if (kCompressed && e > 0.f) {
             // F(p~) - F(p) for |p~ - p| <= eb: 2 eb sqrt(F + e) + (1 + eta) eb^2; cut~ covers 2 eb sqrt(cut + E) + eb^2
             const float eb = pc_err_bound(Rmax, P);
-            tl_point -= (2.0f * eb * sqrtf(e) + (s2 - 1.0f) * eb * eb) * 1.00001f;
+            tl_point -= (2.0f * eb * sqrtf(e) + eta * eb * eb) * 1.00001f;
         }
+        k_line = 2.0f * sqrtf(e) * 1.00001f;
         const float slack = (2.0f * Rmax * sqrtf(e) + 2.0f * e) * 1.00001f;
         tl_node = tl_point - slack - fabsf(tl_point) * 1.2e-7f;
         const float sslack = (2.0f * Smax * sqrtf(e) + 2.0f * e) * 1.00001f;
@@ -1372,11 +1378,11 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
             const float4 c0 = lc0[i], c1 = lc1[i];
             ux[i] = c0.x; uy[i] = c0.y; uz[i] = c0.z;
             mx[i] = c1.x; my[i] = c1.y; mz[i] = c1.z;
-            float tp, tn, ts;
-            thresholds(c0, c1, tp, tn, ts);
+            float tp, tn, ts, kl;
+            thresholds(c0, c1, tp, tn, ts, kl);
             tl[i] = kSuper ? ts : tn;                              // threshold of the records the main loop streams
             // only ever re-read by this warp's queue levels, which need the thresholds rather than |x0| and c
-            slineU[tid + i * kDenseThreads] = make_float4(c0.x, c0.y, c0.z, tn);
+            slineU[tid + i * kDenseThreads] = make_float4(c0.x, c0.y, c0.z, kl);
             slineM[tid + i * kDenseThreads] = make_float4(c1.x, c1.y, c1.z, tp);
         }
     }
@@ -1552,9 +1558,12 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 const int grp = (int)(ent & 0xFFFFFu);                 // group of 4 nodes, relative to the chunk
                 const int q0 = grp * 4;
                 const float4 c0 = slineU[lrel], c1 = slineM[lrel];
-                const float tl_node = c0.w;
-                const float4 *nr4 = node_src + grp * kGrpStride;       // 4 nodes = 2 interleaved pairs (+ 1 pad float4)
-                const float4 A0 = nr4[0], A1 = nr4[1], B0 = nr4[2], B1 = nr4[3];
+                const float4 *nr4 = node_src + grp * kGrpStride;       // 4 nodes = 2 interleaved pairs + their 4 radii
+                const float4 A0 = nr4[0], A1 = nr4[1], B0 = nr4[2], B1 = nr4[3], R4 = nr4[4];
+                // node threshold from the node's own radius: tl_point - (k R_n + k^2 / 2), k = 2 sqrt(e) (0 for |u| <= 1), rounded down
+                const float tl_base = fmaf(-0.5f * c0.w, c0.w * 1.00001f, c1.w) - fabsf(c1.w) * 2.4e-7f;
+                const float tn0 = fmaf(-c0.w, R4.x, tl_base), tn1 = fmaf(-c0.w, R4.y, tl_base);
+                const float tn2 = fmaf(-c0.w, R4.z, tl_base), tn3 = fmaf(-c0.w, R4.w, tl_base);
                 // the records are pair-interleaved ({xA,xB,yA,yB} {zA,zB,wA,wB}): two nodes per packed FMA, as in the main loop
                 const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
                 const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
@@ -1566,7 +1575,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
                 const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
                 const float2 qb = __ffma2_rn(tb, tb, sb);
-                nm = (qa.x > tl_node ? 1u : 0u) | (qa.y > tl_node ? 2u : 0u) | (qb.x > tl_node ? 4u : 0u) | (qb.y > tl_node ? 8u : 0u);
+                nm = (qa.x > tn0 ? 1u : 0u) | (qa.y > tn1 ? 2u : 0u) | (qb.x > tn2 ? 4u : 0u) | (qb.y > tn3 ? 8u : 0u);
                 key = ((unsigned)lrel << 22) | (unsigned)q0;
             }
             int total;
