@@ -827,7 +827,12 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     // barrier per stage), 1024 and 2048 pair registers of the same thread.
     const float P = sqrtf(__uint_as_float(s_red[0]));
     const int E = nfp <= 1024 ? 1 : (nfp <= 2048 ? 2 : 4);
-    unsigned long long v[4];
+    // 32-bit keys: (leading bits of the 30-bit curve key) << idx_bits | index -- 22 / 21 / 20 curve bits for up to 1024 / 2048 /
+    // 4096 triplets, far below a node's extent; half the shuffles, shared-memory traffic and compare instructions of 64-bit keys.
+    // 0xFFFFFFFF = padding: sorts last; its index field is >= nf unless the cloud fills the array, and then there is no padding.
+    unsigned v[4];
+    const int idx_bits = E == 1 ? 10 : (E == 2 ? 11 : 12);
+    unsigned *skeys32 = reinterpret_cast<unsigned *>(skeys);
     int *perm = ws.perm[cloud] + (long long)b * nfp;
     if (reuse) {
         // RRL_REUSE_ORDER: the workspace holds the order of a previous forward of this geometry.  ANY permutation is a
@@ -835,23 +840,23 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int i = e * 1024 + tid;
-            v[e] = (e < E && i < nfp) ? (unsigned long long)(unsigned)perm[i] : 0xFFFFFFFFull;      // -1 (padding) = 0xFFFFFFFF >= nf
+            v[e] = (e < E && i < nfp) ? (unsigned)perm[i] : 0xFFFFFFFFu;                            // -1 (padding) = 0xFFFFFFFF
         }
     } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int i = e * 1024 + tid;
-        v[e] = 0xFFFFFFFFFFFFFFFFull;
+        v[e] = 0xFFFFFFFFu;
         if (e < E && i < nf) {
             const float p[3] = {__ldg(tri + (long long)i * 9), __ldg(tri + (long long)i * 9 + 1), __ldg(tri + (long long)i * 9 + 2)};
             const unsigned key = sorted ? morton_key(p, P) : 0u;
-            v[e] = ((unsigned long long)key << 32) | (unsigned)i;
+            v[e] = ((key >> (idx_bits - 2)) << idx_bits) | (unsigned)i;
         }
     }
     }
     if (sorted && !reuse) {
-        auto cas = [](unsigned long long &lo_el, unsigned long long &hi_el, bool up) {      // lo_el has the lower index
-            const unsigned long long mn = lo_el < hi_el ? lo_el : hi_el, mx = lo_el < hi_el ? hi_el : lo_el;
+        auto cas = [](unsigned &lo_el, unsigned &hi_el, bool up) {      // lo_el has the lower index
+            const unsigned mn = lo_el < hi_el ? lo_el : hi_el, mx = lo_el < hi_el ? hi_el : lo_el;
             lo_el = up ? mn : mx;
             hi_el = up ? mx : mn;
         };
@@ -869,7 +874,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
                         cas(v[1], v[3], (1024 & k) == 0);
                     }
                 } else if (j >= 32) {
-                    unsigned long long *sb = skeys + buf * N;
+                    unsigned *sb = skeys32 + buf * N;
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         if (e < E) sb[e * 1024 + tid] = v[e];
@@ -878,7 +883,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
                     for (int e = 0; e < 4; ++e)
                         if (e < E) {
                             const int i = e * 1024 + tid;
-                            const unsigned long long o = sb[i ^ j];
+                            const unsigned o = sb[i ^ j];
                             const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
                             v[e] = (v[e] < o) == keep_min ? v[e] : o;
                         }
@@ -888,7 +893,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
                     for (int e = 0; e < 4; ++e)
                         if (e < E) {
                             const int i = e * 1024 + tid;
-                            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], j);
+                            const unsigned o = __shfl_xor_sync(0xffffffffu, v[e], j);
                             const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
                             v[e] = (v[e] < o) == keep_min ? v[e] : o;
                         }
@@ -905,7 +910,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     for (int e = 0; e < 4; ++e) {
         const int i = e * 1024 + tid;
         if (e < E && i < nfp) {
-            const unsigned idx = (unsigned)(v[e] & 0xFFFFFFFFull);
+            const unsigned idx = v[e] & ((1u << idx_bits) - 1u);
             sidx[i] = idx < (unsigned)nf ? (int)idx : -1;
         }
     }
@@ -1160,7 +1165,7 @@ struct DenseCfg {
     static constexpr int kTile = LPT >= 4 ? 256 : 128;                 // nodes per TMA stage
     static constexpr int kStage = (kTile / 4) * 5;                     // float4 per stage: 5 per group of 4 nodes
     static constexpr int kWq = LPT >= 4 || (kSuper && LPT > 1) ? 512 : 256;         // per warp: (line, group) entries, or (line, node) when kPerNode
-    static constexpr int kNq = 256;                                    // per warp: (line, node) entries of the 3-level pipeline
+    static constexpr int kNq = 512;                                    // per warp: (line, node) entries of the 3-level pipeline (a level-1 trip appends <= 256)
     static constexpr int kXq = 32 * kNode + 64;                        // per warp: (line, triplet); one level-2 pass appends <= 32 * kNode
     // kPerNode (small clouds): the chunk's point records are staged in shared memory -- the launch sizes the chunks to
     // fit -- and read with LDS; otherwise they are read through L1/L2 with LDG.  Compile-time either way: a pointer that
@@ -1542,45 +1547,46 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     // level 1: node predicate on the 4 nodes of (line, group) entries
     auto run_groups = [&](bool flush) {
         __syncwarp();
-        RRL_COUNT(0, wq_cnt);                                  // (line, group of 4 nodes) entries = node-record fetches of 4 float4
-        for (int base = 0;; base += 32) {
+        RRL_COUNT(0, wq_cnt);                                  // (line, group of 4 nodes) entries = node-record fetches of 5 float4
+        // node predicates of one entry: the records are pair-interleaved ({xA,xB,yA,yB} {zA,zB,wA,wB}, then the 4 radii): two
+        // nodes per packed FMA, as in the main loop; the threshold comes from the node's own radius, tl_point - (k R_n + k^2 / 2),
+        // k = 2 sqrt(e) (0 for |u| <= 1), rounded down
+        auto node_bits = [&](unsigned ent, const float4 &A0, const float4 &A1, const float4 &B0, const float4 &B1, const float4 &R4) -> unsigned {
+            const int lrel = (int)(ent >> 20);
+            const float4 c0 = slineU[lrel], c1 = slineM[lrel];
+            const float tl_base = fmaf(-0.5f * c0.w, c0.w * 1.00001f, c1.w) - fabsf(c1.w) * 2.4e-7f;
+            const float tn0 = fmaf(-c0.w, R4.x, tl_base), tn1 = fmaf(-c0.w, R4.y, tl_base);
+            const float tn2 = fmaf(-c0.w, R4.z, tl_base), tn3 = fmaf(-c0.w, R4.w, tl_base);
+            const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
+            const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
+            const float2 xa = make_float2(A0.x, A0.y), ya = make_float2(A0.z, A0.w), za = make_float2(A1.x, A1.y), wa = make_float2(A1.z, A1.w);
+            const float2 xb = make_float2(B0.x, B0.y), yb = make_float2(B0.z, B0.w), zb = make_float2(B1.x, B1.y), wb = make_float2(B1.z, B1.w);
+            const float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
+            const float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
+            const float2 qa = __ffma2_rn(ta, ta, sa);
+            const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
+            const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
+            const float2 qb = __ffma2_rn(tb, tb, sb);
+            return (qa.x > tn0 ? 1u : 0u) | (qa.y > tn1 ? 2u : 0u) | (qb.x > tn2 ? 4u : 0u) | (qb.y > tn3 ? 8u : 0u);
+        };
+        // TWO entries per lane and trip: a trip is one round trip to L2 for the (scattered) group records and little arithmetic, so
+        // both entries' loads are issued before either is used
+        for (int base = 0;; base += 64) {
             const bool more = base < wq_cnt;
-            if (more ? (nq_cnt + 128 > kNodeCap) : flush) run_nodes(flush && !more);
+            if (more ? (nq_cnt + 256 > kNodeCap) : flush) run_nodes(flush && !more);
             if (!more) break;
-            unsigned nm = 0, key = 0;
-#if RRL_PF_LEVEL1
-            if (base + 32 + lane < wq_cnt)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(node_src + (int)(wq[base + 32 + lane] & 0xFFFFFu) * kGrpStride));
-#endif
-            if (base + lane < wq_cnt) {
-                const unsigned ent = wq[base + lane];
-                const int lrel = (int)(ent >> 20);
-                const int grp = (int)(ent & 0xFFFFFu);                 // group of 4 nodes, relative to the chunk
-                const int q0 = grp * 4;
-                const float4 c0 = slineU[lrel], c1 = slineM[lrel];
-                const float4 *nr4 = node_src + grp * kGrpStride;       // 4 nodes = 2 interleaved pairs + their 4 radii
-                const float4 A0 = nr4[0], A1 = nr4[1], B0 = nr4[2], B1 = nr4[3], R4 = nr4[4];
-                // node threshold from the node's own radius: tl_point - (k R_n + k^2 / 2), k = 2 sqrt(e) (0 for |u| <= 1), rounded down
-                const float tl_base = fmaf(-0.5f * c0.w, c0.w * 1.00001f, c1.w) - fabsf(c1.w) * 2.4e-7f;
-                const float tn0 = fmaf(-c0.w, R4.x, tl_base), tn1 = fmaf(-c0.w, R4.y, tl_base);
-                const float tn2 = fmaf(-c0.w, R4.z, tl_base), tn3 = fmaf(-c0.w, R4.w, tl_base);
-                // the records are pair-interleaved ({xA,xB,yA,yB} {zA,zB,wA,wB}): two nodes per packed FMA, as in the main loop
-                const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
-                const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
-                const float2 xa = make_float2(A0.x, A0.y), ya = make_float2(A0.z, A0.w), za = make_float2(A1.x, A1.y), wa = make_float2(A1.z, A1.w);
-                const float2 xb = make_float2(B0.x, B0.y), yb = make_float2(B0.z, B0.w), zb = make_float2(B1.x, B1.y), wb = make_float2(B1.z, B1.w);
-                const float2 ta = __ffma2_rn(za, u2, __ffma2_rn(ya, u1, __fmul2_rn(xa, u0)));
-                const float2 sa = __ffma2_rn(za, m2, __ffma2_rn(ya, m1, __ffma2_rn(xa, m0, wa)));
-                const float2 qa = __ffma2_rn(ta, ta, sa);
-                const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
-                const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
-                const float2 qb = __ffma2_rn(tb, tb, sb);
-                nm = (qa.x > tn0 ? 1u : 0u) | (qa.y > tn1 ? 2u : 0u) | (qb.x > tn2 ? 4u : 0u) | (qb.y > tn3 ? 8u : 0u);
-                key = ((unsigned)lrel << 22) | (unsigned)q0;
-            }
+            const bool hasA = base + lane < wq_cnt, hasB = base + 32 + lane < wq_cnt;
+            const unsigned entA = hasA ? wq[base + lane] : 0u, entB = hasB ? wq[base + 32 + lane] : 0u;     // (entry 0 = group 0: a valid address)
+            const float4 *pa = node_src + (int)(entA & 0xFFFFFu) * kGrpStride, *pb = node_src + (int)(entB & 0xFFFFFu) * kGrpStride;
+            const float4 a0 = pa[0], a1 = pa[1], a2 = pa[2], a3 = pa[3], a4 = pa[4];
+            const float4 b0 = pb[0], b1 = pb[1], b2 = pb[2], b3 = pb[3], b4 = pb[4];
+            const unsigned nmA = hasA ? node_bits(entA, a0, a1, a2, a3, a4) : 0u;
+            const unsigned nmB = hasB ? node_bits(entB, b0, b1, b2, b3, b4) : 0u;
+            const int cA = __popc(nmA);
             int total;
-            const int pos = nq_cnt + warp_excl_scan<3>(__popc(nm), lane, total);
-            push_bits(nq + pos, nm, key);
+            const int pos = nq_cnt + warp_excl_scan<4>(cA + __popc(nmB), lane, total);
+            push_bits(nq + pos, nmA, ((entA >> 20) << 22) | ((entA & 0xFFFFFu) * 4u));
+            push_bits(nq + pos + cA, nmB, ((entB >> 20) << 22) | ((entB & 0xFFFFFu) * 4u));
             nq_cnt += total;
             __syncwarp();
         }

@@ -1083,6 +1083,35 @@ int launch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int
 #ifndef RRL_BWD_HOIST
 #define RRL_BWD_HOIST 1
 #endif
+// The 9 gradient floats of one hit triplet, added with vector reductions (red.global.add.v2/v4.f32, sm_90+): the scatter is
+// bound by the number of atomic operations L2 retires, and a triplet's 36 bytes take 3-4 of them (by the alignment of its
+// first float) instead of 9.
+__device__ __forceinline__ void add9(float *p, const float (&v)[9]) {
+    switch ((reinterpret_cast<uintptr_t>(p) >> 2) & 3u) {
+    case 0:
+        atomicAdd(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(reinterpret_cast<float4 *>(p + 4), make_float4(v[4], v[5], v[6], v[7]));
+        atomicAdd(p + 8, v[8]);
+        break;
+    case 1:
+        atomicAdd(p, v[0]);
+        atomicAdd(reinterpret_cast<float2 *>(p + 1), make_float2(v[1], v[2]));
+        atomicAdd(reinterpret_cast<float4 *>(p + 3), make_float4(v[3], v[4], v[5], v[6]));
+        atomicAdd(reinterpret_cast<float2 *>(p + 7), make_float2(v[7], v[8]));
+        break;
+    case 2:
+        atomicAdd(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
+        atomicAdd(reinterpret_cast<float4 *>(p + 2), make_float4(v[2], v[3], v[4], v[5]));
+        atomicAdd(reinterpret_cast<float2 *>(p + 6), make_float2(v[6], v[7]));
+        atomicAdd(p + 8, v[8]);
+        break;
+    default:
+        atomicAdd(p, v[0]);
+        atomicAdd(reinterpret_cast<float4 *>(p + 1), make_float4(v[1], v[2], v[3], v[4]));
+        atomicAdd(reinterpret_cast<float4 *>(p + 5), make_float4(v[5], v[6], v[7], v[8]));
+        break;
+    }
+}
 __global__ void __launch_bounds__(128) backward_kernel(Workspace ws, Geometry g, const float *__restrict__ grad_out,
                                                        float *__restrict__ g1, float *__restrict__ g2) {
     const int b = blockIdx.y;
@@ -1120,13 +1149,13 @@ __global__ void __launch_bounds__(128) backward_kernel(Workspace ws, Geometry g,
             if (a >= n) break;
             const long long f = idx[cloud * 4 + a];
             const float gx = G[cloud * 12 + a * 3] * go, gy = G[cloud * 12 + a * 3 + 1] * go, gz = G[cloud * 12 + a * 3 + 2] * go;
+            float v[9];
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 const float w = Wt[cloud * 12 + a * 3 + p];
-                atomicAdd(O + f * 9 + p * 3, w * gx);
-                atomicAdd(O + f * 9 + p * 3 + 1, w * gy);
-                atomicAdd(O + f * 9 + p * 3 + 2, w * gz);
+                v[p * 3] = w * gx; v[p * 3 + 1] = w * gy; v[p * 3 + 2] = w * gz;
             }
+            add9(O + f * 9, v);
         }
     }
 #else
