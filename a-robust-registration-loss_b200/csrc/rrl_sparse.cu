@@ -29,8 +29,19 @@ __device__ __forceinline__ void mark(int i) {
         g_marks[i] = t;
     }
 }
+// start / end of every CTA of one kernel (build_kernel): shows waves, stragglers and the launch's lead-in
+__device__ unsigned long long g_cta_t[2][8192];
+__device__ __forceinline__ void cta_mark(int which) {
+    if (threadIdx.x == 0) {
+        const unsigned id = blockIdx.y * gridDim.x + blockIdx.x;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (id < 8192) g_cta_t[which][id] = t;
+    }
+}
 #else
 __device__ __forceinline__ void mark(int) {}
+__device__ __forceinline__ void cta_mark(int) {}
 #endif
 
 // weights + intersection point of ONE hit triplet
@@ -53,52 +64,71 @@ __device__ __forceinline__ void make_point(const float *__restrict__ tri, int f,
 // range of record slots with ONE atomic.  The records are then built by one thread per (record, cloud, hit slot) --
 // each computes the weights and the intersection point of ONE hit triplet and drops them at the hit's rank among the
 // line's hits (ascending triplet index = nonzero() order) -- and one thread per D entry.
+constexpr int kBuildLines = 512;            // lines per CTA: two per thread (a 15000-line pair is then ONE wave of CTAs on 148 SMs)
+
 __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
                                                     const float *__restrict__ lines, Workspace ws, Geometry g,
                                                     int k_lo, int j_lo, int k_hi, int j_hi) {
-    __shared__ int s_line[256], s_kj[256], s_warp[8], s_hist[16], s_base;
-    __shared__ float s_q[256 * 24];            // intersection points of the block's records: q1[4][3], q2[4][3]
+    __shared__ int s_line[kBuildLines], s_kj[kBuildLines], s_warp[16], s_hist[16], s_base;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int l = blockIdx.x * blockDim.x + tid;
     mark(8);
+    cta_mark(0);
     if (tid < 16) s_hist[tid] = 0;
-    int k = 0, j = 0;
-    bool sel = false;
-    if (l < g.nl) {
-        const long long gl = (long long)b * g.nl + l;
-        k = ws.cnt[0][gl]; j = ws.cnt[1][gl];
-        sel = k >= k_lo && k < k_hi && j >= j_lo && j < j_hi;      // windows are validated to lie inside 1..4
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, sel);
-    if (lane == 0) s_warp[wid] = __popc(bal);
-    __syncthreads();
-    int before = 0, total = 0;
+    int k[2], j[2], l[2];
+    bool sel[2];
+    unsigned bal[2];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        before += w < wid ? s_warp[w] : 0;
-        total += s_warp[w];
+    for (int u = 0; u < 2; ++u) {                              // both halves' counters in flight together
+        l[u] = blockIdx.x * kBuildLines + u * 256 + tid;
+        k[u] = 0; j[u] = 0;
+        if (l[u] < g.nl) {
+            const long long gl = (long long)b * g.nl + l[u];
+            k[u] = ws.cnt[0][gl]; j[u] = ws.cnt[1][gl];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        sel[u] = l[u] < g.nl && k[u] >= k_lo && k[u] < k_hi && j[u] >= j_lo && j[u] < j_hi;      // windows are validated to lie inside 1..4
+        bal[u] = __ballot_sync(0xffffffffu, sel[u]);
+        if (lane == 0) s_warp[u * 8 + wid] = __popc(bal[u]);
+    }
+    __syncthreads();
+    int before[2] = {0, 0}, total = 0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        const int c = s_warp[w];
+        before[0] += w < wid ? c : 0;
+        before[1] += w < 8 + wid ? c : 0;
+        total += c;
     }
     mark(9);
-    if (total == 0) return;
-    if (sel) {
-        const int pos = before + __popc(bal & ((1u << lane) - 1u));
-        s_line[pos] = l;
-        s_kj[pos] = k | (j << 8);
-        atomicAdd(&s_hist[(k - 1) * 4 + (j - 1)], 1);
-    }
+    if (total == 0) { cta_mark(1); return; }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+        if (sel[u]) {                                          // ordered by line index: half 0, then half 1
+            const int pos = before[u] + __popc(bal[u] & ((1u << lane) - 1u));
+            s_line[pos] = l[u];
+            s_kj[pos] = k[u] | (j[u] << 8);
+            atomicAdd(&s_hist[(k[u] - 1) * 4 + (j[u] - 1)], 1);
+        }
     if (tid == 0) s_base = atomicAdd(ws.nrec + b, total);
     __syncthreads();
     mark(10);
     if (tid < 16 && s_hist[tid]) atomicAdd(ws.n_kj + b * 16 + tid, s_hist[tid]);
     const long long r0 = (long long)b * g.nl + s_base;
-    for (int t = tid; t < total * 8; t += 256) {
-        const int rec = t >> 3, cloud = (t >> 2) & 1, a = t & 3;
+    // one thread per (record, cloud, hit slot): the 8 threads of a record are consecutive lanes and exchange their
+    // intersection points with shuffles for the record's 16 D entries (two per lane) -- no shared-memory staging, no barrier
+    const int nt = (total * 8 + 31) & ~31;                     // whole warps (full-mask shuffles)
+    for (int t = tid; t < nt; t += 256) {
+        const bool live = t < total * 8;
+        const int rec = live ? t >> 3 : 0, cloud = (t >> 2) & 1, a = t & 3;
         const int kj = s_kj[rec];
-        const int cnt = cloud ? (kj >> 8) & 255 : kj & 255;
+        const int kk = kj & 255, jj = (kj >> 8) & 255;
+        const int cnt = cloud ? jj : kk;
         const long long gl = (long long)b * g.nl + s_line[rec];
         float w[3] = {0.f, 0.f, 0.f}, q[3] = {0.f, 0.f, 0.f};
         int idx = -1, pos = a;                       // unused slots a >= cnt keep their place behind the hits
-        if (a < cnt) {
+        if (live && a < cnt) {
             const int *h = ws.hits[cloud] + gl * kCap;
             idx = h[a];
             pos = 0;
@@ -111,34 +141,46 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
             make_point(cloud ? tri2 + (long long)b * g.nf2 * 9 : tri1 + (long long)b * g.nf1 * 9, idx, ln, w, q);
         }
         const long long r = r0 + rec;
-        const int o3 = cloud * 12 + pos * 3;
-        ws.recIdx[r * 8 + cloud * 4 + pos] = idx;
+        if (live) {
+            const int o3 = cloud * 12 + pos * 3;
+            ws.recIdx[r * 8 + cloud * 4 + pos] = idx;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            ws.recW[r * 24 + o3 + c] = w[c];
-            ws.recQ[r * 24 + o3 + c] = q[c];
-            s_q[rec * 24 + o3 + c] = q[c];
+            for (int c = 0; c < 3; ++c) {
+                ws.recW[r * 24 + o3 + c] = w[c];
+                ws.recQ[r * 24 + o3 + c] = q[c];
+            }
+        }
+        // points into rank order: lane (cloud, a) fetches the point whose rank is a (pos is a permutation of 0..3 per cloud)
+        const int gbase = lane & ~7, cbase = gbase + cloud * 4;
+        int src = cbase;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int po = __shfl_sync(0xffffffffu, pos, cbase + o);
+            if (po == a) src = cbase + o;
+        }
+        const float sx = __shfl_sync(0xffffffffu, q[0], src), sy = __shfl_sync(0xffffffffu, q[1], src), sz = __shfl_sync(0xffffffffu, q[2], src);
+        // D entries e = 2 jl, 2 jl + 1 of the record (jl = lane within the record): a' = e >> 2 from cloud 1, c' = e & 3 from cloud 2
+        const int jl = lane & 7, e0 = 2 * jl, ap = e0 >> 2, c0 = e0 & 3;
+        const float ax = __shfl_sync(0xffffffffu, sx, gbase + ap), ay = __shfl_sync(0xffffffffu, sy, gbase + ap), az = __shfl_sync(0xffffffffu, sz, gbase + ap);
+        const float bx0 = __shfl_sync(0xffffffffu, sx, gbase + 4 + c0), by0 = __shfl_sync(0xffffffffu, sy, gbase + 4 + c0), bz0 = __shfl_sync(0xffffffffu, sz, gbase + 4 + c0);
+        const float bx1 = __shfl_sync(0xffffffffu, sx, gbase + 5 + c0), by1 = __shfl_sync(0xffffffffu, sy, gbase + 5 + c0), bz1 = __shfl_sync(0xffffffffu, sz, gbase + 5 + c0);
+        if (live) {
+            float d0 = 0.f, d1 = 0.f;
+            if (ap < kk && c0 < jj) d0 = sq3_rn(__fsub_rn(ax, bx0), __fsub_rn(ay, by0), __fsub_rn(az, bz0));
+            if (ap < kk && c0 + 1 < jj) d1 = sq3_rn(__fsub_rn(ax, bx1), __fsub_rn(ay, by1), __fsub_rn(az, bz1));
+            *reinterpret_cast<float2 *>(ws.recD + r * 16 + e0) = make_float2(d0, d1);
         }
     }
-    __syncthreads();
     mark(11);
-    for (int t = tid; t < total * 16; t += 256) {
-        const int rec = t >> 4, a = (t >> 2) & 3, c = t & 3;
-        const int kj = s_kj[rec];
-        const float *q1 = s_q + rec * 24 + a * 3, *q2 = s_q + rec * 24 + 12 + c * 3;
-        float d = 0.f;
-        if (a < (kj & 255) && c < ((kj >> 8) & 255))
-            d = sq3_rn(__fsub_rn(q1[0], q2[0]), __fsub_rn(q1[1], q2[1]), __fsub_rn(q1[2], q2[2]));
-        ws.recD[r0 * 16 + t] = d;
-    }
-    if (tid < total) reinterpret_cast<int2 *>(ws.recMeta)[r0 + tid] = make_int2(s_line[tid], s_kj[tid]);
+    for (int t = tid; t < total; t += 256) reinterpret_cast<int2 *>(ws.recMeta)[r0 + t] = make_int2(s_line[t], s_kj[t]);
     mark(12);
+    cta_mark(1);
 }
 
 int launch_build(const float *tri1, const float *tri2, const float *lines, const Workspace &ws, const Geometry &g,
                  int k_lo, int j_lo, int k_hi, int j_hi, cudaStream_t s) {
     stage_mark(5, s);
-    build_kernel<<<dim3((g.nl + 255) / 256, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi);
+    build_kernel<<<dim3((g.nl + kBuildLines - 1) / kBuildLines, g.B), 256, 0, s>>>(tri1, tri2, lines, ws, g, k_lo, j_lo, k_hi, j_hi);
     count_launch();
     stage_mark(6, s);
     return check_launch();
@@ -1305,5 +1347,8 @@ int launch_export_hits(const Workspace &ws, const Geometry &g, int cloud, int *o
 #ifdef RRL_MARKS
 extern "C" int rrl_debug_read_marks(unsigned long long *out32) {
     return cudaMemcpyFromSymbol(out32, rrl::g_marks, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -3;
+}
+extern "C" int rrl_debug_read_cta_times(unsigned long long *out2x8192) {
+    return cudaMemcpyFromSymbol(out2x8192, rrl::g_cta_t, sizeof(unsigned long long) * 2 * 8192) == cudaSuccess ? 0 : -3;
 }
 #endif

@@ -27,6 +27,17 @@ for name in (sys.argv[1:] or ["dcp"]):
     print(name, "tail marks (us since mark 0):", [round((x - v[0]) / 1e3, 2) if x else None for x in v[:8]], flush=True)
     print(name, "build marks (us since mark 8):", [round((x - v[8]) / 1e3, 2) if x else None for x in v[8:14]], flush=True)
     print(name, "backward marks (us since mark 16):", [round((x - v[16]) / 1e3, 2) if x else None for x in v[16:20]], flush=True)
+    if hasattr(L, "rrl_debug_read_cta_times"):
+        ct = (C.c_ulonglong * (2 * 8192))()
+        L.rrl_debug_read_cta_times.argtypes = [C.POINTER(C.c_ulonglong)]
+        assert L.rrl_debug_read_cta_times(ct) == 0
+        a = np.array(list(ct), dtype=np.int64).reshape(2, 8192)
+        n = min(8192, B * ((nl + 511) // 512))
+        st, en = a[0, :n], a[1, :n]
+        t0 = st.min()
+        print(name, "build CTAs %d: start min/median/max %.2f/%.2f/%.2f us, end min/median/max %.2f/%.2f/%.2f us, life median/max %.2f/%.2f us" %
+              (n, 0.0, (np.median(st) - t0) / 1e3, (st.max() - t0) / 1e3, (en.min() - t0) / 1e3, (np.median(en) - t0) / 1e3, (en.max() - t0) / 1e3,
+               np.median(en - st) / 1e3, (en - st).max() / 1e3), flush=True)
     if hasattr(L, "rrl_debug_read_marks_prep"):
         L.rrl_debug_read_marks_prep.argtypes = [C.POINTER(C.c_ulonglong)]
         assert L.rrl_debug_read_marks_prep(m) == 0
