@@ -94,6 +94,7 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.xcand = reinterpret_cast<uint2 *>(take((size_t)w.xcap * sizeof(uint2)));
     // ---- per record ----
     w.recD = reinterpret_cast<float *>(take(lines * 16 * sizeof(float)));
+    w.dflat = reinterpret_cast<float *>(take(sB * kMedCache * sizeof(float)));
     w.recMeta = reinterpret_cast<int *>(take(lines * 2 * sizeof(int)));
     w.recIdx = reinterpret_cast<int *>(take(lines * 8 * sizeof(int)));
     w.recW = reinterpret_cast<float *>(take(lines * 24 * sizeof(float)));

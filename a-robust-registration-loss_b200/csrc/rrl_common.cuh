@@ -38,6 +38,7 @@ constexpr float kEps24 = 5.9604645e-8f;
 
 // ---- dense kernel geometry ---------------------------------------------------------------------------
 constexpr int kDenseThreads = 256;
+constexpr int kMedCache = 48 * 1024;                            // D entries of a pair the tail kernel selects the median of in shared memory (192 KB)
 constexpr int kNodePad = 16;                                    // node arrays are padded to this multiple (sentinels)
 constexpr int kPointPad = 256;                                  // triplet arrays padded to 16 nodes of 16 (= 32 nodes of 8)
 constexpr int kMinNode = 8;                                     // smallest node size (sizes the node arrays)
@@ -68,10 +69,11 @@ struct Workspace {
     unsigned int *tmax;      // (B,2): bits of the largest threshold thr_f of the cloud (the guards scale with its square)
     unsigned int *bad;       // (B,2): non-zero when the cloud (or, in either slot, a line of the pair) holds a NaN / infinite value
     int *nrec;               // (B)
+    float *dflat;            // (B, kMedCache): the pair's valid D entries, compact, in any order (the median's input); entries beyond the capacity are dropped
     int *n_kj;               // (B,16)
     float *med;              // (B)
     int *flags;              // (B,4): {NaN seen in the Welsch stage, block ticket of the Welsch stage,
-                             //         reserved, reserved}
+                             //         cursor of the pair's compact D list (dflat), reserved}
     unsigned long long *sums;// (B,32): S1[16], S2[16] fixed point
     long long *stats;        // (B, RRL_NSTAT)
     long long *gcounts;      // (B,18) global counts used by welsch/finalize/backward (== local unless line-sharded)

@@ -69,7 +69,7 @@ constexpr int kBuildLines = 512;            // lines per CTA: two per thread (a 
 __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
                                                     const float *__restrict__ lines, Workspace ws, Geometry g,
                                                     int k_lo, int j_lo, int k_hi, int j_hi) {
-    __shared__ int s_line[kBuildLines], s_kj[kBuildLines], s_warp[16], s_hist[16], s_base;
+    __shared__ int s_line[kBuildLines], s_kj[kBuildLines], s_eoff[kBuildLines], s_warp[16], s_ewarp[16], s_hist[16], s_base, s_ebase;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     mark(8);
     cta_mark(0);
@@ -86,20 +86,34 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
             k[u] = ws.cnt[0][gl]; j[u] = ws.cnt[1][gl];
         }
     }
+    // ordered compaction of the selected lines (ballots) and, in the same pass, the exclusive prefix of their k j: where a
+    // record's valid D entries go in the pair's compact D list (what the tail's median reads: n floats in a row instead of a
+    // masked gather over the padded records)
+    int ecnt[2], eincl[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         sel[u] = l[u] < g.nl && k[u] >= k_lo && k[u] < k_hi && j[u] >= j_lo && j[u] < j_hi;      // windows are validated to lie inside 1..4
         bal[u] = __ballot_sync(0xffffffffu, sel[u]);
-        if (lane == 0) s_warp[u * 8 + wid] = __popc(bal[u]);
+        ecnt[u] = sel[u] ? k[u] * j[u] : 0;
+        eincl[u] = ecnt[u];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, eincl[u], d);
+            if (lane >= d) eincl[u] += up;
+        }
+        if (lane == 31) { s_warp[u * 8 + wid] = __popc(bal[u]); s_ewarp[u * 8 + wid] = eincl[u]; }
     }
     __syncthreads();
-    int before[2] = {0, 0}, total = 0;
+    int before[2] = {0, 0}, total = 0, ebefore[2] = {0, 0}, etotal = 0;
 #pragma unroll
     for (int w = 0; w < 16; ++w) {
-        const int c = s_warp[w];
+        const int c = s_warp[w], e = s_ewarp[w];
         before[0] += w < wid ? c : 0;
         before[1] += w < 8 + wid ? c : 0;
         total += c;
+        ebefore[0] += w < wid ? e : 0;
+        ebefore[1] += w < 8 + wid ? e : 0;
+        etotal += e;
     }
     mark(9);
     if (total == 0) { cta_mark(1); return; }
@@ -109,13 +123,16 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
             const int pos = before[u] + __popc(bal[u] & ((1u << lane) - 1u));
             s_line[pos] = l[u];
             s_kj[pos] = k[u] | (j[u] << 8);
+            s_eoff[pos] = ebefore[u] + eincl[u] - ecnt[u];
             atomicAdd(&s_hist[(k[u] - 1) * 4 + (j[u] - 1)], 1);
         }
     if (tid == 0) s_base = atomicAdd(ws.nrec + b, total);
+    if (tid == 32) s_ebase = atomicAdd(ws.flags + b * 4 + 2, etotal);
     __syncthreads();
     mark(10);
     if (tid < 16 && s_hist[tid]) atomicAdd(ws.n_kj + b * 16 + tid, s_hist[tid]);
     const long long r0 = (long long)b * g.nl + s_base;
+    float *dflat = ws.dflat + (long long)b * kMedCache;
     // one thread per (record, cloud, hit slot): the 8 threads of a record are consecutive lanes and exchange their
     // intersection points with shuffles for the record's 16 D entries (two per lane) -- no shared-memory staging, no barrier
     const int nt = (total * 8 + 31) & ~31;                     // whole warps (full-mask shuffles)
@@ -169,6 +186,9 @@ __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tr
             if (ap < kk && c0 < jj) d0 = sq3_rn(__fsub_rn(ax, bx0), __fsub_rn(ay, by0), __fsub_rn(az, bz0));
             if (ap < kk && c0 + 1 < jj) d1 = sq3_rn(__fsub_rn(ax, bx1), __fsub_rn(ay, by1), __fsub_rn(az, bz1));
             *reinterpret_cast<float2 *>(ws.recD + r * 16 + e0) = make_float2(d0, d1);
+            const int ei = s_ebase + s_eoff[rec] + ap * jj + c0;            // valid entries of a record, row major
+            if (ap < kk && c0 < jj && ei < kMedCache) dflat[ei] = d0;
+            if (ap < kk && c0 + 1 < jj && ei + 1 < kMedCache) dflat[ei + 1] = d1;
         }
     }
     mark(11);
@@ -758,7 +778,6 @@ int launch_welsch(const Workspace &ws, const Geometry &g, cudaStream_t s) {
 // second launch and a grid-wide dependency), then takes every S-th slice of the records through the Welsch stage; the
 // last block to finish writes the loss (ticket in flags[b*4+1]).
 constexpr int kTailThreads = 512;
-constexpr int kMedCache = 48 * 1024;        // D slots cached in shared memory (192 KB); the rest is re-read through L2
 
 __global__ void __launch_bounds__(kTailThreads) tail_kernel(Workspace ws, Geometry g, float *out_loss, int *out_status,
                                                              float *out_median, long long *out_stats) {
@@ -766,14 +785,14 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(Workspace ws, Geomet
     __shared__ SelectScratch sc;
     __shared__ unsigned long long s_sum[32];
     __shared__ long long s_gc[16];
-    __shared__ int s_last, s_count;
+    __shared__ int s_last;
     const int b = blockIdx.y, tid = threadIdx.x;
     mark(0);
     if (blockIdx.x == 0 && b == 0 && tid == 0) { ws.hdr[6] = 1; ws.hdr[7] = order_token(g); }   // gradient vectors in place; order complete
     const int nrec = ws.nrec[b];
     if (tid < 16) s_gc[tid] = ws.n_kj[b * 16 + tid];
     if (tid < 32) s_sum[tid] = 0ull;
-    if (tid == 0) { sc.kmin = kNoKey; sc.kmax = 0u; s_count = 0; }
+    if (tid == 0) { sc.kmin = kNoKey; sc.kmax = 0u; }
     __syncthreads();
     long long n = 0;
     int C = 0;
@@ -800,49 +819,12 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(Workspace ws, Geomet
         };
         unsigned mn = kNoKey, mx = 0u;
         if (n <= kMedCache) {
-            // the valid D entries of the pair are compacted into shared memory (their order is irrelevant to a median):
-            // one thread per record, two records in flight, one shared atomic per warp and record batch
-            const float4 *D4 = reinterpret_cast<const float4 *>(D);
-            for (int i0 = 0; i0 < nrec; i0 += 2 * kTailThreads) {                  // block-uniform trip count
-                int kj[2];
-                float4 d[2][4];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int i = i0 + u * kTailThreads + tid;
-                    kj[u] = 0;
-                    if (i < nrec) {
-                        kj[u] = meta[i * 2 + 1];
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) d[u][a] = D4[(long long)i * 4 + a];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int k = kj[u] & 255, j = (kj[u] >> 8) & 255;
-                    const int cnt = k * j;
-                    int inc = cnt;
-#pragma unroll
-                    for (int dd = 1; dd < 32; dd <<= 1) {
-                        const int up = __shfl_up_sync(0xffffffffu, inc, dd);
-                        if ((tid & 31) >= dd) inc += up;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, inc, 31);
-                    int base = 0;
-                    if ((tid & 31) == 0 && total) base = atomicAdd(&s_count, total);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    int pos = base + inc - cnt;
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const float dv[4] = {d[u][a].x, d[u][a].y, d[u][a].z, d[u][a].w};
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (a < k && c < j) {
-                                const unsigned kb = __float_as_uint(dv[c]);
-                                s_keys[pos++] = kb;
-                                mn = min(mn, kb); mx = max(mx, kb);
-                            }
-                    }
-                }
+            // the pair's valid D entries, written compactly by the build stage (their order is irrelevant to a median)
+            const float *df = ws.dflat + (long long)b * kMedCache;
+            for (int i = tid; i < (int)n; i += kTailThreads) {
+                const unsigned kb = __float_as_uint(df[i]);
+                s_keys[i] = kb;
+                mn = min(mn, kb); mx = max(mx, kb);
             }
             block_minmax(mn, mx, sc);
             __syncthreads();
