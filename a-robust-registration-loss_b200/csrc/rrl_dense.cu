@@ -1064,7 +1064,7 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
             if (need > temp_avail) return RRL_ERR_WORKSPACE;
             if (cub::DeviceRadixSort::SortPairs(temp, need, keys_in, keys_out, vals_in, vals_out, (int)ntot, begin_bit, 32, s) != cudaSuccess)
                 return RRL_ERR_CUDA;
-            count_launch((32 - begin_bit + 7) / 8);      // CUB: one kernel per 8-bit pass in the launch list of profiles/
+            count_launch((32 - begin_bit + 7) / 8 + 2);  // CUB: histogram + exclusive sum + one onesweep kernel per 8-bit pass (profiles/r02_launches_large.csv)
             if (!adjacent) {
                 if (cudaMemcpyAsync(perm0, vals_tmp, (size_t)nb * g.nf1p * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
                     cudaMemcpyAsync(perm1, vals_tmp + (size_t)nb * g.nf1p, (size_t)nb * g.nf2p * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
