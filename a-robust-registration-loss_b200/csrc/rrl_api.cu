@@ -82,6 +82,8 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     w.node4[1] = reinterpret_cast<float4 *>(take(sB * (nf2p / kMinNode / 4) * 5 * sizeof(float4)));
     w.super4[0] = reinterpret_cast<float4 *>(take(sB * (pad_supers(nf1p) / 4) * 5 * sizeof(float4)));
     w.super4[1] = reinterpret_cast<float4 *>(take(sB * (pad_supers(nf2p) / 4) * 5 * sizeof(float4)));
+    w.sn8[0] = reinterpret_cast<uint4 *>(take(sB * pad_supers(nf1p) * 9 * sizeof(uint4)));
+    w.sn8[1] = reinterpret_cast<uint4 *>(take(sB * pad_supers(nf2p) * 9 * sizeof(uint4)));
     w.sortbuf_bytes = sort_scratch_bytes(nf1p > nf2p ? nf1p : nf2p, B);
     w.sortbuf = reinterpret_cast<unsigned long long *>(take(w.sortbuf_bytes));
     // ---- per line ----

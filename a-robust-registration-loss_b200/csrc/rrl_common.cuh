@@ -84,6 +84,7 @@ struct Workspace {
     float4 *pt12[2];         // (B, nfp, 2): sorted order, {p1.xyz, cut - |p1|^2}, {p2.xyz, cut - |p2|^2}
     float4 *node4[2];        // (B, nnodes/4, 5): pair-interleaved {xA,xB,yA,yB}{zA,zB,wA,wB} x2 + 1 pad; w = R^2 - |q|^2
     float4 *super4[2];       // (B, nsuperp/4, 5): same layout, one record per kSuperPts sorted triplets (large clouds only)
+    uint4 *sn8[2];           // (B, nsuperp, 9): per super node its 16 node spheres, compressed: {qb, scale} + 16 x {3 x 16-bit offsets, half radius}
     unsigned long long *sortbuf; // scratch for the large-cloud sort (keys/values double buffers + cub temp)
     size_t sortbuf_bytes;
     // per line

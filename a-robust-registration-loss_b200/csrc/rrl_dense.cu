@@ -405,7 +405,7 @@ template <int kNode>
 // pt_base; P_up >= the cloud's extent (for the error bound a record must meet).
 __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, float th, int f, long long i, float E_up,
                                                 float4 *pt_base, float4 *pt12, float4 *node4, int ball_iters, int pt_stride,
-                                                int grp_stride, uint4 *pc = nullptr, float P_up = 0.f) {
+                                                int grp_stride, uint4 *pc = nullptr, float P_up = 0.f, float4 *out_sphere = nullptr) {
     const long long n = i / kNode;
     const int s = (int)(i % kNode);
     double px = 0, py = 0, pz = 0, cut = 0;
@@ -523,6 +523,7 @@ __device__ __forceinline__ float make_node_coop(const float *__restrict__ tri, f
         float *dst = reinterpret_cast<float *>(grp + ((n >> 1) & 1) * 2) + (n & 1);
         dst[0] = rec.x; dst[2] = rec.y; dst[4] = rec.z; dst[6] = rec.w;
         if (grp_stride > 4) reinterpret_cast<float *>(grp + 4)[n & 3] = rad;      // the node's radius (level 1 forms its |u| > 1 slack from it)
+        if (out_sphere) *out_sphere = make_float4(qx, qy, qz, cntv > 0 ? rad : -1.f);      // -1: empty node
     }
     return rad;
 }
@@ -546,7 +547,7 @@ __device__ __forceinline__ float node_slack(unsigned pmax_bits, unsigned xmax_bi
 // argument -- with block-wide instead of lane-group reductions.  Every thread computes the same centre
 // (the partial results are combined in the same order by all).  Thread 0 writes the record.
 __device__ __forceinline__ float make_super_block(const float *__restrict__ tri, float th, int f, long long i, float E_up,
-                                                  float4 *super4, int nsuper, int nsuperp, int ball_iters) {
+                                                  float4 *super4, int nsuper, int nsuperp, int ball_iters, float4 &out_centre) {
     __shared__ float s_sum[8][4];
     __shared__ float s_far[2][8][4];
     __shared__ float s_rad[8];
@@ -626,8 +627,62 @@ __device__ __forceinline__ float make_super_block(const float *__restrict__ tri,
         if (n == nsuper - 1)                                     // sentinels up to the multiple of 4
             for (long long m = nsuper; m < nsuperp; ++m) put(m, make_float4(0.f, 0.f, 0.f, -INFINITY));
     }
+    out_centre = make_float4(qx, qy, qz, cn > 0 ? 1.f : 0.f);     // the same bits in every thread
     __syncthreads();                                             // shared buffers are reused by the next trip
     return rad;
+}
+
+// The 16 node spheres of one super node as ONE 144-byte record {qb, scale} + 16 x {3 x 16-bit offsets, half radius} (pairs of
+// nodes interleaved like the compressed triplet records): level 1 of the super-node mode reads one such record per fired
+// (line, super node) pair instead of four 80-byte group records.  Same construction as the triplet records: the centre is
+// reconstructed as q~ = fma(float(2^23 + u), scale, qb), e >= |q~ - q| is MEASURED here and added to the radius, which is then
+// rounded up to half -- a sphere of radius R~ around q~ contains the node's sphere of radius R around q, so "node passes =>
+// compressed node passes" in exact arithmetic; an empty node gets a NaN radius (no comparison with it holds).
+// Called by all 256 threads of a trip; `sph` is valid in the first lane of every node group.
+__device__ __forceinline__ void write_super_nodes(uint4 *blk, const float4 &sph, bool node_lane, int jn, const float4 &ctr) {
+    __shared__ float4 s_sph[16];
+    __shared__ float s_scale;
+    const int tid = threadIdx.x;
+    if (node_lane) s_sph[jn] = sph;
+    __syncthreads();
+    if (tid < 32) {
+        float am = 0.f;
+        if (tid < 16 && s_sph[tid].w >= 0.f)
+            am = fmaxf(fmaxf(fabsf(s_sph[tid].x - ctr.x), fabsf(s_sph[tid].y - ctr.y)), fabsf(s_sph[tid].z - ctr.z));
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, d));
+        float scale = am * (1.0f / kPcSteps);
+        if (!(scale > 1e-30f)) scale = 1e-30f;
+        if (tid == 0) s_scale = scale;
+    }
+    __syncthreads();
+    if (tid < 16) {
+        const float scale = s_scale;
+        const float qbx = fmaf(-kPcBias, scale, ctr.x), qby = fmaf(-kPcBias, scale, ctr.y), qbz = fmaf(-kPcBias, scale, ctr.z);
+        const float4 sp = s_sph[tid];
+        unsigned ux = 32768u, uy = 32768u, uz = 32768u;
+        unsigned short hb = 0x7E00u;                                  // half NaN: an empty node never fires
+        if (sp.w >= 0.f) {
+            const double inv = 1.0 / (double)scale;
+            auto quant = [&](float qv, float qb) -> unsigned {
+                double u = rint(((double)qv - (double)qb) * inv) - 8388608.0;
+                u = u < 0.0 ? 0.0 : (u > 65535.0 ? 65535.0 : u);
+                return (unsigned)u;
+            };
+            ux = quant(sp.x, qbx); uy = quant(sp.y, qby); uz = quant(sp.z, qbz);
+            const float rx = pc_reconstruct(ux, scale, qbx), ry = pc_reconstruct(uy, scale, qby), rz = pc_reconstruct(uz, scale, qbz);
+            const float dx = fmaxf(fabsf(__fsub_ru(rx, sp.x)), fabsf(__fsub_rd(rx, sp.x)));
+            const float dy = fmaxf(fabsf(__fsub_ru(ry, sp.y)), fabsf(__fsub_rd(ry, sp.y)));
+            const float dz = fmaxf(fabsf(__fsub_ru(rz, sp.z)), fabsf(__fsub_rd(rz, sp.z)));
+            const float e = __fadd_ru(__fsqrt_ru(__fmaf_ru(dz, dz, __fmaf_ru(dy, dy, __fmul_ru(dx, dx)))), 1e-37f);
+            hb = __half_as_ushort(__float2half_ru(__fadd_ru(sp.w, e)));
+        }
+        unsigned short *rec16 = reinterpret_cast<unsigned short *>(blk + 1 + (tid >> 1));
+        const int hs = tid & 1;
+        rec16[0 + hs] = (unsigned short)ux; rec16[2 + hs] = (unsigned short)uy; rec16[4 + hs] = (unsigned short)uz; rec16[6 + hs] = hb;
+        if (tid == 0) blk[0] = make_uint4(__float_as_uint(qbx), __float_as_uint(qby), __float_as_uint(qbz), __float_as_uint(scale));
+    }
+    __syncthreads();                                             // s_sph is reused by the next trip
 }
 
 #ifndef RRL_PF_LEVEL1
@@ -690,12 +745,17 @@ __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const flo
         // lanes of a gather collide in the same L1 sets / L2 slices; the odd strides spread them.)
         const int pt_stride = kNode + 1, grp_stride = 5;
         (void)supers;
+        float4 sph = make_float4(0.f, 0.f, 0.f, -1.f), ctr;
         rad = fmaxf(rad, make_node_coop<kNode>(tri, th, f, i, E, ws.pt4[cloud] + (long long)b * nnodes * pt_stride,
                                                ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * grp_stride,
-                                               ball_iters, pt_stride, grp_stride, pc, P_up));
-        if (supers)
+                                               ball_iters, pt_stride, grp_stride, pc, P_up, &sph));
+        if (supers) {
             srad = fmaxf(srad, make_super_block(tri, th, f, i, E, ws.super4[cloud] + (long long)b * (pad_supers_dev(nfp) / 4) * 5,
-                                                nfp / kSuperPts, pad_supers_dev(nfp), ball_iters));
+                                                nfp / kSuperPts, pad_supers_dev(nfp), ball_iters, ctr));
+            if constexpr (kNode == 16)                             // (a super node = 16 nodes only then; use_supers() requires it)
+                write_super_nodes(ws.sn8[cloud] + ((long long)b * pad_supers_dev(nfp) + i / kSuperPts) * 9, sph, (i % kNode) == 0,
+                                  (int)((i / kNode) % (kSuperPts / kNode)), ctr);
+        }
     }
     // one block-level maximum and one atomic per CTA (thousands of same-address atomics serialise in L2)
     __shared__ unsigned s_radm;
@@ -977,6 +1037,9 @@ int use_supers(const Geometry &g) {
 // compressed triplet records (make_node_coop) wherever level 2 gathers them from L2 instead of a shared-memory copy
 #ifndef RRL_PC8
 #define RRL_PC8 1
+#endif
+#ifndef RRL_SN8
+#define RRL_SN8 1
 #endif
 int use_compressed(const Geometry &g) { return RRL_PC8 && (node_size(g) == 16 || g_param[4] != 0); }
 
@@ -1305,6 +1368,9 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     if constexpr (!kPerNode) pts = pt4_c;
     // compressed records (make_node_coop) of the modes that gather them from L2
     constexpr bool kCompressed = !kPerNode && RRL_PC8;
+    // super-node mode: level 1 reads ONE compressed record of a fired super node's 16 node spheres (write_super_nodes)
+    constexpr bool kSn8 = kSuper && kNode == 16 && RRL_SN8;
+    [[maybe_unused]] const uint4 *sn_src = ws.sn8[cloud] + ((long long)b * pad_supers_dev(nfp) + (kSuper ? n_begin : 0)) * 9;
     constexpr int kPcStride = 1 + kNode / 2;                      // uint4 per node
     const uint4 *pcs = reinterpret_cast<const uint4 *>(ws.pt4[cloud]) + ((long long)b * nnodes + node_begin) * kPcStride;
     // point-1/2 records of the chunk (refine pass before the hand-off to the exact kernel)
@@ -1548,6 +1614,59 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     auto run_groups = [&](bool flush) {
         __syncwarp();
         RRL_COUNT(0, wq_cnt);                                  // (line, group of 4 nodes) entries = node-record fetches of 5 float4
+        if constexpr (kSn8) {
+            // one (line, super node) entry per lane: the 16 node predicates from the super node's compressed record (144 bytes, all
+            // loads in flight together); the node threshold comes from each node's own radius, tl_point - (k R~ + k^2 / 2)
+            for (int base = 0;; base += 32) {
+                const bool more = base < wq_cnt;
+                unsigned nm = 0, key = 0;
+                if (more && base + lane < wq_cnt) {
+                    const unsigned ent = wq[base + lane];
+                    const int lrel = (int)(ent >> 20), srel = (int)(ent & 0xFFFFFu);      // super node, relative to the chunk
+                    const float4 c0 = slineU[lrel], c1 = slineM[lrel];
+                    const uint4 *pp = sn_src + srel * 9;
+                    const uint4 hd = __ldg(pp);
+                    uint4 rec[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rec[j] = __ldg(pp + 1 + j);
+                    const float sc = __uint_as_float(hd.w);
+                    const float2 sc2 = make_float2(sc, sc);
+                    const float2 bx = make_float2(__uint_as_float(hd.x), __uint_as_float(hd.x)), by = make_float2(__uint_as_float(hd.y), __uint_as_float(hd.y));
+                    const float2 bz = make_float2(__uint_as_float(hd.z), __uint_as_float(hd.z));
+                    const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
+                    const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
+                    const float tl_base = fmaf(-0.5f * c0.w, c0.w * 1.00001f, c1.w) - fabsf(c1.w) * 2.4e-7f;
+                    const float2 tlb2 = make_float2(tl_base, tl_base), kn2 = make_float2(-c0.w, -c0.w);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 r = rec[j];
+                        const float2 xu = make_float2(__uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7432)));
+                        const float2 yu = make_float2(__uint_as_float(__byte_perm(r.y, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(r.y, 0x4B000000u, 0x7432)));
+                        const float2 zu = make_float2(__uint_as_float(__byte_perm(r.z, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(r.z, 0x4B000000u, 0x7432)));
+                        const float2 x2 = __ffma2_rn(xu, sc2, bx), y2 = __ffma2_rn(yu, sc2, by), z2 = __ffma2_rn(zu, sc2, bz);
+                        const float2 r2 = __half22float2(*reinterpret_cast<const __half2 *>(&r.w));        // radii (NaN: empty node)
+                        const float2 nx2 = make_float2(-x2.x, -x2.y), ny2 = make_float2(-y2.x, -y2.y), nz2 = make_float2(-z2.x, -z2.y);
+                        const float2 w2 = __ffma2_rn(nz2, z2, __ffma2_rn(ny2, y2, __ffma2_rn(nx2, x2, __fmul2_rn(r2, r2))));
+                        const float2 t2 = __ffma2_rn(z2, u2, __ffma2_rn(y2, u1, __fmul2_rn(x2, u0)));
+                        const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
+                        const float2 q2 = __ffma2_rn(t2, t2, s2);
+                        const float2 tn2 = __ffma2_rn(r2, kn2, tlb2);
+                        nm |= (q2.x > tn2.x) ? (1u << (2 * j)) : 0u;
+                        nm |= (q2.y > tn2.y) ? (2u << (2 * j)) : 0u;
+                    }
+                    key = ((unsigned)lrel << 22) | (unsigned)(srel * 16);
+                }
+                int total = 0, off = 0;
+                if (more) off = warp_excl_scan<5>(__popc(nm), lane, total);
+                if (more ? (nq_cnt + total > kNodeCap) : flush) run_nodes(flush && !more);
+                if (!more) break;
+                push_bits(nq + nq_cnt + off, nm, key);
+                nq_cnt += total;
+                __syncwarp();
+            }
+            wq_cnt = 0;
+            return;
+        }
         // node predicates of one entry: the records are pair-interleaved ({xA,xB,yA,yB} {zA,zB,wA,wB}, then the 4 radii): two
         // nodes per packed FMA, as in the main loop; the threshold comes from the node's own radius, tl_point - (k R_n + k^2 / 2),
         // k = 2 sqrt(e) (0 for |u| <= 1), rounded down
@@ -1642,7 +1761,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 const unsigned node0 = (unsigned)((group0 + w0) * 4);
                 if constexpr (kSuper) {
                     // every fired (line, super node) pair -> the (line, group) entries of its kSuperNodes / 4 node groups
-                    constexpr int kGroupsPer = kSuperNodes / 4;
+                    constexpr int kGroupsPer = kSn8 ? 1 : kSuperNodes / 4;     // (one entry per fired super node with the compressed node records)
                     constexpr int kPart = kWarpQueue / (32 * kGroupsPer);      // bits per part: 32 lanes x kPart x kGroupsPer entries fit
                     static_assert(kPart >= 1 && (kPart & (kPart - 1)) == 0, "part size");
 #pragma unroll 1
@@ -1666,7 +1785,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                             if (!whole) {
                                 mh = (mi >> part) & ((1u << kPart) - 1u);
                                 if (!__any_sync(0xffffffffu, mh != 0u)) continue;
-                                off2 = warp_excl_scan<3>(__popc(mh), lane, tot2);
+                                off2 = warp_excl_scan<(kPart >= 16 ? 5 : (kPart >= 8 ? 4 : 3))>(__popc(mh), lane, tot2);      // counts <= kPart
                             }
                             if (wq_cnt + tot2 * kGroupsPer > kWarpQueue) run_groups(false);
                             int pos = wq_cnt + off2 * kGroupsPer;
