@@ -1412,6 +1412,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
     const float Rmax = __uint_as_float(rmax_bits);
     const float Tmax = __uint_as_float(tmax_bits);
     const float Smax = __uint_as_float(smax_bits);
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
     float ux[kLinesPerThread], uy[kLinesPerThread], uz[kLinesPerThread];
     float mx[kLinesPerThread], my[kLinesPerThread], mz[kLinesPerThread], tl[kLinesPerThread];
     // threshold of the triplet-level predicate and of the node-level predicate for a line
@@ -1555,7 +1556,7 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                 const unsigned ent = nq[base + lane];
                 const int lrel = (int)(ent >> 22), nrel = (int)(ent & 0x3FFFFFu);
                 const float4 c0 = slineU[lrel], c1 = slineM[lrel];
-                const float tl_point = c1.w;
+                const float2 tlp2 = make_float2(c1.w, c1.w);                      // tl_point
                 const float2 u0 = make_float2(c0.x, c0.x), u1 = make_float2(c0.y, c0.y), u2 = make_float2(c0.z, c0.z);
                 const float2 m0 = make_float2(c1.x, c1.x), m1 = make_float2(c1.y, c1.y), m2 = make_float2(c1.z, c1.z);
                 if constexpr (kCompressed) {
@@ -1584,8 +1585,9 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                         const float2 t2 = __ffma2_rn(z2, u2, __ffma2_rn(y2, u1, __fmul2_rn(x2, u0)));
                         const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
                         const float2 q2 = __ffma2_rn(t2, t2, s2);
-                        pm |= (q2.x > tl_point) ? (1u << (2 * j)) : 0u;
-                        pm |= (q2.y > tl_point) ? (2u << (2 * j)) : 0u;
+                        const float2 d2 = __ffma2_rn(q2, neg1, tlp2);             // sign bits into the mask (see the main loop)
+                        pm = __funnelshift_l(__float_as_uint(d2.x), pm, 1);
+                        pm = __funnelshift_l(__float_as_uint(d2.y), pm, 1);
                     }
                 } else {
                     const float4 *pp = pts + nrel * kPtStride;
@@ -1596,10 +1598,12 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                         const float2 t2 = __ffma2_rn(z2, u2, __ffma2_rn(y2, u1, __fmul2_rn(x2, u0)));
                         const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
                         const float2 q2 = __ffma2_rn(t2, t2, s2);
-                        pm |= (q2.x > tl_point) ? (1u << (2 * j)) : 0u;
-                        pm |= (q2.y > tl_point) ? (2u << (2 * j)) : 0u;
+                        const float2 d2 = __ffma2_rn(q2, neg1, tlp2);
+                        pm = __funnelshift_l(__float_as_uint(d2.x), pm, 1);
+                        pm = __funnelshift_l(__float_as_uint(d2.y), pm, 1);
                     }
                 }
+                pm = __brev(pm) >> (32 - kNode);                                  // bit = triplet index inside the node
                 key = ((unsigned)lrel << 22) | (unsigned)(nrel * kNode);
             }
             int total;
@@ -1651,9 +1655,11 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                         const float2 s2 = __ffma2_rn(z2, m2, __ffma2_rn(y2, m1, __ffma2_rn(x2, m0, w2)));
                         const float2 q2 = __ffma2_rn(t2, t2, s2);
                         const float2 tn2 = __ffma2_rn(r2, kn2, tlb2);
-                        nm |= (q2.x > tn2.x) ? (1u << (2 * j)) : 0u;
-                        nm |= (q2.y > tn2.y) ? (2u << (2 * j)) : 0u;
+                        const float2 d2 = __ffma2_rn(q2, neg1, tn2);                  // sign bits into the mask (see the main loop)
+                        nm = __funnelshift_l(__float_as_uint(d2.x), nm, 1);
+                        nm = __funnelshift_l(__float_as_uint(d2.y), nm, 1);
                     }
+                    nm = __brev(nm) >> 16;                                            // bit = node index inside the super node
                     key = ((unsigned)lrel << 22) | (unsigned)(srel * 16);
                 }
                 int total = 0, off = 0;
@@ -1738,8 +1744,6 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                         const float4 a0 = sp[(w0 + gi) * 5 + 0], a1 = sp[(w0 + gi) * 5 + 1], b0 = sp[(w0 + gi) * 5 + 2], b1 = sp[(w0 + gi) * 5 + 3];
                         const float2 xa = make_float2(a0.x, a0.y), ya = make_float2(a0.z, a0.w), za = make_float2(a1.x, a1.y), wa = make_float2(a1.z, a1.w);
                         const float2 xb = make_float2(b0.x, b0.y), yb = make_float2(b0.z, b0.w), zb = make_float2(b1.x, b1.y), wb = make_float2(b1.z, b1.w);
-                        constexpr unsigned one = 1u;
-                        const unsigned bit = one << (gi * 4);
 #pragma unroll
                         for (int i = 0; i < kLinesPerThread; ++i) {
                             const float2 u0 = make_float2(ux[i], ux[i]), u1 = make_float2(uy[i], uy[i]), u2 = make_float2(uz[i], uz[i]);
@@ -1750,13 +1754,20 @@ __global__ void __launch_bounds__(kDenseThreads, DenseCfg<kNode, kPerNode, LPT, 
                             const float2 tb = __ffma2_rn(zb, u2, __ffma2_rn(yb, u1, __fmul2_rn(xb, u0)));
                             const float2 sb = __ffma2_rn(zb, m2, __ffma2_rn(yb, m1, __ffma2_rn(xb, m0, wb)));
                             const float2 qb = __ffma2_rn(tb, tb, sb);
-                            m[i] |= (qa.x > tl[i]) ? bit : 0u;
-                            m[i] |= (qa.y > tl[i]) ? (bit << 1) : 0u;
-                            m[i] |= (qb.x > tl[i]) ? (bit << 2) : 0u;
-                            m[i] |= (qb.y > tl[i]) ? (bit << 3) : 0u;
+                            // Q > tl  <=>  tl - Q < 0 (a rounded difference keeps the sign of the exact one): the SIGN BITS are
+                            // shifted into the mask, one funnel shift per test instead of compare + select + or (records in order,
+                            // first record ends up in the highest bit; reversed below)
+                            const float2 tl2 = make_float2(tl[i], tl[i]);
+                            const float2 da = __ffma2_rn(qa, neg1, tl2), db = __ffma2_rn(qb, neg1, tl2);
+                            m[i] = __funnelshift_l(__float_as_uint(da.x), m[i], 1);
+                            m[i] = __funnelshift_l(__float_as_uint(da.y), m[i], 1);
+                            m[i] = __funnelshift_l(__float_as_uint(db.x), m[i], 1);
+                            m[i] = __funnelshift_l(__float_as_uint(db.y), m[i], 1);
                         }
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < kLinesPerThread; ++i) m[i] = __brev(m[i]) >> (32 - 4 * ng);       // bit = record index inside the window
                 // ordered push of the fired (line, node) pairs: one scan and one bit loop per line
                 const unsigned node0 = (unsigned)((group0 + w0) * 4);
                 if constexpr (kSuper) {
