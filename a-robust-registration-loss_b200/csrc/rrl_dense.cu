@@ -14,14 +14,17 @@
 //   node_kernel    per node of kNode sorted triplets: bounding sphere (centre q, radius R covering every
 //                  triplet's hit cylinder, upper bounds in float with directed rounding) -> node record
 //                  float4(q, R^2 - |q|^2); per triplet the point record float4(p0, cut_f - |p0|^2) in sorted
-//                  order; from 16384 triplets on also one SUPER-node record per 256 sorted triplets.
+//                  order; from 16384 triplets on also one SUPER-node record per 256 sorted triplets, the triplet
+//                  records in compressed form (16-bit offsets + half cut, error measured and folded into the cut) and
+//                  per super node ONE compressed record of its 16 node spheres.
 //   small_prep_kernel  all of the above in one launch for clouds up to 4096 triplets.
 //   dense_kernel   streams tiles of node (or super-node) records through shared memory with 1-D TMA bulk copies
 //                  (cp.async.bulk + mbarrier, double buffered) against register-resident lines.  7 packed FP32
 //                  ops (FFMA2) decide per (line, record) whether the line can touch the sphere; results are
 //                  accumulated branch-free into per-line bit masks and pushed (ordered, by warp scans) to
 //                  warp-private queues; further levels -- node predicate, triplet predicate, refine on points 1
-//                  and 2 -- each run one queue entry per lane with converged warps.
+//                  and 2 -- each run one queue entry per lane with converged warps; every level calls the next from
+//                  ONE site (code size), masks are built from the sign bits of tl - Q.
 //   exact_kernel   the EXACT reference-order test of all three points of every surviving (line, triplet) pair;
 //                  confirmed hits go to fixed-capacity per-line slots.
 //

@@ -3,18 +3,20 @@
 //   build     per line with (k, j) hits inside the window: sort the <=4 hit indices ascending (nonzero() order,
 //             loss.py:125-131), recompute the three exact distances of every hit triplet, weights
 //             w = d / ((d0+d1)+d2) (loss.py:92), intersection points q = ((w0 p0 + w1 p1) + w2 p2) / 3
-//             (loss.py:155-163) and the k x j squared distances (loss.py:38-52,165-166); one record per selected line.
-//   median    exact lower median (torch.median, loss.py:223-224) of all D entries of a pair by an 8-bit radix select on
-//             the float bit patterns.
+//             (loss.py:155-163) and the k x j squared distances (loss.py:38-52,165-166); one record per selected line,
+//             its valid D entries also appended to the pair's compact list.
+//   median    exact lower median (torch.median, loss.py:223-224) of all D entries of a pair by range-refining selection
+//             on the float bit patterns (2^11 buckets over the occupied range per sweep).
 //   welsch    W = 1 - exp(-(D/med)/2) (loss.py:20-21,226), row/column minima with first-index tie breaking (torch.min),
 //             per-(k,j) sums in 2^-40 fixed point (order independent), and the per-record gradient vectors
 //             G1[a] = sum_b coef[a,b] dW/dD 2 (q1_a - q2_b), G2[b] = -sum_a ... (closed form).
 //   finalize  loss = (1/C) sum_kj exp(-|k-j|/2) (S1/(n k) + S2/(n j))   (loss.py:215,227-230)
-//   backward  d loss / d points: scatter (w/3) G grad_out to the hit triplets.
+//   backward  d loss / d points: scatter (w/3) G grad_out to the hit triplets (vector reductions), or contracted to pose
+//             space on the spot (backward_pose_kernel).
 //
-// Launches of the single-GPU forward: select (per line) -> build (per record, dense warps) -> median (one CTA per pair)
-// -> welsch (per record; the last block of a pair also finalizes).  The line-sharded path (rrl_shard_*) runs the
-// same kernels with collectives in between and a separate finalize.
+// Launches of the single-GPU forward: build (select + records) -> tail (median + Welsch + loss in one launch; the last
+// block of a pair finalizes).  The line-sharded path runs build -> shard_tail (exchange over peer memory inside the
+// kernel) or, as the fallback, the NCCL protocol's stage kernels with collectives in between and a separate finalize.
 #include "rrl_common.cuh"
 
 namespace rrl {
@@ -60,10 +62,10 @@ __device__ __forceinline__ void make_point(const float *__restrict__ tri, int f,
         q[c] = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(w[0], v[c]), __fmul_rn(w[1], v[3 + c])), __fmul_rn(w[2], v[6 + c])), 3.0f);
 }
 
-// One thread per line selects; the block compacts its selected lines in shared memory (ordered) and claims a contiguous
+// Two lines per thread select; the block compacts its selected lines in shared memory (ordered) and claims a contiguous
 // range of record slots with ONE atomic.  The records are then built by one thread per (record, cloud, hit slot) --
 // each computes the weights and the intersection point of ONE hit triplet and drops them at the hit's rank among the
-// line's hits (ascending triplet index = nonzero() order) -- and one thread per D entry.
+// line's hits (ascending triplet index = nonzero() order); the 8 threads of a record then form its 16 D entries.
 constexpr int kBuildLines = 512;            // lines per CTA: two per thread (a 15000-line pair is then ONE wave of CTAs on 148 SMs)
 
 __global__ void __launch_bounds__(256) build_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
