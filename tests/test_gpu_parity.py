@@ -468,6 +468,21 @@ def test_large_cloud_path_vs_oracle(rrl):
     _check_against_oracle(out, co.loss(p["tri1"], p["tri2"], p["lines"]))
 
 
+@pytest.mark.parametrize("scale,shift", [(1.0, (7.0, -9.0, 5.0)), (60.0, (0.0, 0.0, 0.0)), (400.0, (900.0, -300.0, 100.0)), (0.02, (0.0, 0.0, 0.0))])
+def test_compressed_records_at_extreme_scales(rrl, scale, shift):
+    """the large-cloud modes read 16-bit offsets + half-precision cuts / radii: clouds far from the origin (offsets
+    tiny against |p|), scaled up until a cut overflows half precision (-> +inf: always a candidate), scaled down into the regime
+    where thr^2 < 2e-4 and nothing can hit; the error of every record is measured and folded in, so the indices stay exact"""
+    p = synth.make_pair(143, 20000, 2500, nf2=17000, zero_frac=0.05)
+    sh = np.array(shift, np.float32)
+    tri1 = (p["tri1"].reshape(-1, 3) * np.float32(scale) + sh).reshape(-1, 9)
+    tri2 = (p["tri2"].reshape(-1, 3) * np.float32(scale) + sh).reshape(-1, 9)
+    lines = p["lines"].copy()
+    lines[:, 3:] = lines[:, 3:] * np.float32(scale) + sh * (np.abs(lines[:, 3:]).sum(1, keepdims=True) > 0)     # all-zero rows stay all-zero
+    out = _run(rrl, tri1, tri2, lines)
+    _check_against_oracle(out, co.loss(tri1, tri2, lines), check_grad=scale <= 60.0)
+
+
 def test_batched_mid_and_large_clouds_share_one_sort(rrl):
     """clouds above 4096 triplets are Hilbert-sorted by ONE radix sort over every cloud of every pair (segment bits above
     a shortened curve index): three ragged pairs per batch, each compared completely with the oracle -- once below
