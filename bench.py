@@ -242,6 +242,44 @@ def cpu_step_reference(ref, tri1, tri2, lines):
     return float(out.item())
 
 
+def reference_on_this_gpu(torch, host_set, dev, budget_s=8.0):
+    """The UNMODIFIED reference (baseline/_ref: code/loss.py) run on THIS GPU through its own `device` argument, one pair per call
+    as its DL hooks call it (Train_DCP.py:266-270): the like-for-like datapoint beside the CPU arm.  Outside every timed region;
+    None when the reference is not there or a pair does not fit (it materialises (nl, nf, 3, 3) temporaries)."""
+    ref = _load_reference()
+    if ref is None:
+        return None
+    tri1, tri2, lines = (x[0] for x in host_set)
+    nl = lines.shape[0]
+    try:
+        t2 = torch.from_numpy(tri2).reshape(1, -1, 9).to(dev)
+        ln = torch.from_numpy(lines).reshape(1, -1, 6).to(dev)
+
+        def one():
+            t1 = torch.from_numpy(tri1).reshape(1, -1, 9).to(dev).requires_grad_(True)
+            out = ref.cal_loss_intersection_batch_whole_median_pts_lines(1, 1, 5, 5, t1, t2, ln, dev)
+            if not isinstance(out, tuple):
+                out.backward()
+            torch.cuda.synchronize(dev)
+            return 0.0 if isinstance(out, tuple) else float(out.item())
+        loss = one()                                        # warm-up (allocator, kernels)
+        times = []
+        t_end = time.perf_counter() + budget_s
+        while len(times) < 5 and time.perf_counter() < t_end:
+            t0 = time.perf_counter()
+            one()
+            times.append(time.perf_counter() - t0)
+        best = min(times)
+        return {"value": nl / best, "unit": "pairs*lines/s", "ms_per_pair": best * 1e3, "loss": loss, "calls": len(times),
+                "note": "the unmodified reference code/loss.py on this GPU (its own device argument; eager PyTorch CUDA, autograd "
+                        "backward), ONE pair per call as its hooks call it, best of %d after a warm-up; a batch of B pairs is B such "
+                        "calls" % len(times)}
+    except Exception as exc:                               # e.g. out of memory on a pair that does not fit
+        return {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+    finally:
+        torch.cuda.empty_cache()
+
+
 def cpu_sample_lines(workload):
     """lines of one pair one CPU step evaluates: the reference materialises 36 * nl * nf bytes per temporary (~10 live)"""
     _, nf, nl, _, _ = WORKLOADS[workload]
@@ -565,6 +603,9 @@ def run_gpu(args):
     roofline = bench_roofline(args, torch, rrl_b200, dev_sets[0], nf, nl, ms_per_step)
     sampled = bench_sampler(torch, rrl_b200, dev_sets[0], nl, kw, world * B * nl, ms_per_step)
     cpu = cpu_baseline(args.workload, inputs=host_sets[0]) if (world == 1 and not args.no_cpu_baseline) else None
+    ref_gpu = None
+    if world == 1 and not args.no_cpu_baseline and args.workload in ("dcp", "rpm", "fmr", "demo"):
+        ref_gpu = reference_on_this_gpu(torch, host_sets[0], dev)
     cfg = config_dict(args.workload, world)
     line = {"metric": METRIC, "value": value, "unit": "pairs*lines/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -577,7 +618,7 @@ def run_gpu(args):
                             "fmr": "rrl_b200.hooks.fmr_twist_loss (Exp -> fused rigid transform -> loss; ExpMap gradient)"}.get(
                                 args.workload, "rrl_b200.intersected_line_loss (torch.autograd.Function over the C ABI), forward + backward")},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "lines_sampled_on_device": sampled, "dropin": dropin, "hooks": hooks, "large": large,
+            "lines_sampled_on_device": sampled, "dropin": dropin, "hooks": hooks, "large": large, "reference_on_this_gpu": ref_gpu,
             "loss_checksum": float(last[0].item())}
     print(json.dumps(line), flush=True)
     if world > 1:
