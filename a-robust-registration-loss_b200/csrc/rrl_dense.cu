@@ -1023,7 +1023,7 @@ size_t sort_scratch_bytes(int nfp_max, int B) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[16] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 6, 1, 0, 0, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode, [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2), [12] lowest key bit the radix sort of the large path looks at (0 = auto, -1 = every bit)
+static int g_param[16] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 6, 1, 0, 0, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode, [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2), [12] lowest key bit the radix sort of the large path looks at (0 = auto, -1 = every bit), [13] CTAs per SM of the exact kernel's grid (0 = 8)
 void set_param(int id, int v) { if (id >= 0 && id < 16) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -2067,7 +2067,7 @@ int launch_dense(const float *tri1, const float *tri2, const float *lines, const
     else if (G == 8) rc = lpt != 4 ? launch_dense_variant<8, false, 2>(a, ws, g, G, s) : launch_dense_variant<8, false, 4>(a, ws, g, G, s);
     else rc = lpt != 4 ? launch_dense_variant<16, false, 2>(a, ws, g, G, s) : launch_dense_variant<16, false, 4>(a, ws, g, G, s);
     if (rc) return rc;
-    const int xgrid = sm_count() * 8;
+    const int xgrid = sm_count() * (g_param[13] > 0 ? g_param[13] : 8);
     if (g_param[11] == 4) exact_kernel<4><<<xgrid, 256, 0, s>>>(a, ws, g);
     else if (g_param[11] == 1) exact_kernel<1><<<xgrid, 256, 0, s>>>(a, ws, g);
     else exact_kernel<2><<<xgrid, 256, 0, s>>>(a, ws, g);

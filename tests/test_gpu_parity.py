@@ -483,6 +483,41 @@ def test_compressed_records_at_extreme_scales(rrl, scale, shift):
     _check_against_oracle(out, co.loss(tri1, tri2, lines), check_grad=scale <= 60.0)
 
 
+@pytest.mark.parametrize("seed", [201, 202, 203, 204, 205, 206])
+def test_randomised_large_cloud_sweep_against_the_bruteforce_kernel(rrl, seed):
+    """random sizes around the super-node threshold, shapes, scales, offsets, unnormalised / zero / duplicated lines: the filtered
+    pipeline (compressed records, per-node slack, super-node level) must report exactly the indices of the device's brute-force
+    formulation (every (line, triplet) tested with the reference-order arithmetic)"""
+    rng = np.random.default_rng(seed)
+    nf1, nf2 = int(rng.integers(16384, 60000)), int(rng.integers(9000, 60000))
+    nl = int(rng.integers(1500, 6000))
+    p = synth.make_pair(seed, nf1, nl, nf2=nf2, shape=["sphere", "torus", "box"][seed % 3],
+                        zero_frac=float(rng.uniform(0, 0.1)), noise=float(rng.choice([0.0, 0.002])), keep_frac=float(rng.choice([1.0, 0.7])))
+    scale = np.float32(10.0 ** rng.uniform(-0.7, 1.7))
+    shift = (rng.uniform(-3, 3, 3) * scale).astype(np.float32)
+    tri1 = (p["tri1"].reshape(-1, 3) * scale + shift).reshape(-1, 9)
+    tri2 = (p["tri2"].reshape(-1, 3) * scale + shift).reshape(-1, 9)
+    lines = p["lines"].copy()
+    nz = np.abs(lines).sum(1, keepdims=True) > 0
+    lines[:, 3:] = lines[:, 3:] * scale + shift * nz
+    k = nl // 10
+    lines[:k, :3] *= rng.uniform(0.5, 1.02, size=(k, 1)).astype(np.float32)          # |u| != 1, both sides
+    lines[k:k + 20] = lines[k + 20]                                                    # duplicates
+    L = rrl._native.lib()
+    try:
+        L.rrl_debug_set_param(5, 1)
+        a = _run(rrl, tri1, tri2, lines)
+    finally:
+        L.rrl_debug_set_param(5, 0)
+    b = _run(rrl, tri1, tri2, lines)
+    for c, h in (("counts1", "hits1"), ("counts2", "hits2")):
+        assert np.array_equal(a[c], b[c])
+        keep = a[c] <= co.CAP
+        assert np.array_equal(a[h][keep], b[h][keep])
+    assert a["median"] == b["median"] and a["loss"] == b["loss"]
+    assert int(a["stats"][5]) == int(b["stats"][5])                                     # the same 1-ulp band tests were seen
+
+
 def test_batched_mid_and_large_clouds_share_one_sort(rrl):
     """clouds above 4096 triplets are Hilbert-sorted by ONE radix sort over every cloud of every pair (segment bits above
     a shortened curve index): three ragged pairs per batch, each compared completely with the oracle -- once below
