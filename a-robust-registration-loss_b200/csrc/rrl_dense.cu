@@ -882,6 +882,7 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     if (tid == 0) {
         ws.pmax[b * 2 + cloud] = s_red[0];
         ws.tmax[b * 2 + cloud] = s_red[3];
+        ws.smax[b * 2 + cloud] = 0u;                     // (no super nodes on this path; the forward's last kernel copies it to `keep`)
         if (cloud == 0) ws.xmax[b * 2] = s_red[1];
         ws.bad[b * 2 + cloud] = bad_any ? 1u : 0u;       // this cloud's points, or any line of the pair (both CTAs scan them)
     }
