@@ -1024,7 +1024,7 @@ size_t sort_scratch_bytes(int nfp_max, int B) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[16] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 6, 1, 0, 0, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode, [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2), [12] lowest key bit the radix sort of the large path looks at (0 = auto, -1 = every bit), [13] CTAs per SM of the exact kernel's grid (0 = 8)
+static int g_param[16] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 1, 0, 0, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode (0 = by the number of line tiles), [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2), [12] lowest key bit the radix sort of the large path looks at (0 = auto, -1 = every bit), [13] CTAs per SM of the exact kernel's grid (0 = 8)
 void set_param(int id, int v) { if (id >= 0 && id < 16) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -2033,7 +2033,11 @@ static int launch_dense_variant(const DenseArgs &a0, const Workspace &ws, const 
     // split the records so that the grid covers the SMs (kMinBlocks CTAs each) g_param[2] times over when the line
     // tiles alone do not; never below g_param[3] records per CTA
     const long long base_ctas = (long long)line_tiles * g.B * 2;
-    const long long target = (long long)sm_count() * Cfg::kMinBlocks * g_param[kSuper ? 9 : 2];
+    // super-node mode: every CTA pays a fixed latency chain (set-up loads, the bulk copies, a final flush through three queue
+    // levels), so few lines want few, fat CTAs -- measured on the 500k pair: 12 500 lines 74.7 / 79.6 / 87.8 us at 1 / 3 / 6 waves,
+    // 50 000 lines 242 / 204 / 213, 100 000 lines 447 / 366 / 364
+    const int super_waves = g_param[9] > 0 ? g_param[9] : (base_ctas < 100 ? 1 : (base_ctas < 300 ? 3 : 6));
+    const long long target = (long long)sm_count() * Cfg::kMinBlocks * (kSuper ? super_waves : g_param[2]);
     int chunks = 1;
     if (base_ctas < target) chunks = (int)((target + base_ctas - 1) / base_ctas);
     int chunk_nodes = (nn_max + chunks - 1) / chunks;
