@@ -1024,7 +1024,7 @@ size_t sort_scratch_bytes(int nfp_max, int B) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[16] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 1, 0, 0, 0, 0, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode (0 = by the number of line tiles), [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2), [12] lowest key bit the radix sort of the large path looks at (0 = auto, -1 = every bit), [13] CTAs per SM of the exact kernel's grid (0 = 8)
+static int g_param[16] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 1, 0, 0, 0, 4, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode (0 = by the number of line tiles), [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2), [12] lowest key bit the radix sort of the large path looks at (0 = auto, -1 = every bit), [13] CTAs per SM of the exact kernel's grid (0 = 8), [14] enclosing-ball refinement steps on the large-cloud path (node_kernel: the steps are a third of that kernel, and every rank of a line shard repeats it)
 void set_param(int id, int v) { if (id >= 0 && id < 16) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -1150,8 +1150,8 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
     stage_mark(2, s);
     int nbx = nfp_max / 256;
     if (nbx > 4096) nbx = 4096;
-    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g), reuse_target, use_compressed(g));
-    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[8], use_supers(g), reuse_target, use_compressed(g));
+    if (G == 8) node_kernel<8><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[14], use_supers(g), reuse_target, use_compressed(g));
+    else node_kernel<16><<<dim3(nbx, g.B * 2), 256, 0, s>>>(tri1, tri2, ws, g, g_param[14], use_supers(g), reuse_target, use_compressed(g));
     count_launch();
     stage_mark(3, s);
     return check_launch();
