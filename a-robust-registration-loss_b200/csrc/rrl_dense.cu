@@ -705,9 +705,115 @@ __device__ __forceinline__ void write_super_nodes(uint4 *blk, const float4 &sph,
 #ifndef RRL_SUPER_MINBLOCKS
 #define RRL_SUPER_MINBLOCKS 0
 #endif
+#ifndef RRL_SUPER_FROM_NODES
+#define RRL_SUPER_FROM_NODES 1                // super-node spheres from the 16 node spheres (one warp) instead of the 256 points (block-wide)
+#endif
 #ifndef RRL_NODE_MINBLOCKS
 #define RRL_NODE_MINBLOCKS 4                  // 64 registers: 4 CTAs per SM (139 registers = ONE CTA per SM took 196 us at 500k, 4 take 84)
 #endif
+// Super node of 16 nodes FROM THE NODE SPHERES (one warp; the 256-point version above costs a quarter of the node kernel in
+// block-wide reductions and barriers): centre = refined centroid of the node centres, R >= |q_n - Q| + R_n for every node, so
+// a line within R_n of q_n is within R of Q -- "node passes => super node passes" by the triangle inequality, and with it
+// "member passes => super node passes" (the |u| > 1 slack has the same form, with the cloud's largest super radius).  A few
+// per cent looser than the sphere of the points themselves.  Also writes the super node's compressed node record
+// (write_super_nodes' format).  Called by all 256 threads of a trip; returns the super radius in thread 0.
+__device__ __forceinline__ float super_from_nodes(float4 *super4, uint4 *blk, long long n, int nsuper, int nsuperp, const float4 &sph,
+                                                  bool node_lane, int jn, int ball_iters) {
+    __shared__ float4 s_sph[16];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (node_lane) s_sph[jn] = sph;
+    __syncthreads();
+    float rad = 0.f;
+    if (tid < 32) {
+        const float4 sp = lane < 16 ? s_sph[lane] : make_float4(0.f, 0.f, 0.f, -1.f);
+        const bool valid = sp.w >= 0.f;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, valid));
+        float cx = valid ? sp.x : 0.f, cy = valid ? sp.y : 0.f, cz = valid ? sp.z : 0.f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            cx += __shfl_xor_sync(0xffffffffu, cx, d);
+            cy += __shfl_xor_sync(0xffffffffu, cy, d);
+            cz += __shfl_xor_sync(0xffffffffu, cz, d);
+        }
+        float Qx = 0.f, Qy = 0.f, Qz = 0.f;
+        if (cnt > 0) { const float inv = __fdividef(1.0f, (float)cnt); Qx = cx * inv; Qy = cy * inv; Qz = cz * inv; }
+        if (cnt > 0 && ball_iters > 0) {                          // centre heuristics (as in make_node_coop)
+            float bx = Qx, by = Qy, bz = Qz, bestR = INFINITY, ccx = Qx, ccy = Qy, ccz = Qz;
+            for (int k = 1; k <= ball_iters + 1; ++k) {
+                const float dx = sp.x - ccx, dy = sp.y - ccy, dz = sp.z - ccz;
+                const float d = valid ? sqrt_approx(dx * dx + dy * dy + dz * dz) + sp.w : -INFINITY;
+                float m = d;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, dd));
+                if (m < bestR) { bestR = m; bx = ccx; by = ccy; bz = ccz; }
+                const unsigned bal = __ballot_sync(0xffffffffu, valid && d == m);
+                const int far = bal ? __ffs(bal) - 1 : 0;
+                const float gx = __shfl_sync(0xffffffffu, sp.x, far), gy = __shfl_sync(0xffffffffu, sp.y, far), gz = __shfl_sync(0xffffffffu, sp.z, far);
+                const float step = __fdividef(1.0f, (float)(k + 1));
+                ccx += (gx - ccx) * step; ccy += (gy - ccy) * step; ccz += (gz - ccz) * step;
+            }
+            if (bestR < INFINITY) { Qx = bx; Qy = by; Qz = bz; }
+        }
+        // radius and the scale of the compressed record, rounded up throughout
+        float R = 0.f, am = 0.f;
+        if (valid) {
+            const float dx = fmaxf(fabsf(__fsub_ru(sp.x, Qx)), fabsf(__fsub_rd(sp.x, Qx)));
+            const float dy = fmaxf(fabsf(__fsub_ru(sp.y, Qy)), fabsf(__fsub_rd(sp.y, Qy)));
+            const float dz = fmaxf(fabsf(__fsub_ru(sp.z, Qz)), fabsf(__fsub_rd(sp.z, Qz)));
+            R = __fadd_ru(__fsqrt_ru(__fmaf_ru(dz, dz, __fmaf_ru(dy, dy, __fmul_ru(dx, dx)))), sp.w);
+            am = fmaxf(fmaxf(dx, dy), dz);
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, d));
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, d));
+        }
+        if (lane == 0) {
+            float4 rec = make_float4(0.f, 0.f, 0.f, -INFINITY);      // empty: never a candidate
+            if (cnt > 0) rec = sphere_record_up(R, Qx, Qy, Qz, rad);
+            auto put = [&](long long m, const float4 &r, float rr) {
+                float4 *grp = super4 + (m >> 2) * 5;
+                float *dst = reinterpret_cast<float *>(grp + ((m >> 1) & 1) * 2) + (m & 1);
+                dst[0] = r.x; dst[2] = r.y; dst[4] = r.z; dst[6] = r.w;
+                reinterpret_cast<float *>(grp + 4)[m & 3] = rr;
+            };
+            put(n, rec, rad);
+            if (n == nsuper - 1)                                     // sentinels up to the multiple of 16
+                for (long long m = nsuper; m < nsuperp; ++m) put(m, make_float4(0.f, 0.f, 0.f, -INFINITY), 0.f);
+        }
+        if (blk) {                                                   // compressed node record (see write_super_nodes)
+            float scale = am * (1.0f / kPcSteps);
+            if (!(scale > 1e-30f)) scale = 1e-30f;
+            const float qbx = fmaf(-kPcBias, scale, Qx), qby = fmaf(-kPcBias, scale, Qy), qbz = fmaf(-kPcBias, scale, Qz);
+            if (lane < 16) {
+                unsigned ux = 32768u, uy = 32768u, uz = 32768u;
+                unsigned short hb = 0x7E00u;                          // half NaN: an empty node never fires
+                if (valid) {
+                    const double inv = 1.0 / (double)scale;
+                    auto quant = [&](float qv, float qb) -> unsigned {
+                        double u = rint(((double)qv - (double)qb) * inv) - 8388608.0;
+                        u = u < 0.0 ? 0.0 : (u > 65535.0 ? 65535.0 : u);
+                        return (unsigned)u;
+                    };
+                    ux = quant(sp.x, qbx); uy = quant(sp.y, qby); uz = quant(sp.z, qbz);
+                    const float rx = pc_reconstruct(ux, scale, qbx), ry = pc_reconstruct(uy, scale, qby), rz = pc_reconstruct(uz, scale, qbz);
+                    const float dx = fmaxf(fabsf(__fsub_ru(rx, sp.x)), fabsf(__fsub_rd(rx, sp.x)));
+                    const float dy = fmaxf(fabsf(__fsub_ru(ry, sp.y)), fabsf(__fsub_rd(ry, sp.y)));
+                    const float dz = fmaxf(fabsf(__fsub_ru(rz, sp.z)), fabsf(__fsub_rd(rz, sp.z)));
+                    const float e = __fadd_ru(__fsqrt_ru(__fmaf_ru(dz, dz, __fmaf_ru(dy, dy, __fmul_ru(dx, dx)))), 1e-37f);
+                    hb = __half_as_ushort(__float2half_ru(__fadd_ru(sp.w, e)));
+                }
+                unsigned short *rec16 = reinterpret_cast<unsigned short *>(blk + 1 + (lane >> 1));
+                const int hs = lane & 1;
+                rec16[0 + hs] = (unsigned short)ux; rec16[2 + hs] = (unsigned short)uy; rec16[4 + hs] = (unsigned short)uz; rec16[6 + hs] = hb;
+                if (lane == 0) blk[0] = make_uint4(__float_as_uint(qbx), __float_as_uint(qby), __float_as_uint(qbz), __float_as_uint(scale));
+            }
+        }
+    }
+    __syncthreads();                                             // s_sph is reused by the next trip
+    return rad;
+}
+
 template <int kNode>
 __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2, Workspace ws, Geometry g, int ball_iters,
                                                    int supers, int reuse_target, int compressed) {
@@ -753,11 +859,18 @@ __global__ void __launch_bounds__(256, RRL_NODE_MINBLOCKS) node_kernel(const flo
                                                ws.pt12[cloud] + (long long)b * nfp * 2, ws.node4[cloud] + (long long)b * (nnodes / 4) * grp_stride,
                                                ball_iters, pt_stride, grp_stride, pc, P_up, &sph));
         if (supers) {
-            srad = fmaxf(srad, make_super_block(tri, th, f, i, E, ws.super4[cloud] + (long long)b * (pad_supers_dev(nfp) / 4) * 5,
-                                                nfp / kSuperPts, pad_supers_dev(nfp), ball_iters, ctr));
-            if constexpr (kNode == 16)                             // (a super node = 16 nodes only then; use_supers() requires it)
-                write_super_nodes(ws.sn8[cloud] + ((long long)b * pad_supers_dev(nfp) + i / kSuperPts) * 9, sph, (i % kNode) == 0,
-                                  (int)((i / kNode) % (kSuperPts / kNode)), ctr);
+            float4 *sup = ws.super4[cloud] + (long long)b * (pad_supers_dev(nfp) / 4) * 5;
+            if constexpr (kNode == 16 && RRL_SUPER_FROM_NODES) {   // (a super node = 16 nodes; use_supers() requires kNode == 16)
+                srad = fmaxf(srad, super_from_nodes(sup, ws.sn8[cloud] + ((long long)b * pad_supers_dev(nfp) + i / kSuperPts) * 9, i / kSuperPts,
+                                                    nfp / kSuperPts, pad_supers_dev(nfp), sph, (i % kNode) == 0,
+                                                    (int)((i / kNode) % (kSuperPts / kNode)), ball_iters));
+                (void)ctr;
+            } else {
+                srad = fmaxf(srad, make_super_block(tri, th, f, i, E, sup, nfp / kSuperPts, pad_supers_dev(nfp), ball_iters, ctr));
+                if constexpr (kNode == 16)
+                    write_super_nodes(ws.sn8[cloud] + ((long long)b * pad_supers_dev(nfp) + i / kSuperPts) * 9, sph, (i % kNode) == 0,
+                                      (int)((i / kNode) % (kSuperPts / kNode)), ctr);
+            }
         }
     }
     // one block-level maximum and one atomic per CTA (thousands of same-address atomics serialise in L2)
