@@ -688,20 +688,8 @@ __device__ __forceinline__ void write_super_nodes(uint4 *blk, const float4 &sph,
     __syncthreads();                                             // s_sph is reused by the next trip
 }
 
-#ifndef RRL_PF_LEVEL1
-#define RRL_PF_LEVEL1 0
-#endif
-#ifndef RRL_PF_LEVEL2
-#define RRL_PF_LEVEL2 0
-#endif
-// measurement only (WRONG results): level 2 reads and tests only the first half of a node's triplets when the records come
-// through L2 -- how much of the large-cloud kernel is the bytes of these gathers?
-#ifndef RRL_EXP_HALF_L2
-#define RRL_EXP_HALF_L2 0
-#endif
-#ifndef RRL_L2_PRELOAD
-#define RRL_L2_PRELOAD 0
-#endif
+// (the prefetch / preload / half-record switches of the level-1 and level-2 gathers -- RRL_PF_LEVEL1/2, RRL_L2_PRELOAD,
+// RRL_EXP_HALF_L2 -- were measurement variants of the fp32 records; DESIGN 5.1 has their numbers, the git history their code)
 #ifndef RRL_SUPER_MINBLOCKS
 #define RRL_SUPER_MINBLOCKS 0
 #endif

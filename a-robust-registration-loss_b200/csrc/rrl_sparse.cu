@@ -1106,9 +1106,6 @@ int launch_finalize(const Workspace &ws, const Geometry &g, float *out_loss, int
 // ------------------------------------------------------------------------------------------------------
 // backward: scatter (w/3) G grad_out
 // ------------------------------------------------------------------------------------------------------
-#ifndef RRL_BWD_HOIST
-#define RRL_BWD_HOIST 1
-#endif
 // The 9 gradient floats of one hit triplet, added with vector reductions (red.global.add.v2/v4.f32, sm_90+): the scatter is
 // bound by the number of atomic operations L2 retires, and a triplet's 36 bytes take 3-4 of them (by the alignment of its
 // first float) instead of 9.
@@ -1146,7 +1143,6 @@ __global__ void __launch_bounds__(128) backward_kernel(Workspace ws, Geometry g,
     if (!hdr_ok(ws, g) || ws.hdr[6] != 1) return;           // no completed forward of this geometry here: gradients stay zero
     if (i >= ws.nrec[b]) return;
     const long long r = (long long)b * g.nl + i;
-#if RRL_BWD_HOIST
     // every load of the record is issued before the first use (the record is whole whatever k and j are: unused slots hold
     // index -1 and zero weights), so the thread waits for ONE round trip to L2 instead of one per hit
     const int4 *I4 = reinterpret_cast<const int4 *>(ws.recIdx + r * 8);
@@ -1184,42 +1180,6 @@ __global__ void __launch_bounds__(128) backward_kernel(Workspace ws, Geometry g,
             add9(O + f * 9, v);
         }
     }
-#else
-    const int meta = ws.recMeta[r * 2 + 1];
-    const int k = meta & 255, j = (meta >> 8) & 255;
-    const float go = grad_out[b] * (1.0f / 3.0f);
-    const float *G = ws.recG + r * 24, *Wt = ws.recW + r * 24;
-    const int *idx = ws.recIdx + r * 8;
-    mark(17);
-    if (g1) {
-        float *O = g1 + (long long)b * g.nf1 * 9;
-        for (int a = 0; a < k; ++a) {
-            const long long f = idx[a];
-            const float gx = G[a * 3] * go, gy = G[a * 3 + 1] * go, gz = G[a * 3 + 2] * go;
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                const float w = Wt[a * 3 + p];
-                atomicAdd(O + f * 9 + p * 3, w * gx);
-                atomicAdd(O + f * 9 + p * 3 + 1, w * gy);
-                atomicAdd(O + f * 9 + p * 3 + 2, w * gz);
-            }
-        }
-    }
-    if (g2) {
-        float *O = g2 + (long long)b * g.nf2 * 9;
-        for (int c = 0; c < j; ++c) {
-            const long long f = idx[4 + c];
-            const float gx = G[12 + c * 3] * go, gy = G[12 + c * 3 + 1] * go, gz = G[12 + c * 3 + 2] * go;
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                const float w = Wt[12 + c * 3 + p];
-                atomicAdd(O + f * 9 + p * 3, w * gx);
-                atomicAdd(O + f * 9 + p * 3 + 1, w * gy);
-                atomicAdd(O + f * 9 + p * 3 + 2, w * gz);
-            }
-        }
-    }
-#endif
     mark(18);
 }
 
