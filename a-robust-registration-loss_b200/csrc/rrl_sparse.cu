@@ -779,7 +779,10 @@ int launch_welsch(const Workspace &ws, const Geometry &g, cudaStream_t s) {
 // pair recomputes the pair's median from the D entries (a few sweeps over <= 192 KB of shared memory; cheaper than a
 // second launch and a grid-wide dependency), then takes every S-th slice of the records through the Welsch stage; the
 // last block to finish writes the loss (ticket in flags[b*4+1]).
-constexpr int kTailThreads = 512;
+#ifndef RRL_TAIL_THREADS
+#define RRL_TAIL_THREADS 512
+#endif
+constexpr int kTailThreads = RRL_TAIL_THREADS;
 
 __global__ void __launch_bounds__(kTailThreads) tail_kernel(Workspace ws, Geometry g, float *out_loss, int *out_status,
                                                              float *out_median, long long *out_stats) {
