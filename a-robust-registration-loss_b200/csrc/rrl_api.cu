@@ -97,6 +97,7 @@ Workspace carve(void *base, int B, int nf1, int nf2, int nl) {
     // ---- per record ----
     w.recD = reinterpret_cast<float *>(take(lines * 16 * sizeof(float)));
     w.dflat = reinterpret_cast<float *>(take(sB * kMedCache * sizeof(float)));
+    w.lpart = reinterpret_cast<unsigned int *>(take(sB * 64 * 2 * sizeof(unsigned int)));
     w.recMeta = reinterpret_cast<int *>(take(lines * 2 * sizeof(int)));
     w.recIdx = reinterpret_cast<int *>(take(lines * 8 * sizeof(int)));
     w.recW = reinterpret_cast<float *>(take(lines * 24 * sizeof(float)));

@@ -69,11 +69,12 @@ struct Workspace {
     unsigned int *tmax;      // (B,2): bits of the largest threshold thr_f of the cloud (the guards scale with its square)
     unsigned int *bad;       // (B,2): non-zero when the cloud (or, in either slot, a line of the pair) holds a NaN / infinite value
     int *nrec;               // (B)
+    unsigned int *lpart;     // (B, 64, 2): per line block of the small-cloud prep kernel {bits of its largest |x0|^2, bad-input flag} (hand-off to the cloud CTAs)
     float *dflat;            // (B, kMedCache): the pair's valid D entries, compact, in any order (the median's input); entries beyond the capacity are dropped
     int *n_kj;               // (B,16)
     float *med;              // (B)
     int *flags;              // (B,4): {NaN seen in the Welsch stage, block ticket of the Welsch stage,
-                             //         cursor of the pair's compact D list (dflat), reserved}
+                             //         cursor of the pair's compact D list (dflat), hand-off counter of the small-cloud prep kernel (self-resetting)}
     unsigned long long *sums;// (B,32): S1[16], S2[16] fixed point
     long long *stats;        // (B, RRL_NSTAT)
     long long *gcounts;      // (B,18) global counts used by welsch/finalize/backward (== local unless line-sharded)

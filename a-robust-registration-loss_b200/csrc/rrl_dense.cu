@@ -910,7 +910,8 @@ __device__ __forceinline__ void line_constants(const float *__restrict__ ln, flo
 template <int kNode>
 __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restrict__ tri1, const float *__restrict__ tri2,
                                                           const float *__restrict__ lines, Workspace ws, Geometry g, int window,
-                                                          int sorted, int line_blocks, int ball_iters, int refine, int reuse, int compressed) {
+                                                          int sorted, int line_blocks, int ball_iters, int refine, int reuse, int compressed,
+                                                          int allow_handoff) {
     extern __shared__ unsigned long long skeys[];
     __shared__ unsigned s_red[4];                        // bits of max |p|^2, max |x0|^2 (scaled), max node radius, max threshold
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -918,15 +919,50 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     // RRL_REUSE_ORDER is honoured only when an earlier forward of this very geometry completed in this workspace (hdr[7]
     // is written by that forward's LAST kernel and by nobody in this launch, so every CTA reads the same value); on a
     // fresh or differently shaped workspace the cloud is simply sorted
-    reuse = reuse && ws.hdr[7] == order_token(g);
+    const bool seen = ws.hdr[7] == order_token(g);
+    reuse = reuse && seen;
+    // Hand-off of the pair's line extent from the line blocks to the cloud CTAs, for SMALL BATCHES only (the launch allows it for
+    // B <= 4): a cloud CTA scanning the pair's 20000 lines itself is 5 us of the demo's 36 us prep kernel, bound by what one SM pulls
+    // through L2.  With many pairs the hand-off does not pay (measured: DCP 40.9 against 40.3 us, RPM far worse), so the cloud CTAs scan
+    // there.  The cloud CTAs come first in the grid (they are the critical path) and wait for blocks dispatched after them -- all CTAs
+    // of such a launch are resident at once -- with a bounded wait and the scan as the fall-back, so the results never depend on the
+    // hand-off.  flags[b*4+3] counts the pair's finished line blocks; the second cloud CTA to have read the partials resets it, so the
+    // counter is zero again when the kernel ends.  That invariant needs ONE earlier forward of this geometry in this workspace (`seen`,
+    // the token RRL_REUSE_ORDER checks: written by a forward's last kernel and by nobody in this launch, so all CTAs decide alike); on a
+    // fresh workspace the cloud CTAs scan and the cloud-0 CTA zeroes the counter.
+    const bool handoff = seen && allow_handoff;
     const float *lb = lines + (long long)b * g.nl * 6;
+    __shared__ unsigned s_lred[2];
     if (blockIdx.y >= 2) {
-        for (int l = (blockIdx.y - 2) * 1024 + tid; l < g.nl; l += line_blocks * 1024) {
+        const int lblk = blockIdx.y - 2;
+        if (tid < 2) s_lred[tid] = 0u;
+        __syncthreads();
+        float xl = 0.f;
+        int badl = 0;
+        for (int l = lblk * 1024 + tid; l < g.nl; l += line_blocks * 1024) {
             const long long gl = (long long)b * g.nl + l;
             float xm;
             line_constants(lb + (long long)l * 6, ws.lineC + gl * 2, xm);
+            if (handoff) {
+                const float *ln = lb + (long long)l * 6;
+                float m = xm + 0.f * (__ldg(ln) + __ldg(ln + 1) + __ldg(ln + 2));       // NaN for a NaN / infinite position OR direction
+                if (!(m < INFINITY)) { m = 0.f; badl = 1; }                             // such a line never hits: it stays out of the extent
+                xl = fmaxf(xl, m);
+            }
             ws.cnt[0][gl] = 0;
             ws.cnt[1][gl] = 0;
+        }
+        if (handoff) {
+            const unsigned a = __reduce_max_sync(0xffffffffu, __float_as_uint(xl));
+            if ((tid & 31) == 0 && a) atomicMax(&s_lred[0], a);
+            const int bad_blk = __syncthreads_or(badl);
+            if (tid == 0) {
+                unsigned int *lp = ws.lpart + ((long long)b * 64 + lblk) * 2;
+                lp[0] = s_lred[0];
+                lp[1] = bad_blk ? 1u : 0u;
+                __threadfence();
+                atomicAdd(ws.flags + b * 4 + 3, 1);
+            }
         }
         return;
     }
@@ -945,13 +981,13 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         if (tid < 32) ws.sums[b * 32 + tid] = 0ull;
         if (tid < RRL_NSTAT) ws.stats[(long long)b * RRL_NSTAT + tid] = 0;
         if (tid < 18) ws.gcounts[b * 18 + tid] = 0;
-        if (tid < 4) ws.flags[b * 4 + tid] = 0;
+        if (tid < (handoff ? 3 : 4)) ws.flags[b * 4 + tid] = 0;          // (the hand-off counter belongs to the line blocks then)
         if (tid == 0) { ws.nrec[b] = 0; ws.med[b] = 0.f; ws.xmax[b * 2 + 1] = 0u; }
     }
     __syncthreads();
     pmark(1);
-    // thresholds, extent of the cloud, extent of the pair's lines
-    float pm = 0.f, xm = 0.f, tm = 0.f;
+    // thresholds, extent of the cloud
+    float pm = 0.f, tm = 0.f;
     int badv = 0;
     for (int f = tid; f < nf; f += 1024) {
         float v[9];
@@ -963,29 +999,43 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
         pm = fmaxf(pm, finite_extent(v, badv));
     }
     pmark(2);
+    // the pair's line extent: here when the launch does not allow the hand-off at all (many pairs: the original order of this kernel),
+    // else further down, from the line blocks or by the same scan
+    auto scan_lines = [&](float &xm_out, int &bad_out) {
+        float xm = 0.f;
 #pragma unroll 4
-    for (int l = tid; l < g.nl; l += 1024) {
-        const float *ln = lb + (long long)l * 6;
-        // float suffices: the sum is within 1.8e-7 of |x0|^2 and the factor keeps it an upper bound
-        const float x = __ldg(ln + 3), y = __ldg(ln + 4), z = __ldg(ln + 5);
-        float m = (x * x + y * y + z * z) * 1.000001f;
-        m += 0.f * (__ldg(ln) + __ldg(ln + 1) + __ldg(ln + 2));      // NaN for a NaN / infinite position OR direction
-        if (!(m < INFINITY)) { m = 0.f; badv = 1; }                  // such a line never hits: it stays out of the extent
-        xm = fmaxf(xm, m);
+        for (int l = tid; l < g.nl; l += 1024) {
+            const float *ln = lb + (long long)l * 6;
+            // float suffices: the sum is within 1.8e-7 of |x0|^2 and the factor keeps it an upper bound
+            const float x = __ldg(ln + 3), y = __ldg(ln + 4), z = __ldg(ln + 5);
+            float m = (x * x + y * y + z * z) * 1.000001f;
+            m += 0.f * (__ldg(ln) + __ldg(ln + 1) + __ldg(ln + 2));      // NaN for a NaN / infinite position OR direction
+            if (!(m < INFINITY)) { m = 0.f; bad_out = 1; }               // such a line never hits: it stays out of the extent
+            xm = fmaxf(xm, m);
+        }
+        xm_out = xm;
+    };
+    if (!allow_handoff) {
+        float xm = 0.f;
+        scan_lines(xm, badv);
+        const unsigned c = __reduce_max_sync(0xffffffffu, __float_as_uint(xm));
+        if ((tid & 31) == 0 && c) atomicMax(&s_red[1], c);
     }
     {
-        const unsigned a = __reduce_max_sync(0xffffffffu, __float_as_uint(pm)), c = __reduce_max_sync(0xffffffffu, __float_as_uint(xm));
+        const unsigned a = __reduce_max_sync(0xffffffffu, __float_as_uint(pm));
         const unsigned t = __reduce_max_sync(0xffffffffu, __float_as_uint(tm));
-        if ((tid & 31) == 0) { atomicMax(&s_red[0], a); atomicMax(&s_red[1], c); atomicMax(&s_red[3], t); }
+        if ((tid & 31) == 0) { atomicMax(&s_red[0], a); atomicMax(&s_red[3], t); }
     }
-    const int bad_any = __syncthreads_or(badv);          // (also the barrier the reductions above need)
+    const int bad_pts = __syncthreads_or(badv);          // (also the barrier the reductions above need)
     pmark(3);
     if (tid == 0) {
         ws.pmax[b * 2 + cloud] = s_red[0];
         ws.tmax[b * 2 + cloud] = s_red[3];
         ws.smax[b * 2 + cloud] = 0u;                     // (no super nodes on this path; the forward's last kernel copies it to `keep`)
-        if (cloud == 0) ws.xmax[b * 2] = s_red[1];
-        ws.bad[b * 2 + cloud] = bad_any ? 1u : 0u;       // this cloud's points, or any line of the pair (both CTAs scan them)
+        if (!allow_handoff) {
+            if (cloud == 0) ws.xmax[b * 2] = s_red[1];
+            ws.bad[b * 2 + cloud] = bad_pts ? 1u : 0u;   // this cloud's points, or any line of the pair (both CTAs scan them)
+        }
     }
     // Hilbert order: element i = e * 1024 + tid lives in register v[e]; n2 = E * 1024 >= nfp keys (sentinels sort last).
     // Compare-exchange distances below 32 are warp shuffles, 32..512 go through shared memory (double buffered: one
@@ -1065,6 +1115,51 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
                 }
             }
     }
+    // ---- the pair's line extent: from the line blocks (hand-off), or scanned here ----
+    if (allow_handoff) {
+        __shared__ int s_have;
+        if (tid == 0) {
+            int have = 0;
+            if (handoff) {
+                const volatile int *cnt = ws.flags + b * 4 + 3;
+                const long long t0 = clock64();
+                while (true) {
+                    if ((*cnt & 0xFFFF) == line_blocks) { have = 1; break; }
+                    if (clock64() - t0 > 200000000LL) break;         // ~0.1 s: never in a sound run; the scan below keeps the result right
+                    __nanosleep(32);
+                }
+                __threadfence();
+            }
+            s_have = have;
+        }
+        __syncthreads();
+        int badl = 0;
+        if (s_have) {
+            if (tid < 32) {
+                unsigned x = 0u;
+                for (int i = tid; i < line_blocks; i += 32) {
+                    x = max(x, __ldcg(ws.lpart + ((long long)b * 64 + i) * 2));
+                    badl |= (int)__ldcg(ws.lpart + ((long long)b * 64 + i) * 2 + 1);
+                }
+                x = __reduce_max_sync(0xffffffffu, x);
+                if (tid == 0) s_red[1] = x;
+            }
+        } else {
+            float xm = 0.f;
+            scan_lines(xm, badl);
+            const unsigned c = __reduce_max_sync(0xffffffffu, __float_as_uint(xm));
+            if ((tid & 31) == 0 && c) atomicMax(&s_red[1], c);
+        }
+        const int bad_lines = __syncthreads_or(badl);    // (also publishes s_red[1])
+        if (tid == 0) {
+            if (cloud == 0) ws.xmax[b * 2] = s_red[1];
+            ws.bad[b * 2 + cloud] = (bad_pts | bad_lines) ? 1u : 0u;     // this cloud's points, or any line of the pair
+            if (s_have) {                                // the second reader of the pair leaves the counter at zero for the next forward
+                const int old = atomicAdd(ws.flags + b * 4 + 3, 0x10000);
+                if ((old >> 16) == 1) atomicExch(ws.flags + b * 4 + 3, 0);
+            }
+        }
+    }
     const int nnodes = nfp / kNode;
     const float Eslack = node_slack(s_red[0], s_red[1], s_red[3]);
     pmark(4);
@@ -1125,7 +1220,7 @@ size_t sort_scratch_bytes(int nfp_max, int B) {
 }
 
 // triplets per bounding-sphere node: small clouds are dense in hits per line and want tighter spheres
-static int g_param[16] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 1, 0, 0, 0, 4, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode (0 = by the number of line tiles), [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2), [12] lowest key bit the radix sort of the large path looks at (0 = auto, -1 = every bit), [13] CTAs per SM of the exact kernel's grid (0 = 8), [14] enclosing-ball refinement steps on the large-cloud path (node_kernel: the steps are a third of that kernel, and every rank of a line shard repeats it)
+static int g_param[16] = {0, 0, 16, 32, 0, 0, 0, 0, 8, 0, 1, 0, 0, 0, 4, 0};   // [0] 1 = unfused prep/sort/node launches for small clouds (A/B), [1] node size override, [2] target waves, [3] min nodes per chunk, [4] group-level pushes for small clouds, [5] brute force, [6] lines per thread (2 or 4, 0 = auto), [7] 1 = no super-node level (A/B), [8] enclosing-ball refinement steps of the node centres (0 = centroid), [9] target waves in super-node mode (0 = by the number of line tiles), [10] k-d refinement of the Hilbert order inside windows of 64 (0 = off, 1 = small clouds, 2 = also the large path), [11] entries in flight per thread of the exact kernel (0 = 2), [12] lowest key bit the radix sort of the large path looks at (0 = auto, -1 = every bit), [13] CTAs per SM of the exact kernel's grid (0 = 8), [15] 1 = no line-extent hand-off in the small-cloud prep kernel (A/B), [14] enclosing-ball refinement steps on the large-cloud path (node_kernel: the steps are a third of that kernel, and every rank of a line shard repeats it)
 void set_param(int id, int v) { if (id >= 0 && id < 16) g_param[id] = v; }
 int node_size(const Geometry &g) {
     if (g_param[1] == 8 || g_param[1] == 16) return g_param[1];
@@ -1162,11 +1257,12 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
         int line_blocks = (g.nl + 1023) / 1024;
         if (line_blocks > 64) line_blocks = 64;
         const dim3 grid(g.B, 2 + line_blocks);
+        const int handoff_ok = g_param[15] == 0 && g.B <= 4;       // (see small_prep_kernel; [15] = 1 switches the hand-off off)
         static unsigned long long attr_mask8 = 0ull, attr_mask16 = 0ull;
         if (ensure_dyn_smem(small_prep_kernel<8>, 65536, attr_mask8) || ensure_dyn_smem(small_prep_kernel<16>, 65536, attr_mask16))
             return RRL_ERR_CUDA;
-        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order, use_compressed(g));
-        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order, use_compressed(g));
+        if (G == 8) small_prep_kernel<8><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order, use_compressed(g), handoff_ok);
+        else small_prep_kernel<16><<<grid, 1024, (size_t)n2 * 16, s>>>(tri1, tri2, lines, ws, g, window, sorted, line_blocks, g_param[8], g_param[10], reuse_order, use_compressed(g), handoff_ok);
         count_launch();
         stage_mark(1, s);
         stage_mark(2, s);
