@@ -919,10 +919,12 @@ __global__ void __launch_bounds__(1024) small_prep_kernel(const float *__restric
     // RRL_REUSE_ORDER is honoured only when an earlier forward of this very geometry completed in this workspace (hdr[7]
     // is written by that forward's LAST kernel and by nobody in this launch, so every CTA reads the same value); on a
     // fresh or differently shaped workspace the cloud is simply sorted
-    const bool seen = ws.hdr[7] == order_token(g);
-    reuse = reuse && seen;
-    // Hand-off of the pair's line extent from the line blocks to the cloud CTAs, for SMALL BATCHES only (the launch allows it for
-    // B <= 4): a cloud CTA scanning the pair's 20000 lines itself is 5 us of the demo's 36 us prep kernel, bound by what one SM pulls
+    const bool seen = reuse && ws.hdr[7] == order_token(g);         // (only read when the caller vouches for the workspace: RRL_REUSE_*)
+    reuse = seen;
+    // Hand-off of the pair's line extent from the line blocks to the cloud CTAs, for SMALL BATCHES inside a SESSION only (the launch
+    // allows it for B <= 4 under RRL_REUSE_ORDER / RRL_REUSE_TARGET, i.e. when the caller keeps the workspace untouched between its
+    // forwards -- the counter below must survive from one forward to the next, which a workspace handed back to an allocator in between
+    // cannot promise): a cloud CTA scanning the pair's 20000 lines itself is 5 us of the demo's 36 us prep kernel, bound by what one SM pulls
     // through L2.  With many pairs the hand-off does not pay (measured: DCP 40.9 against 40.3 us, RPM far worse), so the cloud CTAs scan
     // there.  The cloud CTAs come first in the grid (they are the critical path) and wait for blocks dispatched after them -- all CTAs
     // of such a launch are resident at once -- with a bounded wait and the scan as the fall-back, so the results never depend on the
@@ -1257,7 +1259,7 @@ int launch_prep(const float *tri1, const float *tri2, const float *lines, const 
         int line_blocks = (g.nl + 1023) / 1024;
         if (line_blocks > 64) line_blocks = 64;
         const dim3 grid(g.B, 2 + line_blocks);
-        const int handoff_ok = g_param[15] == 0 && g.B <= 4;       // (see small_prep_kernel; [15] = 1 switches the hand-off off)
+        const int handoff_ok = g_param[15] == 0 && g.B <= 4 && reuse_order;    // (see small_prep_kernel; [15] = 1 switches the hand-off off)
         static unsigned long long attr_mask8 = 0ull, attr_mask16 = 0ull;
         if (ensure_dyn_smem(small_prep_kernel<8>, 65536, attr_mask8) || ensure_dyn_smem(small_prep_kernel<16>, 65536, attr_mask16))
             return RRL_ERR_CUDA;
