@@ -345,8 +345,11 @@ int rrl_measure_stages(const float *tri1, const float *tri2, const float *lines,
 int rrl_debug_set_dense_variant(int variant);
 /* launch-geometry knobs for A/B measurements: id 1 = triplets per node (0 auto, 8, 16), 2 = target waves of CTAs,
  * 3 = minimum nodes per CTA chunk, 5 = brute-force cross-check kernel, 6 = lines per thread, 7 = 1: no super-node level,
- * 8 = enclosing-ball steps of the node centres, 9 = target waves in super-node mode, 10 = k-d refinement of the Hilbert
- * order (0 off, 1 small clouds, 2 everywhere).  Results never depend on them. */
+ * 8 = enclosing-ball steps of the node centres (small clouds), 9 = target waves in super-node mode (0 = by the number of line
+ * tiles), 10 = k-d refinement of the Hilbert order (0 off, 1 small clouds, 2 everywhere), 11 = entries in flight per thread of
+ * the exact kernel, 12 = lowest key bit the large-cloud radix sort looks at (0 auto, -1 every bit), 13 = CTAs per SM of the
+ * exact kernel's grid, 14 = enclosing-ball steps on the large-cloud path, 15 = 1: no line-extent hand-off in the small-cloud
+ * prep kernel.  Results never depend on them. */
 int rrl_debug_set_param(int id, int value);
 
 #ifdef __cplusplus
