@@ -93,6 +93,9 @@ int rrl_loss_forward(const float *tri1, const float *tri2, const float *lines,
  * results (it only decides which triplets share a bounding sphere), so this is safe for clouds that changed -- and
  * pays when they changed little: the steps of a registration loop (the target is fixed, the source moves rigidly:
  * test_demo_optimized_Lie_Algebra.py:46-66) or the iterations of RPM-Net / FMR on one batch.
+ * Contract of both flags: between its forwards the caller keeps `workspace` to itself (nobody else writes it).  Besides the
+ * order, small state survives there from one forward to the next (for batches of up to 4 pairs of small clouds, the
+ * counter by which the prep kernel's CTAs hand each other the pair's line extent).
  */
 #define RRL_REUSE_ORDER 1
 /* RRL_REUSE_TARGET (implies RRL_REUSE_ORDER; clouds above 4096 triplets, ignored below): additionally, cloud 2 -- the
